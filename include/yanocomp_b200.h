@@ -1,0 +1,195 @@
+/*
+ * yanocomp_b200 -- C ABI of the B200 (sm_100a) implementation of the
+ * `yanocomp gmmtest` per-position hot path.
+ *
+ * The reference (bartongroup/yanocomp) is pure Python and has no FFI layer;
+ * its boundary for this path is the Python function
+ *     parallel_test(opts) -> (DataFrame, sm_preds)      yanocomp/gmmtest.py:182
+ * which loops test_chunk (gmmtest.py:139) -> iter_positions (gmmtest.py:81)
+ * -> position_stats (yanocomp/stats.py:445) once per (feature, position).
+ * The entry points below are what a ctypes binding placed inside
+ * `test_chunk` would call instead of that loop.  Every
+ * function cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C, no exceptions across the ABI; every call returns 0 on success
+ *     or a negative YC_E* code / positive cudaError_t, and
+ *     yc_last_error() gives a message for the calling thread;
+ *   - unless a name ends in `_host`, every pointer is a DEVICE pointer owned
+ *     by the caller, and `stream` is a cudaStream_t passed as void* (NULL =
+ *     the legacy default stream).  Calls are asynchronous on that stream;
+ *   - per-position arrays are structure-of-arrays indexed by the GLOBAL
+ *     COLUMN index g = col_off[f] + c  (feature f, column c);
+ *   - per-fit arrays are indexed by the SLOT of the position in `fit_list`.
+ *
+ * Packed ragged batch (what the reworked io.py builds from the prep HDF5,
+ * reference yanocomp/io.py:296-343):
+ *   feature f owns a position-major fp16 matrix
+ *       events[x_off[f] + c*ld[f] + r]     c in [0,n_cols[f]), r in [0,n_reads[f])
+ *   NaN = the read has no event at that position.  Column c is transcript /
+ *   genome position pos0[f] + c.  Reads are sorted by sample: sample s owns
+ *   rows [samp_start[f*(R+1)+s], samp_start[f*(R+1)+s+1]); samples
+ *   0..n_cntrl-1 are the control replicates (`-c` files in order), the rest
+ *   the treatment replicates (`-t` files in order).
+ */
+#ifndef YANOCOMP_B200_H
+#define YANOCOMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YC_MAX_WINDOW   9      /* window sizes 1,3,5,7,9 */
+#define YC_MAX_SAMPLES  16     /* replicates over both conditions */
+#define YC_NCOMP        3      /* two Gaussians + uniform outlier component */
+
+/* error codes (negative; positive values are cudaError_t) */
+#define YC_OK            0
+#define YC_EINVAL       -1     /* bad argument (see yc_last_error) */
+#define YC_ECAPACITY    -2     /* a position needs more shared memory than an SM has */
+#define YC_ENOGPU       -3     /* no sm_100 device */
+
+/* per-position status, written by yc_ks_batch / yc_gmm_*_batch */
+#define YC_ST_NOT_A_WINDOW 0   /* fails the depth / window filters   gmmtest.py:24-61 */
+#define YC_ST_KS_FILTERED  1   /* entered position_stats, failed the gate  stats.py:465 */
+#define YC_ST_TESTED       2   /* fitted and tested (was_tested = True)    stats.py:511 */
+#define YC_ST_FIT_FAILED   3   /* the LinAlgError path                     stats.py:478-479 */
+#define YC_ST_DEGENERATE   4   /* constant column: np.linalg.svd would raise, stats.py:26 */
+#define YC_ST_KS_ONLY      5   /* --no-gmm                                 stats.py:460-462 */
+#define YC_ST_GATED        6   /* transient: passed the gate, waiting for the fit */
+
+typedef struct yc_batch {
+    int32_t  n_features;         /* F */
+    int32_t  n_samples;          /* R  (<= YC_MAX_SAMPLES) */
+    int32_t  n_cntrl;            /* Rc: samples [0,Rc) are control */
+    int32_t  max_reads;          /* max over features of n_reads (sizes shared memory) */
+    int64_t  total_cols;         /* sum of n_cols = number of candidate positions */
+    const uint16_t *events;      /* IEEE binary16 bits, layout above */
+    const int64_t  *x_off;       /* [F]   element offset of each feature matrix */
+    const int32_t  *n_cols;      /* [F] */
+    const int32_t  *n_reads;     /* [F] */
+    const int32_t  *ld;          /* [F]   row stride in elements (>= n_reads) */
+    const int64_t  *col_off;     /* [F+1] prefix sum of n_cols */
+    const int32_t  *samp_start;  /* [F*(R+1)] */
+    const uint64_t *feature_key; /* [F]   FNV-1a 64 of the feature id (RNG key) */
+    const int64_t  *pos0;        /* [F]   position of column 0 */
+    const uint8_t  *reverse;     /* [F]   1 = '-' strand: window columns reversed, gmmtest.py:37-38 */
+    const int32_t  *col_feature; /* [total_cols] feature of each global column (yc_fill_col_feature) */
+} yc_batch_t;
+
+typedef struct yc_params {
+    int32_t  window_size;        /* -w, gmmtest.py:283-285 (odd, <= YC_MAX_WINDOW) */
+    int32_t  min_read_depth;     /* -n, gmmtest.py:245-251, :301-303 */
+    int32_t  max_fit_depth;      /* -d, gmmtest.py:304-305 */
+    int32_t  gmm;                /* --gmm/--no-gmm, gmmtest.py:310-311 */
+    double   min_ks;             /* -k, gmmtest.py:306-307 */
+    double   fdr_threshold;      /* -f, gmmtest.py:308-309 */
+    double   outlier_factor;     /* -e, gmmtest.py:296-298 */
+    uint64_t seed;               /* --random-seed, gmmtest.py:315 */
+} yc_params_t;
+
+/* fitted model + test results of one gated position (slot-indexed SoA) */
+typedef struct yc_fit_out {
+    double  *mu;        /* [n_fit*2*w]     component means            stats.py:277-280 */
+    double  *cov;       /* [n_fit*2*w*w]   component covariances      stats.py:387-392 */
+    double  *box;       /* [n_fit*w*2]     uniform (lo,hi) per column stats.py:183-186 */
+    double  *logw;      /* [n_fit*R*3]     per-sample log weights     stats.py:207-211 */
+    double  *cw;        /* [n_fit*3]       combined weights           stats.py:251-253 */
+    int32_t *iters;     /* [n_fit]         E-steps performed          stats.py:200-222 */
+    double  *loglik;    /* [n_fit]         last log-likelihood sum */
+    /* yc_gtest_smpred_batch */
+    double  *preds;     /* [n_fit*R*3]     np.round(weights*sizes)    stats.py:296 */
+    double  *stats;     /* [n_fit*8]       g, hom_g, p, cntrl_frac, treat_frac,
+                                           log_odds, lower_ci, upper_ci  stats.py:316-355 */
+    int64_t *post_off;  /* [n_fit]         offset (in reads) into `post`, -1 = none */
+} yc_fit_out_t;
+
+const char *yc_version(void);
+const char *yc_last_error(void);
+
+/* how many bytes of dynamic shared memory the kernels need for this batch
+ * (so a caller can reject a batch up front); returns YC_ECAPACITY if any
+ * kernel cannot run. out[0..3] = ks, init, em, gtest. */
+int yc_smem_bytes(const yc_batch_t *batch_host_copy, const yc_params_t *p, int64_t out[4]);
+
+/* col_feature[g] = f for g in [col_off[f], col_off[f+1])  (helper, one launch) */
+int yc_fill_col_feature(int32_t n_features, const int64_t *col_off,
+                        int32_t *col_feature, void *stream);
+
+/*
+ * Kernel 1 -- window filters + PCA + two-sample KS, one CTA per candidate
+ * position.  Replaces, per position: get_valid_pos / get_valid_windows /
+ * index_pos_range / test_depth (gmmtest.py:24-61), subsample (stats.py:52-59),
+ * pca_comp1 (stats.py:20-31), _ks_d / ks_2samp / pca_kstest (stats.py:34-73)
+ * and the gate of position_stats (stats.py:460-465).
+ *   ks_stat, ks_pval [total_cols]; n_c, n_t [total_cols] = complete-window rows
+ *   per condition (before sub-sampling); status [total_cols];
+ *   fit_list [total_cols] receives the global column index of every position
+ *   that passed the gate (unordered), *fit_count their number (device int32,
+ *   zeroed by the call).
+ */
+int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
+                double *ks_stat, double *ks_pval, int32_t *n_c, int32_t *n_t,
+                uint8_t *status, int32_t *fit_list, int32_t *fit_count,
+                void *stream);
+
+/*
+ * Kernel 2a -- model initialisation, one CTA per gated position.  Replaces
+ * the per-replicate subsample of fit_gmm (stats.py:266-269),
+ * kmeans_init_clusters (stats.py:81-124: pm.Kmeans k-means++ x3, MAD outlier
+ * labelling) and initialise_gmms (stats.py:127-191).  Writes mu, cov, box,
+ * logw; status[g] becomes YC_ST_FIT_FAILED on a failed Cholesky / zero-width
+ * box.  labels (optional, may be NULL): [n_fit*max_fit_rows] int8 initial labels
+ * in pooled fit order, for parity tests.
+ */
+int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p,
+                      const int32_t *fit_list, int32_t n_fit,
+                      yc_fit_out_t *out, uint8_t *status,
+                      int8_t *labels, int32_t max_fit_rows, void *stream);
+
+/*
+ * Kernel 2b -- multi-sample EM, one CTA per gated position.  Replaces em
+ * (stats.py:194-225) and the pomegranate calls under it (from_summaries,
+ * GeneralMixtureModel.summarize) plus the weight bookkeeping of
+ * fit_multisamp_gmm (stats.py:250-253).  Updates mu, cov, logw in place,
+ * writes cw, iters, loglik; status[g] = YC_ST_TESTED or YC_ST_FIT_FAILED.
+ */
+int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p,
+                    const int32_t *fit_list, int32_t n_fit,
+                    yc_fit_out_t *out, uint8_t *status, void *stream);
+
+/*
+ * Kernel 3 -- per-sample modified-fraction counts, G-tests, log odds and the
+ * single-molecule posteriors, one CTA per gated position.  Replaces the
+ * rounding of fit_gmm (stats.py:296-297), gmm_g_test (stats.py:316-338),
+ * calculate_fractional_stats (stats.py:341-355) and predict_proba
+ * (stats.py:494-499).  When `post` is not NULL, positions with p < fdr
+ * threshold append 2 doubles per complete-window read (P(dist2), P(outlier),
+ * pooled read order) at post[2*post_off[slot]...]; *post_cursor (device
+ * int64, zeroed by the call) counts reads written; post_capacity is in reads.
+ */
+int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p,
+                          const int32_t *fit_list, int32_t n_fit,
+                          yc_fit_out_t *out, const uint8_t *status,
+                          double *post, int64_t post_capacity,
+                          int64_t *post_cursor, void *stream);
+
+/*
+ * Host-side scalar entry points (no GPU needed): the same code the kernels
+ * run for scipy.stats.kstwobign.sf (stats.py:48), chi2.sf at 1 dof and the
+ * G-test / fraction block (stats.py:302-355), exported so CPU tests can pin
+ * them against SciPy; plus the RNG key functions shared with the oracle.
+ */
+double   yc_kolmogorov_sf_host(double x);
+double   yc_chi2_sf_1dof_host(double g);
+void     yc_gtest_fractions_host(const double *preds, int32_t nrow_c, int32_t nrow_t,
+                                 double thr, double *out8);
+uint64_t yc_position_key_host(uint64_t seed, uint64_t fkey, int64_t pos);
+uint64_t yc_mix64_host(uint64_t z);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YANOCOMP_B200_H */

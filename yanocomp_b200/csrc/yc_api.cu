@@ -1,0 +1,167 @@
+// extern "C" surface of libyanocomp_b200.so (see include/yanocomp_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "yc_internal.h"
+#include "yc_common.cuh"
+#include "yc_stats.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(int e, const char *what) {
+    if (e == 0) return 0;
+    if (e > 0) return fail(e, "%s: %s", what, cudaGetErrorString((cudaError_t)e));
+    return fail(e, "%s: invalid argument", what);
+}
+
+int check_common(const yc_batch_t *b, const yc_params_t *p) {
+    if (!b || !p) return fail(YC_EINVAL, "null batch / params");
+    if (b->n_features < 0 || b->total_cols < 0) return fail(YC_EINVAL, "negative sizes");
+    if (b->n_samples < 2 || b->n_samples > YC_MAX_SAMPLES)
+        return fail(YC_EINVAL, "n_samples=%d outside [2,%d]", b->n_samples, YC_MAX_SAMPLES);
+    if (b->n_cntrl < 1 || b->n_cntrl >= b->n_samples)
+        return fail(YC_EINVAL, "n_cntrl=%d must leave at least one sample per condition", b->n_cntrl);
+    if (p->window_size < 1 || p->window_size > YC_MAX_WINDOW || !(p->window_size & 1))
+        return fail(YC_EINVAL, "window_size=%d must be odd and <= %d", p->window_size, YC_MAX_WINDOW);
+    if (p->max_fit_depth < 1) return fail(YC_EINVAL, "max_fit_depth must be >= 1");
+    if (p->min_read_depth < 1) return fail(YC_EINVAL, "min_read_depth must be >= 1");
+    if (b->total_cols > 0x7fffffffll) return fail(YC_EINVAL, "more than 2^31-1 candidate positions in one batch");
+    return 0;
+}
+
+int smem_limit() {
+    static int limit = -1;
+    if (limit < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+            return 0;
+        limit = v;
+    }
+    return limit;
+}
+
+int check_smem(int need, const char *kernel) {
+    const int lim = smem_limit();
+    if (lim == 0) return fail(YC_ENOGPU, "no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+    if (need > lim)
+        return fail(YC_ECAPACITY, "%s needs %d B of shared memory per position, the device offers %d B "
+                    "(lower --max-fit-depth or split the feature)", kernel, need, lim);
+    return 0;
+}
+
+__global__ void fill_col_feature_kernel(int n_features, const int64_t *__restrict__ col_off,
+                                        int32_t *__restrict__ col_feature) {
+    for (int f = blockIdx.x; f < n_features; f += gridDim.x) {
+        const int64_t a = col_off[f], e = col_off[f + 1];
+        for (int64_t g = a + threadIdx.x; g < e; g += blockDim.x) col_feature[g] = f;
+    }
+}
+
+}  // namespace
+
+namespace yc {
+int ks_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
+}
+
+extern "C" {
+
+const char *yc_version(void) { return "yanocomp_b200 0.1.0 (sm_100a)"; }
+const char *yc_last_error(void) { return g_err; }
+
+int yc_smem_bytes(const yc_batch_t *b, const yc_params_t *p, int64_t out[4]) {
+    if (int e = check_common(b, p)) return e;
+    out[0] = yc::ks_smem_bytes(*b, *p);
+    out[1] = yc::fit_smem_bytes(*b, *p, 0);
+    out[2] = yc::fit_smem_bytes(*b, *p, 1);
+    out[3] = yc::fit_smem_bytes(*b, *p, 2);
+    const int64_t lim = 232448;                 // 227 KB opt-in maximum of sm_100
+    for (int k = 0; k < 4; ++k)
+        if (out[k] > lim) return fail(YC_ECAPACITY, "kernel %d needs %lld B of shared memory (> %lld)",
+                                      k, (long long)out[k], (long long)lim);
+    return 0;
+}
+
+int yc_fill_col_feature(int32_t n_features, const int64_t *col_off, int32_t *col_feature, void *stream) {
+    if (n_features <= 0) return 0;
+    const int grid = n_features < 148 * 8 ? n_features : 148 * 8;
+    fill_col_feature_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_features, col_off, col_feature);
+    return cuda_fail((int)cudaGetLastError(), "yc_fill_col_feature");
+}
+
+int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
+                double *ks_stat, double *ks_pval, int32_t *n_c, int32_t *n_t,
+                uint8_t *status, int32_t *fit_list, int32_t *fit_count, void *stream) {
+    if (int e = check_common(b, p)) return e;
+    if (!ks_stat || !ks_pval || !n_c || !n_t || !status || !fit_list || !fit_count)
+        return fail(YC_EINVAL, "yc_ks_batch: null output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaMemsetAsync(fit_count, 0, sizeof(int32_t), st);
+    if (ce != cudaSuccess) return cuda_fail((int)ce, "yc_ks_batch memset");
+    if (b->total_cols == 0) return 0;
+    if (int e = check_smem(yc::ks_smem_bytes(*b, *p), "yc_ks_batch")) return e;
+    return cuda_fail(yc::ks_dispatch(*b, *p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st),
+                     "yc_ks_batch");
+}
+
+int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
+                      yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows, void *stream) {
+    if (int e = check_common(b, p)) return e;
+    if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_init_batch: null pointer");
+    if (n_fit <= 0) return 0;
+    if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 0), "yc_gmm_init_batch")) return e;
+    return cuda_fail(yc::init_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows,
+                                       (cudaStream_t)stream), "yc_gmm_init_batch");
+}
+
+int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
+                    yc_fit_out_t *out, uint8_t *status, void *stream) {
+    if (int e = check_common(b, p)) return e;
+    if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_em_batch: null pointer");
+    if (n_fit <= 0) return 0;
+    if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 1), "yc_gmm_em_batch")) return e;
+    return cuda_fail(yc::em_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
+                     "yc_gmm_em_batch");
+}
+
+int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
+                          yc_fit_out_t *out, const uint8_t *status, double *post, int64_t post_capacity,
+                          int64_t *post_cursor, void *stream) {
+    if (int e = check_common(b, p)) return e;
+    if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gtest_smpred_batch: null pointer");
+    if (post && !post_cursor) return fail(YC_EINVAL, "yc_gtest_smpred_batch: post without post_cursor");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (post_cursor) {
+        cudaError_t ce = cudaMemsetAsync(post_cursor, 0, sizeof(int64_t), st);
+        if (ce != cudaSuccess) return cuda_fail((int)ce, "yc_gtest_smpred_batch memset");
+    }
+    if (n_fit <= 0) return 0;
+    if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 2), "yc_gtest_smpred_batch")) return e;
+    return cuda_fail(yc::gtest_dispatch(*b, *p, fit_list, n_fit, *out, status, post, post_capacity,
+                                        post_cursor, st), "yc_gtest_smpred_batch");
+}
+
+// ---- host-side scalar entry points: the same __host__ __device__ code the
+// kernels run, callable without a GPU so the CPU test-suite can pin it
+// against SciPy (tests/test_stats_host.py).
+double yc_kolmogorov_sf_host(double x) { return yc::kolmogorov_sf(x); }
+double yc_chi2_sf_1dof_host(double g) { return yc::chi2_sf_1dof(g); }
+void yc_gtest_fractions_host(const double *preds, int32_t nrow_c, int32_t nrow_t, double thr, double *out8) {
+    yc::gtest_fractions(preds, nrow_c, nrow_t, thr, out8);
+}
+uint64_t yc_position_key_host(uint64_t seed, uint64_t fkey, int64_t pos) {
+    return yc::position_key(seed, fkey, pos);
+}
+uint64_t yc_mix64_host(uint64_t z) { return yc::mix64(z); }
+
+}  // extern "C"

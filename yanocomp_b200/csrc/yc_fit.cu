@@ -1,0 +1,845 @@
+// Kernel 2a (model initialisation) and 2b (multi-sample EM), one CTA per
+// gated position.
+//
+// Reference semantics (file:line under /root/reference/yanocomp):
+//   stats.py:266-269   per-REPLICATE sub-sampling to max_fit_depth
+//   stats.py:81-124    pm.Kmeans(2,'kmeans++',n_init=3).fit(X,100,0.5),
+//                      distances to the centroids, MAD outlier labelling
+//   stats.py:127-191   ML Gaussians per label, per-sample initial weights,
+//                      uniform box from the outlier rows
+//   stats.py:194-225   the EM schedule (iteration 0 is E-only; inertia
+//                      1-(0.99*(2+it)^-1e-3); pseudocount 0.5; stop when the
+//                      log-likelihood gain <= 0.1, NaN, or after 1001 E-steps)
+// pomegranate behaviour is restated as documented in oracle/yanocomp_oracle.py
+// (ASSUMPTIONS A1-A7).  The initialisation is arithmetic on exact binary16
+// values (sums of values and of pairwise products are exact in FP64), so it
+// is written with separately rounded operations to reproduce the oracle bit
+// for bit; EM runs in FP64 with fused multiply-adds.
+#include "yc_common.cuh"
+#include "yc_stats.cuh"
+
+namespace yc {
+
+#define YC_LOG_2PI 1.8378770664093453
+
+__host__ __device__ inline int cap_pow2_bytes(int cap) {
+    int P = 32;
+    while (P < cap) P <<= 1;
+    return P * (int)sizeof(double);
+}
+
+struct FitSmem {
+    int xs_off, srow_off, lab_off, sort_off, mask_off, wordoff_off, cnt_off, fstart_off,
+        red_off, hist_off, sel_off, par_off, part_off, wsum_off, total;
+};
+
+// which = 0: init kernel (needs sort buffer + labels), 1: EM / gtest kernels
+__host__ __device__ inline FitSmem fit_smem_layout(int W, int R, int max_reads, int cap, int which) {
+    FitSmem s;
+    const int NS = 1 + W + W * (W + 1) / 2;
+    int o = 0;
+    s.sort_off = o;    o += (which == 0 ? cap_pow2_bytes(cap) : 0);
+    s.red_off = o;     o += 64 * YC_NWARPS * (int)sizeof(double);
+    s.par_off = o;     o += (2 * (W + 2 * W * W + 2) + 2 * W + 3 * YC_MAX_SAMPLES + 8) * (int)sizeof(double);
+    s.part_off = o;    o += (which == 1 ? (YC_NWARPS + 1) * (2 * NS + 1) : 0) * (int)sizeof(double);
+    s.wsum_off = o;    o += (which == 1 ? YC_NWARPS * YC_MAX_SAMPLES * 3 : 0) * (int)sizeof(double);
+    s.sel_off = o;     o += 4 * (int)sizeof(unsigned long long);
+    s.mask_off = o;    o += ((max_reads + 31) / 32 + 1) * (int)sizeof(uint32_t);
+    s.wordoff_off = o; o += ((max_reads + 31) / 32 + 1) * (int)sizeof(int);
+    s.cnt_off = o;     o += (W + 1) * R * (int)sizeof(int);
+    s.fstart_off = o;  o += (YC_MAX_SAMPLES + 2) * (int)sizeof(int);
+    s.hist_off = o;    o += 256 * (int)sizeof(int);
+    s.xs_off = o;      o += W * cap * (int)sizeof(uint16_t);
+    o = (o + 3) & ~3;
+    s.srow_off = o;    o += cap;
+    s.lab_off = o;     o += (which == 0 ? cap : 0);
+    s.total = (o + 15) & ~15;
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// shared front end: complete rows -> per-sample sub-sampling -> compaction
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int block_excl_scan_i(int v, int *scratch, int &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(YC_FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < YC_NWARPS; ++w) { if (w < wid) base += scratch[w]; tot += scratch[w]; }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+// ordered exclusive prefix of popc(mask[wd]) into wordoff[wd]; returns total
+__device__ __forceinline__ int mask_word_prefix(const uint32_t *mask, int nwords, int *wordoff, int *scratch) {
+    const int C = (nwords + YC_BLOCK - 1) / YC_BLOCK;
+    const int w0 = threadIdx.x * C, w1 = min(w0 + C, nwords);
+    int loc = 0;
+    for (int wd = w0; wd < w1; ++wd) loc += __popc(mask[wd]);
+    int total;
+    int run = block_excl_scan_i(loc, scratch, total);
+    for (int wd = w0; wd < w1; ++wd) { wordoff[wd] = run; run += __popc(mask[wd]); }
+    __syncthreads();
+    return total;
+}
+
+template <int W>
+struct FitCtx {
+    Window<W> w;
+    uint16_t *xs;      // [W][cap] binary16 bits of the fit rows, pooled order
+    uint8_t *srow;     // [cap] sample of each fit row
+    int *fstart;       // [R+1] first fit row of each sample
+    int *cnt;          // window_scan counters
+    uint32_t *mask;
+    int *wordoff;
+    int cap, n;        // n = fit rows
+    int n_c, n_t;      // complete rows per condition (before sub-sampling)
+};
+
+template <int W>
+__device__ __forceinline__ bool fit_front_end(const yc_batch_t &b, const yc_params_t &p, int64_t g,
+                                              unsigned char *smem, const FitSmem &L, int cap,
+                                              bool subsample, FitCtx<W> &c) {
+    const int R = b.n_samples, tid = threadIdx.x;
+    c.xs = reinterpret_cast<uint16_t *>(smem + L.xs_off);
+    c.srow = reinterpret_cast<uint8_t *>(smem + L.srow_off);
+    c.fstart = reinterpret_cast<int *>(smem + L.fstart_off);
+    c.cnt = reinterpret_cast<int *>(smem + L.cnt_off);
+    c.mask = reinterpret_cast<uint32_t *>(smem + L.mask_off);
+    c.wordoff = reinterpret_cast<int *>(smem + L.wordoff_off);
+    c.cap = cap;
+    int *hist = reinterpret_cast<int *>(smem + L.hist_off);
+    unsigned long long *sel = reinterpret_cast<unsigned long long *>(smem + L.sel_off);
+    int *iscr = reinterpret_cast<int *>(smem + L.red_off);
+
+    if (!window_setup<W>(b, p, g, c.w)) return false;
+    for (int i = tid; i < (W + 1) * R; i += YC_BLOCK) c.cnt[i] = 0;
+    __syncthreads();
+    window_scan<W>(c.w, R, c.mask, c.cnt);
+    __syncthreads();
+    c.n_c = 0; c.n_t = 0;
+    for (int s = 0; s < R; ++s) { if (s < b.n_cntrl) c.n_c += c.cnt[W * R + s]; else c.n_t += c.cnt[W * R + s]; }
+    if (subsample) {
+        for (int s = 0; s < R; ++s) {
+            const int have = c.cnt[W * R + s];
+            subsample_rows(c.mask, c.w.samp_start[s], c.w.samp_start[s + 1], have, p.max_fit_depth,
+                           c.w.pkey, YC_STREAM_FIT_SAMPLE0 + s, hist, sel);
+        }
+    }
+    if (tid == 0) {
+        int acc = 0;
+        for (int s = 0; s < R; ++s) {
+            c.fstart[s] = acc;
+            const int have = c.cnt[W * R + s];
+            acc += subsample ? min(have, p.max_fit_depth) : have;
+        }
+        c.fstart[R] = acc;
+    }
+    const int nwords = (c.w.n_reads + 31) >> 5;
+    c.n = mask_word_prefix(c.mask, nwords, c.wordoff, iscr);
+    return true;
+}
+
+// copy the selected rows into shared memory (only when they fit: n <= cap)
+template <int W>
+__device__ __forceinline__ void fit_gather(const FitCtx<W> &c, int R) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nwords = (c.w.n_reads + 31) >> 5;
+    for (int wd = wid; wd < nwords; wd += YC_NWARPS) {
+        const uint32_t m = c.mask[wd];
+        if ((m >> lane) & 1u) {
+            const int r = wd * 32 + lane;
+            const int rank = c.wordoff[wd] + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+            for (int j = 0; j < W; ++j) c.xs[j * c.cap + rank] = __ldg(c.w.col[j] + r);
+            int s = 0;
+            while (s + 1 < R && r >= c.w.samp_start[s + 1]) ++s;
+            c.srow[rank] = (uint8_t)s;
+        }
+    }
+    __syncthreads();
+}
+
+// NumPy's add.reduce over a contiguous axis of length W (pairwise_sum with
+// its 8-accumulator unrolling once W >= 8), on separately rounded terms.
+template <int W>
+__device__ __forceinline__ double np_sum(const double (&a)[W]) {
+    if (W < 8) {
+        double s = a[0];
+#pragma unroll
+        for (int j = 1; j < W; ++j) s = add_rn(s, a[j]);
+        return s;
+    } else {
+        double s = add_rn(add_rn(add_rn(a[0], a[1]), add_rn(a[2], a[3])),
+                          add_rn(add_rn(a[4], a[5]), add_rn(a[6], a[7])));
+#pragma unroll
+        for (int j = 8; j < W; ++j) s = add_rn(s, a[j]);
+        return s;
+    }
+}
+template <int W>
+__device__ __forceinline__ double sqdist(const double (&x)[W], const double *c) {
+    double t[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) { const double d = sub_rn(x[j], c[j]); t[j] = mul_rn(d, d); }
+    return np_sum<W>(t);
+}
+template <int W>
+__device__ __forceinline__ void load_row(const FitCtx<W> &c, int i, double (&x)[W]) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) x[j] = h2d(c.xs[j * c.cap + i]);
+}
+
+// Gaussian of one label from its exact sufficient statistics
+// (oracle MVNormal.from_samples: blank N(0,I), one fit at inertia 0).
+template <int W>
+__device__ inline bool ml_gaussian(const double *S, double *mu, double *cov) {
+    // S = [S0, S1[W], S2 upper triangle]
+    const double s0 = S[0];
+    if (s0 < 1e-7) {
+        for (int a = 0; a < W; ++a) { mu[a] = 0.0; for (int c2 = 0; c2 < W; ++c2) cov[a * W + c2] = (a == c2) ? 1.0 : 0.0; }
+        return true;
+    }
+    double u[W];
+    for (int a = 0; a < W; ++a) u[a] = div_rn(S[1 + a], s0);
+    for (int a = 0; a < W; ++a)
+        for (int c2 = 0; c2 < W; ++c2) {
+            const int lo = a < c2 ? a : c2, hi = a < c2 ? c2 : a;
+            const double s2 = S[1 + W + lo * W - lo * (lo - 1) / 2 + (hi - lo)];
+            double t = sub_rn(s2, mul_rn(S[1 + a], u[c2]));
+            t = sub_rn(t, mul_rn(u[a], S[1 + c2]));
+            t = add_rn(t, mul_rn(s0, mul_rn(u[a], u[c2])));
+            cov[a * W + c2] = div_rn(t, s0);
+        }
+    // inertia 0 blend: old*0 + new*1
+    for (int a = 0; a < W; ++a) mu[a] = u[a];
+    double linv[W * W], logdet;
+    return cholesky_inverse<W>(cov, linv, logdet);
+}
+
+// ---------------------------------------------------------------------------
+// Kernel 2a
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(YC_BLOCK)
+gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+                const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+                uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = b.n_samples, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const FitSmem L = fit_smem_layout(W, R, b.max_reads, cap, 0);
+    double *sortbuf = reinterpret_cast<double *>(smem_raw + L.sort_off);
+    double *red = reinterpret_cast<double *>(smem_raw + L.red_off);
+    double *par = reinterpret_cast<double *>(smem_raw + L.par_off);
+    int8_t *lab = reinterpret_cast<int8_t *>(smem_raw + L.lab_off);
+    int *ired = reinterpret_cast<int *>(red);
+    const int slot = blockIdx.x;
+    const int64_t g = fit_list[slot];
+    constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
+
+    FitCtx<W> c;
+    if (!fit_front_end<W>(b, p, g, smem_raw, L, cap, true, c) || c.n > cap || c.n < 1) {
+        if (tid == 0) status[g] = YC_ST_FIT_FAILED;
+        return;
+    }
+    fit_gather<W>(c, R);
+    const int n = c.n;
+    const uint64_t pkey = c.w.pkey;
+
+    // ---------------- k-means++ x3 + Lloyd  (assumption A2)
+    double best[2 * W], best_total = INFINITY;
+    bool have_best = false;
+    const int C = (n + YC_BLOCK - 1) / YC_BLOCK;
+    const int i0c = min(tid * C, n), i1c = min(i0c + C, n);
+    for (int restart = 0; restart < 3; ++restart) {
+        double cen[2 * W];
+        {
+            const double u0 = rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 0);
+            const int i0 = min((int)(u0 * (double)n), n - 1);
+            double x[W];
+            load_row<W>(c, i0, x);
+#pragma unroll
+            for (int j = 0; j < W; ++j) cen[j] = x[j];
+        }
+        {   // second centre: D^2 sampling through the cumulative sum
+            double loc = 0.0;
+            for (int i = i0c; i < i1c; ++i) { double x[W]; load_row<W>(c, i, x); loc = add_rn(loc, sqdist<W>(x, cen)); }
+            // exclusive scan of the chunk sums over the CTA
+            double inc = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(YC_FULL, inc, o); if (lane >= o) inc = add_rn(inc, t); }
+            if (lane == 31) red[wid] = inc;
+            __syncthreads();
+            double base = 0.0, total = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < YC_NWARPS; ++w2) { if (w2 < wid) base = add_rn(base, red[w2]); total = add_rn(total, red[w2]); }
+            __syncthreads();
+            double run = add_rn(base, sub_rn(inc, loc));
+            const double u1 = rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 1);
+            const double target = mul_rn(u1, total);
+            int below = 0;
+            for (int i = i0c; i < i1c; ++i) { double x[W]; load_row<W>(c, i, x); run = add_rn(run, sqdist<W>(x, cen)); below += (run <= target); }
+            below = block_sum_i(below, ired);
+            const int i1 = min(below, n - 1);
+            double x[W];
+            load_row<W>(c, i1, x);
+#pragma unroll
+            for (int j = 0; j < W; ++j) cen[W + j] = x[j];
+        }
+        int iteration = 0;
+        double improvement = INFINITY, last = INFINITY, total = INFINITY;
+        double acc[2 * W + 3];
+        bool have_sums = false;
+        while (improvement > 0.5 && iteration < 101) {
+            if (have_sums) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (acc[2 * W + 1 + k] > 0.0)
+#pragma unroll
+                        for (int j = 0; j < W; ++j) cen[k * W + j] = div_rn(acc[k * W + j], acc[2 * W + 1 + k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2 * W + 3; ++k) acc[k] = 0.0;
+            for (int i = tid; i < n; i += YC_BLOCK) {
+                double x[W];
+                load_row<W>(c, i, x);
+                const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
+                const int k = d1 < d0;
+                acc[2 * W] += k ? d1 : d0;
+                acc[2 * W + 1 + k] += 1.0;
+#pragma unroll
+                for (int j = 0; j < W; ++j) { if (k) acc[W + j] += x[j]; else acc[j] += x[j]; }
+            }
+            block_sum<2 * W + 3>(acc, red);
+            have_sums = true;
+            total = acc[2 * W];
+            if (iteration > 0) improvement = last - total;
+            ++iteration;
+            last = total;
+        }
+        if (total < best_total) {
+            best_total = total; have_best = true;
+#pragma unroll
+            for (int j = 0; j < 2 * W; ++j) best[j] = cen[j];
+        }
+    }
+    if (!have_best) {
+        if (tid == 0) status[g] = YC_ST_FIT_FAILED;
+        return;
+    }
+    // ---------------- distances to the centroids, MAD outliers (stats.py:114-122, A1)
+    const int P = next_pow2(n);
+    for (int i = tid; i < P; i += YC_BLOCK) {
+        double dmin = INFINITY;
+        if (i < n) {
+            double x[W];
+            load_row<W>(c, i, x);
+            const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
+            lab[i] = (int8_t)(d1 < d0);
+            dmin = d1 < d0 ? d1 : d0;
+        }
+        sortbuf[i] = dmin;
+    }
+    __syncthreads();
+    bitonic_sort_segments(sortbuf, P, 1);
+    const double med = (n & 1) ? sortbuf[n >> 1] : mul_rn(add_rn(sortbuf[(n >> 1) - 1], sortbuf[n >> 1]), 0.5);
+    __syncthreads();
+    for (int i = tid; i < P; i += YC_BLOCK) {
+        double dv = INFINITY;
+        if (i < n) {
+            double x[W];
+            load_row<W>(c, i, x);
+            const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
+            dv = fabs(sub_rn(d1 < d0 ? d1 : d0, med));
+        }
+        sortbuf[i] = dv;
+    }
+    __syncthreads();
+    bitonic_sort_segments(sortbuf, P, 1);
+    const double mad = (n & 1) ? sortbuf[n >> 1] : mul_rn(add_rn(sortbuf[(n >> 1) - 1], sortbuf[n >> 1]), 0.5);
+    const double thr = mul_rn(p.outlier_factor, mad);
+    __syncthreads();
+    int n_out = 0;
+    for (int i = tid; i < n; i += YC_BLOCK) {
+        double x[W];
+        load_row<W>(c, i, x);
+        const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
+        if ((d1 < d0 ? d1 : d0) > thr) { lab[i] = 2; ++n_out; }
+    }
+    n_out = block_sum_i(n_out, ired);          // also orders the lab[] writes
+    if (labels_out) for (int i = tid; i < n && i < max_fit_rows; i += YC_BLOCK)
+        labels_out[(size_t)slot * max_fit_rows + i] = lab[i];
+
+    // ---------------- ML Gaussians per label (stats.py:148-152)
+    for (int k = 0; k < 2; ++k) {
+        double S[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) S[q] = 0.0;
+        for (int i = tid; i < n; i += YC_BLOCK) {
+            if (lab[i] == k) {
+                double x[W];
+                load_row<W>(c, i, x);
+                S[0] += 1.0;
+                int q = 1 + W;
+#pragma unroll
+                for (int a = 0; a < W; ++a) {
+                    S[1 + a] += x[a];
+#pragma unroll
+                    for (int c2 = a; c2 < W; ++c2) S[q++] += x[a] * x[c2];
+                }
+            }
+        }
+        block_sum<NS>(S, red);
+        if (tid == k * 32) {
+            double mu[W], cov[W * W];
+            const bool ok = ml_gaussian<W>(S, mu, cov);
+            for (int a = 0; a < W; ++a) out.mu[((size_t)slot * 2 + k) * W + a] = mu[a];
+            for (int a = 0; a < W * W; ++a) out.cov[((size_t)slot * 2 + k) * W * W + a] = cov[a];
+            par[k] = ok ? 1.0 : 0.0;
+        }
+    }
+    // ---------------- uniform box (stats.py:178-187): outlier rows, or all rows if none
+    {
+        double lo[W], hi[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) { lo[j] = INFINITY; hi[j] = -INFINITY; }
+        for (int i = tid; i < n; i += YC_BLOCK) {
+            if (n_out == 0 || lab[i] == 2) {
+                double x[W];
+                load_row<W>(c, i, x);
+#pragma unroll
+                for (int j = 0; j < W; ++j) { lo[j] = fmin(lo[j], x[j]); hi[j] = fmax(hi[j], x[j]); }
+            }
+        }
+        bool box_ok = true;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            lo[j] = block_min1(lo[j], red);
+            hi[j] = block_max1(hi[j], red);
+            box_ok &= hi[j] > lo[j];
+            if (tid == 0) { out.box[((size_t)slot * W + j) * 2] = lo[j]; out.box[((size_t)slot * W + j) * 2 + 1] = hi[j]; }
+        }
+        if (tid == 0) par[2] = box_ok ? 1.0 : 0.0;
+    }
+    // ---------------- per-sample initial weights (stats.py:173-177)
+    for (int s = wid; s < R; s += YC_NWARPS) {
+        const int a = c.fstart[s], e = c.fstart[s + 1];
+        int k0 = 0, k1 = 0, k2 = 0;
+        for (int i = a + lane; i < e; i += 32) { const int l = lab[i]; k0 += l == 0; k1 += l == 1; k2 += l == 2; }
+        k0 = warp_sum_i(k0); k1 = warp_sum_i(k1); k2 = warp_sum_i(k2);
+        if (lane == 0) {
+            double *lw = out.logw + ((size_t)slot * R + s) * 3;
+            if (e > a) {
+                const double den = (double)(e - a) + 1.5;
+                lw[0] = log(((double)k0 + 0.5) / den);
+                lw[1] = log(((double)k1 + 0.5) / den);
+                lw[2] = log(((double)k2 + 0.5) / den);
+            } else { lw[0] = lw[1] = lw[2] = 0.0; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && !(par[0] != 0.0 && par[1] != 0.0 && par[2] != 0.0)) status[g] = YC_ST_FIT_FAILED;
+}
+
+// ---------------------------------------------------------------------------
+// Kernel 2b
+// ---------------------------------------------------------------------------
+// parameter block in shared memory
+template <int W>
+struct EmPar {
+    double mu[2][W];
+    double cov[2][W * W];
+    double linv[2][W * W];
+    double cst[2];            // -0.5 (W log 2pi + log|cov|)
+    double lo[W], hi[W];
+    double ulogp;
+    double logw[YC_MAX_SAMPLES][3];
+    double ll;
+    int ok;
+};
+
+template <int W>
+__global__ void __launch_bounds__(YC_BLOCK)
+gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+              const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+              uint8_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = b.n_samples, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const FitSmem L = fit_smem_layout(W, R, b.max_reads, cap, 1);
+    constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT, NP = 2 * NS + 1;
+    EmPar<W> *par = reinterpret_cast<EmPar<W> *>(smem_raw + L.par_off);
+    double *part = reinterpret_cast<double *>(smem_raw + L.part_off);    // [NWARPS][NP] + carry [2*NS]
+    double *carry = part + YC_NWARPS * NP;
+    double *wsum = reinterpret_cast<double *>(smem_raw + L.wsum_off);    // [NWARPS][R][3]
+    const int slot = blockIdx.x;
+    const int64_t g = fit_list[slot];
+    if (status[g] != YC_ST_GATED) return;                                // init failed
+
+    FitCtx<W> c;
+    if (!fit_front_end<W>(b, p, g, smem_raw, L, cap, true, c) || c.n > cap) {
+        if (tid == 0) status[g] = YC_ST_FIT_FAILED;
+        return;
+    }
+    fit_gather<W>(c, R);
+    const int n = c.n;
+
+    // load the initial model
+    for (int i = tid; i < 2 * W; i += YC_BLOCK) par->mu[i / W][i % W] = out.mu[(size_t)slot * 2 * W + i];
+    for (int i = tid; i < 2 * W * W; i += YC_BLOCK) par->cov[i / (W * W)][i % (W * W)] = out.cov[(size_t)slot * 2 * W * W + i];
+    for (int i = tid; i < W; i += YC_BLOCK) { par->lo[i] = out.box[((size_t)slot * W + i) * 2]; par->hi[i] = out.box[((size_t)slot * W + i) * 2 + 1]; }
+    for (int i = tid; i < R * 3; i += YC_BLOCK) par->logw[i / 3][i % 3] = out.logw[(size_t)slot * R * 3 + i];
+    for (int i = tid; i < 2 * NS; i += YC_BLOCK) carry[i] = 0.0;
+    if (tid == 0) par->ok = 1;
+    __syncthreads();
+    if (tid < 64 && lane == 0) {
+        const int k = wid;
+        double logdet;
+        if (!cholesky_inverse<W>(par->cov[k], par->linv[k], logdet)) par->ok = 0;
+        par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+    }
+    if (tid == 64) {
+        double s = 0.0;
+        for (int j = 0; j < W; ++j) s += log(par->hi[j] - par->lo[j]);
+        par->ulogp = -s;
+    }
+    __syncthreads();
+
+    int iteration = 0;
+    double improvement = INFINITY, last = 0.0;
+    bool failed = par->ok == 0;
+    while (!failed && improvement > 0.1 && iteration < 1001) {
+        // ---- E-step + sufficient statistics (GeneralMixtureModel.summarize, A6)
+        double acc[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[q] = 0.0;
+        for (int q = lane; q < R * 3; q += 32) wsum[wid * YC_MAX_SAMPLES * 3 + q] = 0.0;
+        __syncwarp();
+        double mu0[W], mu1[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) { mu0[j] = par->mu[0][j]; mu1[j] = par->mu[1][j]; }
+        for (int base = wid * 32; base < n; base += YC_NWARPS * 32) {
+            const int i = base + lane;
+            const bool valid = i < n;
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            int s = -1;
+            if (valid) {
+                double x[W];
+                load_row<W>(c, i, x);
+                s = c.srow[i];
+                double q0 = 0.0, q1 = 0.0;
+                bool inside = true;
+#pragma unroll
+                for (int a = 0; a < W; ++a) {
+                    double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+                    for (int bb = 0; bb <= a; ++bb) {
+                        y0 = fma(par->linv[0][a * W + bb], x[bb] - mu0[bb], y0);
+                        y1 = fma(par->linv[1][a * W + bb], x[bb] - mu1[bb], y1);
+                    }
+                    q0 = fma(y0, y0, q0);
+                    q1 = fma(y1, y1, q1);
+                    inside &= (x[a] >= par->lo[a]) && (x[a] <= par->hi[a]);
+                }
+                const double l0 = par->cst[0] - 0.5 * q0 + par->logw[s][0];
+                const double l1 = par->cst[1] - 0.5 * q1 + par->logw[s][1];
+                const double l2 = inside ? par->ulogp + par->logw[s][2] : -INFINITY;
+                const double m = fmax(fmax(l0, l1), l2);
+                const double e0 = exp(l0 - m), e1 = exp(l1 - m), e2 = exp(l2 - m);
+                const double se = e0 + e1 + e2;
+                const double inv = 1.0 / se;
+                r0 = e0 * inv; r1 = e1 * inv; r2 = e2 * inv;
+                acc[2 * NS] += m + log(se);
+                acc[0] += r0; acc[NS] += r1;
+                int q = 1 + W;
+#pragma unroll
+                for (int a = 0; a < W; ++a) {
+                    const double xa0 = r0 * x[a], xa1 = r1 * x[a];
+                    acc[1 + a] += xa0; acc[NS + 1 + a] += xa1;
+#pragma unroll
+                    for (int bb = a; bb < W; ++bb) { acc[q] = fma(xa0, x[bb], acc[q]); acc[NS + q] = fma(xa1, x[bb], acc[NS + q]); ++q; }
+                }
+            }
+            // per-sample responsibility sums (gmm.summaries): a 32-row chunk spans few samples
+            const int s_lo = __shfl_sync(YC_FULL, s, 0);
+            const int s_hi = c.srow[min(base + 31, n - 1)];
+            for (int ss = s_lo; ss <= s_hi; ++ss) {
+                const bool mine = valid && s == ss;
+                const double t0 = warp_sum(mine ? r0 : 0.0), t1 = warp_sum(mine ? r1 : 0.0), t2 = warp_sum(mine ? r2 : 0.0);
+                if (lane == 0) {
+                    double *ws = wsum + (wid * YC_MAX_SAMPLES + ss) * 3;
+                    ws[0] += t0; ws[1] += t1; ws[2] += t2;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const double t = warp_sum(acc[q]);
+            if (lane == 0) part[wid * NP + q] = t;
+        }
+        __syncthreads();
+        // ---- bookkeeping of em(): likelihood, stop rule
+        double ll = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < YC_NWARPS; ++w2) ll += part[w2 * NP + 2 * NS];
+        if (iteration > 0) improvement = ll - last;
+        ++iteration;
+        last = ll;
+        if (!isfinite(ll)) { failed = true; break; }                     // assumption A5
+        const bool again = improvement > 0.1 && iteration < 1001;
+        if (!again) break;            // the last E-step's summaries are discarded (stats.py:224)
+        // ---- M-step of the NEXT iteration (stats.py:202-211)
+        const double step = 1.0 - (0.99 * pow(2.0 + (double)iteration, -1e-3));
+        if (tid < 64 && lane == 0) {
+            const int k = wid;
+            double S[NS];
+            for (int q = 0; q < NS; ++q) {
+                double t = carry[k * NS + q];
+                for (int w2 = 0; w2 < YC_NWARPS; ++w2) t += part[w2 * NP + k * NS + q];
+                S[q] = t;
+            }
+            if (S[0] < 1e-7) {                                           // A3: skipped, summaries kept
+                for (int q = 0; q < NS; ++q) carry[k * NS + q] = S[q];
+            } else {
+                for (int q = 0; q < NS; ++q) carry[k * NS + q] = 0.0;
+                double u[W];
+                for (int a = 0; a < W; ++a) u[a] = S[1 + a] / S[0];
+                for (int a = 0; a < W; ++a)
+                    for (int c2 = 0; c2 < W; ++c2) {
+                        const int lo = a < c2 ? a : c2, hi = a < c2 ? c2 : a;
+                        const double s2 = S[1 + W + lo * W - lo * (lo - 1) / 2 + (hi - lo)];
+                        const double cv = (s2 - S[1 + a] * u[c2] - u[a] * S[1 + c2] + S[0] * (u[a] * u[c2])) / S[0];
+                        par->cov[k][a * W + c2] = par->cov[k][a * W + c2] * step + cv * (1.0 - step);
+                    }
+                for (int a = 0; a < W; ++a) par->mu[k][a] = par->mu[k][a] * step + u[a] * (1.0 - step);
+                double logdet;
+                if (!cholesky_inverse<W>(par->cov[k], par->linv[k], logdet)) par->ok = 0;   // A4
+                par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+            }
+        }
+        if (tid >= 64 && tid < 64 + R) {
+            const int s = tid - 64;
+            if (c.fstart[s + 1] > c.fstart[s]) {
+                double v[3] = {0.0, 0.0, 0.0};
+                for (int w2 = 0; w2 < YC_NWARPS; ++w2)
+                    for (int k = 0; k < 3; ++k) v[k] += wsum[(w2 * YC_MAX_SAMPLES + s) * 3 + k];
+                if (v[0] + v[1] + v[2] != 0.0) {
+                    v[0] += 0.5; v[1] += 0.5; v[2] += 0.5;
+                    const double t = v[0] + v[1] + v[2];
+                    for (int k = 0; k < 3; ++k) par->logw[s][k] = log(v[k] / t);
+                }
+            }
+        }
+        __syncthreads();
+        failed = par->ok == 0;
+    }
+    // ---- results (fit_multisamp_gmm, stats.py:250-253)
+    if (tid == 0) {
+        if (failed) {
+            status[g] = YC_ST_FIT_FAILED;
+        } else {
+            status[g] = YC_ST_TESTED;
+            double cw[3] = {0.0, 0.0, 0.0}, tot = 0.0;
+            for (int s = 0; s < R; ++s) {
+                const double ns = (double)(c.fstart[s + 1] - c.fstart[s]);
+                if (ns > 0.0) { for (int k = 0; k < 3; ++k) cw[k] += exp(par->logw[s][k]) * ns; tot += ns; }
+            }
+            for (int k = 0; k < 3; ++k) out.cw[(size_t)slot * 3 + k] = cw[k] / tot;
+        }
+        out.iters[slot] = iteration;
+        out.loglik[slot] = last;
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * W; i += YC_BLOCK) out.mu[(size_t)slot * 2 * W + i] = par->mu[i / W][i % W];
+    for (int i = tid; i < 2 * W * W; i += YC_BLOCK) out.cov[(size_t)slot * 2 * W * W + i] = par->cov[i / (W * W)][i % (W * W)];
+    for (int i = tid; i < R * 3; i += YC_BLOCK) out.logw[(size_t)slot * R * 3 + i] = par->logw[i / 3][i % 3];
+}
+
+// ---------------------------------------------------------------------------
+// Kernel 3
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(YC_BLOCK)
+gtest_smpred_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+                    const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+                    const uint8_t *__restrict__ status, double *__restrict__ post,
+                    const long long post_capacity, unsigned long long *__restrict__ post_cursor) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = b.n_samples, Rc = b.n_cntrl, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const FitSmem L = fit_smem_layout(W, R, b.max_reads, cap, 1);
+    EmPar<W> *par = reinterpret_cast<EmPar<W> *>(smem_raw + L.par_off);
+    long long *soff = reinterpret_cast<long long *>(smem_raw + L.sel_off);
+    const int slot = blockIdx.x;
+    const int64_t g = fit_list[slot];
+    if (status[g] != YC_ST_TESTED) {
+        if (tid == 0) out.post_off[slot] = -1;
+        return;
+    }
+    FitCtx<W> c;
+    fit_front_end<W>(b, p, g, smem_raw, L, cap, false, c);      // all complete rows, no sub-sampling
+    const int n_all = c.n;
+    if (tid == 0) {
+        // preds = np.round(weights * ORIGINAL sizes)  (stats.py:296), present samples only
+        double pr[YC_MAX_SAMPLES * 3];
+        int rows_c = 0, rows_t = 0, q = 0;
+        for (int s = 0; s < R; ++s) {
+            const int sz = c.cnt[W * R + s];
+            double *po = out.preds + ((size_t)slot * R + s) * 3;
+            if (sz > 0) {
+                for (int k = 0; k < 3; ++k) {
+                    const double v = rint(exp(out.logw[((size_t)slot * R + s) * 3 + k]) * (double)sz);
+                    pr[q * 3 + k] = v; po[k] = v;
+                }
+                ++q;
+                if (s < Rc) ++rows_c; else ++rows_t;
+            } else { po[0] = po[1] = po[2] = 0.0; }
+        }
+        double st[8];
+        gtest_fractions(pr, rows_c, rows_t, p.fdr_threshold, st);
+        for (int k = 0; k < 8; ++k) out.stats[(size_t)slot * 8 + k] = st[k];
+        long long off = -1;
+        if (post != nullptr && st[2] < p.fdr_threshold) {
+            off = (long long)atomicAdd(post_cursor, (unsigned long long)n_all);
+            if (off + n_all > post_capacity) off = -2;           // caller sized the buffer too small
+        }
+        out.post_off[slot] = off;
+        soff[0] = off;
+    }
+    __syncthreads();
+    const long long off = soff[0];
+    if (off < 0) return;
+    // ---- posteriors of every complete-window read under the combined weights (stats.py:494-499)
+    for (int i = tid; i < 2 * W; i += YC_BLOCK) par->mu[i / W][i % W] = out.mu[(size_t)slot * 2 * W + i];
+    for (int i = tid; i < 2 * W * W; i += YC_BLOCK) par->cov[i / (W * W)][i % (W * W)] = out.cov[(size_t)slot * 2 * W * W + i];
+    for (int i = tid; i < W; i += YC_BLOCK) { par->lo[i] = out.box[((size_t)slot * W + i) * 2]; par->hi[i] = out.box[((size_t)slot * W + i) * 2 + 1]; }
+    __syncthreads();
+    if (tid < 64 && lane == 0) {
+        const int k = wid;
+        double logdet;
+        cholesky_inverse<W>(par->cov[k], par->linv[k], logdet);
+        par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+    }
+    if (tid == 64) {
+        double s = 0.0;
+        for (int j = 0; j < W; ++j) s += log(par->hi[j] - par->lo[j]);
+        par->ulogp = -s;
+        const double *cw = out.cw + (size_t)slot * 3;
+        const double t = cw[0] + cw[1] + cw[2];                  // A7
+        for (int k = 0; k < 3; ++k) par->logw[0][k] = log(cw[k] / t);
+    }
+    __syncthreads();
+    const int nwords = (c.w.n_reads + 31) >> 5;
+    for (int wd = wid; wd < nwords; wd += YC_NWARPS) {
+        const uint32_t m = c.mask[wd];
+        if ((m >> lane) & 1u) {
+            const int r = wd * 32 + lane;
+            const int rank = c.wordoff[wd] + __popc(m & ((1u << lane) - 1u));
+            double x[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) x[j] = h2d(__ldg(c.w.col[j] + r));
+            double q0 = 0.0, q1 = 0.0;
+            bool inside = true;
+#pragma unroll
+            for (int a = 0; a < W; ++a) {
+                double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+                for (int bb = 0; bb <= a; ++bb) {
+                    y0 = fma(par->linv[0][a * W + bb], x[bb] - par->mu[0][bb], y0);
+                    y1 = fma(par->linv[1][a * W + bb], x[bb] - par->mu[1][bb], y1);
+                }
+                q0 = fma(y0, y0, q0); q1 = fma(y1, y1, q1);
+                inside &= (x[a] >= par->lo[a]) && (x[a] <= par->hi[a]);
+            }
+            const double l0 = par->cst[0] - 0.5 * q0 + par->logw[0][0];
+            const double l1 = par->cst[1] - 0.5 * q1 + par->logw[0][1];
+            const double l2 = inside ? par->ulogp + par->logw[0][2] : -INFINITY;
+            const double mx = fmax(fmax(l0, l1), l2);
+            const double e0 = exp(l0 - mx), e1 = exp(l1 - mx), e2 = exp(l2 - mx);
+            const double inv = 1.0 / (e0 + e1 + e2);
+            post[2 * (off + rank)] = e1 * inv;
+            post[2 * (off + rank) + 1] = e2 * inv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+int fit_cap(const yc_batch_t &b, const yc_params_t &p) {
+    long long cap = (long long)b.n_samples * p.max_fit_depth;
+    if (cap > b.max_reads) cap = b.max_reads;
+    cap = (cap + 7) & ~7ll;
+    return cap < 32 ? 32 : (int)cap;
+}
+
+template <int W_> struct WTag { static constexpr int value = W_; };
+template <typename F>
+static int dispatch_w(int W, F &&f) {
+    switch (W) {
+        case 1: return f(WTag<1>());
+        case 3: return f(WTag<3>());
+        case 5: return f(WTag<5>());
+        case 7: return f(WTag<7>());
+        case 9: return f(WTag<9>());
+    }
+    return YC_EINVAL;
+}
+
+int fit_smem_bytes(const yc_batch_t &b, const yc_params_t &p, int which) {
+    // which 0 = init, 1 = em, 2 = gtest (all complete rows are never staged: cap as em)
+    return fit_smem_layout(p.window_size, b.n_samples, b.max_reads, fit_cap(b, p), which == 0 ? 0 : 1).total;
+}
+
+int init_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
+                  const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st) {
+    if (n_fit <= 0) return 0;
+    const int cap = fit_cap(b, p);
+    const int smem = fit_smem_bytes(b, p, 0);
+    return dispatch_w(p.window_size, [&](auto tag) -> int {
+        constexpr int W_ = decltype(tag)::value;
+        cudaError_t e = cudaFuncSetAttribute(gmm_init_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        gmm_init_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
+        return (int)cudaGetLastError();
+    });
+}
+
+int em_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
+                const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
+    if (n_fit <= 0) return 0;
+    const int cap = fit_cap(b, p);
+    const int smem = fit_smem_bytes(b, p, 1);
+    return dispatch_w(p.window_size, [&](auto tag) -> int {
+        constexpr int W_ = decltype(tag)::value;
+        cudaError_t e = cudaFuncSetAttribute(gmm_em_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        gmm_em_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, out, status);
+        return (int)cudaGetLastError();
+    });
+}
+
+int gtest_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
+                   const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
+                   int64_t *post_cursor, cudaStream_t st) {
+    if (n_fit <= 0) return 0;
+    const int cap = fit_cap(b, p);
+    const int smem = fit_smem_bytes(b, p, 2);
+    return dispatch_w(p.window_size, [&](auto tag) -> int {
+        constexpr int W_ = decltype(tag)::value;
+        cudaError_t e = cudaFuncSetAttribute(gtest_smpred_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        gtest_smpred_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(
+            b, p, cap, fit_list, out, status, post, (long long)post_capacity,
+            reinterpret_cast<unsigned long long *>(post_cursor));
+        return (int)cudaGetLastError();
+    });
+}
+
+}  // namespace yc

@@ -1,0 +1,179 @@
+'''
+Runs the kernels of libyanocomp_b200 over one packed batch.
+
+This is the device half of `test_chunk` (reference yanocomp/gmmtest.py:139-179):
+instead of calling `position_stats` once per position it launches
+  yc_ks_batch -> yc_gmm_init_batch -> yc_gmm_em_batch -> yc_gtest_smpred_batch
+over every candidate position of every feature in the batch.  torch is used
+for device memory and streams only.
+'''
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .batch import DeviceBatch, HostBatch
+
+
+@dataclasses.dataclass
+class EngineParams:
+    window_size: int = 3
+    min_read_depth: int = None
+    max_fit_depth: int = 1000
+    min_ks: float = 0.2
+    fdr_threshold: float = 0.05
+    outlier_factor: float = 0.5
+    gmm: bool = True
+    generate_sm_preds: bool = False
+    seed: int = 0
+
+    def __post_init__(self):
+        if self.min_read_depth is None:
+            self.min_read_depth = max(2 * self.window_size, 5)   # reference gmmtest.py:245-251
+
+    def struct(self):
+        return N.Params(window_size=self.window_size, min_read_depth=self.min_read_depth,
+                        max_fit_depth=self.max_fit_depth, gmm=int(self.gmm),
+                        min_ks=self.min_ks, fdr_threshold=self.fdr_threshold,
+                        outlier_factor=self.outlier_factor, seed=int(self.seed) & ((1 << 64) - 1))
+
+
+@dataclasses.dataclass
+class BatchResult:
+    '''host copies of everything the host tail needs'''
+    status: np.ndarray          # (total_cols,) uint8
+    ks_stat: np.ndarray         # (total_cols,) float64
+    ks_pval: np.ndarray         # (total_cols,) float64
+    n_c: np.ndarray             # (total_cols,) complete-window control rows
+    n_t: np.ndarray
+    fit_list: np.ndarray        # (n_fit,) global column of each gated position
+    mu: np.ndarray              # (n_fit, 2, w)
+    cov: np.ndarray             # (n_fit, 2, w, w)
+    box: np.ndarray             # (n_fit, w, 2)
+    logw: np.ndarray            # (n_fit, R, 3)
+    cw: np.ndarray              # (n_fit, 3)
+    iters: np.ndarray           # (n_fit,)
+    loglik: np.ndarray
+    preds: np.ndarray           # (n_fit, R, 3)
+    stats: np.ndarray           # (n_fit, 8)
+    post_off: np.ndarray        # (n_fit,)
+    post: np.ndarray            # (reads written, 2) or None
+    labels: np.ndarray = None   # (n_fit, max_fit_rows) initial labels (debug / parity)
+    launches: int = 0
+    d2h_bytes: int = 0
+
+    @property
+    def n_tested(self):
+        '''positions that entered position_stats (the BASELINE.json metric unit)'''
+        return int(np.count_nonzero(self.status != N.ST_NOT_A_WINDOW))
+
+    @property
+    def n_fitted(self):
+        return int(len(self.fit_list))
+
+
+class Engine:
+    '''owns the per-device scratch and launches the kernels of one batch'''
+
+    def __init__(self, params, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('yanocomp_b200.engine needs a CUDA device: there is no CPU fallback')
+        self.lib = N.lib()
+        self.params = params
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def upload(self, host: HostBatch) -> DeviceBatch:
+        return DeviceBatch(host, self.device)
+
+    def run(self, dev: DeviceBatch, want_labels=False, fetch=True):
+        '''
+        Launch the whole path on the current stream.  Returns a BatchResult
+        (host arrays) when `fetch`, else the dict of device tensors.
+        '''
+        lib, p = self.lib, self.params
+        ps = p.struct()
+        b = dev.struct
+        d = self.device
+        n = max(dev.host.total_cols, 1)
+        w, R = p.window_size, dev.host.n_samples
+        stream = torch.cuda.current_stream(d).cuda_stream
+        f64, i32 = torch.float64, torch.int32
+        ks_stat = torch.empty(n, dtype=f64, device=d)
+        ks_pval = torch.empty(n, dtype=f64, device=d)
+        n_c = torch.empty(n, dtype=i32, device=d)
+        n_t = torch.empty(n, dtype=i32, device=d)
+        status = torch.empty(n, dtype=torch.uint8, device=d)
+        fit_list = torch.empty(n, dtype=i32, device=d)
+        fit_count = torch.empty(1, dtype=i32, device=d)
+        launches = 0
+        N.check(lib.yc_ks_batch(b, ps, ks_stat.data_ptr(), ks_pval.data_ptr(), n_c.data_ptr(),
+                                n_t.data_ptr(), status.data_ptr(), fit_list.data_ptr(),
+                                fit_count.data_ptr(), stream))
+        launches += 1 if dev.host.total_cols else 0
+        n_fit = int(fit_count.item()) if (p.gmm and dev.host.total_cols) else 0   # 4-byte D2H + sync
+        m = max(n_fit, 1)
+        out_t = dict(
+            mu=torch.empty(m * 2 * w, dtype=f64, device=d),
+            cov=torch.empty(m * 2 * w * w, dtype=f64, device=d),
+            box=torch.empty(m * w * 2, dtype=f64, device=d),
+            logw=torch.empty(m * R * 3, dtype=f64, device=d),
+            cw=torch.zeros(m * 3, dtype=f64, device=d),
+            iters=torch.zeros(m, dtype=i32, device=d),
+            loglik=torch.zeros(m, dtype=f64, device=d),
+            preds=torch.zeros(m * R * 3, dtype=f64, device=d),
+            stats=torch.full((m * 8,), float('nan'), dtype=f64, device=d),
+            post_off=torch.full((m,), -1, dtype=torch.int64, device=d),
+        )
+        out = N.FitOut(**{k: v.data_ptr() for k, v in out_t.items()})
+        labels = None
+        max_fit_rows = 0
+        post = None
+        post_cursor = torch.zeros(1, dtype=torch.int64, device=d)
+        if n_fit:
+            fl = fit_list[:n_fit]
+            # deterministic slot order: sort the gated positions by global column
+            fl, _ = torch.sort(fl)
+            fit_list[:n_fit] = fl
+            if want_labels:
+                max_fit_rows = int(min(dev.host.max_reads, R * p.max_fit_depth))
+                labels = torch.full((n_fit, max_fit_rows), -1, dtype=torch.int8, device=d)
+            N.check(lib.yc_gmm_init_batch(b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                                          labels.data_ptr() if labels is not None else None,
+                                          max_fit_rows, stream))
+            N.check(lib.yc_gmm_em_batch(b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(), stream))
+            cap = 0
+            if p.generate_sm_preds:
+                # upper bound: every gated position writes all of its complete-window reads
+                idx = fit_list[:n_fit].long()
+                cap = int((n_c[idx].long() + n_t[idx].long()).sum().item())
+                post = torch.empty(max(cap, 1) * 2, dtype=f64, device=d)
+            N.check(lib.yc_gtest_smpred_batch(b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                                              post.data_ptr() if post is not None else None, cap,
+                                              post_cursor.data_ptr(), stream))
+            launches += 3
+        if not fetch:
+            return dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
+                        fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
+                        labels=labels, launches=launches, **out_t)
+        nc = dev.host.total_cols
+        used = int(post_cursor.item()) if post is not None else 0
+        host = dict(
+            status=status[:nc].cpu().numpy(), ks_stat=ks_stat[:nc].cpu().numpy(),
+            ks_pval=ks_pval[:nc].cpu().numpy(), n_c=n_c[:nc].cpu().numpy(), n_t=n_t[:nc].cpu().numpy(),
+            fit_list=fit_list[:n_fit].cpu().numpy(),
+            mu=out_t['mu'][:n_fit * 2 * w].cpu().numpy().reshape(n_fit, 2, w),
+            cov=out_t['cov'][:n_fit * 2 * w * w].cpu().numpy().reshape(n_fit, 2, w, w),
+            box=out_t['box'][:n_fit * w * 2].cpu().numpy().reshape(n_fit, w, 2),
+            logw=out_t['logw'][:n_fit * R * 3].cpu().numpy().reshape(n_fit, R, 3),
+            cw=out_t['cw'][:n_fit * 3].cpu().numpy().reshape(n_fit, 3),
+            iters=out_t['iters'][:n_fit].cpu().numpy(),
+            loglik=out_t['loglik'][:n_fit].cpu().numpy(),
+            preds=out_t['preds'][:n_fit * R * 3].cpu().numpy().reshape(n_fit, R, 3),
+            stats=out_t['stats'][:n_fit * 8].cpu().numpy().reshape(n_fit, 8),
+            post_off=out_t['post_off'][:n_fit].cpu().numpy(),
+            post=post[:used * 2].cpu().numpy().reshape(used, 2) if post is not None else None,
+            labels=labels.cpu().numpy() if labels is not None else None,
+        )
+        d2h = sum(v.nbytes for v in host.values() if isinstance(v, np.ndarray))
+        return BatchResult(launches=launches, d2h_bytes=d2h, **host)

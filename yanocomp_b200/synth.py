@@ -1,0 +1,83 @@
+'''
+Synthetic event data of the shapes named in BASELINE.json.
+
+Values are drawn in float32 and rounded to binary16 exactly as `yanocomp prep`
+stores them (reference yanocomp/io.py:155-162); per-position expected levels
+follow the range of the bundled ONT 5-mer model.  A fraction of positions is
+planted "modified": a per-condition fraction of reads is shifted by 1-3 sigma
+at the site and its two neighbours; a small fraction of events is replaced by
+uniform outliers.  Everything derives from one seed.
+'''
+import numpy as np
+
+from .batch import Feature
+
+_BASES = np.array(list('ACGT'))
+
+
+def random_kmers(rng, n):
+    idx = rng.integers(0, 4, size=(n + 4))
+    seq = _BASES[idx]
+    return [''.join(seq[i:i + 5]) for i in range(n)]
+
+
+def make_feature(rng, feature_id, n_pos, reads_per_sample, n_cntrl, n_treat,
+                 planted_frac=0.05, outlier_frac=0.02, dropout=0.0,
+                 mod_frac_cntrl=0.8, mod_frac_treat=0.2, strand='+', pos0=100,
+                 with_ids=False):
+    R = n_cntrl + n_treat
+    if np.isscalar(reads_per_sample):
+        reads_per_sample = [int(reads_per_sample)] * R
+    samp_start = np.zeros(R + 1, dtype=np.int32)
+    samp_start[1:] = np.cumsum(reads_per_sample)
+    n_reads = int(samp_start[-1])
+    mu = rng.uniform(70.0, 135.0, size=n_pos).astype(np.float32)
+    sd = rng.uniform(1.5, 4.0, size=n_pos).astype(np.float32)
+    X = rng.standard_normal((n_pos, n_reads), dtype=np.float32)
+    X *= sd[:, None]
+    X += mu[:, None]
+    # planted sites: control reads modified with prob mod_frac_cntrl, treatment with mod_frac_treat
+    n_sites = int(round(planted_frac * n_pos))
+    if n_sites:
+        sites = rng.choice(np.arange(1, n_pos - 1), size=min(n_sites, max(n_pos - 2, 0)), replace=False)
+        is_treat = np.arange(n_reads) >= samp_start[n_cntrl]
+        pmod = np.where(is_treat, mod_frac_treat, mod_frac_cntrl)
+        for p in sites:
+            modified = rng.random(n_reads) < pmod
+            shift = rng.uniform(1.0, 3.0, size=3).astype(np.float32) * rng.choice([-1.0, 1.0], size=3).astype(np.float32)
+            for k, c in enumerate((p - 1, p, p + 1)):
+                X[c, modified] += shift[k] * sd[c]
+    if outlier_frac > 0:
+        m = rng.random(X.shape, dtype=np.float32) < outlier_frac
+        X[m] = rng.uniform(50.0, 150.0, size=int(m.sum())).astype(np.float32)
+    X16 = X.astype(np.float16)
+    if dropout > 0:
+        X16[rng.random(X.shape, dtype=np.float32) < dropout] = np.nan
+    kmers = dict(zip(range(pos0, pos0 + n_pos), random_kmers(rng, n_pos)))
+    read_ids = None
+    if with_ids:
+        read_ids = []
+        for s in range(R):
+            ids = sorted(f'{feature_id[-6:]}-s{s}-{i:06d}' for i in range(reads_per_sample[s]))
+            read_ids += ids
+    return Feature(feature_id=feature_id, chrom='.', strand=strand, pos0=pos0, X=X16,
+                   samp_start=samp_start, read_ids=read_ids, kmers=kmers)
+
+
+def make_dataset(seed, n_features, n_pos, reads_per_sample, n_cntrl=2, n_treat=2, **kw):
+    rng = np.random.default_rng(seed)
+    return [make_feature(rng, f'SYNT{seed:02d}{i:07d}', n_pos, reads_per_sample, n_cntrl, n_treat, **kw)
+            for i in range(n_features)]
+
+
+# the BASELINE.json configurations (index = position in `configs`)
+CONFIGS = {
+    2: dict(name='cfg2: 1k transcripts x 500 positions, 2x2 replicates, 100 reads/condition, window 3',
+            seed=1, n_features=1000, n_pos=500, reads_per_sample=50, n_cntrl=2, n_treat=2, window=3),
+    3: dict(name='cfg3: 20k transcripts x 500 positions, 2x2 replicates, 200 reads/condition, window 3',
+            seed=2, n_features=20000, n_pos=500, reads_per_sample=100, n_cntrl=2, n_treat=2, window=3),
+    4: dict(name='cfg4: 1k transcripts x 500 positions, 2x2 replicates, 2k reads/condition, window 5, sm-preds',
+            seed=3, n_features=1000, n_pos=500, reads_per_sample=1000, n_cntrl=2, n_treat=2, window=5),
+    5: dict(name='cfg5: 20k transcripts x 500 positions, 3x3 replicates, 100 reads/replicate, all positions fitted',
+            seed=4, n_features=20000, n_pos=500, reads_per_sample=100, n_cntrl=3, n_treat=3, window=3),
+}
