@@ -188,6 +188,12 @@ void     yc_gtest_fractions_host(const double *preds, int32_t nrow_c, int32_t nr
                                  double thr, double *out8);
 uint64_t yc_position_key_host(uint64_t seed, uint64_t fkey, int64_t pos);
 uint64_t yc_mix64_host(uint64_t z);
+/* first right singular vector of Z with numpy.linalg.svd's (LAPACK dgesdd) sign,
+ * from G = Z^T Z (d x d) and T = Z[0:d, :] (d x d), both row-major; stats.py:26-29 */
+int      yc_first_right_singular_vector_host(int32_t d, const double *G, const double *T, double *v);
+/* the same routine run on the device for `count` independent problems (device pointers) */
+int      yc_first_right_singular_vector_device(int32_t d, const double *G, const double *T, double *v,
+                                               int32_t count, void *stream);
 
 #ifdef __cplusplus
 }

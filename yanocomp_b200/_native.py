@@ -73,6 +73,8 @@ _PROTOTYPES = {
     'yc_gtest_fractions_host': (None, [_P(C.c_double), C.c_int32, C.c_int32, C.c_double, _P(C.c_double)]),
     'yc_position_key_host': (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_int64]),
     'yc_mix64_host': (C.c_uint64, [C.c_uint64]),
+    'yc_first_right_singular_vector_device': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    'yc_first_right_singular_vector_host': (C.c_int, [C.c_int32, _P(C.c_double), _P(C.c_double), _P(C.c_double)]),
 }
 
 EXPORTS = tuple(_PROTOTYPES)

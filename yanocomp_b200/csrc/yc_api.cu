@@ -5,6 +5,7 @@
 #include "yc_internal.h"
 #include "yc_common.cuh"
 #include "yc_stats.cuh"
+#include "yc_svdsign.cuh"
 
 namespace {
 
@@ -66,6 +67,13 @@ __global__ void fill_col_feature_kernel(int n_features, const int64_t *__restric
         const int64_t a = col_off[f], e = col_off[f + 1];
         for (int64_t g = a + threadIdx.x; g < e; g += blockDim.x) col_feature[g] = f;
     }
+}
+
+template <int D>
+__global__ void svd_v1_kernel(const double *__restrict__ G, const double *__restrict__ T,
+                              double *__restrict__ v, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) yc::lapack::first_right_singular_vector<D>(G + (size_t)i * D * D, T + (size_t)i * D * D, v + (size_t)i * D);
 }
 
 }  // namespace
@@ -163,5 +171,30 @@ uint64_t yc_position_key_host(uint64_t seed, uint64_t fkey, int64_t pos) {
     return yc::position_key(seed, fkey, pos);
 }
 uint64_t yc_mix64_host(uint64_t z) { return yc::mix64(z); }
+int yc_first_right_singular_vector_device(int32_t d, const double *G, const double *T, double *v,
+                                          int32_t count, void *stream) {
+    if (count <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (count + 63) / 64;
+    switch (d) {
+        case 1: svd_v1_kernel<1><<<grid, 64, 0, st>>>(G, T, v, count); break;
+        case 3: svd_v1_kernel<3><<<grid, 64, 0, st>>>(G, T, v, count); break;
+        case 5: svd_v1_kernel<5><<<grid, 64, 0, st>>>(G, T, v, count); break;
+        case 7: svd_v1_kernel<7><<<grid, 64, 0, st>>>(G, T, v, count); break;
+        case 9: svd_v1_kernel<9><<<grid, 64, 0, st>>>(G, T, v, count); break;
+        default: return fail(YC_EINVAL, "window size %d is not supported", d);
+    }
+    return cuda_fail((int)cudaGetLastError(), "yc_first_right_singular_vector_device");
+}
+int yc_first_right_singular_vector_host(int32_t d, const double *G, const double *T, double *v) {
+    switch (d) {
+        case 1: yc::lapack::first_right_singular_vector<1>(G, T, v); return 0;
+        case 3: yc::lapack::first_right_singular_vector<3>(G, T, v); return 0;
+        case 5: yc::lapack::first_right_singular_vector<5>(G, T, v); return 0;
+        case 7: yc::lapack::first_right_singular_vector<7>(G, T, v); return 0;
+        case 9: yc::lapack::first_right_singular_vector<9>(G, T, v); return 0;
+    }
+    return fail(YC_EINVAL, "window size %d is not supported", d);
+}
 
 }  // extern "C"

@@ -16,6 +16,7 @@
 // are computed in FP64 and only their order is used.
 #include "yc_common.cuh"
 #include "yc_stats.cuh"
+#include "yc_svdsign.cuh"
 
 namespace yc {
 
@@ -30,7 +31,7 @@ __host__ __device__ inline KsSmem ks_smem_layout(int W, int R, int max_reads, in
     s.sort_off = o; o += 2 * sort_cap * (int)sizeof(double);
     s.red_off = o;  o += 48 * YC_NWARPS * (int)sizeof(double);
     s.sel_off = o;  o += 4 * (int)sizeof(unsigned long long);
-    s.misc_off = o; o += 16 * (int)sizeof(double);
+    s.misc_off = o; o += (16 + 2 * YC_MAX_WINDOW * YC_MAX_WINDOW) * (int)sizeof(double);
     s.mask_off = o; o += ((max_reads + 31) / 32 + 1) * (int)sizeof(uint32_t);
     s.cnt_off = o;  o += (W + 1) * R * (int)sizeof(int);
     s.hist_off = o; o += 256 * (int)sizeof(int);
@@ -156,16 +157,30 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
         }
         return;
     }
-    // ---- first principal axis of the standardised data: top eigenvector of Z^T Z
+    // ---- first principal axis of the standardised data, oriented as LAPACK's dgesdd
+    // orients it (yc_svdsign.cuh): needs G = Z^T Z and the first W pooled rows of Z
     if (tid == 0) {
-        double G[W * W], v[W];
+        // G and T live in shared memory: handing thread-local arrays to the (large) routine
+        // was observed to be miscompiled (the callee's zero-initialised workspace aliased T)
+        double *G = misc + 16, *T = misc + 16 + W * W;
+        double v[W];
         int k = 0;
         for (int a = 0; a < W; ++a)
             for (int c2 = a; c2 < W; ++c2) {
                 const double gv = cm[k++] / (sig[a] * sig[c2]);
                 G[a * W + c2] = gv; G[c2 * W + a] = gv;
             }
-        top_eigenvector<W>(G, v);
+        int found = 0;
+        for (int r = 0; r < n && found < W; ++r) {
+            if ((mask[r >> 5] >> (r & 31)) & 1u) {
+#pragma unroll
+                for (int j = 0; j < W; ++j)
+                    T[found * W + j] = div_rn(sub_rn(h2d(__ldg(w.col[j] + r)), mu[j]), sig[j]);
+                ++found;
+            }
+        }
+        for (; found < W; ++found) for (int j = 0; j < W; ++j) T[found * W + j] = 0.0;
+        lapack::first_right_singular_vector<W>(G, T, v);
         for (int a = 0; a < W; ++a) misc[a] = v[a];
         icnt[0] = 0; icnt[1] = 0;
     }
