@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+'''
+bench.py -- positions tested / s of the gmmtest hot path (KS + GMM + G-test).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
+
+One "step" = one pass of the whole hot path (yc_ks_batch -> yc_gmm_init_batch
+-> yc_gmm_em_batch -> yc_gtest_smpred_batch) over one synthetic batch of the
+BASELINE.json configuration (default configs[1]: 1k transcripts x 500
+positions, 2x2 replicates, 100 reads/condition, window 3).  With N > 1
+(launched under torchrun) every rank runs its own batch of the same shape
+(features are independent: the path shards by gene with no data-path
+collective), so scaling is "weak"; time = max over ranks.
+
+Printed JSON (one line, rank 0):
+  value      positions entering position_stats / s, inputs resident in HBM,
+             timed with CUDA events on the launching stream
+  e2e        the same through the public host-buffer call
+             (yanocomp_b200.api.test_host_batch: pinned host -> device copy of
+             the packed batch, kernels, device -> host copy of all results, BH)
+  roofline   dominant kernel (by measured time) against the measured HBM peak,
+             algorithmic bytes as in DESIGN.md; fp64 figures beside it
+  cpu_baseline  the CPU oracle (NumPy/SciPy restatement of the reference; the
+             reference itself cannot be installed offline) on a bounded sample
+             of the same workload on the host cores
+`--impl reference` times that CPU path alone (all host cores) and prints the
+same line with "impl": "reference".
+'''
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+
+METRIC = 'positions tested/sec (KS+GMM+G-test)'
+UNIT = 'positions/s'
+
+
+def load_peaks():
+    fn = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(fn):
+        with open(fn) as fh:
+            d = json.load(fh)
+        return float(d['hbm_gbs']), float(d.get('sm_max_mhz', 1965.0)), 'measured'
+    return 6650.0, 1965.0, 'fallback'
+
+
+# --------------------------------------------------------------------------
+# CPU arm: the oracle over a bounded sample, one process per core
+# --------------------------------------------------------------------------
+def _cpu_worker(args):
+    cfg, seed, feat_index, opts_kw = args
+    import oracle_bridge as ob
+    import yanocomp_oracle as yo
+    from yanocomp_b200 import synth
+    rng = np.random.default_rng([seed, feat_index])
+    f = synth.make_feature(rng, f'CPU{seed:02d}{feat_index:07d}', cfg['n_pos'], cfg['reads_per_sample'],
+                           cfg['n_cntrl'], cfg['n_treat'])
+    opts = yo.Options(**opts_kw)
+    t0 = time.perf_counter()
+    r = ob.run_feature(f, cfg['n_cntrl'] + cfg['n_treat'], cfg['n_cntrl'], opts)
+    dt = time.perf_counter() - t0
+    fitted = sum(1 for x in r.values() if x.status in (yo.ST_TESTED, yo.ST_FIT_FAILED))
+    return len(r), fitted, dt
+
+
+def cpu_sample(cfg, n_features, cores, seed, opts_kw, pool):
+    '''positions/s of the oracle on n_features synthetic features over `cores` processes'''
+    t0 = time.perf_counter()
+    out = pool.map(_cpu_worker, [(cfg, seed, i, opts_kw) for i in range(n_features)], chunksize=1)
+    wall = time.perf_counter() - t0
+    pos = sum(o[0] for o in out)
+    return pos / wall, pos, sum(o[1] for o in out), wall
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, cfg, opts_kw):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = min(host_cores(), 64)
+    n_feat = max(3 * cores, 8)      # three features (~1500 positions, ~10 s) per core per step
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_sample(cfg, min(n_feat, cores), cores, 900, opts_kw, pool)
+        t0 = time.perf_counter()
+        pos = fit = 0
+        for k in range(args.steps):
+            _, p, f, _ = cpu_sample(cfg, n_feat, cores, 1000 + k, opts_kw, pool)
+            pos += p
+            fit += f
+        wall = time.perf_counter() - t0
+    value = pos / wall
+    sample = (f'{n_feat} synthetic transcripts x {cfg["n_pos"]} positions per step '
+              f'({pos // max(args.steps, 1)} positions, {fit // max(args.steps, 1)} GMM fits), '
+              f'{cores} processes')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * wall / max(args.steps, 1), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': cfg['name'], 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                         'note': 'NumPy/SciPy restatement of yanocomp/stats.py (oracle/); the pomegranate-based '
+                                 'reference is not installable offline'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                      '-i', str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def run_gpu(args, cfg, opts_kw):
+    import torch
+    import torch.distributed as dist
+    from yanocomp_b200 import synth
+    from yanocomp_b200.api import test_host_batch, tested_table
+    from yanocomp_b200.batch import HostBatch
+    from yanocomp_b200.engine import Engine, EngineParams
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (there is no CPU fallback for the product path)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    R, Rc = cfg['n_cntrl'] + cfg['n_treat'], cfg['n_cntrl']
+    params = EngineParams(window_size=cfg['window'], generate_sm_preds=cfg.get('sm_preds', False),
+                          min_ks=opts_kw.get('min_ks', 0.2), fdr_threshold=opts_kw.get('fdr_threshold', 0.05))
+    # every rank: its own batch of the configured shape (weak scaling, gene-sharded)
+    feats = synth.make_dataset(cfg['seed'] + 100 * rank, cfg['n_features'], cfg['n_pos'],
+                               cfg['reads_per_sample'], cfg['n_cntrl'], cfg['n_treat'])
+    host = HostBatch(feats, R, Rc)
+    del feats
+    eng = Engine(params)
+    dev = eng.upload(host)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident: kernels only, inputs already in HBM (inputs are larger than L2)
+    for _ in range(args.warmup):
+        out = eng.run(dev, fetch=False)
+    torch.cuda.synchronize()
+    events = []
+    start = torch.cuda.Event(enable_timing=True)
+    stop = torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(torch.cuda.current_device())
+    barrier()
+    with sampler:
+        start.record()
+        for _ in range(args.steps):
+            out = eng.run(dev, fetch=False, events=events)
+        stop.record()
+        barrier()
+    ms_resident = start.elapsed_time(stop)
+    launches = out['launches'] * args.steps
+    n_tested = int((out['status'][:host.total_cols] != 0).sum().item())
+    n_fit = int(out['fit_list'].numel())
+    iters = out['iters'][:max(n_fit, 1)].double()
+    mean_iters = float(iters.mean().item()) if n_fit else 0.0
+    sum_iters = float(iters.sum().item()) if n_fit else 0.0
+    kms = {}
+    for name, a, e in events:
+        kms.setdefault(name, []).append(a.elapsed_time(e))
+    kavg = {k: float(np.mean(v)) for k, v in kms.items()}
+
+    # ---- end to end: host buffers in, host results out, every step
+    for _ in range(max(1, min(args.warmup, 2))):
+        res = test_host_batch(host, params, eng)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = test_host_batch(host, params, eng)
+        table = tested_table(host, res)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t_res = torch.tensor([ms_resident, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+    cnt = torch.tensor([n_tested, n_fit], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_resident_max, ms_e2e_max = [float(x) for x in t_res.tolist()]
+    tot_tested, tot_fit = [float(x) for x in cnt.tolist()]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_peak, sm_max, peak_kind = load_peaks()
+    value = tot_tested * args.steps / (ms_resident_max * 1e-3)
+    e2e_value = tot_tested * args.steps / (ms_e2e_max * 1e-3)
+    # roofline of the dominant kernel: gather model, binary16 window
+    # columns re-read by every position + one double result row
+    w = cfg['window']
+    Nreads = host.max_reads
+    bytes_per_pos = 2 * w * Nreads
+    alg = {
+        'ks': host.total_cols * bytes_per_pos + n_tested * 8 * 3,
+        'gmm_init': n_fit * (bytes_per_pos + 8 * (2 * w + 2 * w * w + 2 * w + 3 * R)),
+        'gmm_em': n_fit * (bytes_per_pos + 2 * 8 * (2 * w + 2 * w * w + 3 * R)),
+        'gtest_smpred': n_fit * (bytes_per_pos + 8 * (3 * R + 8)),
+    }
+    dom = max(kavg, key=kavg.get) if kavg else 'ks'
+    achieved = alg[dom] / (kavg[dom] * 1e-3) / 1e9 if kavg else 0.0
+    # FP64 work of the EM kernel: flop/read/E-step from DESIGN.md section 5
+    d = w
+    flop_read_iter = 2 * (d * (d + 1) + 2 * d) + 2 * (1 + d + d * (d + 1)) + 120
+    em_flops = sum_iters * Nreads * flop_read_iter
+    fp64_peak = 148 * 64 * 2 * sm_max * 1e6      # 64 FP64 FMA lanes / SM / clk
+    roofline = {
+        'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+        'frac': achieved / hbm_peak, 'traffic': None, 'peak_kind': peak_kind,
+        'kernel_ms': kavg, 'algorithmic_bytes': alg,
+        'note': 'the path is FP64-latency bound, not HBM bound (DESIGN.md section 5); fp64 block below',
+        'fp64': {'kernel': 'gmm_em', 'achieved_tflops': em_flops / (kavg.get('gmm_em', float('inf')) * 1e-3) / 1e12,
+                 'peak_tflops': fp64_peak / 1e12, 'frac': em_flops / (kavg.get('gmm_em', float('inf')) * 1e-3) / fp64_peak,
+                 'flop_per_read_iter': flop_read_iter, 'mean_em_iters': mean_iters},
+    }
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = min(host_cores(), 64)
+        n_feat = max(3 * cores, 8)
+        ctx = mp.get_context('spawn')
+        with ctx.Pool(cores) as pool:
+            v, pos, fit, wall = cpu_sample(cfg, n_feat, cores, 777, opts_kw, pool)
+        cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'{n_feat} synthetic transcripts x {cfg["n_pos"]} positions ({pos} positions, {fit} GMM fits) '
+                         f'in {wall:.1f} s; CPU oracle (oracle/yanocomp_oracle.py), one process per core'}
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_resident_max / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': cfg['name'], 'per_gpu_positions_tested': n_tested, 'per_gpu_positions_fitted': n_fit,
+                   'mean_em_iterations': mean_iters, 'input_bytes_per_gpu': host.nbytes,
+                   'cache': 'inputs (%.0f MB) larger than the 126 MB L2; no flush' % (host.nbytes / 1e6),
+                   'sharding': 'features (genes) split across ranks, no data-path collective'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e_max / args.steps,
+                'h2d_bytes_per_step': host.nbytes, 'd2h_bytes_per_step': res.d2h_bytes,
+                'tested_rows': int(len(table['g']))},
+        'gpu_launches': launches,
+        'clocks': sampler.summary(),
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', type=int, default=2, help='index into BASELINE.json configs (2..5 here)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--features', type=int, default=None, help='override the number of transcripts (debug)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    from yanocomp_b200 import synth
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.features:
+        cfg['n_features'] = args.features
+        cfg['name'] += f' [REDUCED to {args.features} transcripts]'
+    opts_kw = dict(window_size=cfg['window'])
+    if args.config == 4:
+        cfg['sm_preds'] = True
+        opts_kw['generate_sm_preds'] = True
+    if args.config == 5:
+        opts_kw.update(min_ks=0.0, fdr_threshold=1.0)
+    if args.impl == 'reference':
+        run_reference(args, cfg, opts_kw)
+    else:
+        run_gpu(args, cfg, opts_kw)
+
+
+if __name__ == '__main__':
+    main()

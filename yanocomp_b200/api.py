@@ -1,0 +1,42 @@
+'''
+Public entry points over packed batches.
+
+`test_host_batch` is the in-memory equivalent of the reference's `test_chunk`
+(reference yanocomp/gmmtest.py:139-179): host buffers in, host results out,
+with the host->device and device->host copies inside the call.
+'''
+import numpy as np
+
+from . import _native as N
+from .batch import HostBatch
+from .engine import Engine, EngineParams, BatchResult
+from .stats import benjamini_hochberg
+
+
+def test_host_batch(host: HostBatch, params: EngineParams, engine: Engine = None) -> BatchResult:
+    '''upload -> KS -> GMM -> G-test (-> posteriors) -> fetch, on the current device'''
+    eng = engine or Engine(params)
+    dev = eng.upload(host)
+    res = eng.run(dev)
+    res.h2d_bytes = host.nbytes
+    return res
+
+
+def tested_table(host: HostBatch, res: BatchResult, gmm=True):
+    '''
+    Rows of the reference's result DataFrame (gmmtest.py:216-224) as arrays:
+    only was_tested positions, NaN p-values dropped, BH-FDR over the rest.
+    '''
+    if gmm:
+        keep = res.status[res.fit_list] == N.ST_TESTED
+        g = res.fit_list[keep]
+        p = res.stats[keep, 2]
+        slots = np.flatnonzero(keep)
+    else:
+        g = np.flatnonzero(res.status == N.ST_KS_ONLY)
+        p = res.ks_pval[g]
+        slots = np.full(len(g), -1)
+    ok = ~np.isnan(p)
+    g, p, slots = g[ok], p[ok], slots[ok]
+    fdr = benjamini_hochberg(p) if len(p) else p
+    return dict(g=g, slot=slots, p_val=p, fdr=fdr)

@@ -62,6 +62,7 @@ class BatchResult:
     labels: np.ndarray = None   # (n_fit, max_fit_rows) initial labels (debug / parity)
     launches: int = 0
     d2h_bytes: int = 0
+    h2d_bytes: int = 0
 
     @property
     def n_tested(self):
@@ -86,11 +87,24 @@ class Engine:
     def upload(self, host: HostBatch) -> DeviceBatch:
         return DeviceBatch(host, self.device)
 
-    def run(self, dev: DeviceBatch, want_labels=False, fetch=True):
+    def run(self, dev: DeviceBatch, want_labels=False, fetch=True, events=None):
         '''
         Launch the whole path on the current stream.  Returns a BatchResult
-        (host arrays) when `fetch`, else the dict of device tensors.
+        (host arrays) when `fetch`, else the dict of device tensors.  `events`
+        (a list) receives (kernel name, start event, end event) per launch so
+        that bench.py can time each kernel on the launching stream.
         '''
+        def timed(name, call):
+            if events is None:
+                return call()
+            a = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = call()
+            e.record()
+            events.append((name, a, e))
+            return r
+
         lib, p = self.lib, self.params
         ps = p.struct()
         b = dev.struct
@@ -107,9 +121,9 @@ class Engine:
         fit_list = torch.empty(n, dtype=i32, device=d)
         fit_count = torch.empty(1, dtype=i32, device=d)
         launches = 0
-        N.check(lib.yc_ks_batch(b, ps, ks_stat.data_ptr(), ks_pval.data_ptr(), n_c.data_ptr(),
-                                n_t.data_ptr(), status.data_ptr(), fit_list.data_ptr(),
-                                fit_count.data_ptr(), stream))
+        N.check(timed('ks', lambda: lib.yc_ks_batch(
+            b, ps, ks_stat.data_ptr(), ks_pval.data_ptr(), n_c.data_ptr(), n_t.data_ptr(),
+            status.data_ptr(), fit_list.data_ptr(), fit_count.data_ptr(), stream)))
         launches += 1 if dev.host.total_cols else 0
         n_fit = int(fit_count.item()) if (p.gmm and dev.host.total_cols) else 0   # 4-byte D2H + sync
         m = max(n_fit, 1)
@@ -138,19 +152,20 @@ class Engine:
             if want_labels:
                 max_fit_rows = int(min(dev.host.max_reads, R * p.max_fit_depth))
                 labels = torch.full((n_fit, max_fit_rows), -1, dtype=torch.int8, device=d)
-            N.check(lib.yc_gmm_init_batch(b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
-                                          labels.data_ptr() if labels is not None else None,
-                                          max_fit_rows, stream))
-            N.check(lib.yc_gmm_em_batch(b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(), stream))
+            N.check(timed('gmm_init', lambda: lib.yc_gmm_init_batch(
+                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                labels.data_ptr() if labels is not None else None, max_fit_rows, stream)))
+            N.check(timed('gmm_em', lambda: lib.yc_gmm_em_batch(
+                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(), stream)))
             cap = 0
             if p.generate_sm_preds:
                 # upper bound: every gated position writes all of its complete-window reads
                 idx = fit_list[:n_fit].long()
                 cap = int((n_c[idx].long() + n_t[idx].long()).sum().item())
                 post = torch.empty(max(cap, 1) * 2, dtype=f64, device=d)
-            N.check(lib.yc_gtest_smpred_batch(b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
-                                              post.data_ptr() if post is not None else None, cap,
-                                              post_cursor.data_ptr(), stream))
+            N.check(timed('gtest_smpred', lambda: lib.yc_gtest_smpred_batch(
+                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
             launches += 3
         if not fetch:
             return dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
