@@ -26,8 +26,11 @@
  * reference yanocomp/io.py:296-343):
  *   feature f owns a position-major fp16 matrix
  *       events[x_off[f] + c*ld[f] + r]     c in [0,n_cols[f]), r in [0,n_reads[f])
- *   NaN = the read has no event at that position.  Column c is transcript /
- *   genome position pos0[f] + c.  Reads are sorted by sample: sample s owns
+ *   NaN = the read has no event at that position.  Column c holds transcript /
+ *   genome position col_pos[col_off[f] + c]; positions are strictly increasing
+ *   inside a feature but need not be consecutive (columns without any event
+ *   may be dropped); a window is valid only over w consecutive positions.
+ *   Reads are sorted by sample: sample s owns
  *   rows [samp_start[f*(R+1)+s], samp_start[f*(R+1)+s+1]); samples
  *   0..n_cntrl-1 are the control replicates (`-c` files in order), the rest
  *   the treatment replicates (`-t` files in order).
@@ -74,7 +77,7 @@ typedef struct yc_batch {
     const int64_t  *col_off;     /* [F+1] prefix sum of n_cols */
     const int32_t  *samp_start;  /* [F*(R+1)] */
     const uint64_t *feature_key; /* [F]   FNV-1a 64 of the feature id (RNG key) */
-    const int64_t  *pos0;        /* [F]   position of column 0 */
+    const int64_t  *col_pos;     /* [total_cols] position of each global column */
     const uint8_t  *reverse;     /* [F]   1 = '-' strand: window columns reversed, gmmtest.py:37-38 */
     const int32_t  *col_feature; /* [total_cols] feature of each global column (yc_fill_col_feature) */
 } yc_batch_t;

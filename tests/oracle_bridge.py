@@ -15,7 +15,7 @@ def cond_events(feature, s0, s1, rep0=1):
     rep = np.zeros(e - a, dtype=np.int64)
     for s in range(s0, s1):
         rep[ss[s] - a:ss[s + 1] - a] = s - s0 + rep0
-    positions = feature.pos0 + np.arange(feature.n_cols, dtype=np.int64)
+    positions = np.asarray(feature.positions, dtype=np.int64)
     ids = feature.read_ids[a:e] if feature.read_ids is not None else [''] * (e - a)
     return yo.CondEvents(X, positions, rep, list(ids))
 

@@ -72,7 +72,7 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
         r = ref[feat.feature_id]
         for c in range(feat.n_cols):
             g = int(host.col_off[fi] + c)
-            pos = int(feat.pos0 + c)
+            pos = int(feat.positions[c])
             st = int(res.status[g])
             key = (feat.feature_id, pos)
             if pos not in r:

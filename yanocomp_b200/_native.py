@@ -33,7 +33,7 @@ class Batch(C.Structure):
         ('events', C.c_void_p), ('x_off', C.c_void_p), ('n_cols', C.c_void_p),
         ('n_reads', C.c_void_p), ('ld', C.c_void_p), ('col_off', C.c_void_p),
         ('samp_start', C.c_void_p), ('feature_key', C.c_void_p),
-        ('pos0', C.c_void_p), ('reverse', C.c_void_p), ('col_feature', C.c_void_p),
+        ('col_pos', C.c_void_p), ('reverse', C.c_void_p), ('col_feature', C.c_void_p),
     ]
 
 

@@ -34,11 +34,22 @@ class Feature:
     feature_id: str
     chrom: str
     strand: str
-    pos0: int                   # position of column 0
+    pos0: int                   # position of column 0 (when `positions` is None: consecutive)
     X: np.ndarray               # (n_cols, n_reads) float16, NaN = no event
     samp_start: np.ndarray      # (R+1,) first read row of each sample
     read_ids: list = None       # per read row (only needed for sm_preds)
     kmers: dict = None          # pos -> kmer (only needed for output)
+    positions: np.ndarray = None  # (n_cols,) strictly increasing positions; None = pos0 + arange
+
+    def __post_init__(self):
+        if self.positions is None:
+            self.positions = self.pos0 + np.arange(self.X.shape[0], dtype=np.int64)
+        else:
+            self.positions = np.asarray(self.positions, dtype=np.int64)
+            if len(self.positions) != self.X.shape[0]:
+                raise ValueError(f'{self.feature_id}: positions do not match the matrix')
+            if len(self.positions):
+                self.pos0 = int(self.positions[0])
 
     @property
     def n_cols(self):
@@ -72,7 +83,8 @@ class HostBatch:
         total = int(sizes.sum())
         self.samp_start = np.zeros((F, n_samples + 1), dtype=np.int32)
         self.feature_key = np.zeros(F, dtype=np.uint64)
-        self.pos0 = np.zeros(F, dtype=np.int64)
+        self.col_pos = (np.concatenate([f.positions for f in self.features]).astype(np.int64)
+                        if F else np.zeros(0, dtype=np.int64))
         self.reverse = np.zeros(F, dtype=np.uint8)
         self.events = self._alloc_events(total, pin)
         ev16 = self.events.view(np.float16)
@@ -86,7 +98,6 @@ class HostBatch:
             block[:, f.n_reads:] = np.nan
             self.samp_start[i] = f.samp_start
             self.feature_key[i] = feature_key(f.feature_id)
-            self.pos0[i] = f.pos0
             self.reverse[i] = f.strand == '-'
         self.total_cols = int(self.col_off[-1])
         self.max_reads = int(self.n_reads.max()) if F else 0
@@ -109,12 +120,12 @@ class HostBatch:
         '''bytes copied host->device for this batch'''
         return int(self.events.nbytes + self.x_off.nbytes + self.n_cols.nbytes + self.n_reads.nbytes
                    + self.ld.nbytes + self.col_off.nbytes + self.samp_start.nbytes
-                   + self.feature_key.nbytes + self.pos0.nbytes + self.reverse.nbytes)
+                   + self.feature_key.nbytes + self.col_pos.nbytes + self.reverse.nbytes)
 
     def position_of(self, g):
         '''(feature index, position) of global column g'''
         f = int(np.searchsorted(self.col_off, g, side='right') - 1)
-        return f, int(self.pos0[f] + (g - self.col_off[f]))
+        return f, int(self.col_pos[g])
 
 
 class DeviceBatch:
@@ -142,7 +153,7 @@ class DeviceBatch:
         self.col_off = up(host.col_off, np.int64)
         self.samp_start = up(host.samp_start.reshape(-1), np.int32)
         self.feature_key = up(host.feature_key.view(np.int64), np.int64)
-        self.pos0 = up(host.pos0, np.int64)
+        self.col_pos = up(host.col_pos, np.int64) if host.total_cols else torch.zeros(1, dtype=torch.int64, device=dev)
         self.reverse = up(host.reverse, np.uint8)
         self.col_feature = torch.empty(max(host.total_cols, 1), dtype=torch.int32, device=dev)
         s = torch.cuda.current_stream(dev).cuda_stream
@@ -155,5 +166,5 @@ class DeviceBatch:
             n_cols=self.n_cols.data_ptr(), n_reads=self.n_reads.data_ptr(),
             ld=self.ld.data_ptr(), col_off=self.col_off.data_ptr(),
             samp_start=self.samp_start.data_ptr(), feature_key=self.feature_key.data_ptr(),
-            pos0=self.pos0.data_ptr(), reverse=self.reverse.data_ptr(),
+            col_pos=self.col_pos.data_ptr(), reverse=self.reverse.data_ptr(),
             col_feature=self.col_feature.data_ptr())

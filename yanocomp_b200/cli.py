@@ -1,0 +1,45 @@
+'''
+`yanocomp` command group (reference yanocomp/cli.py).  Only `gmmtest` is
+provided: `prep` is the upstream text-parsing step and is out of scope
+(DESIGN.md section 8).  click_log is not a dependency here, so the
+`-v/--verbosity` option it provides is re-created by hand.
+'''
+import logging
+
+import click
+
+from . import dist as ycdist
+from .gmmtest import gmm_test
+
+
+def get_logger(name):
+    logger = logging.getLogger(name)
+    if not logger.handlers:
+        handler = logging.StreamHandler()
+        handler.setFormatter(logging.Formatter('{asctime} {levelname:8s} {message}', style='{'))
+        logger.addHandler(handler)
+        logger.propagate = False
+    return logger
+
+
+logger = get_logger('yanocomp')
+
+
+def _set_verbosity(ctx, param, value):
+    level = getattr(logging, str(value).upper(), None)
+    if not isinstance(level, int):
+        raise click.BadParameter('Must be CRITICAL, ERROR, WARNING, INFO or DEBUG, not {}'.format(value))
+    logger.setLevel(level)
+    return value
+
+
+@click.group(commands={'gmmtest': gmm_test})
+@click.option('-v', '--verbosity', default='INFO', metavar='LVL', expose_value=False,
+              callback=_set_verbosity, is_eager=True,
+              help='Either CRITICAL, ERROR, WARNING, INFO or DEBUG')
+def cli():
+    ycdist.init_from_env()
+
+
+if __name__ == '__main__':
+    cli()

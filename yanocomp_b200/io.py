@@ -1,0 +1,222 @@
+'''
+I/O of the gmmtest path: prep-HDF5 -> packed ragged features, kmer model
+priors, BED and single-molecule JSON writers.
+
+This is the reworked gmmtest half of the reference's io.py
+(reference yanocomp/io.py:246-415).  Instead of one pandas read x position
+DataFrame per gene it produces `batch.Feature` objects: a position-major
+binary16 matrix per gene / transcript with the reads sorted by sample, which
+`batch.HostBatch` concatenates into the buffers the kernels read.  Output
+byte formats are those of the reference (io.py:365-415).
+'''
+import gzip
+import json
+import logging
+import os
+from contextlib import contextmanager
+
+import numpy as np
+
+from . import h5lite
+from .batch import Feature
+
+logger = logging.getLogger('yanocomp')
+
+DEFAULT_PRIORS_MODEL_FN = os.path.join(
+    os.path.split(os.path.abspath(__file__))[0],
+    'data', 'r9.4_70bps.u_to_t_rna.5mer.template.model')
+
+
+@contextmanager
+def hdf5_list(hdf5_fns):
+    '''context manager for a list of HDF5 files (reference io.py:246-256)'''
+    handles = [h5lite.File(fn, 'r') for fn in hdf5_fns]
+    try:
+        yield handles
+    finally:
+        for f in handles:
+            f.close()
+
+
+def get_shared_keys(hdf5_handles):
+    '''genes present in every file (reference io.py:259-267)'''
+    genes = set(hdf5_handles[0].keys())
+    for d in hdf5_handles[1:]:
+        genes.intersection_update(set(d.keys()))
+    return list(genes)
+
+
+def load_gene_kmers(gene_id, datasets):
+    '''pos -> kmer over all datasets, later files win (reference io.py:270-281)'''
+    kmers = {}
+    for d in datasets:
+        k = d[f'{gene_id}/kmers'][:]
+        pos = k['pos'].tolist()
+        km = np.char.decode(k['kmer'], 'ascii').tolist() if k['kmer'].dtype.kind == 'S' else k['kmer'].tolist()
+        kmers.update(zip(pos, km))
+    return kmers
+
+
+def load_gene_attrs(gene_id, datasets):
+    '''chrom, strand from the first dataset (reference io.py:284-293)'''
+    a = datasets[0][gene_id].attrs
+    return str(a['chrom']), str(a['strand'])
+
+
+def _clean_events(d, gene_id):
+    '''
+    One file's events with the reference's row semantics (io.py:308-319):
+    keep-first de-duplication on (read_idx, pos), rows with log10(dwell) > 0
+    (or NaN) dropped, read ids truncated to 32 characters.
+    '''
+    e = d[f'{gene_id}/events'][:]
+    key = (e['read_idx'].astype(np.int64) << 32) | e['pos'].astype(np.int64)
+    _, first = np.unique(key, return_index=True)
+    if len(first) != len(e):
+        e = e[np.sort(first)]
+    dur = e['duration'].astype(np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        keep = np.log10(dur) <= 0
+    if not keep.all():
+        e = e[keep]
+    r_ids = d[f'{gene_id}/read_ids'][:]
+    if r_ids.dtype.kind == 'S':
+        r_ids = np.char.decode(r_ids, 'ascii')
+    return e, r_ids.astype('U32')
+
+
+def _sample_block(e, r_ids):
+    '''(sorted unique read ids, sorted positions, row index, col index, means) of one sample'''
+    ids = r_ids[e['read_idx']]
+    uniq_ids, row = np.unique(ids, return_inverse=True)
+    positions, col = np.unique(e['pos'].astype(np.int64), return_inverse=True)
+    return uniq_ids, positions, row, col, e['mean']
+
+
+def _build_feature(feature_id, chrom, strand, blocks, n_samples, kmers):
+    '''
+    blocks[s] = _sample_block of sample s or None.  Columns = union of the
+    positions with at least one event; reads sorted by (sample, read id) as
+    the reference's unstack/concat orders them (io.py:329-341).
+    '''
+    present = [b for b in blocks if b is not None]
+    if not present:
+        return None
+    positions = np.unique(np.concatenate([b[1] for b in present]))
+    samp_start = np.zeros(n_samples + 1, dtype=np.int32)
+    for s, b in enumerate(blocks):
+        samp_start[s + 1] = samp_start[s] + (len(b[0]) if b is not None else 0)
+    X = np.full((len(positions), int(samp_start[-1])), np.nan, dtype=np.float16)
+    read_ids = []
+    for s, b in enumerate(blocks):
+        if b is None:
+            continue
+        uniq_ids, pos_s, row, col, mean = b
+        X[np.searchsorted(positions, pos_s)[col], samp_start[s] + row] = mean
+        read_ids.extend(uniq_ids.tolist())
+    return Feature(feature_id=feature_id, chrom=chrom, strand=strand, pos0=0, X=X,
+                   samp_start=samp_start, read_ids=read_ids, kmers=kmers, positions=positions)
+
+
+def load_gene_features(gene_id, cntrl_datasets, treat_datasets, by_transcript_ids=False):
+    '''
+    The packed replacement of load_gene_events x2 + load_gene_kmers +
+    load_gene_attrs (reference io.py:270-343, gmmtest.py:81-117).  Returns a
+    list of Features: one for the gene, or one per transcript that has events
+    in both conditions when `by_transcript_ids`.
+    '''
+    datasets = list(cntrl_datasets) + list(treat_datasets)
+    n_cntrl, R = len(cntrl_datasets), len(datasets)
+    chrom, strand = load_gene_attrs(gene_id, cntrl_datasets)
+    kmers = load_gene_kmers(gene_id, datasets)
+    if not by_transcript_ids:
+        blocks = []
+        for d in datasets:
+            e, r_ids = _clean_events(d, gene_id)
+            blocks.append(_sample_block(e, r_ids) if len(e) else None)
+        f = _build_feature(gene_id, chrom, strand, blocks, R, kmers)
+        return [f] if f is not None else []
+    per_t = {}
+    for s, d in enumerate(datasets):
+        e, r_ids = _clean_events(d, gene_id)
+        t_ids = [str(t) for t in d[f'{gene_id}/transcript_ids'][:]]
+        for t_idx, t_id in enumerate(t_ids):
+            et = e[e['transcript_idx'] == t_idx]
+            if len(et):
+                per_t.setdefault(t_id, [None] * R)[s] = _sample_block(et, r_ids)
+    feats = []
+    for t_id in sorted(per_t):
+        blocks = per_t[t_id]
+        # valid_transcripts = in both conditions (reference gmmtest.py:99)
+        if all(b is None for b in blocks[:n_cntrl]) or all(b is None for b in blocks[n_cntrl:]):
+            continue
+        f = _build_feature(t_id, chrom, strand, blocks, R, kmers)
+        if f is not None:
+            feats.append(f)
+    return feats
+
+
+def load_model_priors(model_fn=None):
+    '''
+    Expected kmer current levels (reference io.py:352-362); returned as
+    {kmer: (level_mean, level_stdv)}.
+    '''
+    if model_fn is None:
+        model_fn = DEFAULT_PRIORS_MODEL_FN
+    model = {}
+    header = None
+    with open(model_fn) as fh:
+        for line in fh:
+            if line.startswith('#') or not line.strip():
+                continue
+            fields = line.rstrip('\n').split('\t')
+            if header is None:
+                header = {name: i for i, name in enumerate(fields)}
+                continue
+            model[fields[header['kmer']]] = (float(fields[header['level_mean']]),
+                                             float(fields[header['level_stdv']]))
+    return model
+
+
+def save_gmmtest_results(res, output_bed_fn):
+    '''main results as BED, byte-compatible with reference io.py:365-399'''
+    res = res.sort_values(by=['chrom', 'pos'])
+    logger.info(f'Writing output to {os.path.abspath(output_bed_fn)}')
+    with open(output_bed_fn, 'w') as bed:
+        for record in res.itertuples(index=False):
+            (chrom, pos, gene_id, strand, kmer, kmers, centre, log_odds, lb, ub, pval, fdr,
+             c_fm, t_fm, g_stat, hom_g_stat, unmod_mus, unmod_stds, mod_mus, mod_stds, ks) = record
+            try:
+                unmod_mu, unmod_std = unmod_mus[centre], unmod_stds[centre]
+                mod_mu, mod_std = mod_mus[centre], mod_stds[centre]
+            except TypeError:
+                unmod_mu = unmod_std = mod_mu = mod_std = np.nan      # --no-gmm
+            with np.errstate(divide='ignore'):
+                score = int(round(min(-np.log10(fdr), 100)))
+            bed.write(
+                f'{chrom:s}\t{pos - 2:d}\t{pos + 3:d}\t'
+                f'{gene_id}:{kmer}\t{score:d}\t{strand:s}\t'
+                f'{log_odds:.2f}[{lb:.2f},{ub:.2f}]\t'
+                f'{pval:.2g}\t{fdr:.2g}\t'
+                f'{c_fm:.2f}\t{t_fm:.2f}\t'
+                f'{g_stat:.2f}\t{hom_g_stat:.2f}\t'
+                f'{unmod_mu:.2f}\t{unmod_std:.2f}\t'
+                f'{mod_mu:.2f}\t{mod_std:.2f}\t'
+                f'{ks:.2f}\n')
+
+
+def save_sm_preds(sm_preds, cntrl_hdf5_fns, treat_hdf5_fns, output_json_fn):
+    '''single-molecule predictions as JSON(.gz), reference io.py:402-415'''
+    sm_preds_json = {
+        'input_fns': {
+            'cntrl': dict(enumerate(cntrl_hdf5_fns)),
+            'treat': dict(enumerate(treat_hdf5_fns)),
+        },
+        'single_molecule_predictions': sm_preds,
+    }
+    if os.path.splitext(output_json_fn)[1] == '.gz':
+        handle = gzip.open(output_json_fn, 'wt', encoding='ascii')
+    else:
+        handle = open(output_json_fn, 'w')
+    with handle:
+        json.dump(sm_preds_json, handle)

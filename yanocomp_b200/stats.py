@@ -25,3 +25,99 @@ def benjamini_hochberg(p):
     out = np.empty(n, dtype=np.float64)
     out[order] = adj
     return out
+
+
+# ---------------------------------------------------------------------------
+# single-molecule prediction dictionaries (reference yanocomp/stats.py:358-419)
+# ---------------------------------------------------------------------------
+def format_model(mu, cov, box, cw):
+    '''JSON-serialisable GMM parameters (reference stats.py:382-419)'''
+    w = np.asarray(cw, dtype=np.float64)
+    w = w / w.sum()
+    return {
+        'unmod': {'mu': mu[0].tolist(), 'cov': cov[0].tolist()},
+        'mod': {'mu': mu[1].tolist(), 'cov': cov[1].tolist()},
+        'outlier': {'bounds': [[float(lo), float(hi)] for lo, hi in box]},
+        'weights': np.exp(np.log(w)).tolist(),
+    }
+
+
+def format_sm_preds(preds, outlier, events, reps, read_ids):
+    '''per-replicate read ids / events / predictions (reference stats.py:358-379)'''
+    out = {}
+    for r_id, rep, ev, p, o in zip(read_ids, reps, events, preds, outlier):
+        entry = out.get(rep)
+        if entry is None:
+            entry = out[rep] = {'read_ids': [], 'events': [], 'preds': [], 'outlier_preds': []}
+        entry['read_ids'].append(r_id)
+        entry['events'].append(ev)
+        entry['preds'].append(p)
+        entry['outlier_preds'].append(o)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# modified-distribution assignment (reference yanocomp/stats.py:516-599)
+# ---------------------------------------------------------------------------
+def calculate_kmer_shift_directions(results, expected_model):
+    '''
+    Per kmer: is the upper or the lower fitted component further from the
+    expected ONT level, over all significant records (reference stats.py:516-534).
+    expected_model: {kmer: (level_mean, level_stdv)}.
+    '''
+    lower, upper = {}, {}
+    for kmers, m1, m2 in zip(results['kmers'], results['dist1_means'], results['dist2_means']):
+        for k, lm, um in zip(kmers, m1, m2):
+            if lm > um:
+                lm, um = um, lm
+            exp = expected_model[k][0]
+            lower.setdefault(k, []).append(abs(lm - exp))
+            upper.setdefault(k, []).append(abs(um - exp))
+    return {k: 1 if np.median(upper[k]) > np.median(lower[k]) else 0 for k in lower}
+
+
+def dist1_is_modified(kmers, dist1_means, dist2_means, kmer_shift_dirs):
+    '''reference stats.py:537-554'''
+    s1 = s2 = 0
+    for k, d in zip(kmers, np.asarray(dist1_means) - np.asarray(dist2_means)):
+        if kmer_shift_dirs[k] ^ (d < 0):
+            s1 += abs(d)
+        else:
+            s2 += abs(d)
+    return s1 > s2
+
+
+def assign_modified_distribution(results, sm_preds, model):
+    '''
+    Decide for every significant record which fitted component is the modified
+    one and flip the record (and its single-molecule predictions) when it is
+    dist1 (reference stats.py:557-599).  `results` is the DataFrame of
+    gmmtest.parallel_test; modified in place and returned.
+    '''
+    if not len(results):
+        return results, sm_preds
+    dirs = calculate_kmer_shift_directions(results, model)
+    for i in results.index:
+        kmers, m1, m2 = results.at[i, 'kmers'], results.at[i, 'dist1_means'], results.at[i, 'dist2_means']
+        if not dist1_is_modified(kmers, m1, m2, dirs):
+            continue
+        results.at[i, 'cntrl_frac_mod'] = 1 - results.at[i, 'cntrl_frac_mod']
+        results.at[i, 'treat_frac_mod'] = 1 - results.at[i, 'treat_frac_mod']
+        results.at[i, 'log_odds'] = np.negative(results.at[i, 'log_odds'])
+        lo, hi = results.at[i, 'log_odds_lower_ci'], results.at[i, 'log_odds_upper_ci']
+        results.at[i, 'log_odds_lower_ci'], results.at[i, 'log_odds_upper_ci'] = np.negative(hi), np.negative(lo)
+        results.at[i, 'dist1_means'], results.at[i, 'dist2_means'] = m2, m1
+        s1, s2 = results.at[i, 'dist1_stds'], results.at[i, 'dist2_stds']
+        results.at[i, 'dist1_stds'], results.at[i, 'dist2_stds'] = s2, s1
+        gene_id, pos = results.at[i, 'gene_id'], results.at[i, 'pos']
+        try:
+            pos_sm_preds = sm_preds[gene_id][pos]
+        except KeyError:
+            continue
+        m = pos_sm_preds['model']
+        m['unmod'], m['mod'] = m['mod'], m['unmod']
+        for cond in ('cntrl', 'treat'):
+            for rep_sm_preds in pos_sm_preds[cond].values():
+                rep_sm_preds['preds'] = [1 - (p + o) for p, o in
+                                         zip(rep_sm_preds['preds'], rep_sm_preds['outlier_preds'])]
+    return results, sm_preds
