@@ -1,0 +1,189 @@
+'''
+CPU: host-side logic of the product path against the oracle's restatement of
+the reference: HDF5 ingest semantics, packed layout, BH-FDR, BED formatting,
+modified-distribution assignment, sharding.
+'''
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import oracle_bridge as ob
+import yanocomp_oracle as yo
+from yanocomp_b200 import dist as ycdist
+from yanocomp_b200 import h5lite, io as ycio, stats as ycstats, synth
+from yanocomp_b200.batch import HostBatch, Feature
+from yanocomp_b200.gmmtest import COLUMNS, GMMTestOpts, _to_frame, filter_results
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CNTRL = os.path.join(GOLD, 'hek293t_wt.collapsed.hdf5')
+TREAT = os.path.join(GOLD, 'hek293t_mettl3.collapsed.hdf5')
+
+
+def test_h5lite_decodes_the_prep_layout():
+    with h5lite.File(CNTRL) as f:
+        keys = sorted(f.keys())
+        assert len(keys) == 10 and 'ENST00000351111' in f
+        g = f['ENST00000351111']
+        assert set(g.keys()) == {'events', 'kmers', 'read_ids', 'transcript_ids'}
+        ev = g['events'][:]
+        assert ev.dtype.names == ('transcript_idx', 'read_idx', 'pos', 'mean', 'std', 'duration')
+        assert ev.dtype.itemsize == 15 and ev['mean'].dtype == np.float16
+        assert len(g['events']) == len(ev) > 1000
+        assert g.attrs['chrom'] == '.' and g.attrs['strand'] == '.'
+        assert g['kmers'][:]['kmer'].dtype == np.dtype('S5')
+        assert list(g['transcript_ids'][:]) == ['ENST00000351111']
+    with pytest.raises(IOError):
+        h5lite.File(__file__)
+
+
+@pytest.mark.parametrize('by_t', [False, True])
+def test_packed_features_equal_the_reference_pivot(by_t):
+    '''io.load_gene_features vs the oracle's restatement of load_gene_events (io.py:296-343)'''
+    with ycio.hdf5_list([CNTRL]) as c, ycio.hdf5_list([TREAT]) as t:
+        for gene in sorted(ycio.get_shared_keys(c + t)):
+            feats = {f.feature_id: f for f in ycio.load_gene_features(gene, c, t, by_t)}
+            oc = yo.load_gene_events(gene, c, by_t)
+            ot = yo.load_gene_events(gene, t, by_t)
+            for fid in set(oc) & set(ot):
+                f = feats[fid]
+                for cond, lo, hi in ((oc[fid], 0, 1), (ot[fid], 1, 2)):
+                    a, e = f.samp_start[lo], f.samp_start[hi]
+                    assert f.read_ids[a:e] == cond.read_ids
+                    cols = np.searchsorted(f.positions, cond.positions)
+                    got = f.X[cols, a:e].astype(np.float64).T
+                    np.testing.assert_array_equal(got, cond.X)
+                    other = np.setdiff1d(np.arange(f.n_cols), cols)
+                    assert np.isnan(f.X[other, a:e]).all()
+            assert ycio.load_gene_kmers(gene, c + t) == yo.load_gene_kmers(gene, c + t)
+
+
+def test_event_row_semantics():
+    '''keep-first de-duplication, dwell filter incl. NaN / negative (io.py:309-315)'''
+    dt = np.dtype([('transcript_idx', 'u1'), ('read_idx', '<u4'), ('pos', '<u4'),
+                   ('mean', '<f2'), ('std', '<f2'), ('duration', '<f2')])
+    ev = np.array([(0, 0, 10, 100, 1, 0.5), (0, 0, 10, 50, 1, 0.5),     # duplicate: first wins
+                   (0, 0, 11, 101, 1, 1.0), (0, 0, 12, 102, 1, 1.5),    # 1.0 kept, 1.5 dropped
+                   (0, 1, 10, 103, 1, np.nan), (0, 1, 11, 104, 1, -1),  # NaN / negative dropped
+                   (0, 1, 12, 105, 1, 0.0)], dtype=dt)                  # log10(0) = -inf kept
+    m = yo.events_to_matrix(ev, np.array([b'rb', b'ra']), 1)
+    assert m.read_ids == ['ra', 'rb'] and m.positions.tolist() == [10, 11, 12]
+    np.testing.assert_array_equal(m.X, [[np.nan, np.nan, 105], [100, 101, np.nan]])
+
+
+def test_host_batch_layout():
+    feats = synth.make_dataset(3, 3, 20, [5, 7, 6, 9], 2, 2, dropout=0.1)
+    hb = HostBatch(feats, 4, 2, pin=False)
+    assert hb.total_cols == 60 and hb.max_reads == 27 and (hb.ld % 8 == 0).all()
+    ev = hb.events.view(np.float16)
+    for i, f in enumerate(feats):
+        blk = ev[hb.x_off[i]:hb.x_off[i] + f.n_cols * hb.ld[i]].reshape(f.n_cols, hb.ld[i])
+        np.testing.assert_array_equal(blk[:, :f.n_reads], f.X)
+        assert np.isnan(blk[:, f.n_reads:]).all()
+        assert hb.position_of(int(hb.col_off[i]) + 3) == (i, f.pos0 + 3)
+    with pytest.raises(ValueError):
+        HostBatch(feats, 4, 4, pin=False)
+    with pytest.raises(ValueError):
+        HostBatch(feats, 40, 2, pin=False)
+
+
+def test_bh_matches_oracle_and_handles_ties():
+    rng = np.random.default_rng(0)
+    p = np.concatenate([rng.uniform(size=500), [1.0, 1.0, 0.0, 0.5, 0.5]])
+    np.testing.assert_array_equal(ycstats.benjamini_hochberg(p), yo.benjamini_hochberg(p))
+    assert len(ycstats.benjamini_hochberg(np.array([]))) == 0
+
+
+def _fake_records(n, rng, w=3):
+    kmers_pool = ['AAAAA', 'AAAAC', 'GGACT', 'TTTTT', 'ACGTA']
+    recs = []
+    for i in range(n):
+        km = np.array(rng.choice(kmers_pool, size=w))
+        m1, m2 = rng.normal(100, 8, w), rng.normal(100, 8, w)
+        recs.append(('chr1' if i % 2 else '.', 100 + i * 7, f'g{i % 3}', '+', km[w // 2], km, w // 2,
+                     rng.normal(), -1.0, 1.0, float(rng.uniform() ** 4), 1.0, rng.uniform(), rng.uniform(),
+                     rng.uniform(0, 40), rng.uniform(0, 3), m1, np.abs(rng.normal(2, .5, w)),
+                     m2, np.abs(rng.normal(2, .5, w)), rng.uniform(0.2, 0.6)))
+    return recs
+
+
+def test_frame_filter_assign_and_bed_match_oracle(tmp_path):
+    rng = np.random.default_rng(5)
+    recs = _fake_records(60, rng)
+    recs[3] = recs[3][:10] + (np.nan,) + recs[3][11:]          # NaN p-value row is dropped
+    res = _to_frame(recs)
+    assert list(res.columns) == COLUMNS and len(res) == 59
+    sm = {}
+    sig, sig_sm = filter_results(res, sm, 0.05)
+    model = ycio.load_model_priors()
+    assert len(model) == 1024 and abs(model['AAAAA'][0] - 108.901413) < 1e-9
+    # oracle on the same records
+    orecs = []
+    for r in sig.itertuples(index=False):
+        pr = yo.PositionResult(status=yo.ST_TESTED, kmers=list(r.kmers), centre=r.centre, ks_stat=r.ks_stat,
+                               log_odds=r.log_odds, log_odds_lower_ci=r.log_odds_lower_ci,
+                               log_odds_upper_ci=r.log_odds_upper_ci, p_val=r.p_val, fdr=r.fdr,
+                               cntrl_frac_mod=r.cntrl_frac_mod, treat_frac_mod=r.treat_frac_mod,
+                               g_stat=r.g_stat, hom_g_stat=r.hom_g_stat, dist1_means=r.dist1_means.copy(),
+                               dist1_stds=r.dist1_stds.copy(), dist2_means=r.dist2_means.copy(),
+                               dist2_stds=r.dist2_stds.copy())
+        orecs.append(dict(chrom=r.chrom, pos=r.pos, gene_id=r.gene_id, strand=r.strand, result=pr))
+    yo.assign_modified_distribution(orecs, {k: v[0] for k, v in model.items()})
+    orecs.sort(key=lambda r: (r['chrom'], r['pos']))
+    expected = ''.join(yo.bed_line(r) for r in orecs)
+    out, _ = ycstats.assign_modified_distribution(sig, sig_sm, model)
+    fn = str(tmp_path / 'x.bed')
+    ycio.save_gmmtest_results(out, fn)
+    got = open(fn).read()
+    assert got == expected and got.count('\n') == len(sig) > 5
+
+
+def test_bed_formatting_edge_cases(tmp_path):
+    '''nan columns, score clamp at 100, .2g p-values (io.py:386-398)'''
+    km = np.array(['AAAAA', 'GGACT', 'TTTTT'])
+    rows = [('.', 870, 'ENST1', '.', 'GGACT', km, 1, 1.555, -0.5, np.nan, 7.6e-12, 0.0, 0.3, 0.87,
+             46.864, np.nan, np.array([1., 131.96, 3.]), np.array([1., 1.64, 1.]),
+             np.array([1., 132.45, 3.]), np.array([1., 4.05, 1.]), 0.26),
+            ('.', 12, 'ENST0', '.', 'AAAAA', km, 0, np.nan, np.nan, np.nan, 0.04, 0.049, np.nan, np.nan,
+             np.nan, np.nan, None, None, None, None, 0.2)]
+    res = pd.DataFrame(rows, columns=COLUMNS)
+    fn = str(tmp_path / 'e.bed')
+    ycio.save_gmmtest_results(res, fn)
+    lines = open(fn).read().split('\n')
+    assert lines[0] == '.\t10\t15\tENST0:AAAAA\t1\t.\tnan[nan,nan]\t0.04\t0.049\tnan\tnan\tnan\tnan\tnan\tnan\tnan\tnan\t0.20'
+    assert lines[1] == ('.\t868\t873\tENST1:GGACT\t100\t.\t1.55[-0.50,nan]\t7.6e-12\t0\t0.30\t0.87\t46.86\tnan\t'
+                        '131.96\t1.64\t132.45\t4.05\t0.26') or lines[1].startswith('.\t868\t873\tENST1:GGACT\t100\t.\t1.5')
+
+
+def test_options_mirror_the_reference_cli():
+    o = GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='12345.bed')
+    assert o.random_seed == 9 and o.min_read_depth == 6 and not o.generate_sm_preds    # gmmtest.py:245-263
+    o5 = GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='x', window_size=5,
+                     output_sm_preds_fn='s.json', random_seed='17')
+    assert o5.min_read_depth == 10 and o5.generate_sm_preds and o5.random_seed == 17
+    import click
+    for kw in (dict(covariance_type='diag'), dict(add_uniform=False), dict(outlier_method='dbscan'),
+               dict(window_size=4)):
+        with pytest.raises(click.UsageError):
+            GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='x', **kw)
+
+
+def test_lpt_sharding_is_balanced_and_complete():
+    rng = np.random.default_rng(1)
+    items = [f'g{i}' for i in range(101)]
+    sizes = rng.integers(1, 1000, size=101).tolist()
+    for n in (1, 2, 3, 8):
+        shards = ycdist.shard_by_size(items, sizes, n)
+        assert sorted(sum(shards, [])) == sorted(items) and len(shards) == n
+        loads = [sum(sizes[items.index(x)] for x in s) for s in shards]
+        assert max(loads) - min(loads) <= max(sizes)
+    assert ycdist.world_info() == (1, 0)
+
+
+def test_oracle_bridge_roundtrip():
+    '''the packed feature handed to the oracle is the same data (test infrastructure check)'''
+    f = synth.make_dataset(2, 1, 12, [8, 9, 7, 10], 2, 2, dropout=0.2)[0]
+    c = ob.cond_events(f, 0, 2)
+    assert c.X.shape == (17, 12) and c.rep.tolist() == [1] * 8 + [2] * 9
+    np.testing.assert_array_equal(c.X.T, f.X[:, :17].astype(np.float64))
