@@ -38,7 +38,11 @@ def _set_verbosity(ctx, param, value):
               callback=_set_verbosity, is_eager=True,
               help='Either CRITICAL, ERROR, WARNING, INFO or DEBUG')
 def cli():
-    ycdist.init_from_env()
+    world, _ = ycdist.init_from_env()
+    if world > 1:
+        import atexit
+        import torch.distributed as dist
+        atexit.register(lambda: dist.is_initialized() and dist.destroy_process_group())
 
 
 if __name__ == '__main__':

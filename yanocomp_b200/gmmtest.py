@@ -216,6 +216,9 @@ def test_chunk(opts, gene_ids):
 
 
 def _to_frame(records):
+    # canonical row order (feature, position): the output must not depend on how genes were
+    # sharded over ranks / batches (the reference's order depends on its pool scheduling)
+    records = sorted(records, key=lambda r: (r[2], r[1]))
     res = pd.DataFrame(records, columns=COLUMNS)
     res.dropna(subset=['p_val'], inplace=True)            # reference gmmtest.py:221
     if len(res):
@@ -238,7 +241,8 @@ def parallel_test(opts):
     mine = ycdist.shard_by_size(gene_ids, sizes, world)[rank]
     res, sm_preds = test_chunk(opts, (mine, opts.random_seed))
     res, sm_preds = ycdist.gather_results(res, sm_preds)
-    logger.info(f'Complete. Tested {len(res):,} positions')
+    if rank == 0:
+        logger.info(f'Complete. Tested {len(res):,} positions')
     return _to_frame(res), sm_preds
 
 

@@ -180,7 +180,7 @@ def load_model_priors(model_fn=None):
 
 def save_gmmtest_results(res, output_bed_fn):
     '''main results as BED, byte-compatible with reference io.py:365-399'''
-    res = res.sort_values(by=['chrom', 'pos'])
+    res = res.sort_values(by=['chrom', 'pos'], kind='stable')
     logger.info(f'Writing output to {os.path.abspath(output_bed_fn)}')
     with open(output_bed_fn, 'w') as bed:
         for record in res.itertuples(index=False):
