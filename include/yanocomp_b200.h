@@ -68,6 +68,8 @@ typedef struct yc_batch {
     int32_t  n_samples;          /* R  (<= YC_MAX_SAMPLES) */
     int32_t  n_cntrl;            /* Rc: samples [0,Rc) are control */
     int32_t  max_reads;          /* max over features of n_reads (sizes shared memory) */
+    int32_t  max_cond_reads;     /* max over features of max(control rows, treatment rows) */
+    int32_t  reserved0;
     int64_t  total_cols;         /* sum of n_cols = number of candidate positions */
     const uint16_t *events;      /* IEEE binary16 bits, layout above */
     const int64_t  *x_off;       /* [F]   element offset of each feature matrix */

@@ -155,13 +155,68 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
     return dict(windows=n_windows, fitted=n_fit, res=res, ref=ref, host=host, errs=errs)
 
 
-def test_small_synthetic_w3():
+@pytest.fixture(params=['warp', 'cta'])
+def ks_path(request, monkeypatch):
+    '''run the KS stage through both kernels (warp-per-position fast path, CTA-per-position general path)'''
+    if request.param == 'cta':
+        monkeypatch.setenv('YC_KS_PATH', 'cta')
+    else:
+        monkeypatch.delenv('YC_KS_PATH', raising=False)
+    return request.param
+
+
+def test_small_synthetic_w3(ks_path):
     feats = synth.make_dataset(11, 4, 60, 30, 2, 2, planted_frac=0.2)
     out = compare(feats, 4, 2, window_size=3)
     assert out['windows'] > 200 and out['fitted'] > 5
 
 
-def test_small_synthetic_w5_dropout():
+def test_small_synthetic_w5_dropout(ks_path):
     feats = synth.make_dataset(12, 3, 50, [25, 31, 40, 28], 2, 2, planted_frac=0.2, dropout=0.05)
     out = compare(feats, 4, 2, window_size=5)
     assert out['windows'] > 50
+
+
+def test_reverse_strand_and_3x3_replicates(ks_path):
+    feats = synth.make_dataset(13, 3, 40, [20, 24, 22, 30, 21, 26], 3, 3, planted_frac=0.25, strand='-')
+    out = compare(feats, 6, 3, window_size=3)
+    assert out['windows'] > 80 and out['fitted'] > 5
+
+
+def test_window_1_and_low_depth(ks_path):
+    feats = synth.make_dataset(14, 2, 40, [9, 7, 8, 11], 2, 2, planted_frac=0.3, dropout=0.1)
+    out = compare(feats, 4, 2, window_size=1, min_read_depth=5, max_fit_discordance=0.1)
+    assert out['windows'] > 30
+
+
+def test_ragged_gaps_missing_sample_and_constant_column(ks_path):
+    rng = np.random.default_rng(15)
+    f0 = synth.make_feature(rng, 'GAPS', 40, [30, 28, 33, 29], 2, 2, planted_frac=0.2)
+    keep = np.ones(40, dtype=bool)
+    keep[[7, 8, 20]] = False                          # columns without events are dropped: windows must not span gaps
+    f0 = type(f0)(feature_id='GAPS', chrom='.', strand='+', pos0=0, X=f0.X[keep].copy(), samp_start=f0.samp_start,
+                  kmers=f0.kmers, positions=f0.positions[keep])
+    f1 = synth.make_feature(rng, 'NOSAMPLE', 30, [25, 0, 31, 27], 2, 2, planted_frac=0.2)   # control rep 2 has no reads
+    f2 = synth.make_feature(rng, 'CONST', 30, 20, 2, 2, planted_frac=0.0, outlier_frac=0.0)
+    f2.X[10, :] = np.float16(101.5)                  # constant column -> np.linalg.svd would raise (A9)
+    f3 = synth.make_feature(rng, 'SHALLOW', 20, [3, 30, 30, 30], 2, 2)                      # never reaches min depth
+    out = compare([f0, f1, f2, f3], 4, 2, window_size=3)
+    st = out['res'].status
+    assert (st == N.ST_DEGENERATE).sum() == 3 and out['windows'] > 60
+    assert (st[out['host'].col_off[3]:out['host'].col_off[4]] == N.ST_NOT_A_WINDOW).all()
+
+
+def test_subsampling_uses_the_shared_counter_based_stream():
+    '''max_fit_depth below the depth: per-condition (KS) and per-replicate (fit) sub-sampling (stats.py:52-59)'''
+    feats = synth.make_dataset(16, 2, 30, [60, 75, 66, 90], 2, 2, planted_frac=0.3)
+    out = compare(feats, 4, 2, window_size=3, max_fit_depth=50, max_fit_discordance=0.05)
+    assert out['fitted'] > 5
+    feats = synth.make_dataset(17, 1, 16, [700, 900, 650, 1200], 2, 2, planted_frac=0.3)
+    out = compare(feats, 4, 2, window_size=3, max_fit_depth=400, max_fit_discordance=0.05)
+    assert out['windows'] == 14
+
+
+def test_no_gmm_mode(ks_path):
+    feats = synth.make_dataset(18, 2, 40, 25, 2, 2, planted_frac=0.2)
+    out = compare(feats, 4, 2, window_size=3, gmm=False)
+    assert (out['res'].status == N.ST_KS_ONLY).sum() == out['windows'] and out['res'].n_fitted == 0

@@ -91,7 +91,7 @@ def test_rng_shared_with_oracle():
 
 def test_bad_arguments_are_rejected_without_a_gpu():
     lib = N.lib()
-    b = N.Batch(n_features=1, n_samples=40, n_cntrl=1, max_reads=10, total_cols=1)
+    b = N.Batch(n_features=1, n_samples=40, n_cntrl=1, max_reads=10, max_cond_reads=5, total_cols=1)
     p = N.Params(window_size=3, min_read_depth=6, max_fit_depth=1000, gmm=1)
     out = (C.c_int64 * 4)()
     assert lib.yc_smem_bytes(C.byref(b), C.byref(p), out) == N.YC_EINVAL

@@ -101,6 +101,8 @@ class HostBatch:
             self.reverse[i] = f.strand == '-'
         self.total_cols = int(self.col_off[-1])
         self.max_reads = int(self.n_reads.max()) if F else 0
+        split = self.samp_start[:, n_cntrl] if F else np.zeros(0, dtype=np.int32)
+        self.max_cond_reads = int(max(split.max(), (self.n_reads - split).max())) if F else 0
 
     @staticmethod
     def _alloc_events(total, pin):
@@ -161,7 +163,7 @@ class DeviceBatch:
             N.check(N.lib().yc_fill_col_feature(F, self.col_off.data_ptr(), self.col_feature.data_ptr(), s))
         self.struct = N.Batch(
             n_features=F, n_samples=host.n_samples, n_cntrl=host.n_cntrl,
-            max_reads=host.max_reads, total_cols=host.total_cols,
+            max_reads=host.max_reads, max_cond_reads=host.max_cond_reads, total_cols=host.total_cols,
             events=self.events.data_ptr(), x_off=self.x_off.data_ptr(),
             n_cols=self.n_cols.data_ptr(), n_reads=self.n_reads.data_ptr(),
             ld=self.ld.data_ptr(), col_off=self.col_off.data_ptr(),

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "yc_internal.h"
 #include "yc_common.cuh"
 #include "yc_stats.cuh"
@@ -117,6 +118,13 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
     cudaError_t ce = cudaMemsetAsync(fit_count, 0, sizeof(int32_t), st);
     if (ce != cudaSuccess) return cuda_fail((int)ce, "yc_ks_batch memset");
     if (b->total_cols == 0) return 0;
+    // small windows: one warp per position (yc_ks_warp.cu); otherwise one CTA per position.
+    // YC_KS_PATH=cta forces the general kernel (used by the tests to cover both).
+    const char *force = getenv("YC_KS_PATH");
+    const bool want_cta = force && strcmp(force, "cta") == 0;
+    if (!want_cta && yc::ks_warp_eligible(*b, *p) && yc::ks_warp_smem_bytes(*b, *p) <= smem_limit())
+        return cuda_fail(yc::ks_warp_dispatch(*b, *p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st),
+                         "yc_ks_batch (warp path)");
     if (int e = check_smem(yc::ks_smem_bytes(*b, *p), "yc_ks_batch")) return e;
     return cuda_fail(yc::ks_dispatch(*b, *p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st),
                      "yc_ks_batch");

@@ -1,0 +1,340 @@
+// Kernel 1, small-window fast path: one WARP per position, 32 consecutive
+// positions per warp, no block barriers.
+//
+// Same arithmetic as ks_kernel (yc_ks.cu) -- see there for the reference
+// citations -- reorganised after the round-1 profile (profiles/r01_summary.md):
+// in the CTA-per-position kernel 127 threads waited at a barrier for the
+// single-thread LAPACK axis replay and the block-wide bitonic sort paid 28
+// barriers per position.  Here a warp walks a group of 32 adjacent columns in
+// four phases:
+//   1. per position (all 32 lanes on one position): complete-row mask, depth
+//      counters, exact column sums, centred moments -> G = Z^T Z, the first w
+//      rows of Z, means and stds parked in shared memory;
+//   2. lane q replays dgesdd for position q -- 32 positions at once, every
+//      lane busy on the serial part;
+//   3. per position: projections, ordered append (ballot prefix, no atomics),
+//      warp-synchronous bitonic sort, D by upper-bound searches;
+//   4. lane q finalises position q: Kolmogorov p-value, gate, coalesced
+//      stores, one atomic per warp to reserve fit_list slots.
+// Adjacent columns share w-1 rows of the position-major matrix, so the warp's
+// 32+w-1 rows stay L1-resident across the phases.
+// Eligibility (checked by the dispatcher): w <= 5, reads per feature <= 1024
+// and no sub-sampling possible (reads per condition <= max_fit_depth).
+#include "yc_common.cuh"
+#include "yc_stats.cuh"
+#include "yc_svdsign.cuh"
+
+namespace yc {
+
+#define YC_KW_WARPS 4
+
+struct KwSmem {
+    int sort_off, gt_off, v_off, st_off, mask_off, cnt_off, ridx_off, wc_off, per_warp;
+};
+
+__host__ __device__ inline KwSmem kw_layout(int W, int R, int max_reads, int P) {
+    KwSmem s;
+    int o = 0;
+    s.sort_off = o; o += 2 * P * (int)sizeof(double);
+    s.gt_off = o;   o += 32 * (2 * W * W + 2 * W) * (int)sizeof(double);
+    s.v_off = o;    o += 32 * W * (int)sizeof(double);
+    s.wc_off = o;   o += 32 * W * (int)sizeof(void *);
+    s.st_off = o;   o += 32 * 8 * (int)sizeof(int);
+    s.mask_off = o; o += 32 * ((max_reads + 31) / 32) * (int)sizeof(uint32_t);
+    s.cnt_off = o;  o += (W + 1) * R * (int)sizeof(int);
+    s.ridx_off = o; o += 16 * (int)sizeof(int);
+    s.per_warp = (o + 15) & ~15;
+    return s;
+}
+
+__device__ __forceinline__ void warp_bitonic(double *a, int P, int nseg, int lane) {
+    const int total = P * nseg;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < total; i += 32) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (((i & (P - 1)) & k) == 0);
+                    const double x = a[i], y = a[l];
+                    if ((x > y) == up) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// warp-local window_scan: counters are private to the warp, so no atomics
+template <int W>
+__device__ __forceinline__ void warp_window_scan(const Window<W> &w, int R, uint32_t *mask, int *cnt, int lane) {
+    const int n = w.n_reads;
+    for (int base = 0; base < n; base += 32) {
+        const int r = base + lane;
+        const bool inb = r < n;
+        uint32_t m_all = YC_FULL, m_mine = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const uint16_t v = inb ? __ldg(w.col[j] + r) : (uint16_t)0x7e00;
+            const uint32_t m = __ballot_sync(YC_FULL, inb && !h_isnan(v));
+            m_all &= m;
+            if (lane == j) m_mine = m;
+        }
+        if (lane == W) m_mine = m_all;
+        if (lane == 0) mask[base >> 5] = m_all;
+        if (lane <= W) {
+            for (int s = 0; s < R; ++s) {
+                const int a = max(w.samp_start[s], base), e = min(w.samp_start[s + 1], base + 32);
+                if (e > a) {
+                    const uint32_t seg = (e - a == 32) ? YC_FULL : (((1u << (e - a)) - 1u) << (a - base));
+                    cnt[lane * R + s] += __popc(m_mine & seg);
+                }
+            }
+        }
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(YC_KW_WARPS * 32)
+ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
+               double *__restrict__ ks_stat, double *__restrict__ ks_pval,
+               int32_t *__restrict__ n_c_out, int32_t *__restrict__ n_t_out,
+               uint8_t *__restrict__ status, int32_t *__restrict__ fit_list,
+               int32_t *__restrict__ fit_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = b.n_samples, Rc = b.n_cntrl;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const KwSmem L = kw_layout(W, R, b.max_reads, P);
+    unsigned char *base_ptr = smem_raw + (size_t)wid * L.per_warp;
+    double *sortbuf = reinterpret_cast<double *>(base_ptr + L.sort_off);
+    double *gt = reinterpret_cast<double *>(base_ptr + L.gt_off);
+    double *vbuf = reinterpret_cast<double *>(base_ptr + L.v_off);
+    const uint16_t **wcache = reinterpret_cast<const uint16_t **>(base_ptr + L.wc_off);
+    int *st = reinterpret_cast<int *>(base_ptr + L.st_off);       // [32][8]: state, n_c, n_t, n_reads, split
+    uint32_t *masks = reinterpret_cast<uint32_t *>(base_ptr + L.mask_off);
+    int *cnt = reinterpret_cast<int *>(base_ptr + L.cnt_off);
+    int *ridx = reinterpret_cast<int *>(base_ptr + L.ridx_off);
+    const int nwords_max = (b.max_reads + 31) / 32;
+    constexpr int NT = W * (W + 1) / 2, GT = 2 * W * W + 2 * W;
+
+    const int64_t g0 = ((int64_t)blockIdx.x * YC_KW_WARPS + wid) * 32;
+    if (g0 >= b.total_cols) return;                 // no block-level synchronisation anywhere below
+
+    // ------------------------------------------------------------ phase 1
+    for (int q = 0; q < 32; ++q) {
+        const int64_t g = g0 + q;
+        int state = 0, n_c = 0, n_t = 0, n = 0, split = 0;    // state 0: not a window
+        Window<W> w;
+        if (g < b.total_cols && window_setup<W>(b, p, g, w)) {
+            n = w.n_reads;
+            split = w.samp_start[Rc];
+            uint32_t *mask = masks + q * nwords_max;
+            for (int i = lane; i < (W + 1) * R; i += 32) cnt[i] = 0;
+            __syncwarp();
+            warp_window_scan<W>(w, R, mask, cnt, lane);
+            __syncwarp();
+            if (window_depth_ok<W>(w, R, Rc, p.min_read_depth, cnt, n_c, n_t)) {
+                state = (n_c == 0 || n_t == 0) ? 1 : 2;       // 1: degenerate
+            }
+            if (state == 2) {
+                const int ntot = n_c + n_t;
+                double mu[W], cm[NT], sig[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) mu[j] = 0.0;
+                for (int r = lane; r < n; r += 32)
+                    if ((mask[r >> 5] >> (r & 31)) & 1u) {
+#pragma unroll
+                        for (int j = 0; j < W; ++j) mu[j] += h2d(__ldg(w.col[j] + r));
+                    }
+#pragma unroll
+                for (int j = 0; j < W; ++j) mu[j] = div_rn(warp_sum(mu[j]), (double)ntot);
+#pragma unroll
+                for (int k = 0; k < NT; ++k) cm[k] = 0.0;
+                for (int r = lane; r < n; r += 32)
+                    if ((mask[r >> 5] >> (r & 31)) & 1u) {
+                        double dlt[W];
+#pragma unroll
+                        for (int j = 0; j < W; ++j) dlt[j] = h2d(__ldg(w.col[j] + r)) - mu[j];
+                        int k = 0;
+#pragma unroll
+                        for (int a = 0; a < W; ++a)
+#pragma unroll
+                            for (int c2 = a; c2 < W; ++c2) cm[k++] += dlt[a] * dlt[c2];
+                    }
+#pragma unroll
+                for (int k = 0; k < NT; ++k) cm[k] = warp_sum(cm[k]);
+                {
+                    int k = 0;
+#pragma unroll
+                    for (int a = 0; a < W; ++a) {
+                        sig[a] = sqrt(cm[k] / (double)ntot);
+                        if (!(sig[a] > 0.0)) state = 1;          // constant column (assumption A9)
+                        k += W - a;
+                    }
+                }
+                if (state == 2) {
+                    // first W complete rows (pooled order) for the Householder pivots
+                    if (lane == 0) {
+                        int found = 0;
+                        for (int r = 0; r < n && found < W; ++r)
+                            if ((mask[r >> 5] >> (r & 31)) & 1u) ridx[found++] = r;
+                        for (; found < W; ++found) ridx[found] = -1;
+                    }
+                    __syncwarp();
+                    double *slot = gt + q * GT;                 // G[W*W], T[W*W], mu[W], sig[W]
+                    if (lane == 0) {
+                        int k = 0;
+                        for (int a = 0; a < W; ++a)
+                            for (int c2 = a; c2 < W; ++c2) {
+                                const double gv = cm[k++] / (sig[a] * sig[c2]);
+                                slot[a * W + c2] = gv; slot[c2 * W + a] = gv;
+                            }
+                        for (int a = 0; a < W; ++a) { slot[2 * W * W + a] = mu[a]; slot[2 * W * W + W + a] = sig[a]; }
+                    }
+                    if (lane < W * W) {
+                        const int k = lane / W, j = lane % W;
+                        const int r = ridx[k];
+                        // mu / sig are identical in every lane; select without dynamic indexing
+                        double muj = 0.0, sigj = 1.0;
+#pragma unroll
+                        for (int jj = 0; jj < W; ++jj) if (jj == j) { muj = mu[jj]; sigj = sig[jj]; }
+                        const uint16_t *cp = w.col[0];
+#pragma unroll
+                        for (int jj = 0; jj < W; ++jj) if (jj == j) cp = w.col[jj];
+                        slot[W * W + lane] = r >= 0 ? div_rn(sub_rn(h2d(__ldg(cp + r)), muj), sigj) : 0.0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < W; ++j) if (lane == j) wcache[q * W + j] = w.col[j];
+        }
+        if (lane == 0) { int *s = st + q * 8; s[0] = state; s[1] = n_c; s[2] = n_t; s[3] = n; s[4] = split; }
+        __syncwarp();
+    }
+    // ------------------------------------------------------------ phase 2
+    if (st[lane * 8] == 2) {
+        const double *slot = gt + lane * GT;
+        lapack::first_right_singular_vector<W>(slot, slot + W * W, vbuf + lane * W);
+    }
+    __syncwarp();
+    // ------------------------------------------------------------ phase 3
+    double my_d = 0.0;
+    for (int q = 0; q < 32; ++q) {
+        const int *s = st + q * 8;
+        if (s[0] != 2) continue;                                // warp-uniform
+        const int n1 = s[1], n2 = s[2], n = s[3], split = s[4];
+        const uint32_t *mask = masks + q * nwords_max;
+        const double *slot = gt + q * GT;
+        double mu[W], sig[W], vv[W];
+        const uint16_t *col[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            mu[j] = slot[2 * W * W + j]; sig[j] = slot[2 * W * W + W + j];
+            vv[j] = vbuf[q * W + j]; col[j] = wcache[q * W + j];
+        }
+        const int Pq = next_pow2(max(n1, n2));
+        for (int i = lane; i < 2 * Pq; i += 32) sortbuf[i] = INFINITY;
+        __syncwarp();
+        int ca = 0, cb = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (int base = 0; base < n; base += 32) {
+            const int r = base + lane;
+            const bool bit = r < n && ((mask[r >> 5] >> (r & 31)) & 1u);
+            const bool cond = r >= split;
+            double y = 0.0;
+            if (bit) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const double z = div_rn(sub_rn(h2d(__ldg(col[j] + r)), mu[j]), sig[j]);
+                    y = fma(z, vv[j], y);
+                }
+            }
+            const uint32_t ma = __ballot_sync(YC_FULL, bit && !cond), mb = __ballot_sync(YC_FULL, bit && cond);
+            if (bit) sortbuf[cond ? Pq + cb + __popc(mb & lt) : ca + __popc(ma & lt)] = y;
+            ca += __popc(ma); cb += __popc(mb);
+        }
+        __syncwarp();
+        warp_bitonic(sortbuf, Pq, 2, lane);
+        const double *A = sortbuf, *B = sortbuf + Pq;
+        const double fn1 = (double)n1, fn2 = (double)n2;
+        double dmax = 0.0;
+        for (int i = lane; i < n1 + n2; i += 32) {
+            const double v = (i < n1) ? A[i] : B[i - n1];
+            const int c1 = upper_bound(A, n1, v), c2 = upper_bound(B, n2, v);
+            dmax = fmax(dmax, fabs(sub_rn(div_rn((double)c1, fn1), div_rn((double)c2, fn2))));
+        }
+        dmax = warp_max(dmax);
+        if (lane == q) my_d = dmax;
+        __syncwarp();
+    }
+    // ------------------------------------------------------------ phase 4
+    const int64_t g = g0 + lane;
+    bool gated = false;
+    if (g < b.total_cols) {
+        const int *s = st + lane * 8;
+        const int state = s[0], n1 = s[1], n2 = s[2];
+        double d = nan(""), pv = nan("");
+        uint8_t code = YC_ST_NOT_A_WINDOW;
+        if (state == 1) code = YC_ST_DEGENERATE;
+        else if (state == 2) {
+            d = my_d;
+            const double en = __dsqrt_rn(div_rn((double)((int64_t)n1 * (int64_t)n2), (double)(n1 + n2)));
+            pv = kolmogorov_sf(mul_rn(add_rn(add_rn(en, 0.12), div_rn(0.11, en)), d));
+            if (!p.gmm) code = YC_ST_KS_ONLY;
+            else if (d >= p.min_ks && pv < p.fdr_threshold) { code = YC_ST_GATED; gated = true; }
+            else code = YC_ST_KS_FILTERED;
+        }
+        ks_stat[g] = d; ks_pval[g] = pv;
+        n_c_out[g] = state ? n1 : 0; n_t_out[g] = state ? n2 : 0;
+        status[g] = code;
+    }
+    const uint32_t gm = __ballot_sync(YC_FULL, gated);
+    if (gm) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(fit_count, __popc(gm));
+        base = __shfl_sync(YC_FULL, base, 0);
+        if (gated) fit_list[base + __popc(gm & ((1u << lane) - 1u))] = (int32_t)g;
+    }
+}
+
+static int kw_sort_cap(const yc_batch_t &b) {
+    int P = 32;
+    while (P < b.max_cond_reads) P <<= 1;
+    return P;
+}
+
+bool ks_warp_eligible(const yc_batch_t &b, const yc_params_t &p) {
+    return p.window_size <= 5 && b.max_reads <= 1024 && b.max_cond_reads <= p.max_fit_depth &&
+           b.max_cond_reads > 0;
+}
+
+int ks_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p) {
+    return kw_layout(p.window_size, b.n_samples, b.max_reads, kw_sort_cap(b)).per_warp * YC_KW_WARPS;
+}
+
+template <int W>
+static int launch_kw(const yc_batch_t &b, const yc_params_t &p, double *ks_stat, double *ks_pval,
+                     int32_t *n_c, int32_t *n_t, uint8_t *status, int32_t *fit_list, int32_t *fit_count,
+                     cudaStream_t st) {
+    const int P = kw_sort_cap(b);
+    const int smem = kw_layout(W, b.n_samples, b.max_reads, P).per_warp * YC_KW_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(ks_warp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t groups = (b.total_cols + 31) / 32;
+    const unsigned grid = (unsigned)((groups + YC_KW_WARPS - 1) / YC_KW_WARPS);
+    ks_warp_kernel<W><<<grid, YC_KW_WARPS * 32, smem, st>>>(b, p, P, ks_stat, ks_pval, n_c, n_t, status,
+                                                            fit_list, fit_count);
+    return (int)cudaGetLastError();
+}
+
+int ks_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, double *ks_stat, double *ks_pval,
+                     int32_t *n_c, int32_t *n_t, uint8_t *status, int32_t *fit_list, int32_t *fit_count,
+                     cudaStream_t st) {
+    switch (p.window_size) {
+        case 1: return launch_kw<1>(b, p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st);
+        case 3: return launch_kw<3>(b, p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st);
+        case 5: return launch_kw<5>(b, p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st);
+    }
+    return YC_EINVAL;
+}
+
+}  // namespace yc
