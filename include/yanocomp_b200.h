@@ -182,6 +182,21 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p,
                           int64_t *post_cursor, void *stream);
 
 /*
+ * Kernels 2a + 2b + 3 in one call.  For small windows (w <= 5, <= 1024 reads
+ * per feature, no sub-sampling possible) this is ONE fused kernel, one warp
+ * per gated position, that keeps the model in shared memory from the k-means
+ * initialisation to the posteriors; otherwise it launches the three kernels
+ * above back to back.  Same outputs as the three separate calls.
+ * (YC_FIT_PATH=cta in the environment forces the general path.)
+ */
+int yc_gmm_fit_fused_batch(const yc_batch_t *b, const yc_params_t *p,
+                           const int32_t *fit_list, int32_t n_fit,
+                           yc_fit_out_t *out, uint8_t *status,
+                           int8_t *labels, int32_t max_fit_rows,
+                           double *post, int64_t post_capacity,
+                           int64_t *post_cursor, void *stream);
+
+/*
  * Host-side scalar entry points (no GPU needed): the same code the kernels
  * run for scipy.stats.kstwobign.sf (stats.py:48), chi2.sf at 1 dof and the
  * G-test / fraction block (stats.py:302-355), exported so CPU tests can pin

@@ -17,13 +17,14 @@ pytestmark = pytest.mark.gpu
 
 PARAM_RTOL = 1e-4      # north_star: 1e-4 on fitted parameters
 STAT_RTOL = 1e-4
+SPLIT_FIT = {'on': False}
 KS_ORIENTATION_EXACT = True    # the kernel reproduces LAPACK's axis orientation (yc_svdsign.cuh)
 
 
 def _run_gpu(features, R, Rc, **kw):
     from yanocomp_b200.engine import Engine, EngineParams
     params = EngineParams(**kw)
-    eng = Engine(params)
+    eng = Engine(params, split_fit=SPLIT_FIT.get('on', False))
     host = HostBatch(features, R, Rc)
     dev = eng.upload(host)
     return host, eng.run(dev, want_labels=True), params
@@ -155,14 +156,22 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
     return dict(windows=n_windows, fitted=n_fit, res=res, ref=ref, host=host, errs=errs)
 
 
-@pytest.fixture(params=['warp', 'cta'])
+@pytest.fixture(params=['warp', 'cta', 'cta-split'])
 def ks_path(request, monkeypatch):
-    '''run the KS stage through both kernels (warp-per-position fast path, CTA-per-position general path)'''
-    if request.param == 'cta':
+    '''
+    Run every stage through both families of kernels: the warp-per-position fast paths
+    (yc_ks_warp.cu, yc_fit_warp.cu) and the CTA-per-position general kernels (yc_ks.cu, yc_fit.cu;
+    'cta-split' calls the three fit entry points separately instead of yc_gmm_fit_fused_batch).
+    '''
+    SPLIT_FIT['on'] = request.param == 'cta-split'
+    if request.param != 'warp':
         monkeypatch.setenv('YC_KS_PATH', 'cta')
+        monkeypatch.setenv('YC_FIT_PATH', 'cta')
     else:
         monkeypatch.delenv('YC_KS_PATH', raising=False)
-    return request.param
+        monkeypatch.delenv('YC_FIT_PATH', raising=False)
+    yield request.param
+    SPLIT_FIT['on'] = False
 
 
 def test_small_synthetic_w3(ks_path):

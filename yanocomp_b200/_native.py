@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libyanocomp_b200.so')
+LIB_PATH = os.environ.get('YC_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libyanocomp_b200.so')
 
 YC_MAX_WINDOW = 9
 YC_MAX_SAMPLES = 16
@@ -69,6 +69,8 @@ _PROTOTYPES = {
                                   C.c_void_p, C.c_void_p]),
     'yc_gtest_smpred_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut),
                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'yc_gmm_fit_fused_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut), C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'yc_kolmogorov_sf_host': (C.c_double, [C.c_double]),
     'yc_chi2_sf_1dof_host': (C.c_double, [C.c_double]),
     'yc_gtest_fractions_host': (None, [_P(C.c_double), C.c_int32, C.c_int32, C.c_double, _P(C.c_double)]),

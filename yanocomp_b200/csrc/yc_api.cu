@@ -167,6 +167,33 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p, const int32
                                         post_cursor, st), "yc_gtest_smpred_batch");
 }
 
+int yc_gmm_fit_fused_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
+                           yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows,
+                           double *post, int64_t post_capacity, int64_t *post_cursor, void *stream) {
+    if (int e = check_common(b, p)) return e;
+    if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_fit_fused_batch: null pointer");
+    if (post && !post_cursor) return fail(YC_EINVAL, "yc_gmm_fit_fused_batch: post without post_cursor");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (post_cursor) {
+        cudaError_t ce = cudaMemsetAsync(post_cursor, 0, sizeof(int64_t), st);
+        if (ce != cudaSuccess) return cuda_fail((int)ce, "yc_gmm_fit_fused_batch memset");
+    }
+    if (n_fit <= 0) return 0;
+    const char *force = getenv("YC_FIT_PATH");
+    const bool want_cta = force && strcmp(force, "cta") == 0;
+    if (!want_cta && yc::fit_warp_eligible(*b, *p) && yc::fit_warp_smem_bytes(*b, *p) <= smem_limit())
+        return cuda_fail(yc::fit_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows,
+                                               post, post_capacity, post_cursor, st),
+                         "yc_gmm_fit_fused_batch (warp path)");
+    // general path: the three CTA-per-position kernels back to back
+    if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 0), "yc_gmm_init_batch")) return e;
+    if (int e = cuda_fail(yc::init_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows, st),
+                          "yc_gmm_init_batch")) return e;
+    if (int e = cuda_fail(yc::em_dispatch(*b, *p, fit_list, n_fit, *out, status, st), "yc_gmm_em_batch")) return e;
+    return cuda_fail(yc::gtest_dispatch(*b, *p, fit_list, n_fit, *out, status, post, post_capacity, post_cursor, st),
+                     "yc_gtest_smpred_batch");
+}
+
 // ---- host-side scalar entry points: the same __host__ __device__ code the
 // kernels run, callable without a GPU so the CPU test-suite can pin it
 // against SciPy (tests/test_stats_host.py).

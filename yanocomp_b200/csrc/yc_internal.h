@@ -14,6 +14,11 @@ int ks_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
 int ks_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, double *ks_stat, double *ks_pval,
                      int32_t *n_c, int32_t *n_t, uint8_t *status, int32_t *fit_list, int32_t *fit_count,
                      cudaStream_t st);
+bool fit_warp_eligible(const yc_batch_t &b, const yc_params_t &p);
+int fit_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
+int fit_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
+                      const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows,
+                      double *post, int64_t post_capacity, int64_t *post_cursor, cudaStream_t st);
 int fit_cap(const yc_batch_t &b, const yc_params_t &p);
 int fit_smem_bytes(const yc_batch_t &b, const yc_params_t &p, int which);
 int init_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,

@@ -9,8 +9,10 @@
 
 #ifdef __CUDACC__
 #define YC_HD __host__ __device__ inline
+#define YC_HD_COLD __host__ __device__ __noinline__ inline      /* serial, cold: keep one copy */
 #else
 #define YC_HD inline
+#define YC_HD_COLD inline
 #endif
 
 namespace yc {
@@ -19,7 +21,7 @@ namespace yc {
 // Two-series evaluation (Kolmogorov 1933; cutover as in SciPy's cephes port):
 //   x <= 0.82:  1 - sqrt(2 pi)/x * sum_{k>=1} exp(-(2k-1)^2 pi^2 / (8 x^2))
 //   x >  0.82:  2 * sum_{k>=1} (-1)^(k-1) exp(-2 k^2 x^2)
-YC_HD double kolmogorov_sf(double x) {
+YC_HD_COLD double kolmogorov_sf(double x) {
     if (isnan(x)) return x;
     if (x <= 0.040611972203751713) return 1.0;      // cdf underflows to 0
     const double pi = 3.14159265358979323846;
@@ -62,19 +64,25 @@ YC_HD double xlogy(double x, double y) { return x == 0.0 ? 0.0 : x * log(y); }
 // G statistic of an nrow x ncol table without continuity correction
 // (scipy.stats.chi2_contingency(lambda_='log-likelihood'), dof != 1);
 // zero expected cell or dof 0 -> 0.0  (two_cond_g_test, stats.py:302-313).
-YC_HD double g_stat_table(const double *obs, int nrow, int ncol) {
+YC_HD_COLD double g_stat_table(const double *obs, int nrow, int ncol) {
     double rs[YC_MAX_SAMPLES], cs[YC_NCOMP] = {0.0, 0.0, 0.0}, tot = 0.0;
+    _Pragma("unroll 1")
     for (int i = 0; i < nrow; ++i) {
         rs[i] = 0.0;
+        _Pragma("unroll 1")
         for (int j = 0; j < ncol; ++j) { rs[i] += obs[i * ncol + j]; cs[j] += obs[i * ncol + j]; }
         tot += rs[i];
     }
     if (!(tot > 0.0)) return 0.0;
+    _Pragma("unroll 1")
     for (int i = 0; i < nrow; ++i) if (rs[i] == 0.0) return 0.0;
+    _Pragma("unroll 1")
     for (int j = 0; j < ncol; ++j) if (cs[j] == 0.0) return 0.0;
     if ((nrow - 1) * (ncol - 1) == 0) return 0.0;
     double g = 0.0;
+    _Pragma("unroll 1")
     for (int i = 0; i < nrow; ++i)
+        _Pragma("unroll 1")
         for (int j = 0; j < ncol; ++j) {
             const double e = rs[i] * cs[j] / tot;
             g += 2.0 * xlogy(obs[i * ncol + j], obs[i * ncol + j] / e);
@@ -86,10 +94,12 @@ YC_HD double g_stat_table(const double *obs, int nrow, int ncol) {
 // preds: [nrow_c + nrow_t][3] rounded counts of the PRESENT samples, control
 // rows first.  gmm_g_test (stats.py:316-338) + calculate_fractional_stats
 // (stats.py:341-355).
-YC_HD void gtest_fractions(const double *preds, int nrow_c, int nrow_t, double thr, double *out) {
+YC_HD_COLD void gtest_fractions(const double *preds, int nrow_c, int nrow_t, double thr, double *out) {
     const double nan_ = nan("");
     double c[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+    _Pragma("unroll 1")
     for (int i = 0; i < nrow_c; ++i) for (int j = 0; j < 3; ++j) c[j] += preds[i * 3 + j];
+    _Pragma("unroll 1")
     for (int i = 0; i < nrow_t; ++i) for (int j = 0; j < 3; ++j) t[j] += preds[(nrow_c + i) * 3 + j];
     // heterogeneity 2x2 with Yates' correction, magnitude min(0.5, |E - O|)
     double o[4] = {c[0], c[1], t[0], t[1]};
@@ -103,6 +113,7 @@ YC_HD void gtest_fractions(const double *preds, int nrow_c, int nrow_t, double t
     } else {
         const double e[4] = {r0 * c0 / tot, r0 * c1 / tot, r1 * c0 / tot, r1 * c1 / tot};
         het = 0.0;
+        _Pragma("unroll 1")
         for (int k = 0; k < 4; ++k) {
             const double diff = e[k] - o[k];
             const double mag = fmin(0.5, fabs(diff));
@@ -125,6 +136,7 @@ YC_HD void gtest_fractions(const double *preds, int nrow_c, int nrow_t, double t
     // Table2x2(shift_zeros=True)
     double f[4] = {c[0], c[1], t[0], t[1]};
     if (f[0] == 0.0 || f[1] == 0.0 || f[2] == 0.0 || f[3] == 0.0)
+        _Pragma("unroll 1")
         for (int k = 0; k < 4; ++k) f[k] += 0.5;
     const double lor = log(f[0]) - log(f[1]) - log(f[2]) + log(f[3]);
     const double se = sqrt(1.0 / f[0] + 1.0 / f[1] + 1.0 / f[2] + 1.0 / f[3]);

@@ -33,7 +33,7 @@ namespace lapack {
 
 __host__ __device__ __forceinline__ double fsign(double a, double b) { return copysign(a, b); }
 
-__host__ __device__ inline void dlartg(double f, double g, double &c, double &s, double &r) {
+__host__ __device__ __noinline__ inline void dlartg(double f, double g, double &c, double &s, double &r) {
     if (g == 0.0) { c = 1.0; s = 0.0; r = f; }
     else if (f == 0.0) { c = 0.0; s = fsign(1.0, g); r = fabs(g); }
     else {
@@ -44,7 +44,7 @@ __host__ __device__ inline void dlartg(double f, double g, double &c, double &s,
     }
 }
 
-__host__ __device__ inline void dlas2(double f, double g, double h, double &ssmin, double &ssmax) {
+__host__ __device__ __noinline__ inline void dlas2(double f, double g, double h, double &ssmin, double &ssmax) {
     const double fa = fabs(f), ga = fabs(g), ha = fabs(h);
     const double fhmn = fmin(fa, ha), fhmx = fmax(fa, ha);
     if (fhmn == 0.0) {
@@ -68,7 +68,7 @@ __host__ __device__ inline void dlas2(double f, double g, double h, double &ssmi
     }
 }
 
-__host__ __device__ inline void dlasv2(double f, double g, double h, double &ssmin, double &ssmax,
+__host__ __device__ __noinline__ inline void dlasv2(double f, double g, double h, double &ssmin, double &ssmax,
                               double &snr, double &csr, double &snl, double &csl) {
     double ft = f, fa = fabs(f), ht = h, ha = fabs(h);
     int pmax = 1;
@@ -122,11 +122,13 @@ __host__ __device__ inline void dlasv2(double f, double g, double h, double &ssm
 
 // dlasr('L','V',dir): rotation j acts on rows (ll+j, ll+j+1) of VT (D columns)
 template <int D>
-__host__ __device__ inline void dlasr_lv(double *VT, int ll, int nrot, const double *cs, const double *sn, bool forward) {
+__host__ __device__ __noinline__ inline void dlasr_lv(double *VT, int ll, int nrot, const double *cs, const double *sn, bool forward) {
+    _Pragma("unroll 1")
     for (int q = 0; q < nrot; ++q) {
         const int j = forward ? q : nrot - 1 - q;
         const double c = cs[j], s = sn[j];
         if (c != 1.0 || s != 0.0) {
+            _Pragma("unroll 1")
             for (int k = 0; k < D; ++k) {
                 const double a = VT[(ll + j + 1) * D + k], b = VT[(ll + j) * D + k];
                 VT[(ll + j + 1) * D + k] = c * a - s * b;
@@ -141,18 +143,21 @@ __host__ __device__ inline void dlasr_lv(double *VT, int ll, int nrot, const dou
 // Indices in the comments are LAPACK's 1-based ones.  Returns false if the
 // iteration limit is hit (never observed).
 template <int D>
-__host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
+__host__ __device__ __noinline__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
     const int n = D;
     if (n > 1) {
         const double eps = YC_LAPACK_EPS;
         const double tolmul = fmax(10.0, fmin(100.0, pow(eps, -0.125)));
         const double tol = tolmul * eps;
         double smax = 0.0;
+        _Pragma("unroll 1")
         for (int i = 0; i < n; ++i) smax = fmax(smax, fabs(d[i]));
+        _Pragma("unroll 1")
         for (int i = 0; i < n - 1; ++i) smax = fmax(smax, fabs(e[i]));
         double sminoa = fabs(d[0]);
         if (sminoa != 0.0) {
             double mu = sminoa;
+            _Pragma("unroll 1")
             for (int i = 1; i < n; ++i) {
                 mu = fabs(d[i]) * (mu / (mu + fabs(e[i - 1])));
                 sminoa = fmin(sminoa, mu);
@@ -171,6 +176,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
             smax = fabs(d[m - 1]);
             bool found = false;
             int ll = 0;
+            _Pragma("unroll 1")
             for (int lll = 1; lll < m; ++lll) {
                 ll = m - lll;
                 const double abss = fabs(d[ll - 1]), abse = fabs(e[ll - 1]);
@@ -186,6 +192,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
                 double sigmn, sigmx, sinr, cosr, sinl, cosl;
                 dlasv2(d[m - 2], e[m - 2], d[m - 1], sigmn, sigmx, sinr, cosr, sinl, cosl);
                 d[m - 2] = sigmx; e[m - 2] = 0.0; d[m - 1] = sigmn;
+                _Pragma("unroll 1")
                 for (int k = 0; k < D; ++k) {        // drot(VT(m-1,:), VT(m,:), cosr, sinr)
                     const double x = VT[(m - 2) * D + k], y = VT[(m - 1) * D + k];
                     VT[(m - 2) * D + k] = cosr * x + sinr * y;
@@ -201,6 +208,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
                 if (fabs(e[m - 2]) <= fabs(tol) * fabs(d[m - 1])) { e[m - 2] = 0.0; continue; }
                 double mu = fabs(d[ll - 1]);
                 smin = mu;
+                _Pragma("unroll 1")
                 for (int lll = ll; lll < m; ++lll) {
                     if (fabs(e[lll - 1]) <= tol * mu) { e[lll - 1] = 0.0; conv = true; break; }
                     mu = fabs(d[lll]) * (mu / (mu + fabs(e[lll - 1])));
@@ -210,6 +218,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
                 if (fabs(e[ll - 1]) <= fabs(tol) * fabs(d[ll - 1])) { e[ll - 1] = 0.0; continue; }
                 double mu = fabs(d[m - 1]);
                 smin = mu;
+                _Pragma("unroll 1")
                 for (int lll = m - 1; lll >= ll; --lll) {
                     if (fabs(e[lll - 1]) <= tol * mu) { e[lll - 1] = 0.0; conv = true; break; }
                     mu = fabs(d[lll - 1]) * (mu / (mu + fabs(e[lll - 1])));
@@ -231,6 +240,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
             if (shift == 0.0) {
                 if (idir == 1) {
                     double cs = 1.0, sn = 0.0, oldcs = 1.0, oldsn = 0.0, r;
+                    _Pragma("unroll 1")
                     for (int i = ll; i < m; ++i) {
                         dlartg(d[i - 1] * cs, e[i - 1], cs, sn, r);
                         if (i > ll) e[i - 2] = oldsn * r;
@@ -243,6 +253,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
                     if (fabs(e[m - 2]) <= thresh) e[m - 2] = 0.0;
                 } else {
                     double cs = 1.0, sn = 0.0, oldcs = 1.0, oldsn = 0.0, r;
+                    _Pragma("unroll 1")
                     for (int i = m; i > ll; --i) {
                         dlartg(d[i - 1] * cs, e[i - 2], cs, sn, r);
                         if (i < m) e[i - 1] = oldsn * r;
@@ -258,6 +269,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
                 if (idir == 1) {
                     double f = (fabs(d[ll - 1]) - shift) * (fsign(1.0, d[ll - 1]) + shift / d[ll - 1]);
                     double g = e[ll - 1];
+                    _Pragma("unroll 1")
                     for (int i = ll; i < m; ++i) {
                         double cosr, sinr, cosl, sinl, r;
                         dlartg(f, g, cosr, sinr, r);
@@ -279,6 +291,7 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
                 } else {
                     double f = (fabs(d[m - 1]) - shift) * (fsign(1.0, d[m - 1]) + shift / d[m - 1]);
                     double g = e[m - 2];
+                    _Pragma("unroll 1")
                     for (int i = m; i > ll; --i) {
                         double cosr, sinr, cosl, sinl, r;
                         dlartg(f, g, cosr, sinr, r);
@@ -301,15 +314,19 @@ __host__ __device__ inline bool dbdsqr_vt(double *d, double *e, double *VT) {
             }
         }
     }
+    _Pragma("unroll 1")
     for (int i = 0; i < n; ++i)
         if (d[i] < 0.0) { d[i] = -d[i]; for (int k = 0; k < D; ++k) VT[i * D + k] = -VT[i * D + k]; }
+    _Pragma("unroll 1")
     for (int i = 1; i < n; ++i) {       // sort into decreasing order
         int isub = 0;
         double smin = d[0];
+        _Pragma("unroll 1")
         for (int j = 1; j < n + 1 - i; ++j) if (d[j] <= smin) { isub = j; smin = d[j]; }
         const int last = n - i;
         if (isub != last) {
             d[isub] = d[last]; d[last] = smin;
+            _Pragma("unroll 1")
             for (int k = 0; k < D; ++k) { const double t = VT[isub * D + k]; VT[isub * D + k] = VT[last * D + k]; VT[last * D + k] = t; }
         }
     }
@@ -322,12 +339,15 @@ template <int D>
 __host__ __device__ __noinline__ void first_right_singular_vector(const double *G, const double *Tin, double *v) {
     if (D == 1) { v[0] = 1.0; return; }          // dbdsdc: N = 1 -> VT = 1
     double S[D * D], T[D * D], A[D * D];
+    _Pragma("unroll 1")
     for (int i = 0; i < D * D; ++i) { S[i] = G[i]; T[i] = Tin[i]; A[i] = 0.0; }
     // ---- R of dgeqr2 from the Gram matrix and the Householder pivots
+    _Pragma("unroll 1")
     for (int i = 0; i < D; ++i) {
         const double alpha = T[i * D + i];
         const double xn2 = S[i * D + i] - alpha * alpha;
         if (!(xn2 > 0.0)) {
+            _Pragma("unroll 1")
             for (int j = i; j < D; ++j) A[i * D + j] = T[i * D + j];
         } else {
             const double beta = -fsign(sqrt(S[i * D + i]), alpha);
@@ -335,25 +355,32 @@ __host__ __device__ __noinline__ void first_right_singular_vector(const double *
             const double inv = 1.0 / (alpha - beta);
             double w[D];
             A[i * D + i] = beta;
+            _Pragma("unroll 1")
             for (int j = i + 1; j < D; ++j) {
                 w[j] = T[i * D + j] + (S[i * D + j] - alpha * T[i * D + j]) * inv;
                 A[i * D + j] = T[i * D + j] - tau * w[j];
             }
+            _Pragma("unroll 1")
             for (int r = i + 1; r < D; ++r) {
                 const double vr = T[r * D + i] * inv;
+                _Pragma("unroll 1")
                 for (int j = i + 1; j < D; ++j) T[r * D + j] -= tau * vr * w[j];
             }
         }
+        _Pragma("unroll 1")
         for (int j = i + 1; j < D; ++j)
+            _Pragma("unroll 1")
             for (int k = i + 1; k < D; ++k) S[j * D + k] -= A[i * D + j] * A[i * D + k];
     }
     // ---- dgebd2 on R (upper triangular, in A)
     double d[D], e[D], taup[D], vp[D * D];
+    _Pragma("unroll 1")
     for (int i = 0; i < D; ++i) {
         // left reflector H(i) from A(i:, i)
         {
             const double alpha = A[i * D + i];
             double xn2 = 0.0;
+            _Pragma("unroll 1")
             for (int r = i + 1; r < D; ++r) xn2 += A[r * D + i] * A[r * D + i];
             if (xn2 == 0.0) d[i] = alpha;
             else {
@@ -363,10 +390,14 @@ __host__ __device__ __noinline__ void first_right_singular_vector(const double *
                 const double inv = 1.0 / (alpha - beta);
                 double vv[D];
                 vv[i] = 1.0;
+                _Pragma("unroll 1")
                 for (int r = i + 1; r < D; ++r) vv[r] = A[r * D + i] * inv;
+                _Pragma("unroll 1")
                 for (int j = i + 1; j < D; ++j) {
                     double wj = 0.0;
+                    _Pragma("unroll 1")
                     for (int r = i; r < D; ++r) wj += A[r * D + j] * vv[r];
+                    _Pragma("unroll 1")
                     for (int r = i; r < D; ++r) A[r * D + j] -= tau * vv[r] * wj;
                 }
                 d[i] = beta;
@@ -377,6 +408,7 @@ __host__ __device__ __noinline__ void first_right_singular_vector(const double *
             // right reflector G(i) from A(i, i+1:)
             const double alpha = A[i * D + i + 1];
             double xn2 = 0.0;
+            _Pragma("unroll 1")
             for (int c = i + 2; c < D; ++c) xn2 += A[i * D + c] * A[i * D + c];
             vp[i * D + i + 1] = 1.0;
             if (xn2 == 0.0) { e[i] = alpha; taup[i] = 0.0; }
@@ -385,10 +417,14 @@ __host__ __device__ __noinline__ void first_right_singular_vector(const double *
                 const double beta = -fsign(hypot(alpha, xnorm), alpha);
                 const double tau = (beta - alpha) / beta;
                 const double inv = 1.0 / (alpha - beta);
+                _Pragma("unroll 1")
                 for (int c = i + 2; c < D; ++c) vp[i * D + c] = A[i * D + c] * inv;
+                _Pragma("unroll 1")
                 for (int r = i + 1; r < D; ++r) {
                     double wr = 0.0;
+                    _Pragma("unroll 1")
                     for (int c = i + 1; c < D; ++c) wr += A[r * D + c] * vp[i * D + c];
+                    _Pragma("unroll 1")
                     for (int c = i + 1; c < D; ++c) A[r * D + c] -= tau * wr * vp[i * D + c];
                 }
                 e[i] = beta; taup[i] = tau;
@@ -397,19 +433,26 @@ __host__ __device__ __noinline__ void first_right_singular_vector(const double *
         }
     }
     double VT[D * D];
+    _Pragma("unroll 1")
     for (int i = 0; i < D * D; ++i) VT[i] = 0.0;
+    _Pragma("unroll 1")
     for (int i = 0; i < D; ++i) VT[i * D + i] = 1.0;
     dbdsqr_vt<D>(d, e, VT);
     // ---- dormbr('P','R','T'): VT <- VT G(n-1) ... G(1)  (only row 0 is needed)
     double row[D];
+    _Pragma("unroll 1")
     for (int k = 0; k < D; ++k) row[k] = VT[k];
+    _Pragma("unroll 1")
     for (int i = D - 2; i >= 0; --i) {
         if (taup[i] != 0.0) {
             double wv = 0.0;
+            _Pragma("unroll 1")
             for (int c = i + 1; c < D; ++c) wv += row[c] * vp[i * D + c];
+            _Pragma("unroll 1")
             for (int c = i + 1; c < D; ++c) row[c] -= taup[i] * wv * vp[i * D + c];
         }
     }
+    _Pragma("unroll 1")
     for (int k = 0; k < D; ++k) v[k] = row[k];
 }
 
