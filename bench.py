@@ -271,7 +271,6 @@ def run_gpu(args, cfg, opts_kw):
         'gmm_init': n_fit * (bytes_per_pos + 8 * (2 * w + 2 * w * w + 2 * w + 3 * R)),
         'gmm_em': n_fit * (bytes_per_pos + 2 * 8 * (2 * w + 2 * w * w + 3 * R)),
         'gtest_smpred': n_fit * (bytes_per_pos + 8 * (3 * R + 8)),
-        'gmm_fit_fused': n_fit * (bytes_per_pos + 8 * (2 * w + 2 * w * w + 2 * w + 6 * R + 11)),
     }
     dom = max(kavg, key=kavg.get) if kavg else 'ks'
     achieved = alg[dom] / (kavg[dom] * 1e-3) / 1e9 if kavg else 0.0
@@ -280,7 +279,7 @@ def run_gpu(args, cfg, opts_kw):
     flop_read_iter = 2 * (d * (d + 1) + 2 * d) + 2 * (1 + d + d * (d + 1)) + 120
     em_flops = sum_iters * Nreads * flop_read_iter
     fp64_peak = 148 * 64 * 2 * sm_max * 1e6      # 64 FP64 FMA lanes / SM / clk
-    em_name = 'gmm_fit_fused' if 'gmm_fit_fused' in kavg else 'gmm_em'
+    em_name = 'gmm_em'
     em_ms = kavg.get(em_name, float('inf'))
     roofline = {
         'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
@@ -289,7 +288,6 @@ def run_gpu(args, cfg, opts_kw):
         'note': 'the path is FP64-latency bound, not HBM bound (DESIGN.md section 5); fp64 block below',
         'fp64': {'kernel': em_name, 'achieved_tflops': em_flops / (em_ms * 1e-3) / 1e12,
                  'peak_tflops': fp64_peak / 1e12, 'frac': em_flops / (em_ms * 1e-3) / fp64_peak,
-                 'counts': 'EM E-steps only (k-means init, M-steps and G-tests of the fused kernel are not counted)',
                  'flop_per_read_iter': flop_read_iter, 'mean_em_iters': mean_iters},
     }
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)

@@ -182,19 +182,21 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p,
                           int64_t *post_cursor, void *stream);
 
 /*
- * Kernels 2a + 2b + 3 in one call.  For small windows (w <= 5, <= 1024 reads
- * per feature, no sub-sampling possible) this is ONE fused kernel, one warp
- * per gated position, that keeps the model in shared memory from the k-means
- * initialisation to the posteriors; otherwise it launches the three kernels
- * above back to back.  Same outputs as the three separate calls.
- * (YC_FIT_PATH=cta in the environment forces the general path.)
+ * Kernels 2a + 2b + 3 back to back on one stream (convenience; same outputs
+ * as the three calls above).
+ *
+ * Each of the three stages has two implementations chosen per batch: for
+ * small windows (w <= 5, <= 1024 reads per feature, no sub-sampling possible)
+ * one WARP per gated position (csrc/yc_fit_warp.cu), otherwise one 128-thread
+ * CTA per gated position (csrc/yc_fit.cu).  YC_FIT_PATH=cta / YC_KS_PATH=cta in
+ * the environment force the general kernels.
  */
-int yc_gmm_fit_fused_batch(const yc_batch_t *b, const yc_params_t *p,
-                           const int32_t *fit_list, int32_t n_fit,
-                           yc_fit_out_t *out, uint8_t *status,
-                           int8_t *labels, int32_t max_fit_rows,
-                           double *post, int64_t post_capacity,
-                           int64_t *post_cursor, void *stream);
+int yc_gmm_fit_batch(const yc_batch_t *b, const yc_params_t *p,
+                     const int32_t *fit_list, int32_t n_fit,
+                     yc_fit_out_t *out, uint8_t *status,
+                     int8_t *labels, int32_t max_fit_rows,
+                     double *post, int64_t post_capacity,
+                     int64_t *post_cursor, void *stream);
 
 /*
  * Host-side scalar entry points (no GPU needed): the same code the kernels

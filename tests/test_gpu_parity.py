@@ -24,7 +24,7 @@ KS_ORIENTATION_EXACT = True    # the kernel reproduces LAPACK's axis orientation
 def _run_gpu(features, R, Rc, **kw):
     from yanocomp_b200.engine import Engine, EngineParams
     params = EngineParams(**kw)
-    eng = Engine(params, split_fit=SPLIT_FIT.get('on', False))
+    eng = Engine(params)
     host = HostBatch(features, R, Rc)
     dev = eng.upload(host)
     return host, eng.run(dev, want_labels=True), params
@@ -156,12 +156,11 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
     return dict(windows=n_windows, fitted=n_fit, res=res, ref=ref, host=host, errs=errs)
 
 
-@pytest.fixture(params=['warp', 'cta', 'cta-split'])
+@pytest.fixture(params=['warp', 'cta'])
 def ks_path(request, monkeypatch):
     '''
     Run every stage through both families of kernels: the warp-per-position fast paths
-    (yc_ks_warp.cu, yc_fit_warp.cu) and the CTA-per-position general kernels (yc_ks.cu, yc_fit.cu;
-    'cta-split' calls the three fit entry points separately instead of yc_gmm_fit_fused_batch).
+    (yc_ks_warp.cu, yc_fit_warp.cu) and the CTA-per-position general kernels (yc_ks.cu, yc_fit.cu).
     '''
     SPLIT_FIT['on'] = request.param == 'cta-split'
     if request.param != 'warp':

@@ -69,7 +69,7 @@ _PROTOTYPES = {
                                   C.c_void_p, C.c_void_p]),
     'yc_gtest_smpred_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut),
                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    'yc_gmm_fit_fused_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut), C.c_void_p,
+    'yc_gmm_fit_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut), C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'yc_kolmogorov_sf_host': (C.c_double, [C.c_double]),
     'yc_chi2_sf_1dof_host': (C.c_double, [C.c_double]),

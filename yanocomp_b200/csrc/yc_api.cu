@@ -62,6 +62,14 @@ int check_smem(int need, const char *kernel) {
     return 0;
 }
 
+// small windows take the warp-per-position kernels (yc_fit_warp.cu); YC_FIT_PATH=cta forces the
+// general CTA-per-position kernels (the tests run both)
+bool use_warp_fit(const yc_batch_t &b, const yc_params_t &p) {
+    const char *force = getenv("YC_FIT_PATH");
+    if (force && strcmp(force, "cta") == 0) return false;
+    return yc::fit_warp_eligible(b, p) && yc::fit_warp_smem_bytes(b, p) <= smem_limit();
+}
+
 __global__ void fill_col_feature_kernel(int n_features, const int64_t *__restrict__ col_off,
                                         int32_t *__restrict__ col_feature) {
     for (int f = blockIdx.x; f < n_features; f += gridDim.x) {
@@ -135,6 +143,9 @@ int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *
     if (int e = check_common(b, p)) return e;
     if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_init_batch: null pointer");
     if (n_fit <= 0) return 0;
+    if (use_warp_fit(*b, *p))
+        return cuda_fail(yc::init_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows,
+                                                (cudaStream_t)stream), "yc_gmm_init_batch (warp path)");
     if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 0), "yc_gmm_init_batch")) return e;
     return cuda_fail(yc::init_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows,
                                        (cudaStream_t)stream), "yc_gmm_init_batch");
@@ -145,6 +156,9 @@ int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fi
     if (int e = check_common(b, p)) return e;
     if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_em_batch: null pointer");
     if (n_fit <= 0) return 0;
+    if (use_warp_fit(*b, *p))
+        return cuda_fail(yc::em_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
+                         "yc_gmm_em_batch (warp path)");
     if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 1), "yc_gmm_em_batch")) return e;
     return cuda_fail(yc::em_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
                      "yc_gmm_em_batch");
@@ -162,36 +176,20 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p, const int32
         if (ce != cudaSuccess) return cuda_fail((int)ce, "yc_gtest_smpred_batch memset");
     }
     if (n_fit <= 0) return 0;
+    if (use_warp_fit(*b, *p))
+        return cuda_fail(yc::gtest_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, post, post_capacity,
+                                                 post_cursor, st), "yc_gtest_smpred_batch (warp path)");
     if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 2), "yc_gtest_smpred_batch")) return e;
     return cuda_fail(yc::gtest_dispatch(*b, *p, fit_list, n_fit, *out, status, post, post_capacity,
                                         post_cursor, st), "yc_gtest_smpred_batch");
 }
 
-int yc_gmm_fit_fused_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
-                           yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows,
-                           double *post, int64_t post_capacity, int64_t *post_cursor, void *stream) {
-    if (int e = check_common(b, p)) return e;
-    if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_fit_fused_batch: null pointer");
-    if (post && !post_cursor) return fail(YC_EINVAL, "yc_gmm_fit_fused_batch: post without post_cursor");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (post_cursor) {
-        cudaError_t ce = cudaMemsetAsync(post_cursor, 0, sizeof(int64_t), st);
-        if (ce != cudaSuccess) return cuda_fail((int)ce, "yc_gmm_fit_fused_batch memset");
-    }
-    if (n_fit <= 0) return 0;
-    const char *force = getenv("YC_FIT_PATH");
-    const bool want_cta = force && strcmp(force, "cta") == 0;
-    if (!want_cta && yc::fit_warp_eligible(*b, *p) && yc::fit_warp_smem_bytes(*b, *p) <= smem_limit())
-        return cuda_fail(yc::fit_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows,
-                                               post, post_capacity, post_cursor, st),
-                         "yc_gmm_fit_fused_batch (warp path)");
-    // general path: the three CTA-per-position kernels back to back
-    if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 0), "yc_gmm_init_batch")) return e;
-    if (int e = cuda_fail(yc::init_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows, st),
-                          "yc_gmm_init_batch")) return e;
-    if (int e = cuda_fail(yc::em_dispatch(*b, *p, fit_list, n_fit, *out, status, st), "yc_gmm_em_batch")) return e;
-    return cuda_fail(yc::gtest_dispatch(*b, *p, fit_list, n_fit, *out, status, post, post_capacity, post_cursor, st),
-                     "yc_gtest_smpred_batch");
+int yc_gmm_fit_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
+                     yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows,
+                     double *post, int64_t post_capacity, int64_t *post_cursor, void *stream) {
+    if (int e = yc_gmm_init_batch(b, p, fit_list, n_fit, out, status, labels, max_fit_rows, stream)) return e;
+    if (int e = yc_gmm_em_batch(b, p, fit_list, n_fit, out, status, stream)) return e;
+    return yc_gtest_smpred_batch(b, p, fit_list, n_fit, out, status, post, post_capacity, post_cursor, stream);
 }
 
 // ---- host-side scalar entry points: the same __host__ __device__ code the

@@ -1,17 +1,22 @@
-// Kernels 2a + 2b + 3 fused, small-window fast path: ONE WARP (one 32-thread
-// CTA) per gated position does model initialisation, EM, the G-tests and the
-// single-molecule posteriors without leaving the SM.
+// Kernels 2a / 2b / 3, small-window fast path: ONE WARP (a 32-thread CTA) per
+// gated position.
 //
 // Same arithmetic as gmm_init_kernel / gmm_em_kernel / gtest_smpred_kernel in
-// yc_fit.cu (see there for the reference citations); reorganised after the
-// round-1 profile: with ~200 reads per position a 128-thread CTA spends its
-// time in block barriers around 2-3 busy threads (M-step, Cholesky).  A warp
-// needs no barriers (`__syncwarp`), keeps the model in shared memory across
-// the three stages (no global round trip, one launch instead of three), and
-// the hardware scheduler load-balances the very uneven EM lengths (2..1001
-// E-steps) because every position is its own CTA.
+// yc_fit.cu (see there for the reference citations), reorganised after the
+// round-1 profiles (profiles/r01_summary.md):
+//  * with ~200 reads per position a 128-thread CTA spends its time in block
+//    barriers around 2-3 busy threads (M-step, Cholesky); a warp needs only
+//    `__syncwarp`, and because every position is its own CTA the hardware
+//    scheduler balances the very uneven EM lengths (2..1001 E-steps);
+//  * a first fused init+EM+G-test warp kernel was 240 KB of SASS and lost 55 %
+//    of its issue slots to instruction-cache misses ("no_instructions"
+//    stalls): the three stages are separate kernels again, serial code is
+//    __noinline__ with rolled loops, and wide reductions go through shared
+//    memory instead of unrolled shuffle trees, so that each kernel's hot loop
+//    stays inside the 32 KB instruction cache.
 // Eligibility (dispatcher): w <= 5, <= 1024 reads per feature, no sub-sampling
 // possible (reads per condition <= max_fit_depth).
+#include <type_traits>
 #include "yc_fit_common.cuh"
 #include "yc_stats.cuh"
 
@@ -31,7 +36,7 @@ __host__ __device__ inline FwSmem fw_layout(int W, int R, int cap) {
     s.wtmp_off = o;   o += 2 * YC_MAX_SAMPLES * (int)sizeof(double);
     s.red_off = o;    o += (2 * (1 + W + W * (W + 1) / 2) + 1) * 33 * (int)sizeof(double);
     s.mask_off = o;   o += ((cap + 31) / 32 + 1) * (int)sizeof(uint32_t);
-    s.cnt_off = o;    o += (W + 1) * R * (int)sizeof(int);
+    s.cnt_off = o;    o += (YC_MAX_SAMPLES + 2) * (int)sizeof(int);
     s.fstart_off = o; o += (YC_MAX_SAMPLES + 2) * (int)sizeof(int);
     s.xs_off = o;     o += W * cap * (int)sizeof(uint16_t);
     o = (o + 3) & ~3;
@@ -42,14 +47,51 @@ __host__ __device__ inline FwSmem fw_layout(int W, int R, int cap) {
 }
 
 template <int W>
+struct FwCtx {
+    EmPar<W> *par;
+    double *buf, *red, *wtmp;
+    uint32_t *mask;
+    int *fstart;
+    uint16_t *xs;
+    uint8_t *srow;
+    int8_t *lab;
+    int n, cap;
+    uint64_t pkey;
+};
+
+template <int W>
 __device__ __forceinline__ void fw_row(const uint16_t *xs, int cap, int i, double (&x)[W]) {
 #pragma unroll
     for (int j = 0; j < W; ++j) x[j] = h2d(xs[j * cap + i]);
 }
 
-__device__ __forceinline__ void warp_bitonic1(double *a, int P, int lane) {
+// Sum K per-lane values over the warp through shared memory (row stride 33:
+// conflict-free); every lane gets the totals.  Deterministic; ~K stores +
+// 32 loads + K broadcast loads instead of 10*K shuffles, and compact code.
+template <int K>
+__device__ __forceinline__ void warp_sum_smem(double (&v)[K], double *red, int lane) {
+#pragma unroll
+    for (int q = 0; q < K; ++q) red[q * 33 + lane] = v[q];
+    __syncwarp();
+#pragma unroll 1
+    for (int q = lane; q < K; q += 32) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int l2 = 0; l2 < 32; ++l2) t += red[q * 33 + l2];
+        red[q * 33 + 32] = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < K; ++q) v[q] = red[q * 33 + 32];
+    __syncwarp();
+}
+
+__device__ __noinline__ void warp_bitonic1(double *a, int P, int lane) {
+#pragma unroll 1
     for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
             for (int i = lane; i < P; i += 32) {
                 const int l = i ^ j;
                 if (l > i) {
@@ -63,6 +105,331 @@ __device__ __forceinline__ void warp_bitonic1(double *a, int P, int lane) {
     }
 }
 
+// complete-window rows of position g -> shared memory (binary16, pooled order), per-sample offsets
+template <int W>
+__device__ __noinline__ bool fw_front(const yc_batch_t &b, const yc_params_t &p, int64_t g,
+                                      unsigned char *smem, const FwSmem &L, int cap, int lane, bool gather,
+                                      FwCtx<W> &c) {
+    const int R = b.n_samples;
+    c.buf = reinterpret_cast<double *>(smem + L.buf_off);
+    c.par = reinterpret_cast<EmPar<W> *>(smem + L.par_off);
+    c.red = reinterpret_cast<double *>(smem + L.red_off);
+    c.wtmp = reinterpret_cast<double *>(smem + L.wtmp_off);
+    c.mask = reinterpret_cast<uint32_t *>(smem + L.mask_off);
+    int *cnt = reinterpret_cast<int *>(smem + L.cnt_off);
+    c.fstart = reinterpret_cast<int *>(smem + L.fstart_off);
+    c.xs = reinterpret_cast<uint16_t *>(smem + L.xs_off);
+    c.srow = reinterpret_cast<uint8_t *>(smem + L.srow_off);
+    c.lab = reinterpret_cast<int8_t *>(smem + L.lab_off);
+    c.cap = cap;
+    c.n = 0;
+    Window<W> w;
+    if (!window_setup<W>(b, p, g, w)) return false;
+    c.pkey = w.pkey;
+    if (lane <= R) cnt[lane] = 0;
+    __syncwarp();
+    const int nr = w.n_reads;
+#pragma unroll 1
+    for (int base = 0; base < nr; base += 32) {
+        const int r = base + lane;
+        const bool inb = r < nr;
+        uint32_t m_all = YC_FULL;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const uint16_t v = inb ? __ldg(w.col[j] + r) : (uint16_t)0x7e00;
+            m_all &= __ballot_sync(YC_FULL, inb && !h_isnan(v));
+        }
+        if (lane == 0) c.mask[base >> 5] = m_all;
+        if (lane < R) {                                     // lane s counts the complete rows of sample s
+            const int a = max(w.samp_start[lane], base), e = min(w.samp_start[lane + 1], base + 32);
+            if (e > a) {
+                const uint32_t seg = (e - a == 32) ? YC_FULL : (((1u << (e - a)) - 1u) << (a - base));
+                cnt[lane] += __popc(m_all & seg);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int acc = 0;
+#pragma unroll 1
+        for (int s = 0; s < R; ++s) { c.fstart[s] = acc; acc += cnt[s]; }
+        c.fstart[R] = acc;
+    }
+    __syncwarp();
+    c.n = c.fstart[R];
+    if (c.n < 1 || c.n > cap) return false;
+    if (gather) {
+        const uint32_t lt = (1u << lane) - 1u;
+        int run = 0;
+#pragma unroll 1
+        for (int base = 0; base < nr; base += 32) {
+            const uint32_t m = c.mask[base >> 5];
+            if ((m >> lane) & 1u) {
+                const int r = base + lane, rank = run + __popc(m & lt);
+#pragma unroll
+                for (int j = 0; j < W; ++j) c.xs[j * cap + rank] = __ldg(w.col[j] + r);
+                int s = 0;
+                while (s + 1 < R && r >= w.samp_start[s + 1]) ++s;
+                c.srow[rank] = (uint8_t)s;
+            }
+            run += __popc(m);
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// ===========================================================================
+// Kernel 2a (warp): k-means++ x3, MAD outliers, ML Gaussians, weights, box
+// ===========================================================================
+template <int W>
+__global__ void __launch_bounds__(32)
+init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+                 const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+                 uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = b.n_samples, lane = threadIdx.x;
+    const FwSmem L = fw_layout(W, R, cap);
+    constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
+    const int slot = blockIdx.x;
+    const int64_t g = fit_list[slot];
+    FwCtx<W> c;
+    if (!fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c)) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
+    const int n = c.n;
+    const uint16_t *xs = c.xs;
+    double *buf = c.buf, *red = c.red;
+    int8_t *lab = c.lab;
+    const uint64_t pkey = c.pkey;
+
+    // ---- k-means++ x3 + Lloyd  (assumption A2)
+    double best[2 * W], best_total = INFINITY;
+    bool have_best = false;
+    const int C = (n + 31) / 32;
+    const int i0c = min(lane * C, n), i1c = min(i0c + C, n);
+#pragma unroll 1
+    for (int restart = 0; restart < 3; ++restart) {
+        double cen[2 * W];
+        {
+            const double u0 = rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 0);
+            double x[W];
+            fw_row<W>(xs, cap, min((int)(u0 * (double)n), n - 1), x);
+#pragma unroll
+            for (int j = 0; j < W; ++j) cen[j] = x[j];
+        }
+        {   // second centre: D^2 sampling through the (exact) cumulative sum
+            double loc = 0.0;
+#pragma unroll 1
+            for (int i = i0c; i < i1c; ++i) { double x[W]; fw_row<W>(xs, cap, i, x); loc = add_rn(loc, sqdist<W>(x, cen)); }
+            double inc = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(YC_FULL, inc, o); if (lane >= o) inc = add_rn(inc, t); }
+            const double total = __shfl_sync(YC_FULL, inc, 31);
+            double run = sub_rn(inc, loc);
+            const double target = mul_rn(rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 1), total);
+            int below = 0;
+#pragma unroll 1
+            for (int i = i0c; i < i1c; ++i) { double x[W]; fw_row<W>(xs, cap, i, x); run = add_rn(run, sqdist<W>(x, cen)); below += (run <= target); }
+            below = warp_sum_i(below);
+            double x[W];
+            fw_row<W>(xs, cap, min(below, n - 1), x);
+#pragma unroll
+            for (int j = 0; j < W; ++j) cen[W + j] = x[j];
+        }
+        int iteration = 0;
+        double improvement = INFINITY, last = INFINITY, total = INFINITY;
+        double acc[2 * W + 3];
+        bool have_sums = false;
+#pragma unroll 1
+        while (improvement > 0.5 && iteration < 101) {
+            if (have_sums) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (acc[2 * W + 1 + k] > 0.0)
+#pragma unroll
+                        for (int j = 0; j < W; ++j) cen[k * W + j] = div_rn(acc[k * W + j], acc[2 * W + 1 + k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2 * W + 3; ++k) acc[k] = 0.0;
+#pragma unroll 1
+            for (int i = lane; i < n; i += 32) {
+                double x[W];
+                fw_row<W>(xs, cap, i, x);
+                const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
+                const bool k = d1 < d0;
+                acc[2 * W] += k ? d1 : d0;
+                acc[2 * W + 1] += k ? 0.0 : 1.0;
+                acc[2 * W + 2] += k ? 1.0 : 0.0;
+#pragma unroll
+                for (int j = 0; j < W; ++j) { acc[j] += k ? 0.0 : x[j]; acc[W + j] += k ? x[j] : 0.0; }
+            }
+            warp_sum_smem<2 * W + 3>(acc, red, lane);
+            have_sums = true;
+            total = acc[2 * W];
+            if (iteration > 0) improvement = last - total;
+            ++iteration;
+            last = total;
+        }
+        if (total < best_total) {
+            best_total = total; have_best = true;
+#pragma unroll
+            for (int j = 0; j < 2 * W; ++j) best[j] = cen[j];
+        }
+    }
+    if (!have_best) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
+
+    // ---- MAD outliers (stats.py:114-122, A1)
+    int P = 32;
+    while (P < n) P <<= 1;
+#pragma unroll 1
+    for (int i = lane; i < P; i += 32) {
+        double dmin = INFINITY;
+        if (i < n) {
+            double x[W];
+            fw_row<W>(xs, cap, i, x);
+            const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
+            lab[i] = (int8_t)(d1 < d0);
+            dmin = d1 < d0 ? d1 : d0;
+        }
+        buf[i] = dmin;
+    }
+    __syncwarp();
+    warp_bitonic1(buf, P, lane);
+    const double med = (n & 1) ? buf[n >> 1] : mul_rn(add_rn(buf[(n >> 1) - 1], buf[n >> 1]), 0.5);
+    // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are
+    // V-shaped, i.e. two ascending runs (left of the median walked outwards, right of it), so the
+    // order statistics of their union follow from merge ranks found by binary search.
+    double *wsel = c.wtmp;
+    const int m_le = upper_bound(buf, n, med);            // elements <= med form the left run
+    const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {
+        const double dv = fabs(sub_rn(buf[i], med));
+        int rank;
+        if (i < m_le) {                                    // left run, index m_le-1-i; count right-run elements < dv
+            int lo = 0, hi = n - m_le;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(buf[m_le + mid], med)) < dv) lo = mid + 1; else hi = mid; }
+            rank = (m_le - 1 - i) + lo;
+        } else {                                           // right run, index i-m_le; count left-run elements <= dv
+            int lo = 0, hi = m_le;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(buf[m_le - 1 - mid], med)) <= dv) lo = mid + 1; else hi = mid; }
+            rank = (i - m_le) + lo;
+        }
+        if (rank == k_lo) wsel[0] = dv;
+        if (rank == k_hi) wsel[1] = dv;
+    }
+    __syncwarp();
+    const double mad = (n & 1) ? wsel[1] : mul_rn(add_rn(wsel[0], wsel[1]), 0.5);
+    const double thr = mul_rn(p.outlier_factor, mad);
+    __syncwarp();
+    int n_out = 0;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {
+        double x[W];
+        fw_row<W>(xs, cap, i, x);
+        const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
+        if ((d1 < d0 ? d1 : d0) > thr) { lab[i] = 2; ++n_out; }
+    }
+    n_out = warp_sum_i(n_out);
+    __syncwarp();
+    if (labels_out)
+        for (int i = lane; i < n && i < max_fit_rows; i += 32) labels_out[(size_t)slot * max_fit_rows + i] = lab[i];
+
+    // ---- ML Gaussians per label from exact sufficient statistics (stats.py:148-152)
+    bool ok_all = true;
+    {
+        double S[2 * NS];
+#pragma unroll
+        for (int q = 0; q < 2 * NS; ++q) S[q] = 0.0;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+            const int l = lab[i];
+            if (l < 2) {
+                double x[W];
+                fw_row<W>(xs, cap, i, x);
+                const double f0 = l == 0 ? 1.0 : 0.0, f1 = 1.0 - f0;
+                S[0] += f0; S[NS] += f1;
+                int q = 1 + W;
+#pragma unroll
+                for (int a = 0; a < W; ++a) {
+                    S[1 + a] += f0 * x[a]; S[NS + 1 + a] += f1 * x[a];
+#pragma unroll
+                    for (int c2 = a; c2 < W; ++c2) { const double pr = x[a] * x[c2]; S[q] += f0 * pr; S[NS + q] += f1 * pr; ++q; }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2 * NS; ++q) red[q * 33 + lane] = S[q];
+        __syncwarp();
+        double tot_q[2];                                    // lane q sums rows q and q+32
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = lane + 32 * h;
+            double t = 0.0;
+            if (q < 2 * NS) {
+#pragma unroll 8
+                for (int l2 = 0; l2 < 32; ++l2) t += red[q * 33 + l2];
+            }
+            tot_q[h] = t;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) if (lane + 32 * h < 2 * NS) red[lane + 32 * h] = tot_q[h];   // compact totals
+        __syncwarp();
+        bool ok = true;
+        if (lane < 2) {
+            double mu[W], cov[W * W];
+            ok = ml_gaussian<W>(red + lane * NS, mu, cov);
+#pragma unroll 1
+            for (int a = 0; a < W; ++a) out.mu[((size_t)slot * 2 + lane) * W + a] = mu[a];
+#pragma unroll 1
+            for (int a = 0; a < W * W; ++a) out.cov[((size_t)slot * 2 + lane) * W * W + a] = cov[a];
+        }
+        ok_all = __all_sync(YC_FULL, ok);
+    }
+    // ---- uniform box (stats.py:178-187): outlier rows, or all rows if none
+    {
+        double lo[W], hi[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) { lo[j] = INFINITY; hi[j] = -INFINITY; }
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+            if (n_out == 0 || lab[i] == 2) {
+                double x[W];
+                fw_row<W>(xs, cap, i, x);
+#pragma unroll
+                for (int j = 0; j < W; ++j) { lo[j] = fmin(lo[j], x[j]); hi[j] = fmax(hi[j], x[j]); }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            lo[j] = warp_min(lo[j]); hi[j] = warp_max(hi[j]);
+            ok_all &= hi[j] > lo[j];
+            if (lane == 0) { out.box[((size_t)slot * W + j) * 2] = lo[j]; out.box[((size_t)slot * W + j) * 2 + 1] = hi[j]; }
+        }
+    }
+    // ---- per-sample initial weights (stats.py:173-177): lane k writes component k
+#pragma unroll 1
+    for (int s = 0; s < R; ++s) {
+        const int a = c.fstart[s], e = c.fstart[s + 1];
+        int k0 = 0, k1 = 0;
+#pragma unroll 1
+        for (int i = a + lane; i < e; i += 32) { const int l = lab[i]; k0 += l == 0; k1 += l == 1; }
+        k0 = warp_sum_i(k0); k1 = warp_sum_i(k1);
+        if (lane < 3) {
+            double v = 0.0;
+            if (e > a) {
+                const int kk = lane == 0 ? k0 : (lane == 1 ? k1 : (e - a) - k0 - k1);
+                v = log(((double)kk + 0.5) / ((double)(e - a) + 1.5));
+            }
+            out.logw[((size_t)slot * R + s) * 3 + lane] = v;
+        }
+    }
+    if (lane == 0 && !ok_all) status[g] = YC_ST_FIT_FAILED;
+}
+
+// ===========================================================================
+// Kernel 2b (warp): EM
+// ===========================================================================
 // M-step of one shared Gaussian (reference stats.py:202-205 via pomegranate from_summaries,
 // assumptions A3/A4).  Cold, serial code: one copy, rolled loops.
 template <int W>
@@ -99,36 +466,28 @@ __device__ __noinline__ void em_mstep(EmPar<W> *par, int k, const double *red, d
     par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
 }
 
-// counts -> G-tests -> fractions of one fitted position (lane 0); returns the combined weights
+// model of slot -> shared memory parameter block (+ Cholesky factors, uniform log density)
 template <int W>
-__device__ __noinline__ void fit_finalize(EmPar<W> *par, const int *fstart, int R, int Rc, double thr,
-                                          double *preds_out, double *cw_out, double *stats_out) {
-    double cw[3] = {0.0, 0.0, 0.0}, tot = 0.0;
-    double pr[YC_MAX_SAMPLES * 3];
-    int rows_c = 0, rows_t = 0, q = 0;
-#pragma unroll 1
-    for (int s = 0; s < R; ++s) {
-        const int sz = fstart[s + 1] - fstart[s];
-        double *po = preds_out + s * 3;
-        if (sz > 0) {
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
-                const double wk = exp(par->logw[s][k]);
-                cw[k] += wk * (double)sz;
-                const double v = rint(wk * (double)sz);                  // np.round(weights * sizes), stats.py:296
-                pr[q * 3 + k] = v; po[k] = v;
-            }
-            tot += (double)sz;
-            ++q;
-            if (s < Rc) ++rows_c; else ++rows_t;
-        } else { po[0] = po[1] = po[2] = 0.0; }
+__device__ __noinline__ void load_model(EmPar<W> *par, const yc_fit_out_t &out, int slot, int lane,
+                                        const double *logw_src, int n_logw) {
+    for (int i = lane; i < 2 * W; i += 32) par->mu[i / W][i % W] = out.mu[(size_t)slot * 2 * W + i];
+    for (int i = lane; i < 2 * W * W; i += 32) par->cov[i / (W * W)][i % (W * W)] = out.cov[(size_t)slot * 2 * W * W + i];
+    for (int i = lane; i < W; i += 32) { par->lo[i] = out.box[((size_t)slot * W + i) * 2]; par->hi[i] = out.box[((size_t)slot * W + i) * 2 + 1]; }
+    for (int i = lane; i < n_logw; i += 32) par->logw[i / 3][i % 3] = logw_src[i];
+    if (lane == 0) par->ok = 1;
+    __syncwarp();
+    if (lane < 2) {
+        double logdet;
+        if (!cholesky_inverse<W>(par->cov[lane], par->linv[lane], logdet)) par->ok = 0;
+        par->cst[lane] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
     }
+    if (lane == 2) {
+        double s = 0.0;
 #pragma unroll 1
-    for (int k = 0; k < 3; ++k) { cw[k] /= tot; cw_out[k] = cw[k]; }
-    gtest_fractions(pr, rows_c, rows_t, thr, stats_out);
-    const double t = cw[0] + cw[1] + cw[2];                               // A7
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k) par->logw[0][k] = log(cw[k] / t);
+        for (int j = 0; j < W; ++j) s += log(par->hi[j] - par->lo[j]);
+        par->ulogp = -s;
+    }
+    __syncwarp();
 }
 
 #ifndef YC_FW_MINBLOCKS
@@ -137,300 +496,33 @@ __device__ __noinline__ void fit_finalize(EmPar<W> *par, const int *fstart, int 
 
 template <int W>
 __global__ void __launch_bounds__(32, YC_FW_MINBLOCKS)
-fit_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
-                const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
-                uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows,
-                double *__restrict__ post, const long long post_capacity,
-                unsigned long long *__restrict__ post_cursor) {
+em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+               const int32_t *__restrict__ fit_list, const yc_fit_out_t out, uint8_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R = b.n_samples, Rc = b.n_cntrl, lane = threadIdx.x;
+    const int R = b.n_samples, lane = threadIdx.x;
     const FwSmem L = fw_layout(W, R, cap);
-    double *buf = reinterpret_cast<double *>(smem_raw + L.buf_off);
-    EmPar<W> *par = reinterpret_cast<EmPar<W> *>(smem_raw + L.par_off);
-    uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + L.mask_off);
-    int *cnt = reinterpret_cast<int *>(smem_raw + L.cnt_off);
-    int *fstart = reinterpret_cast<int *>(smem_raw + L.fstart_off);
-    uint16_t *xs = reinterpret_cast<uint16_t *>(smem_raw + L.xs_off);
-    uint8_t *srow = reinterpret_cast<uint8_t *>(smem_raw + L.srow_off);
-    int8_t *lab = reinterpret_cast<int8_t *>(smem_raw + L.lab_off);
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT, NP = 2 * NS + 1;
-    const uint32_t lt = (1u << lane) - 1u;
-
     const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
-    if (lane == 0) out.post_off[slot] = -1;
-
-    // ------------------------------------------------ front end: complete rows -> shared memory
-    Window<W> w;
-    if (!window_setup<W>(b, p, g, w)) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
-    for (int i = lane; i < (W + 1) * R; i += 32) cnt[i] = 0;
-    __syncwarp();
-    {   // warp-local scan (same as yc_ks_warp.cu)
-        const int nr = w.n_reads;
-        for (int base = 0; base < nr; base += 32) {
-            const int r = base + lane;
-            const bool inb = r < nr;
-            uint32_t m_all = YC_FULL;
-#pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const uint16_t v = inb ? __ldg(w.col[j] + r) : (uint16_t)0x7e00;
-                m_all &= __ballot_sync(YC_FULL, inb && !h_isnan(v));
-            }
-            if (lane == 0) mask[base >> 5] = m_all;
-            if (lane == 0) {
-                for (int s = 0; s < R; ++s) {
-                    const int a = max(w.samp_start[s], base), e = min(w.samp_start[s + 1], base + 32);
-                    if (e > a) {
-                        const uint32_t seg = (e - a == 32) ? YC_FULL : (((1u << (e - a)) - 1u) << (a - base));
-                        cnt[W * R + s] += __popc(m_all & seg);
-                    }
-                }
-            }
-        }
-    }
-    __syncwarp();
-    if (lane == 0) {
-        int acc = 0;
-        for (int s = 0; s < R; ++s) { fstart[s] = acc; acc += cnt[W * R + s]; }
-        fstart[R] = acc;
-    }
-    __syncwarp();
-    const int n = fstart[R];
-    if (n < 1 || n > cap) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
-    {   // ordered compaction
-        int run = 0;
-        const int nr = w.n_reads;
-        for (int base = 0; base < nr; base += 32) {
-            const uint32_t m = mask[base >> 5];
-            if ((m >> lane) & 1u) {
-                const int r = base + lane, rank = run + __popc(m & lt);
-#pragma unroll
-                for (int j = 0; j < W; ++j) xs[j * cap + rank] = __ldg(w.col[j] + r);
-                int s = 0;
-                while (s + 1 < R && r >= w.samp_start[s + 1]) ++s;
-                srow[rank] = (uint8_t)s;
-            }
-            run += __popc(m);
-        }
-    }
-    __syncwarp();
-    const uint64_t pkey = w.pkey;
-
-    // ------------------------------------------------ k-means++ x3 + Lloyd  (assumption A2)
-    double best[2 * W], best_total = INFINITY;
-    bool have_best = false;
-    const int C = (n + 31) / 32;
-    const int i0c = min(lane * C, n), i1c = min(i0c + C, n);
-    for (int restart = 0; restart < 3; ++restart) {
-        double cen[2 * W];
-        {
-            const double u0 = rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 0);
-            const int i0 = min((int)(u0 * (double)n), n - 1);
-            double x[W];
-            fw_row<W>(xs, cap, i0, x);
-#pragma unroll
-            for (int j = 0; j < W; ++j) cen[j] = x[j];
-        }
-        {
-            double loc = 0.0;
-            for (int i = i0c; i < i1c; ++i) { double x[W]; fw_row<W>(xs, cap, i, x); loc = add_rn(loc, sqdist<W>(x, cen)); }
-            double inc = loc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(YC_FULL, inc, o); if (lane >= o) inc = add_rn(inc, t); }
-            const double total = __shfl_sync(YC_FULL, inc, 31);
-            double run = sub_rn(inc, loc);
-            const double target = mul_rn(rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 1), total);
-            int below = 0;
-            for (int i = i0c; i < i1c; ++i) { double x[W]; fw_row<W>(xs, cap, i, x); run = add_rn(run, sqdist<W>(x, cen)); below += (run <= target); }
-            below = warp_sum_i(below);
-            double x[W];
-            fw_row<W>(xs, cap, min(below, n - 1), x);
-#pragma unroll
-            for (int j = 0; j < W; ++j) cen[W + j] = x[j];
-        }
-        int iteration = 0;
-        double improvement = INFINITY, last = INFINITY, total = INFINITY;
-        double acc[2 * W + 3];
-        bool have_sums = false;
-        while (improvement > 0.5 && iteration < 101) {
-            if (have_sums) {
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    if (acc[2 * W + 1 + k] > 0.0)
-#pragma unroll
-                        for (int j = 0; j < W; ++j) cen[k * W + j] = div_rn(acc[k * W + j], acc[2 * W + 1 + k]);
-            }
-#pragma unroll
-            for (int k = 0; k < 2 * W + 3; ++k) acc[k] = 0.0;
-            for (int i = lane; i < n; i += 32) {
-                double x[W];
-                fw_row<W>(xs, cap, i, x);
-                const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
-                const int k = d1 < d0;
-                acc[2 * W] += k ? d1 : d0;
-                acc[2 * W + 1 + k] += 1.0;
-#pragma unroll
-                for (int j = 0; j < W; ++j) { if (k) acc[W + j] += x[j]; else acc[j] += x[j]; }
-            }
-#pragma unroll
-            for (int k = 0; k < 2 * W + 3; ++k) acc[k] = warp_sum(acc[k]);
-            have_sums = true;
-            total = acc[2 * W];
-            if (iteration > 0) improvement = last - total;
-            ++iteration;
-            last = total;
-        }
-        if (total < best_total) {
-            best_total = total; have_best = true;
-#pragma unroll
-            for (int j = 0; j < 2 * W; ++j) best[j] = cen[j];
-        }
-    }
-    if (!have_best) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
-
-    // ------------------------------------------------ MAD outliers (stats.py:114-122, A1)
-    int P = 32;
-    while (P < n) P <<= 1;
-    for (int i = lane; i < P; i += 32) {
-        double dmin = INFINITY;
-        if (i < n) {
-            double x[W];
-            fw_row<W>(xs, cap, i, x);
-            const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
-            lab[i] = (int8_t)(d1 < d0);
-            dmin = d1 < d0 ? d1 : d0;
-        }
-        buf[i] = dmin;
-    }
-    __syncwarp();
-    warp_bitonic1(buf, P, lane);
-    const double med = (n & 1) ? buf[n >> 1] : mul_rn(add_rn(buf[(n >> 1) - 1], buf[n >> 1]), 0.5);
-    // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are
-    // V-shaped, i.e. two ascending runs (left of the median walked outwards, right of it), so the
-    // order statistics of their union follow from merge ranks found by binary search.
-    double *wsel = reinterpret_cast<double *>(smem_raw + L.wtmp_off);
-    const int m_le = upper_bound(buf, n, med);            // elements <= med form the left run
-    const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
-    for (int i = lane; i < n; i += 32) {
-        const double dv = fabs(sub_rn(buf[i], med));
-        int rank;
-        if (i < m_le) {                                    // left run, index m_le-1-i; count right-run elements < dv
-            int lo = 0, hi = n - m_le;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(buf[m_le + mid], med)) < dv) lo = mid + 1; else hi = mid; }
-            rank = (m_le - 1 - i) + lo;
-        } else {                                           // right run, index i-m_le; count left-run elements <= dv
-            int lo = 0, hi = m_le;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(buf[m_le - 1 - mid], med)) <= dv) lo = mid + 1; else hi = mid; }
-            rank = (i - m_le) + lo;
-        }
-        if (rank == k_lo) wsel[0] = dv;
-        if (rank == k_hi) wsel[1] = dv;
-    }
-    __syncwarp();
-    const double mad = (n & 1) ? wsel[1] : mul_rn(add_rn(wsel[0], wsel[1]), 0.5);
-    const double thr = mul_rn(p.outlier_factor, mad);
-    __syncwarp();
-    int n_out = 0;
-    for (int i = lane; i < n; i += 32) {
-        double x[W];
-        fw_row<W>(xs, cap, i, x);
-        const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
-        if ((d1 < d0 ? d1 : d0) > thr) { lab[i] = 2; ++n_out; }
-    }
-    n_out = warp_sum_i(n_out);
-    __syncwarp();
-    if (labels_out) for (int i = lane; i < n && i < max_fit_rows; i += 32)
-        labels_out[(size_t)slot * max_fit_rows + i] = lab[i];
-
-    // ------------------------------------------------ ML Gaussians, weights, box (stats.py:148-187)
-    if (lane == 0) par->ok = 1;
-    {
-        double S0[NS], S1[NS];
-#pragma unroll
-        for (int q = 0; q < NS; ++q) { S0[q] = 0.0; S1[q] = 0.0; }
-        for (int i = lane; i < n; i += 32) {
-            const int l = lab[i];
-            if (l < 2) {
-                double x[W];
-                fw_row<W>(xs, cap, i, x);
-                const double f0 = l == 0 ? 1.0 : 0.0, f1 = 1.0 - f0;
-                S0[0] += f0; S1[0] += f1;
-                int q = 1 + W;
-#pragma unroll
-                for (int a = 0; a < W; ++a) {
-                    S0[1 + a] += f0 * x[a]; S1[1 + a] += f1 * x[a];
-#pragma unroll
-                    for (int c2 = a; c2 < W; ++c2) { const double pr = x[a] * x[c2]; S0[q] += f0 * pr; S1[q] += f1 * pr; ++q; }
-                }
-            }
-        }
-        double S[NS];
-#pragma unroll
-        for (int q = 0; q < NS; ++q) {
-            const double t0 = warp_sum(S0[q]), t1 = warp_sum(S1[q]);
-            S[q] = lane == 1 ? t1 : t0;
-        }
-        __syncwarp();
-        if (lane < 2) {
-            double mu[W], cov[W * W];
-            const bool ok = ml_gaussian<W>(S, mu, cov);
-            for (int a = 0; a < W; ++a) par->mu[lane][a] = mu[a];
-            for (int a = 0; a < W * W; ++a) par->cov[lane][a] = cov[a];
-            double logdet;
-            if (!ok || !cholesky_inverse<W>(par->cov[lane], par->linv[lane], logdet)) par->ok = 0;
-            else par->cst[lane] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
-        }
-    }
-    {
-        double lo[W], hi[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) { lo[j] = INFINITY; hi[j] = -INFINITY; }
-        for (int i = lane; i < n; i += 32) {
-            if (n_out == 0 || lab[i] == 2) {
-                double x[W];
-                fw_row<W>(xs, cap, i, x);
-#pragma unroll
-                for (int j = 0; j < W; ++j) { lo[j] = fmin(lo[j], x[j]); hi[j] = fmax(hi[j], x[j]); }
-            }
-        }
-        bool box_ok = true;
-        double ul = 0.0;
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-            lo[j] = warp_min(lo[j]); hi[j] = warp_max(hi[j]);
-            box_ok &= hi[j] > lo[j];
-            if (lane == 0) { par->lo[j] = lo[j]; par->hi[j] = hi[j]; }
-            ul += log(hi[j] - lo[j]);
-        }
-        __syncwarp();
-        if (lane == 0) { par->ulogp = -ul; if (!box_ok) par->ok = 0; }
-    }
-    for (int s = 0; s < R; ++s) {
-        const int a = fstart[s], e = fstart[s + 1];
-        int k0 = 0, k1 = 0, k2 = 0;
-        for (int i = a + lane; i < e; i += 32) { const int l = lab[i]; k0 += l == 0; k1 += l == 1; k2 += l == 2; }
-        k0 = warp_sum_i(k0); k1 = warp_sum_i(k1); k2 = warp_sum_i(k2);
-        if (lane == 0) {
-            if (e > a) {
-                const double den = (double)(e - a) + 1.5;
-                par->logw[s][0] = log(((double)k0 + 0.5) / den);
-                par->logw[s][1] = log(((double)k1 + 0.5) / den);
-                par->logw[s][2] = log(((double)k2 + 0.5) / den);
-            } else { par->logw[s][0] = par->logw[s][1] = par->logw[s][2] = 0.0; }
-        }
-    }
-    __syncwarp();
+    if (status[g] != YC_ST_GATED) return;                               // the initialisation failed
+    FwCtx<W> c;
+    if (!fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c)) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
+    const int n = c.n;
+    const uint16_t *xs = c.xs;
+    const uint8_t *srow = c.srow;
+    EmPar<W> *par = c.par;
+    double *red = c.red, *wtmp = c.wtmp;
+    double *rb0 = c.buf, *rb1 = c.buf + cap;            // responsibilities of components 0 / 1 per fit row
+    const int *fstart = c.fstart;
+    load_model<W>(par, out, slot, lane, out.logw + (size_t)slot * R * 3, R * 3);
     bool failed = par->ok == 0;
 
-    // ------------------------------------------------ EM (stats.py:194-225)
-    double carry[NS];                       // lanes 0/1: summaries kept when S0 < 1e-7 (A3)
+    double carry[NS];                                   // lanes 0/1: summaries kept when S0 < 1e-7 (A3)
 #pragma unroll
     for (int q = 0; q < NS; ++q) carry[q] = 0.0;
-    double *rb0 = buf, *rb1 = buf + cap;     // responsibilities of components 0 / 1 per fit row
-    double *wtmp = reinterpret_cast<double *>(smem_raw + L.wtmp_off);
-    double *red = reinterpret_cast<double *>(smem_raw + L.red_off);
     int iteration = 0;
     double improvement = INFINITY, last = 0.0;
+#pragma unroll 1
     while (!failed && improvement > 0.1 && iteration < 1001) {
         double acc[NP];
 #pragma unroll
@@ -446,6 +538,8 @@ fit_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 for (int bb = 0; bb <= a; ++bb) { li0[q] = par->linv[0][a * W + bb]; li1[q] = par->linv[1][a * W + bb]; ++q; }
         }
         const double c0 = par->cst[0], c1 = par->cst[1], ul = par->ulogp;
+        // ---- E-step + sufficient statistics (GeneralMixtureModel.summarize, A6)
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) {
             double x[W];
             fw_row<W>(xs, cap, i, x);
@@ -480,11 +574,11 @@ fit_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 for (int bb = a; bb < W; ++bb) { acc[qq] = fma(xa0, x[bb], acc[qq]); acc[NS + qq] = fma(xa1, x[bb], acc[NS + qq]); ++qq; }
             }
         }
-        // 43 (w=3: 21) partial sums x 32 lanes: park them in shared memory (row stride 33 -> no
-        // bank conflicts) and let lane q add up row q; 105 shuffle pairs become 21 stores + 32 loads
+        // per-lane partial sums -> totals in red[q*33 + 32]
 #pragma unroll
         for (int q = 0; q < NP; ++q) red[q * 33 + lane] = acc[q];
         __syncwarp();
+#pragma unroll 1
         for (int q = lane; q < NP; q += 32) {
             double t = 0.0;
 #pragma unroll 8
@@ -498,17 +592,19 @@ fit_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         last = ll;
         if (!isfinite(ll)) { failed = true; break; }                     // assumption A5
         if (!(improvement > 0.1 && iteration < 1001)) break;             // last E-step's summaries discarded
-        __syncwarp();
         // ---- per-sample responsibility sums -> weights (stats.py:206-211); the uniform
         //      component's sum is n_s - sum r0 - sum r1 (responsibilities sum to one)
+#pragma unroll 1
         for (int s = 0; s < R; ++s) {
             const int a = fstart[s], e = fstart[s + 1];
             double t0 = 0.0, t1 = 0.0;
+#pragma unroll 1
             for (int i = a + lane; i < e; i += 32) { t0 += rb0[i]; t1 += rb1[i]; }
             t0 = warp_sum(t0); t1 = warp_sum(t1);
             if (lane == 0) { wtmp[2 * s] = t0; wtmp[2 * s + 1] = t1; }
         }
         __syncwarp();
+#pragma unroll 1
         for (int q = lane; q < 3 * R; q += 32) {        // one lane per (sample, component): logs in parallel
             const int s = q / 3, k = q - 3 * s;
             const int ns = fstart[s + 1] - fstart[s];
@@ -527,23 +623,76 @@ fit_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         __syncwarp();
         failed = par->ok == 0;
     }
-
-    // ------------------------------------------------ results of the fit (stats.py:250-253, 277-280)
-    if (failed) { if (lane == 0) { status[g] = YC_ST_FIT_FAILED; out.iters[slot] = iteration; out.loglik[slot] = last; } return; }
+    // ---- results (fit_multisamp_gmm, stats.py:250-253)
+    if (lane == 0) {
+        out.iters[slot] = iteration;
+        out.loglik[slot] = last;
+        if (failed) status[g] = YC_ST_FIT_FAILED;
+        else {
+            status[g] = YC_ST_TESTED;
+            double cw[3] = {0.0, 0.0, 0.0}, tot = 0.0;
+#pragma unroll 1
+            for (int s = 0; s < R; ++s) {
+                const double ns = (double)(fstart[s + 1] - fstart[s]);
+                if (ns > 0.0) {
+#pragma unroll 1
+                    for (int k = 0; k < 3; ++k) cw[k] += exp(par->logw[s][k]) * ns;
+                    tot += ns;
+                }
+            }
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) out.cw[(size_t)slot * 3 + k] = cw[k] / tot;
+        }
+    }
+    if (failed) return;
     __syncwarp();
     for (int i = lane; i < 2 * W; i += 32) out.mu[(size_t)slot * 2 * W + i] = par->mu[i / W][i % W];
     for (int i = lane; i < 2 * W * W; i += 32) out.cov[(size_t)slot * 2 * W * W + i] = par->cov[i / (W * W)][i % (W * W)];
-    for (int i = lane; i < W; i += 32) { out.box[((size_t)slot * W + i) * 2] = par->lo[i]; out.box[((size_t)slot * W + i) * 2 + 1] = par->hi[i]; }
     for (int i = lane; i < R * 3; i += 32) out.logw[(size_t)slot * R * 3 + i] = par->logw[i / 3][i % 3];
-    __syncwarp();                                   // fit_finalize overwrites par->logw[0] with the combined weights
+}
+
+// ===========================================================================
+// Kernel 3 (warp): rounded counts, G-tests, fractions, posteriors
+// ===========================================================================
+template <int W>
+__global__ void __launch_bounds__(32)
+gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+                  const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+                  const uint8_t *__restrict__ status, double *__restrict__ post,
+                  const long long post_capacity, unsigned long long *__restrict__ post_cursor) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = b.n_samples, Rc = b.n_cntrl, lane = threadIdx.x;
+    const FwSmem L = fw_layout(W, R, cap);
+    const int slot = blockIdx.x;
+    const int64_t g = fit_list[slot];
+    if (status[g] != YC_ST_TESTED) { if (lane == 0) out.post_off[slot] = -1; return; }
+    FwCtx<W> c;
+    fw_front<W>(b, p, g, smem_raw, L, cap, lane, post != nullptr, c);
+    const int n = c.n;
     long long off = -1;
     if (lane == 0) {
-        status[g] = YC_ST_TESTED;
-        out.iters[slot] = iteration;
-        out.loglik[slot] = last;
-        fit_finalize<W>(par, fstart, R, Rc, p.fdr_threshold, out.preds + (size_t)slot * R * 3,
-                        out.cw + (size_t)slot * 3, out.stats + (size_t)slot * 8);
-        if (post != nullptr && out.stats[(size_t)slot * 8 + 2] < p.fdr_threshold) {
+        // preds = np.round(weights * ORIGINAL sizes)  (stats.py:296), present samples only
+        double pr[YC_MAX_SAMPLES * 3];
+        int rows_c = 0, rows_t = 0, q = 0;
+#pragma unroll 1
+        for (int s = 0; s < R; ++s) {
+            const int sz = c.fstart[s + 1] - c.fstart[s];
+            double *po = out.preds + ((size_t)slot * R + s) * 3;
+            if (sz > 0) {
+#pragma unroll 1
+                for (int k = 0; k < 3; ++k) {
+                    const double v = rint(exp(out.logw[((size_t)slot * R + s) * 3 + k]) * (double)sz);
+                    pr[q * 3 + k] = v; po[k] = v;
+                }
+                ++q;
+                if (s < Rc) ++rows_c; else ++rows_t;
+            } else { po[0] = po[1] = po[2] = 0.0; }
+        }
+        double st8[8];
+        gtest_fractions(pr, rows_c, rows_t, p.fdr_threshold, st8);
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) out.stats[(size_t)slot * 8 + k] = st8[k];
+        if (post != nullptr && st8[2] < p.fdr_threshold) {
             off = (long long)atomicAdd(post_cursor, (unsigned long long)n);
             if (off + n > post_capacity) off = -2;
         }
@@ -551,11 +700,20 @@ fit_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     }
     off = __shfl_sync(YC_FULL, off, 0);
     if (off < 0) return;
+    // ---- posteriors of every complete-window read under the combined weights (stats.py:494-499)
+    EmPar<W> *par = c.par;
+    load_model<W>(par, out, slot, lane, out.cw + (size_t)slot * 3, 0);
+    if (lane == 0) {
+        const double *cw = out.cw + (size_t)slot * 3;
+        const double t = cw[0] + cw[1] + cw[2];                          // A7
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) par->logw[0][k] = log(cw[k] / t);
+    }
     __syncwarp();
-    // ------------------------------------------------ posteriors of every complete-window read (stats.py:494-499)
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) {
         double x[W];
-        fw_row<W>(xs, cap, i, x);
+        fw_row<W>(c.xs, cap, i, x);
         double q0 = 0.0, q1 = 0.0;
         bool inside = true;
 #pragma unroll
@@ -580,6 +738,9 @@ fit_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     }
 }
 
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
 static int fw_cap(const yc_batch_t &b) {
     int cap = (b.max_reads + 7) & ~7;
     return cap < 32 ? 32 : cap;
@@ -593,30 +754,55 @@ int fit_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p) {
     return fw_layout(p.window_size, b.n_samples, fw_cap(b)).total;
 }
 
-template <int W>
-static int launch_fw(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                     const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows,
-                     double *post, int64_t post_capacity, int64_t *post_cursor, cudaStream_t st) {
-    const int cap = fw_cap(b);
-    const int smem = fw_layout(W, b.n_samples, cap).total;
-    cudaError_t e = cudaFuncSetAttribute(fit_warp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    fit_warp_kernel<W><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows, post,
-                                                (long long)post_capacity,
-                                                reinterpret_cast<unsigned long long *>(post_cursor));
-    return (int)cudaGetLastError();
-}
-
-int fit_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                      const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows,
-                      double *post, int64_t post_capacity, int64_t *post_cursor, cudaStream_t st) {
-    if (n_fit <= 0) return 0;
-    switch (p.window_size) {
-        case 1: return launch_fw<1>(b, p, fit_list, n_fit, out, status, labels, max_fit_rows, post, post_capacity, post_cursor, st);
-        case 3: return launch_fw<3>(b, p, fit_list, n_fit, out, status, labels, max_fit_rows, post, post_capacity, post_cursor, st);
-        case 5: return launch_fw<5>(b, p, fit_list, n_fit, out, status, labels, max_fit_rows, post, post_capacity, post_cursor, st);
+template <typename F>
+static int dispatch_w135(int W, F &&f) {
+    switch (W) {
+        case 1: return f(std::integral_constant<int, 1>());
+        case 3: return f(std::integral_constant<int, 3>());
+        case 5: return f(std::integral_constant<int, 5>());
     }
     return YC_EINVAL;
+}
+
+int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
+                       const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st) {
+    if (n_fit <= 0) return 0;
+    const int cap = fw_cap(b), smem = fit_warp_smem_bytes(b, p);
+    return dispatch_w135(p.window_size, [&](auto tag) -> int {
+        constexpr int W_ = decltype(tag)::value;
+        cudaError_t e = cudaFuncSetAttribute(init_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        init_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
+        return (int)cudaGetLastError();
+    });
+}
+
+int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
+                     const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
+    if (n_fit <= 0) return 0;
+    const int cap = fw_cap(b), smem = fit_warp_smem_bytes(b, p);
+    return dispatch_w135(p.window_size, [&](auto tag) -> int {
+        constexpr int W_ = decltype(tag)::value;
+        cudaError_t e = cudaFuncSetAttribute(em_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        em_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status);
+        return (int)cudaGetLastError();
+    });
+}
+
+int gtest_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
+                        const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
+                        int64_t *post_cursor, cudaStream_t st) {
+    if (n_fit <= 0) return 0;
+    const int cap = fw_cap(b), smem = fit_warp_smem_bytes(b, p);
+    return dispatch_w135(p.window_size, [&](auto tag) -> int {
+        constexpr int W_ = decltype(tag)::value;
+        cudaError_t e = cudaFuncSetAttribute(gtest_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        gtest_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, post, (long long)post_capacity,
+                                                       reinterpret_cast<unsigned long long *>(post_cursor));
+        return (int)cudaGetLastError();
+    });
 }
 
 }  // namespace yc

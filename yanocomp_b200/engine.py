@@ -77,20 +77,12 @@ class BatchResult:
 class Engine:
     '''owns the per-device scratch and launches the kernels of one batch'''
 
-    def __init__(self, params, device=None, split_fit=False):
+    def __init__(self, params, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError('yanocomp_b200.engine needs a CUDA device: there is no CPU fallback')
         self.lib = N.lib()
         self.params = params
-        self.split_fit = split_fit      # True: call the three fit entry points separately
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-
-    def fused_is_one_kernel(self, dev):
-        '''mirrors the eligibility test of yc_gmm_fit_fused_batch (csrc/yc_fit_warp.cu)'''
-        import os
-        h, p = dev.host, self.params
-        return (os.environ.get('YC_FIT_PATH') != 'cta' and p.window_size <= 5 and h.max_reads <= 1024
-                and 0 < h.max_cond_reads <= p.max_fit_depth)
 
     def upload(self, host: HostBatch) -> DeviceBatch:
         return DeviceBatch(host, self.device)
@@ -166,22 +158,15 @@ class Engine:
                 idx = fit_list[:n_fit].long()
                 cap = int((n_c[idx].long() + n_t[idx].long()).sum().item())
                 post = torch.empty(max(cap, 1) * 2, dtype=f64, device=d)
-            if self.split_fit:
-                N.check(timed('gmm_init', lambda: lib.yc_gmm_init_batch(
-                    b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
-                    labels.data_ptr() if labels is not None else None, max_fit_rows, stream)))
-                N.check(timed('gmm_em', lambda: lib.yc_gmm_em_batch(
-                    b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(), stream)))
-                N.check(timed('gtest_smpred', lambda: lib.yc_gtest_smpred_batch(
-                    b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
-                    post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
-                launches += 3
-            else:
-                N.check(timed('gmm_fit_fused', lambda: lib.yc_gmm_fit_fused_batch(
-                    b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
-                    labels.data_ptr() if labels is not None else None, max_fit_rows,
-                    post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
-                launches += 1 if self.fused_is_one_kernel(dev) else 3
+            N.check(timed('gmm_init', lambda: lib.yc_gmm_init_batch(
+                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                labels.data_ptr() if labels is not None else None, max_fit_rows, stream)))
+            N.check(timed('gmm_em', lambda: lib.yc_gmm_em_batch(
+                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(), stream)))
+            N.check(timed('gtest_smpred', lambda: lib.yc_gtest_smpred_batch(
+                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
+            launches += 3
         if not fetch:
             return dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
                         fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
