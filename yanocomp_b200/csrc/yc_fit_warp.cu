@@ -87,18 +87,17 @@ __device__ __forceinline__ void warp_sum_smem(double (&v)[K], double *red, int l
 }
 
 __device__ __noinline__ void warp_bitonic1(double *a, int P, int lane) {
+    const int pairs = P >> 1;
 #pragma unroll 1
     for (int k = 2; k <= P; k <<= 1) {
 #pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll 1
-            for (int i = lane; i < P; i += 32) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = ((i & k) == 0);
-                    const double x = a[i], y = a[l];
-                    if ((x > y) == up) { a[i] = y; a[l] = x; }
-                }
+            for (int t = lane; t < pairs; t += 32) {       // every lane owns one compare-exchange
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const bool up = ((i & k) == 0);
+                const double x = a[i], y = a[l];
+                if ((x > y) == up) { a[i] = y; a[l] = x; }
             }
             __syncwarp();
         }
@@ -524,46 +523,60 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     double improvement = INFINITY, last = 0.0;
 #pragma unroll 1
     while (!failed && improvement > 0.1 && iteration < 1001) {
+        // ---- E-step (GeneralMixtureModel.summarize, A6) in two passes over the rows so that neither
+        //      needs both the model (24 doubles) and the 2 NS + 1 accumulators in registers at once:
+        //      pass 1 writes the responsibilities and the log-likelihood, pass 2 the sufficient statistics.
+        double llsum = 0.0;
+        {
+            double mu0[W], mu1[W], li0[NT], li1[NT], blo[W], bhi[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) { mu0[j] = par->mu[0][j]; mu1[j] = par->mu[1][j]; blo[j] = par->lo[j]; bhi[j] = par->hi[j]; }
+            {
+                int q = 0;
+#pragma unroll
+                for (int a = 0; a < W; ++a)
+#pragma unroll
+                    for (int bb = 0; bb <= a; ++bb) { li0[q] = par->linv[0][a * W + bb]; li1[q] = par->linv[1][a * W + bb]; ++q; }
+            }
+            const double c0 = par->cst[0], c1 = par->cst[1], ul = par->ulogp;
+#pragma unroll 2
+            for (int i = lane; i < n; i += 32) {
+                double x[W];
+                fw_row<W>(xs, cap, i, x);
+                const int s = srow[i];
+                double q0 = 0.0, q1 = 0.0;
+                bool inside = true;
+                int q = 0;
+#pragma unroll
+                for (int a = 0; a < W; ++a) {
+                    double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+                    for (int bb = 0; bb <= a; ++bb) { y0 = fma(li0[q], x[bb] - mu0[bb], y0); y1 = fma(li1[q], x[bb] - mu1[bb], y1); ++q; }
+                    q0 = fma(y0, y0, q0); q1 = fma(y1, y1, q1);
+                    inside &= (x[a] >= blo[a]) && (x[a] <= bhi[a]);
+                }
+                const double l0 = c0 - 0.5 * q0 + par->logw[s][0];
+                const double l1 = c1 - 0.5 * q1 + par->logw[s][1];
+                const double l2 = inside ? ul + par->logw[s][2] : -INFINITY;
+                // exp(l_max - l_max) = 1 exactly: only the two non-maximal terms need an exp
+                const double m = fmax(fmax(l0, l1), l2);
+                const bool m0 = l0 == m, m1 = !m0 && l1 == m;
+                const double ea = exp((m0 ? l1 : l0) - m), eb = exp(((m0 || m1) ? l2 : l1) - m);
+                const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
+                const double se = e0 + e1 + e2, inv = 1.0 / se;
+                rb0[i] = e0 * inv; rb1[i] = e1 * inv;
+                llsum += m + log(se);
+            }
+        }
         double acc[NP];
 #pragma unroll
         for (int q = 0; q < NP; ++q) acc[q] = 0.0;
-        double mu0[W], mu1[W], li0[NT], li1[NT], blo[W], bhi[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) { mu0[j] = par->mu[0][j]; mu1[j] = par->mu[1][j]; blo[j] = par->lo[j]; bhi[j] = par->hi[j]; }
-        {
-            int q = 0;
-#pragma unroll
-            for (int a = 0; a < W; ++a)
-#pragma unroll
-                for (int bb = 0; bb <= a; ++bb) { li0[q] = par->linv[0][a * W + bb]; li1[q] = par->linv[1][a * W + bb]; ++q; }
-        }
-        const double c0 = par->cst[0], c1 = par->cst[1], ul = par->ulogp;
-        // ---- E-step + sufficient statistics (GeneralMixtureModel.summarize, A6)
-#pragma unroll 1
+        acc[2 * NS] = llsum;
+#pragma unroll 2
         for (int i = lane; i < n; i += 32) {
             double x[W];
             fw_row<W>(xs, cap, i, x);
-            const int s = srow[i];
-            double q0 = 0.0, q1 = 0.0;
-            bool inside = true;
-            int q = 0;
-#pragma unroll
-            for (int a = 0; a < W; ++a) {
-                double y0 = 0.0, y1 = 0.0;
-#pragma unroll
-                for (int bb = 0; bb <= a; ++bb) { y0 = fma(li0[q], x[bb] - mu0[bb], y0); y1 = fma(li1[q], x[bb] - mu1[bb], y1); ++q; }
-                q0 = fma(y0, y0, q0); q1 = fma(y1, y1, q1);
-                inside &= (x[a] >= blo[a]) && (x[a] <= bhi[a]);
-            }
-            const double l0 = c0 - 0.5 * q0 + par->logw[s][0];
-            const double l1 = c1 - 0.5 * q1 + par->logw[s][1];
-            const double l2 = inside ? ul + par->logw[s][2] : -INFINITY;
-            const double m = fmax(fmax(l0, l1), l2);
-            const double e0 = exp(l0 - m), e1 = exp(l1 - m), e2 = exp(l2 - m);
-            const double se = e0 + e1 + e2, inv = 1.0 / se;
-            const double r0 = e0 * inv, r1 = e1 * inv;
-            rb0[i] = r0; rb1[i] = r1;
-            acc[2 * NS] += m + log(se);
+            const double r0 = rb0[i], r1 = rb1[i];
             acc[0] += r0; acc[NS] += r1;
             int qq = 1 + W;
 #pragma unroll

@@ -47,17 +47,18 @@ __host__ __device__ inline KwSmem kw_layout(int W, int R, int max_reads, int P) 
     return s;
 }
 
-__device__ __forceinline__ void warp_bitonic(double *a, int P, int nseg, int lane) {
-    const int total = P * nseg;
+__device__ __noinline__ void warp_bitonic(double *a, int P, int nseg, int lane) {
+    const int pairs = (P * nseg) >> 1;
+#pragma unroll 1
     for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < total; i += 32) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (((i & (P - 1)) & k) == 0);
-                    const double x = a[i], y = a[l];
-                    if ((x > y) == up) { a[i] = y; a[l] = x; }
-                }
+#pragma unroll 1
+            for (int t = lane; t < pairs; t += 32) {       // every lane owns one compare-exchange
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const bool up = (((i & (P - 1)) & k) == 0);
+                const double x = a[i], y = a[l];
+                if ((x > y) == up) { a[i] = y; a[l] = x; }
             }
             __syncwarp();
         }
@@ -137,31 +138,35 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
             }
             if (state == 2) {
                 const int ntot = n_c + n_t;
+                // one pass: exact raw first and second moments (binary16 inputs: every partial sum is an
+                // exactly representable double), centred afterwards: C_ab = S2_ab - S1_a S1_b / n
                 double mu[W], cm[NT], sig[W];
 #pragma unroll
                 for (int j = 0; j < W; ++j) mu[j] = 0.0;
-                for (int r = lane; r < n; r += 32)
-                    if ((mask[r >> 5] >> (r & 31)) & 1u) {
-#pragma unroll
-                        for (int j = 0; j < W; ++j) mu[j] += h2d(__ldg(w.col[j] + r));
-                    }
-#pragma unroll
-                for (int j = 0; j < W; ++j) mu[j] = div_rn(warp_sum(mu[j]), (double)ntot);
 #pragma unroll
                 for (int k = 0; k < NT; ++k) cm[k] = 0.0;
                 for (int r = lane; r < n; r += 32)
                     if ((mask[r >> 5] >> (r & 31)) & 1u) {
-                        double dlt[W];
+                        double x[W];
 #pragma unroll
-                        for (int j = 0; j < W; ++j) dlt[j] = h2d(__ldg(w.col[j] + r)) - mu[j];
+                        for (int j = 0; j < W; ++j) { x[j] = h2d(__ldg(w.col[j] + r)); mu[j] += x[j]; }
                         int k = 0;
 #pragma unroll
                         for (int a = 0; a < W; ++a)
 #pragma unroll
-                            for (int c2 = a; c2 < W; ++c2) cm[k++] += dlt[a] * dlt[c2];
+                            for (int c2 = a; c2 < W; ++c2) cm[k++] += x[a] * x[c2];
                     }
 #pragma unroll
-                for (int k = 0; k < NT; ++k) cm[k] = warp_sum(cm[k]);
+                for (int j = 0; j < W; ++j) mu[j] = warp_sum(mu[j]);
+                {
+                    int k = 0;
+#pragma unroll
+                    for (int a = 0; a < W; ++a)
+#pragma unroll
+                        for (int c2 = a; c2 < W; ++c2) { cm[k] = sub_rn(warp_sum(cm[k]), div_rn(mul_rn(mu[a], mu[c2]), (double)ntot)); ++k; }
+                }
+#pragma unroll
+                for (int j = 0; j < W; ++j) mu[j] = div_rn(mu[j], (double)ntot);
                 {
                     int k = 0;
 #pragma unroll
@@ -258,8 +263,20 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
         const double fn1 = (double)n1, fn2 = (double)n2;
         double dmax = 0.0;
         for (int i = lane; i < n1 + n2; i += 32) {
-            const double v = (i < n1) ? A[i] : B[i - n1];
-            const int c1 = upper_bound(A, n1, v), c2 = upper_bound(B, n2, v);
+            // ECDF counts at pooled point v: in its own (sorted) sample the count is the index of the
+            // last element equal to v plus one; only the other sample needs a binary search
+            int c1, c2;
+            if (i < n1) {
+                const double v = A[i];
+                int e = i + 1;
+                while (e < n1 && A[e] == v) ++e;
+                c1 = e; c2 = upper_bound(B, n2, v);
+            } else {
+                const double v = B[i - n1];
+                int e = i - n1 + 1;
+                while (e < n2 && B[e] == v) ++e;
+                c2 = e; c1 = upper_bound(A, n1, v);
+            }
             dmax = fmax(dmax, fabs(sub_rn(div_rn((double)c1, fn1), div_rn((double)c2, fn2))));
         }
         dmax = warp_max(dmax);
