@@ -13,11 +13,12 @@ from .engine import Engine, EngineParams, BatchResult
 from .stats import benjamini_hochberg
 
 
-def test_host_batch(host: HostBatch, params: EngineParams, engine: Engine = None) -> BatchResult:
+def test_host_batch(host: HostBatch, params: EngineParams, engine: Engine = None,
+                    fetch='records') -> BatchResult:
     '''upload -> KS -> GMM -> G-test (-> posteriors) -> fetch, on the current device'''
     eng = engine or Engine(params)
     dev = eng.upload(host)
-    res = eng.run(dev)
+    res = eng.run(dev, fetch=fetch)
     res.h2d_bytes = host.nbytes
     return res
 
@@ -28,7 +29,7 @@ def tested_table(host: HostBatch, res: BatchResult, gmm=True):
     only was_tested positions, NaN p-values dropped, BH-FDR over the rest.
     '''
     if gmm:
-        keep = res.status[res.fit_list] == N.ST_TESTED
+        keep = res.status_fit == N.ST_TESTED
         g = res.fit_list[keep]
         p = res.stats[keep, 2]
         slots = np.flatnonzero(keep)

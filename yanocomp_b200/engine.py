@@ -41,25 +41,35 @@ class EngineParams:
 
 @dataclasses.dataclass
 class BatchResult:
-    '''host copies of everything the host tail needs'''
-    status: np.ndarray          # (total_cols,) uint8
-    ks_stat: np.ndarray         # (total_cols,) float64
-    ks_pval: np.ndarray         # (total_cols,) float64
-    n_c: np.ndarray             # (total_cols,) complete-window control rows
-    n_t: np.ndarray
-    fit_list: np.ndarray        # (n_fit,) global column of each gated position
-    mu: np.ndarray              # (n_fit, 2, w)
-    cov: np.ndarray             # (n_fit, 2, w, w)
-    box: np.ndarray             # (n_fit, w, 2)
-    logw: np.ndarray            # (n_fit, R, 3)
-    cw: np.ndarray              # (n_fit, 3)
-    iters: np.ndarray           # (n_fit,)
-    loglik: np.ndarray
-    preds: np.ndarray           # (n_fit, R, 3)
-    stats: np.ndarray           # (n_fit, 8)
-    post_off: np.ndarray        # (n_fit,)
-    post: np.ndarray            # (reads written, 2) or None
-    labels: np.ndarray = None   # (n_fit, max_fit_rows) initial labels (debug / parity)
+    '''
+    Host copies of the results of one batch.  The arrays are views into the
+    engine's pinned staging buffer: they stay valid until the engine's next
+    `run(fetch=...)`.  `fetch='records'` (the production path) copies only what
+    the host tail needs; `fetch='full'` (tests) copies every per-position and
+    per-fit array.
+    '''
+    status: np.ndarray                # (total_cols,) uint8
+    fit_list: np.ndarray              # (n_fit,) global column of each gated position
+    status_fit: np.ndarray            # (n_fit,) status of each gated position
+    ks_stat_fit: np.ndarray           # (n_fit,) KS D of each gated position
+    mu: np.ndarray                    # (n_fit, 2, w)
+    stds: np.ndarray                  # (n_fit, 2, w) sqrt of the covariance diagonals
+    stats: np.ndarray                 # (n_fit, 8) g, hom_g, p, cntrl_frac, treat_frac, log_odds, lo, hi
+    ks_stat: np.ndarray = None        # (total_cols,)            full / --no-gmm
+    ks_pval: np.ndarray = None        # (total_cols,)            full / --no-gmm
+    n_c: np.ndarray = None            # (total_cols,) complete-window control rows        full
+    n_t: np.ndarray = None
+    nall_fit: np.ndarray = None       # (n_fit,) complete-window rows of each gated position (sm-preds)
+    cov: np.ndarray = None            # (n_fit, 2, w, w)         full / sm-preds
+    box: np.ndarray = None            # (n_fit, w, 2)
+    cw: np.ndarray = None             # (n_fit, 3)
+    logw: np.ndarray = None           # (n_fit, R, 3)            full
+    iters: np.ndarray = None          # (n_fit,)
+    loglik: np.ndarray = None
+    preds: np.ndarray = None          # (n_fit, R, 3)
+    post_off: np.ndarray = None       # (n_fit,)                 sm-preds
+    post: np.ndarray = None           # (reads written, 2)
+    labels: np.ndarray = None         # (n_fit, max_fit_rows) initial labels (parity tests)
     launches: int = 0
     d2h_bytes: int = 0
     h2d_bytes: int = 0
@@ -82,15 +92,17 @@ class Engine:
             raise RuntimeError('yanocomp_b200.engine needs a CUDA device: there is no CPU fallback')
         self.lib = N.lib()
         self.params = params
+        self._stage = None              # pinned device->host staging buffer, grown on demand
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
     def upload(self, host: HostBatch) -> DeviceBatch:
         return DeviceBatch(host, self.device)
 
-    def run(self, dev: DeviceBatch, want_labels=False, fetch=True, events=None):
+    def run(self, dev: DeviceBatch, want_labels=False, fetch='full', events=None):
         '''
         Launch the whole path on the current stream.  Returns a BatchResult
-        (host arrays) when `fetch`, else the dict of device tensors.  `events`
+        (host arrays; fetch = 'full' | 'records') or, with fetch=False, the dict
+        of device tensors.  `events`
         (a list) receives (kernel name, start event, end event) per launch so
         that bench.py can time each kernel on the launching stream.
         '''
@@ -172,23 +184,47 @@ class Engine:
                         fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
                         labels=labels, launches=launches, **out_t)
         nc = dev.host.total_cols
+        level = 'full' if fetch is True else fetch
         used = int(post_cursor.item()) if post is not None else 0
-        host = dict(
-            status=status[:nc].cpu().numpy(), ks_stat=ks_stat[:nc].cpu().numpy(),
-            ks_pval=ks_pval[:nc].cpu().numpy(), n_c=n_c[:nc].cpu().numpy(), n_t=n_t[:nc].cpu().numpy(),
-            fit_list=fit_list[:n_fit].cpu().numpy(),
-            mu=out_t['mu'][:n_fit * 2 * w].cpu().numpy().reshape(n_fit, 2, w),
-            cov=out_t['cov'][:n_fit * 2 * w * w].cpu().numpy().reshape(n_fit, 2, w, w),
-            box=out_t['box'][:n_fit * w * 2].cpu().numpy().reshape(n_fit, w, 2),
-            logw=out_t['logw'][:n_fit * R * 3].cpu().numpy().reshape(n_fit, R, 3),
-            cw=out_t['cw'][:n_fit * 3].cpu().numpy().reshape(n_fit, 3),
-            iters=out_t['iters'][:n_fit].cpu().numpy(),
-            loglik=out_t['loglik'][:n_fit].cpu().numpy(),
-            preds=out_t['preds'][:n_fit * R * 3].cpu().numpy().reshape(n_fit, R, 3),
-            stats=out_t['stats'][:n_fit * 8].cpu().numpy().reshape(n_fit, 8),
-            post_off=out_t['post_off'][:n_fit].cpu().numpy(),
-            post=post[:used * 2].cpu().numpy().reshape(used, 2) if post is not None else None,
-            labels=labels.cpu().numpy() if labels is not None else None,
-        )
-        d2h = sum(v.nbytes for v in host.values() if isinstance(v, np.ndarray))
+        fl = fit_list[:n_fit]
+        fli = fl.long()
+        cov = out_t['cov'][:n_fit * 2 * w * w].view(n_fit, 2, w, w)
+        want = dict(
+            status=status[:nc], fit_list=fl, status_fit=status[fli], ks_stat_fit=ks_stat[fli],
+            mu=out_t['mu'][:n_fit * 2 * w].view(n_fit, 2, w),
+            stds=torch.sqrt(torch.diagonal(cov, dim1=2, dim2=3)).contiguous(),
+            stats=out_t['stats'][:n_fit * 8].view(n_fit, 8))
+        if level == 'full' or not p.gmm:
+            want.update(ks_stat=ks_stat[:nc], ks_pval=ks_pval[:nc])
+        if level == 'full' or p.generate_sm_preds:
+            want.update(nall_fit=(n_c[fli] + n_t[fli]), cov=cov,
+                        box=out_t['box'][:n_fit * w * 2].view(n_fit, w, 2),
+                        cw=out_t['cw'][:n_fit * 3].view(n_fit, 3), post_off=out_t['post_off'][:n_fit])
+            if post is not None:
+                want['post'] = post[:used * 2].view(used, 2)
+        if level == 'full':
+            want.update(n_c=n_c[:nc], n_t=n_t[:nc],
+                        logw=out_t['logw'][:n_fit * R * 3].view(n_fit, R, 3), iters=out_t['iters'][:n_fit],
+                        loglik=out_t['loglik'][:n_fit], preds=out_t['preds'][:n_fit * R * 3].view(n_fit, R, 3))
+            if labels is not None:
+                want['labels'] = labels
+        host, d2h = self._fetch(want)
         return BatchResult(launches=launches, d2h_bytes=d2h, **host)
+
+    def _fetch(self, tensors):
+        '''device tensors -> numpy views of one pinned staging buffer (async copies, one sync)'''
+        align = 256
+        sizes = {k: t.numel() * t.element_size() for k, t in tensors.items()}
+        total = sum((v + align - 1) // align * align for v in sizes.values()) + align
+        if self._stage is None or self._stage.numel() < total:
+            self._stage = torch.empty(int(total * 1.25), dtype=torch.uint8, pin_memory=True)
+        out, off = {}, 0
+        for k, t in tensors.items():
+            nb = sizes[k]
+            dst = self._stage[off:off + nb].view(t.dtype).view(t.shape)
+            if nb:
+                dst.copy_(t, non_blocking=True)
+            out[k] = dst
+            off += (nb + align - 1) // align * align
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: v.numpy() for k, v in out.items()}, sum(sizes.values())

@@ -148,25 +148,24 @@ def _batch_records(host, res, opts):
             sm.setdefault(f.feature_id, {})[pos] = None
         return records, sm
     for s, g in enumerate(res.fit_list):
-        if res.status[g] != N.ST_TESTED:
+        if res.status_fit[s] != N.ST_TESTED:
             continue                                            # LinAlgError path: dropped
         fi, c = locate(g)
         f = feats[fi]
         pos = int(f.positions[c])
         kmers = _window_kmers(f, pos, w, f.strand == '-')
         g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = res.stats[s].tolist()
-        mu, cov = res.mu[s], res.cov[s]
+        mu, sd = res.mu[s], res.stds[s]
         records.append((f.chrom, pos, f.feature_id, f.strand, kmers[centre], kmers, centre,
                         lor, lo, hi, p_val, 1., c_frac, t_frac, g_stat, hom_g,
-                        mu[0].copy(), np.sqrt(np.diagonal(cov[0])),
-                        mu[1].copy(), np.sqrt(np.diagonal(cov[1])), float(res.ks_stat[g])))
+                        mu[0].copy(), sd[0].copy(), mu[1].copy(), sd[1].copy(), float(res.ks_stat_fit[s])))
         pos_sm = None
-        off = int(res.post_off[s])
+        off = int(res.post_off[s]) if res.post_off is not None else -1
         if off >= 0 and res.post is not None:
-            n_all = int(res.n_c[g] + res.n_t[g])
+            n_all = int(res.nall_fit[s])
             pos_sm = _position_sm_preds(f, c, kmers, opts, n_cntrl,
-                                        format_model(mu, cov, res.box[s], res.cw[s]),
-                                        res.post[off:off + n_all])
+                                        format_model(mu, res.cov[s], res.box[s], res.cw[s]),
+                                        res.post[off:off + n_all].copy())
         elif off == -2:
             raise RuntimeError('single-molecule posterior buffer overflow (internal sizing error)')
         sm.setdefault(f.feature_id, {})[pos] = pos_sm
@@ -194,7 +193,7 @@ def test_chunk(opts, gene_ids):
         if not features:
             return
         host = HostBatch(features, R, len(opts.cntrl_hdf5_fns))
-        res = engine.run(engine.upload(host))
+        res = engine.run(engine.upload(host), fetch='records')
         recs, sm = _batch_records(host, res, opts)
         chunk_res.extend(recs)
         for k, v in sm.items():
