@@ -430,39 +430,86 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 // Kernel 2b (warp): EM
 // ===========================================================================
 // M-step of one shared Gaussian (reference stats.py:202-205 via pomegranate from_summaries,
-// assumptions A3/A4).  Cold, serial code: one copy, rolled loops.
+// assumptions A3/A4).  One lane per component runs it, so it is written for latency: everything
+// in registers, fully unrolled for the small W of this path, reciprocals instead of divisions,
+// one log for the determinant (log of the product of the Cholesky pivots).  Unlike the
+// initialisation (cholesky_inverse, bit-exact with the oracle) EM is compared with a tolerance.
 template <int W>
 __device__ __noinline__ void em_mstep(EmPar<W> *par, int k, const double *red, double *carry, double step) {
-    constexpr int NS = 1 + W + W * (W + 1) / 2;
+    constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
     double S[NS];
-#pragma unroll 1
+#pragma unroll
     for (int q = 0; q < NS; ++q) S[q] = red[(k * NS + q) * 33 + 32] + carry[q];
     if (S[0] < 1e-7) {                                                   // skipped, summaries kept
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < NS; ++q) carry[q] = S[q];
         return;
     }
-#pragma unroll 1
+#pragma unroll
     for (int q = 0; q < NS; ++q) carry[q] = 0.0;
-    double u[W];
     const double inv0 = 1.0 / S[0], keep = 1.0 - step;
-#pragma unroll 1
-    for (int a = 0; a < W; ++a) u[a] = S[1 + a] * inv0;
-#pragma unroll 1
+    double u[W], A[NT];                                                  // A: blended covariance, upper triangle
+#pragma unroll
     for (int a = 0; a < W; ++a) {
-#pragma unroll 1
-        for (int c2 = a; c2 < W; ++c2) {
-            const double s2 = S[1 + W + a * W - a * (a - 1) / 2 + (c2 - a)];
-            const double cv = (s2 - S[1 + a] * u[c2] - u[a] * S[1 + c2] + S[0] * (u[a] * u[c2])) * inv0;
-            const double nv = par->cov[k][a * W + c2] * step + cv * keep;
-            par->cov[k][a * W + c2] = nv; par->cov[k][c2 * W + a] = nv;
+        u[a] = S[1 + a] * inv0;
+        par->mu[k][a] = par->mu[k][a] * step + u[a] * keep;
+    }
+    {
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < W; ++a)
+#pragma unroll
+            for (int c2 = a; c2 < W; ++c2) {
+                const double cv = (S[1 + W + q] - S[1 + a] * u[c2] - u[a] * S[1 + c2] + S[0] * (u[a] * u[c2])) * inv0;
+                const double nv = par->cov[k][a * W + c2] * step + cv * keep;
+                par->cov[k][a * W + c2] = nv; par->cov[k][c2 * W + a] = nv;
+                A[q++] = nv;
+            }
+    }
+    // Cholesky A = L L^T (L lower, packed by rows), L^-1, log|A| = log prod(pivots)
+    double Lp[NT], Li[NT], rinv[W], prod = 1.0, sumlog = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            // A(i,j) with j <= i lives in the upper triangle at (j,i)
+            double sacc = A[j * W - j * (j - 1) / 2 + (i - j)];
+#pragma unroll
+            for (int t = 0; t < j; ++t) sacc = fma(-Lp[i * (i + 1) / 2 + t], Lp[j * (j + 1) / 2 + t], sacc);
+            if (i == j) {
+                ok &= (sacc > 0.0) && isfinite(sacc);
+                prod *= sacc;
+                const double d = sqrt(sacc);
+                Lp[i * (i + 1) / 2 + i] = d;
+                rinv[i] = 1.0 / d;
+            } else {
+                Lp[i * (i + 1) / 2 + j] = sacc * rinv[j];
+            }
         }
     }
-#pragma unroll 1
-    for (int a = 0; a < W; ++a) par->mu[k][a] = par->mu[k][a] * step + u[a] * keep;
-    double logdet;
-    if (!cholesky_inverse<W>(par->cov[k], par->linv[k], logdet)) par->ok = 0;
-    par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+    if (!ok) { par->ok = 0; return; }                                    // A4
+    if (!(prod > 1e-290 && prod < 1e290)) {                              // product out of range: sum of logs
+        prod = 1.0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) sumlog += 2.0 * log(Lp[i * (i + 1) / 2 + i]);
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < W; ++c2) {
+        Li[c2 * (c2 + 1) / 2 + c2] = rinv[c2];
+#pragma unroll
+        for (int r = c2 + 1; r < W; ++r) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int t = c2; t < r; ++t) sacc = fma(-Lp[r * (r + 1) / 2 + t], Li[t * (t + 1) / 2 + c2], sacc);
+            Li[r * (r + 1) / 2 + c2] = sacc * rinv[r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < W; ++r)
+#pragma unroll
+        for (int c2 = 0; c2 <= r; ++c2) par->linv[k][r * W + c2] = Li[r * (r + 1) / 2 + c2];
+    par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + log(prod) + sumlog);
 }
 
 // model of slot -> shared memory parameter block (+ Cholesky factors, uniform log density)
