@@ -1,0 +1,47 @@
+'''
+GPU: the pipelined public call (batch split into feature ranges, upload of range k+1 overlapping
+the kernels of range k) gives exactly the results of the single-batch call.
+'''
+import numpy as np
+import pytest
+
+from yanocomp_b200 import synth
+from yanocomp_b200.batch import HostBatch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pipelined_equals_single_batch():
+    from yanocomp_b200.api import test_host_batch as run_single, test_host_batch_pipelined as run_piped
+    from yanocomp_b200.engine import Engine, EngineParams
+    feats = synth.make_dataset(21, 9, 40, [22, 30, 25, 28], 2, 2, planted_frac=0.25, with_ids=True)
+    host = HostBatch(feats, 4, 2)
+    params = EngineParams(window_size=3, generate_sm_preds=True)
+    eng = Engine(params)
+    one = run_single(host, params, eng, fetch='full')
+    ref = {}
+    for s, g in enumerate(one.fit_list):
+        fi, pos = host.position_of(int(g))
+        ref[(fi, pos)] = (one.status_fit[s], one.ks_stat_fit[s], one.mu[s].copy(), one.stats[s].copy(),
+                          int(one.nall_fit[s]),
+                          one.post[one.post_off[s]:one.post_off[s] + one.nall_fit[s]].copy() if one.post_off[s] >= 0 else None)
+    status_ref = one.status.copy()
+    parts = run_piped(host, params, Engine(params), fetch='records', chunks=4)
+    assert len(parts) == 4 and sum(h.n_features for h, _ in parts) == 9
+    f0 = 0
+    seen = 0
+    for h, r in parts:
+        c0 = int(host.col_off[f0])
+        np.testing.assert_array_equal(r.status, status_ref[c0:c0 + h.total_cols])
+        for s, g in enumerate(r.fit_list):
+            fi, pos = h.position_of(int(g))
+            st, ks, mu, stats, nall, post = ref[(f0 + fi, pos)]
+            assert r.status_fit[s] == st and r.ks_stat_fit[s] == ks and int(r.nall_fit[s]) == nall
+            np.testing.assert_array_equal(r.mu[s], mu)
+            np.testing.assert_array_equal(r.stats[s], stats)
+            if post is not None:
+                off = int(r.post_off[s])
+                np.testing.assert_array_equal(r.post[off:off + nall], post)
+            seen += 1
+        f0 += h.n_features
+    assert seen == len(ref) > 20

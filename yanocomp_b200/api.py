@@ -23,6 +23,16 @@ def test_host_batch(host: HostBatch, params: EngineParams, engine: Engine = None
     return res
 
 
+def test_host_batch_pipelined(host: HostBatch, params: EngineParams, engine: Engine = None,
+                              fetch='records', chunks=4):
+    '''
+    Same as test_host_batch with the batch cut into `chunks` feature ranges (views, no copy) whose
+    host->device copies overlap the kernels of the previous range.  Returns [(sub-batch, result)].
+    '''
+    eng = engine or Engine(params)
+    return list(eng.run_pipelined(host.split(chunks), fetch=fetch, keep_results=True))
+
+
 def tested_table(host: HostBatch, res: BatchResult, gmm=True):
     '''
     Rows of the reference's result DataFrame (gmmtest.py:216-224) as arrays:

@@ -104,6 +104,43 @@ class HostBatch:
         split = self.samp_start[:, n_cntrl] if F else np.zeros(0, dtype=np.int32)
         self.max_cond_reads = int(max(split.max(), (self.n_reads - split).max())) if F else 0
 
+    def view(self, f0, f1):
+        '''features [f0, f1) as a HostBatch sharing this batch's (pinned) buffers: no copy'''
+        v = object.__new__(HostBatch)
+        v.features = self.features[f0:f1]
+        v.n_samples, v.n_cntrl = self.n_samples, self.n_cntrl
+        v.n_cols, v.n_reads, v.ld = self.n_cols[f0:f1], self.n_reads[f0:f1], self.ld[f0:f1]
+        e0 = int(self.x_off[f0]) if f0 < len(self.x_off) else len(self.events)
+        e1 = int(self.x_off[f1]) if f1 < len(self.x_off) else len(self.events)
+        v.x_off = self.x_off[f0:f1] - e0
+        c0, c1 = int(self.col_off[f0]), int(self.col_off[f1])
+        v.col_off = self.col_off[f0:f1 + 1] - c0
+        v.samp_start = self.samp_start[f0:f1]
+        v.feature_key = self.feature_key[f0:f1]
+        v.reverse = self.reverse[f0:f1]
+        v.col_pos = self.col_pos[c0:c1]
+        v.events = self.events[e0:e1]
+        v.total_cols = c1 - c0
+        v.max_reads = int(v.n_reads.max()) if f1 > f0 else 0
+        split = v.samp_start[:, v.n_cntrl] if f1 > f0 else np.zeros(0, dtype=np.int32)
+        v.max_cond_reads = int(max(split.max(), (v.n_reads - split).max())) if f1 > f0 else 0
+        return v
+
+    def split(self, k):
+        '''at most k views with balanced event bytes (for host->device / compute pipelining)'''
+        F = self.n_features
+        if k <= 1 or F < 2:
+            return [self]
+        sizes = self.n_cols.astype(np.int64) * self.ld
+        cum = np.cumsum(sizes)
+        cuts = [0]
+        for j in range(1, k):
+            c = int(np.searchsorted(cum, cum[-1] * j / k, side='left')) + 1
+            if cuts[-1] < c < F:
+                cuts.append(c)
+        cuts.append(F)
+        return [self.view(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+
     @staticmethod
     def _alloc_events(total, pin):
         if pin:

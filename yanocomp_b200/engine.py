@@ -92,13 +92,45 @@ class Engine:
             raise RuntimeError('yanocomp_b200.engine needs a CUDA device: there is no CPU fallback')
         self.lib = N.lib()
         self.params = params
-        self._stage = None              # pinned device->host staging buffer, grown on demand
+        self._stages = {}               # pinned device->host staging buffers (one per pipeline slot)
+        self._copy_stream = None
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
     def upload(self, host: HostBatch) -> DeviceBatch:
         return DeviceBatch(host, self.device)
 
-    def run(self, dev: DeviceBatch, want_labels=False, fetch='full', events=None):
+    def run_pipelined(self, hosts, fetch='records', keep_results=False, **kw):
+        '''
+        Yield (host batch, BatchResult) for every batch of the iterable `hosts`, uploading batch k+1
+        on a copy stream while the kernels of batch k run: the host->device copy (PCIe, ~55 GB/s)
+        hides behind the compute.  `hosts` is consumed lazily with one batch of look-ahead.  A result
+        stays valid until the batch after the next one has run (two staging buffers), or for ever
+        with keep_results=True (one staging buffer per batch).
+        '''
+        it = iter(hosts)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        compute = torch.cuda.current_stream(self.device)
+
+        def up():
+            h = next(it, None)
+            if h is None:
+                return None
+            self._copy_stream.wait_stream(compute)          # buffers freed by earlier batches are safe to reuse
+            with torch.cuda.stream(self._copy_stream):
+                dev = self.upload(h)
+                return h, dev, self._copy_stream.record_event()
+
+        nxt = up()
+        i = 0
+        while nxt is not None:
+            h, dev, ready = nxt
+            nxt = up()
+            compute.wait_event(ready)
+            yield h, self.run(dev, fetch=fetch, stage_key=i if keep_results else i % 2, **kw)
+            i += 1
+
+    def run(self, dev: DeviceBatch, want_labels=False, fetch='full', events=None, stage_key=0):
         '''
         Launch the whole path on the current stream.  Returns a BatchResult
         (host arrays; fetch = 'full' | 'records') or, with fetch=False, the dict
@@ -208,20 +240,21 @@ class Engine:
                         loglik=out_t['loglik'][:n_fit], preds=out_t['preds'][:n_fit * R * 3].view(n_fit, R, 3))
             if labels is not None:
                 want['labels'] = labels
-        host, d2h = self._fetch(want)
+        host, d2h = self._fetch(want, stage_key)
         return BatchResult(launches=launches, d2h_bytes=d2h, **host)
 
-    def _fetch(self, tensors):
+    def _fetch(self, tensors, stage_key=0):
         '''device tensors -> numpy views of one pinned staging buffer (async copies, one sync)'''
         align = 256
         sizes = {k: t.numel() * t.element_size() for k, t in tensors.items()}
         total = sum((v + align - 1) // align * align for v in sizes.values()) + align
-        if self._stage is None or self._stage.numel() < total:
-            self._stage = torch.empty(int(total * 1.25), dtype=torch.uint8, pin_memory=True)
+        stage = self._stages.get(stage_key)
+        if stage is None or stage.numel() < total:
+            stage = self._stages[stage_key] = torch.empty(int(total * 1.25), dtype=torch.uint8, pin_memory=True)
         out, off = {}, 0
         for k, t in tensors.items():
             nb = sizes[k]
-            dst = self._stage[off:off + nb].view(t.dtype).view(t.shape)
+            dst = stage[off:off + nb].view(t.dtype).view(t.shape)
             if nb:
                 dst.copy_(t, non_blocking=True)
             out[k] = dst

@@ -189,28 +189,28 @@ def test_chunk(opts, gene_ids):
     R = len(opts.cntrl_hdf5_fns) + len(opts.treat_hdf5_fns)
     chunk_res, chunk_sm = [], {}
 
-    def flush(features):
-        if not features:
-            return
-        host = HostBatch(features, R, len(opts.cntrl_hdf5_fns))
-        res = engine.run(engine.upload(host), fetch='records')
+    def batches():
+        '''packed batches of ~BATCH_EVENT_BYTES, decoded by `processes` host threads'''
+        with hdf5_list(opts.cntrl_hdf5_fns) as cntrl_h5, hdf5_list(opts.treat_hdf5_fns) as treat_h5:
+            pending, nbytes = [], 0
+            with ThreadPoolExecutor(max(1, opts.processes)) as pool:
+                loaded = pool.map(lambda gid: load_gene_features(gid, cntrl_h5, treat_h5, by_t), list(gene_ids))
+                for feats in loaded:
+                    for f in feats:
+                        pending.append(f)
+                        nbytes += f.X.nbytes
+                    if nbytes >= BATCH_EVENT_BYTES:
+                        yield HostBatch(pending, R, len(opts.cntrl_hdf5_fns))
+                        pending, nbytes = [], 0
+                if pending:
+                    yield HostBatch(pending, R, len(opts.cntrl_hdf5_fns))
+
+    # upload of batch k+1 overlaps the kernels of batch k (engine.run_pipelined)
+    for host, res in engine.run_pipelined(batches()):
         recs, sm = _batch_records(host, res, opts)
         chunk_res.extend(recs)
         for k, v in sm.items():
             chunk_sm.setdefault(k, {}).update(v)
-
-    with hdf5_list(opts.cntrl_hdf5_fns) as cntrl_h5, hdf5_list(opts.treat_hdf5_fns) as treat_h5:
-        pending, nbytes = [], 0
-        with ThreadPoolExecutor(max(1, opts.processes)) as pool:
-            loaded = pool.map(lambda gid: load_gene_features(gid, cntrl_h5, treat_h5, by_t), list(gene_ids))
-            for feats in loaded:
-                for f in feats:
-                    pending.append(f)
-                    nbytes += f.X.nbytes
-                if nbytes >= BATCH_EVENT_BYTES:
-                    flush(pending)
-                    pending, nbytes = [], 0
-            flush(pending)
     return chunk_res, chunk_sm
 
 
