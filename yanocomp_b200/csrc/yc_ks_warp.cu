@@ -29,19 +29,21 @@ namespace yc {
 #define YC_KW_WARPS 4
 
 struct KwSmem {
-    int sort_off, gt_off, v_off, st_off, mask_off, cnt_off, ridx_off, wc_off, per_warp;
+    int sort_off, gt_off, v_off, st_off, mask_off, cnt_off, ridx_off, wc_off, cm_off, tab_off, per_warp;
 };
 
 __host__ __device__ inline KwSmem kw_layout(int W, int R, int max_reads, int P) {
     KwSmem s;
     int o = 0;
     s.sort_off = o; o += 2 * P * (int)sizeof(double);
+    s.tab_off = o;  o += 2 * (P + 1) * (int)sizeof(double);
     s.gt_off = o;   o += 32 * (2 * W * W + 2 * W) * (int)sizeof(double);
     s.v_off = o;    o += 32 * W * (int)sizeof(double);
     s.wc_off = o;   o += 32 * W * (int)sizeof(void *);
     s.st_off = o;   o += 32 * 8 * (int)sizeof(int);
     s.mask_off = o; o += 32 * ((max_reads + 31) / 32) * (int)sizeof(uint32_t);
     s.cnt_off = o;  o += (W + 1) * R * (int)sizeof(int);
+    s.cm_off = o;   o += W * ((max_reads + 31) / 32) * (int)sizeof(uint32_t);
     s.ridx_off = o; o += 16 * (int)sizeof(int);
     s.per_warp = (o + 15) & ~15;
     return s;
@@ -65,32 +67,39 @@ __device__ __noinline__ void warp_bitonic(double *a, int P, int nseg, int lane) 
     }
 }
 
-// warp-local window_scan: counters are private to the warp, so no atomics
+// warp-local window scan: per-column non-null masks and the complete-row mask go to shared
+// memory; afterwards one lane per (column, sample) counts its depth with popcounts over the
+// sample's row range (reads are sorted by sample), instead of a per-chunk loop over samples.
+//   colmask[j * nwords + wd], j < W: non-null mask of window column j; mask[wd]: complete rows
 template <int W>
-__device__ __forceinline__ void warp_window_scan(const Window<W> &w, int R, uint32_t *mask, int *cnt, int lane) {
+__device__ __forceinline__ void warp_window_scan(const Window<W> &w, int R, uint32_t *mask, uint32_t *colmask,
+                                                 int nwords_max, int *cnt, int lane) {
     const int n = w.n_reads;
     for (int base = 0; base < n; base += 32) {
         const int r = base + lane;
         const bool inb = r < n;
-        uint32_t m_all = YC_FULL, m_mine = 0;
+        uint32_t m_all = YC_FULL;
 #pragma unroll
         for (int j = 0; j < W; ++j) {
             const uint16_t v = inb ? __ldg(w.col[j] + r) : (uint16_t)0x7e00;
             const uint32_t m = __ballot_sync(YC_FULL, inb && !h_isnan(v));
             m_all &= m;
-            if (lane == j) m_mine = m;
+            if (lane == j) colmask[j * nwords_max + (base >> 5)] = m;
         }
-        if (lane == W) m_mine = m_all;
-        if (lane == 0) mask[base >> 5] = m_all;
-        if (lane <= W) {
-            for (int s = 0; s < R; ++s) {
-                const int a = max(w.samp_start[s], base), e = min(w.samp_start[s + 1], base + 32);
-                if (e > a) {
-                    const uint32_t seg = (e - a == 32) ? YC_FULL : (((1u << (e - a)) - 1u) << (a - base));
-                    cnt[lane * R + s] += __popc(m_mine & seg);
-                }
-            }
+        if (lane == W) mask[base >> 5] = m_all;
+    }
+    __syncwarp();
+    for (int q = lane; q < (W + 1) * R; q += 32) {
+        const int j = q / R, s = q - j * R;
+        const uint32_t *mm = j < W ? colmask + j * nwords_max : mask;
+        const int a = w.samp_start[s], e = w.samp_start[s + 1];
+        int c = 0;
+        for (int wd = a >> 5; wd * 32 < e; ++wd) {
+            const int lo = max(a, wd * 32) - wd * 32, hi = min(e, wd * 32 + 32) - wd * 32;   // bits [lo, hi)
+            const uint32_t seg = (hi - lo == 32) ? YC_FULL : (((1u << (hi - lo)) - 1u) << lo);
+            c += __popc(mm[wd] & seg);
         }
+        cnt[q] = c;
     }
 }
 
@@ -114,6 +123,8 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
     uint32_t *masks = reinterpret_cast<uint32_t *>(base_ptr + L.mask_off);
     int *cnt = reinterpret_cast<int *>(base_ptr + L.cnt_off);
     int *ridx = reinterpret_cast<int *>(base_ptr + L.ridx_off);
+    uint32_t *colmask = reinterpret_cast<uint32_t *>(base_ptr + L.cm_off);
+    double *tabA = reinterpret_cast<double *>(base_ptr + L.tab_off), *tabB = tabA + (P + 1);
     const int nwords_max = (b.max_reads + 31) / 32;
     constexpr int NT = W * (W + 1) / 2, GT = 2 * W * W + 2 * W;
 
@@ -129,9 +140,7 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
             n = w.n_reads;
             split = w.samp_start[Rc];
             uint32_t *mask = masks + q * nwords_max;
-            for (int i = lane; i < (W + 1) * R; i += 32) cnt[i] = 0;
-            __syncwarp();
-            warp_window_scan<W>(w, R, mask, cnt, lane);
+            warp_window_scan<W>(w, R, mask, colmask, nwords_max, cnt, lane);
             __syncwarp();
             if (window_depth_ok<W>(w, R, Rc, p.min_read_depth, cnt, n_c, n_t)) {
                 state = (n_c == 0 || n_t == 0) ? 1 : 2;       // 1: degenerate
@@ -223,19 +232,24 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
     __syncwarp();
     // ------------------------------------------------------------ phase 3
     double my_d = 0.0;
+    int tab_n1 = -1, tab_n2 = -1;           // ECDF ratio tables c/n1, c/n2 (IEEE divisions), rebuilt when n changes
     for (int q = 0; q < 32; ++q) {
         const int *s = st + q * 8;
         if (s[0] != 2) continue;                                // warp-uniform
         const int n1 = s[1], n2 = s[2], n = s[3], split = s[4];
         const uint32_t *mask = masks + q * nwords_max;
         const double *slot = gt + q * GT;
-        double mu[W], sig[W], vv[W];
+        // Only the ORDER of the projections y = sum_j z_j v_j enters D, and
+        // sum_j x_j (v_j / sig_j) differs from y by a constant: no centring, no division per read.
+        double cj[W];
         const uint16_t *col[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            mu[j] = slot[2 * W * W + j]; sig[j] = slot[2 * W * W + W + j];
-            vv[j] = vbuf[q * W + j]; col[j] = wcache[q * W + j];
+            cj[j] = vbuf[q * W + j] / slot[2 * W * W + W + j];
+            col[j] = wcache[q * W + j];
         }
+        if (n1 != tab_n1) { for (int i = lane; i <= n1; i += 32) tabA[i] = div_rn((double)i, (double)n1); tab_n1 = n1; }
+        if (n2 != tab_n2) { for (int i = lane; i <= n2; i += 32) tabB[i] = div_rn((double)i, (double)n2); tab_n2 = n2; }
         const int Pq = next_pow2(max(n1, n2));
         for (int i = lane; i < 2 * Pq; i += 32) sortbuf[i] = INFINITY;
         __syncwarp();
@@ -248,10 +262,7 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
             double y = 0.0;
             if (bit) {
 #pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    const double z = div_rn(sub_rn(h2d(__ldg(col[j] + r)), mu[j]), sig[j]);
-                    y = fma(z, vv[j], y);
-                }
+                for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(col[j] + r)), cj[j], y);
             }
             const uint32_t ma = __ballot_sync(YC_FULL, bit && !cond), mb = __ballot_sync(YC_FULL, bit && cond);
             if (bit) sortbuf[cond ? Pq + cb + __popc(mb & lt) : ca + __popc(ma & lt)] = y;
@@ -260,7 +271,6 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
         __syncwarp();
         warp_bitonic(sortbuf, Pq, 2, lane);
         const double *A = sortbuf, *B = sortbuf + Pq;
-        const double fn1 = (double)n1, fn2 = (double)n2;
         double dmax = 0.0;
         for (int i = lane; i < n1 + n2; i += 32) {
             // ECDF counts at pooled point v: in its own (sorted) sample the count is the index of the
@@ -277,7 +287,7 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
                 while (e < n2 && B[e] == v) ++e;
                 c2 = e; c1 = upper_bound(A, n1, v);
             }
-            dmax = fmax(dmax, fabs(sub_rn(div_rn((double)c1, fn1), div_rn((double)c2, fn2))));
+            dmax = fmax(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
         }
         dmax = warp_max(dmax);
         if (lane == q) my_d = dmax;
