@@ -308,9 +308,14 @@ def run_gpu(args, cfg, opts_kw):
     fp64_peak = 148 * 64 * 2 * sm_max * 1e6      # 64 FP64 FMA lanes / SM / clk
     em_name = 'gmm_em'
     em_ms = kavg.get(em_name, float('inf'))
+    traffic = None
+    tfn = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tfn) and args.config == 2 and not args.features:
+        with open(tfn) as fh:
+            traffic = json.load(fh).get(dom)        # ncu --set full capture of the same workload
     roofline = {
         'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-        'frac': achieved / hbm_peak, 'traffic': None, 'peak_kind': peak_kind,
+        'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_kind': peak_kind,
         'kernel_ms': kavg, 'algorithmic_bytes': alg,
         'note': 'the path is FP64-latency bound, not HBM bound (DESIGN.md section 5); fp64 block below',
         'fp64': {'kernel': em_name, 'achieved_tflops': em_flops / (em_ms * 1e-3) / 1e12,
