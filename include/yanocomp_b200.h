@@ -89,6 +89,8 @@ typedef struct yc_params {
     int32_t  min_read_depth;     /* -n, gmmtest.py:245-251, :301-303 */
     int32_t  max_fit_depth;      /* -d, gmmtest.py:304-305 */
     int32_t  gmm;                /* --gmm/--no-gmm, gmmtest.py:310-311 */
+    int32_t  add_uniform;        /* -u/--add-uniform / --no-uniform, gmmtest.py:290-292 (1 = 3-component GMM) */
+    int32_t  reserved0;
     double   min_ks;             /* -k, gmmtest.py:306-307 */
     double   fdr_threshold;      /* -f, gmmtest.py:308-309 */
     double   outlier_factor;     /* -e, gmmtest.py:296-298 */
@@ -208,6 +210,9 @@ double   yc_kolmogorov_sf_host(double x);
 double   yc_chi2_sf_1dof_host(double g);
 void     yc_gtest_fractions_host(const double *preds, int32_t nrow_c, int32_t nrow_t,
                                  double thr, double *out8);
+/* the same for the two-component model of --no-uniform: the third column of preds is ignored */
+void     yc_gtest_fractions2_host(const double *preds, int32_t nrow_c, int32_t nrow_t,
+                                  double thr, double *out8);
 uint64_t yc_position_key_host(uint64_t seed, uint64_t fkey, int64_t pos);
 uint64_t yc_mix64_host(uint64_t z);
 /* first right singular vector of Z with numpy.linalg.svd's (LAPACK dgesdd) sign,

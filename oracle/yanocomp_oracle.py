@@ -407,32 +407,35 @@ def median_absolute_deviation(arr):
     return np.median(np.abs(arr - np.median(arr)))
 
 
-def kmeans_init_clusters(X, pkey, outlier_factor=0.5):
-    '''stats.py:81-124, `mad` branch'''
+def kmeans_init_clusters(X, pkey, outlier_factor=0.5, detect_outliers=True):
+    '''stats.py:81-124, `mad` branch (detect_outliers=False: --no-uniform, stats.py:115)'''
     centroids = kmeans_fit(X, pkey)
     d2 = _sqdist(X, centroids)                                     # A1
     init_pred = np.argmin(d2, axis=1)
+    if not detect_outliers:
+        return init_pred
     dists = np.min(d2, axis=1)
     mad = median_absolute_deviation(dists)
     init_pred[dists > outlier_factor * mad] = N_COMPONENTS
     return init_pred
 
 
-def initialise_gmms(samples, pkey, outlier_factor=0.5, pseudocount=0.5):
-    '''stats.py:127-191 (full covariance, MAD outliers, uniform component)'''
+def initialise_gmms(samples, pkey, outlier_factor=0.5, pseudocount=0.5, add_uniform=True):
+    '''stats.py:127-191 (full covariance; MAD outliers + uniform component unless --no-uniform)'''
     sizes = [len(s) for s in samples]
     pooled = np.concatenate(samples)
-    init_pred = kmeans_init_clusters(pooled, pkey, outlier_factor)
+    init_pred = kmeans_init_clusters(pooled, pkey, outlier_factor, add_uniform)
     dists = [MVNormal.from_samples(pooled[init_pred == i])
              for i in range(N_COMPONENTS)]
-    ncomp = N_COMPONENTS + 1
+    ncomp = N_COMPONENTS + int(add_uniform)
     per_samp = np.array_split(init_pred, np.cumsum(sizes)[:-1])
     weights = [(np.bincount(p, minlength=ncomp) + pseudocount)
                / (len(p) + pseudocount * ncomp) for p in per_samp]
-    outliers = pooled[init_pred == N_COMPONENTS]
-    if len(outliers) == 0:
-        outliers = pooled
-    dists.append(UniformBox(outliers.min(axis=0), outliers.max(axis=0)))
+    if add_uniform:
+        outliers = pooled[init_pred == N_COMPONENTS]
+        if len(outliers) == 0:
+            outliers = pooled
+        dists.append(UniformBox(outliers.min(axis=0), outliers.max(axis=0)))
     return [Mixture(dists, w) for w in weights], dists, init_pred
 
 
@@ -477,7 +480,7 @@ class GMMFit:
 
 
 def fit_gmm(cntrl, treat, pkey, outlier_factor=0.5, max_fit_depth=1000,
-            sample_ids=None, sample_rows=None):
+            sample_ids=None, sample_rows=None, add_uniform=True):
     '''
     stats.py:228-299 (`full`, `mad`); cntrl / treat are lists of (n_s, d).
     sample_ids[s] = packed sample index (selects the sub-sampling stream),
@@ -497,7 +500,7 @@ def fit_gmm(cntrl, treat, pkey, outlier_factor=0.5, max_fit_depth=1000,
         samples.append(samp if idx is None else samp[idx])
     trace = []
     with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
-        gmms, dists, init_pred = initialise_gmms(samples, pkey, outlier_factor)
+        gmms, dists, init_pred = initialise_gmms(samples, pkey, outlier_factor, add_uniform=add_uniform)
         iters = em(samples, gmms, dists, trace=trace)
     if not all(np.isfinite(trace)):
         raise FitError('non-finite likelihood')                       # A5
@@ -572,6 +575,7 @@ class Options:
     min_ks: float = 0.2
     fdr_threshold: float = 0.05
     outlier_factor: float = 0.5
+    add_uniform: bool = True
     gmm: bool = True
     generate_sm_preds: bool = False
     test_level: str = 'gene'
@@ -636,13 +640,15 @@ def _split_by_replicate(cw):
 def format_model(fit):
     '''stats.py:382-419'''
     w = fit.combined_weights / fit.combined_weights.sum()            # A7
-    return {
+    model = {
         'unmod': {'mu': fit.dists[0].mu.tolist(), 'cov': fit.dists[0].cov.tolist()},
         'mod': {'mu': fit.dists[1].mu.tolist(), 'cov': fit.dists[1].cov.tolist()},
-        'outlier': {'bounds': [[float(a), float(b)] for a, b in
-                               zip(fit.dists[2].lo, fit.dists[2].hi)]},
-        'weights': np.exp(np.log(w)).tolist(),
     }
+    if len(fit.dists) == N_COMPONENTS + 1:
+        model['outlier'] = {'bounds': [[float(a), float(b)] for a, b in
+                                       zip(fit.dists[2].lo, fit.dists[2].hi)]}
+    model['weights'] = np.exp(np.log(w)).tolist()
+    return model
 
 
 def format_sm_preds(prob, outlier, cw):
@@ -685,7 +691,7 @@ def position_stats(cntrl, treat, kmers, opts, pkey, n_cntrl_files=None):
     sample_ids = [rep - 1 for rep in c_reps] + [n_cntrl_files + rep - 1 for rep in t_reps]
     try:
         fit = fit_gmm(cntrl_fit, treat_fit, pkey, opts.outlier_factor,
-                      opts.max_fit_depth, sample_ids, c_rows + t_rows)
+                      opts.max_fit_depth, sample_ids, c_rows + t_rows, opts.add_uniform)
     except np.linalg.LinAlgError:
         r.status = ST_FIT_FAILED
         return r
@@ -703,6 +709,12 @@ def position_stats(cntrl, treat, kmers, opts, pkey, n_cntrl_files=None):
         gmm = Mixture(fit.dists, fit.combined_weights)
         cp = gmm.predict_proba(np.concatenate(cntrl_fit))[:, 1:].T
         tp = gmm.predict_proba(np.concatenate(treat_fit))[:, 1:].T
+        if not opts.add_uniform:
+            # stats.py:500-502 sets the outlier predictions to zeros_like of a (1, n) array and then
+            # zips it with the reads, which keeps a single entry; the evident intent (one prediction
+            # per read, outlier probability 0) is restated here instead of that bug.
+            cp = np.vstack([cp[0], np.zeros_like(cp[0])])
+            tp = np.vstack([tp[0], np.zeros_like(tp[0])])
         r.sm_preds = {
             'kmers': list(kmers),
             'model': format_model(fit),

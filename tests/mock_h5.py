@@ -5,6 +5,8 @@ layout `yanocomp prep` writes (reference yanocomp/io.py:155-243).  Lets the
 ingest path be tested on multi-replicate, multi-transcript genes without an
 HDF5 writer.
 '''
+import zlib
+
 import numpy as np
 
 EVENT_DTYPE = np.dtype([('transcript_idx', 'u1'), ('read_idx', '<u4'), ('pos', '<u4'),
@@ -51,7 +53,7 @@ def random_file(rng, genes, n_reads, strand='+', chrom='chr1', mod=None, dup_fra
     for gene, (pos0, n_pos, t_ids) in genes.items():
         g = MockGroup()
         g.attrs = {'chrom': chrom, 'strand': strand}
-        level = np.random.default_rng(abs(hash(gene)) % (2 ** 32)).uniform(75, 130, n_pos)
+        level = np.random.default_rng(zlib.crc32(gene.encode())).uniform(75, 130, n_pos)
         rows = []
         ids = []
         for r in range(n_reads):
@@ -69,7 +71,7 @@ def random_file(rng, genes, n_reads, strand='+', chrom='chr1', mod=None, dup_fra
                 if rng.random() < dup_frac:
                     rows.append((t, r, pos0 + c, mean + 7.0, 1.0, 0.01))      # duplicate: the first one wins
         ev = np.array(rows, dtype=EVENT_DTYPE)
-        kseq = bases[np.random.default_rng(abs(hash(gene + 'k')) % (2 ** 32)).integers(0, 4, n_pos + 4)]
+        kseq = bases[np.random.default_rng(zlib.crc32((gene + 'k').encode())).integers(0, 4, n_pos + 4)]
         km = np.array([(pos0 + c, ''.join(kseq[c:c + 5]).encode()) for c in range(n_pos)], dtype=KMER_DTYPE)
         g['events'] = _DS(ev)
         g['kmers'] = _DS(km)

@@ -35,6 +35,7 @@ def _oracle_opts(params):
                       max_fit_depth=params.max_fit_depth, min_ks=params.min_ks,
                       fdr_threshold=params.fdr_threshold, outlier_factor=params.outlier_factor,
                       gmm=params.gmm, generate_sm_preds=params.generate_sm_preds,
+                      add_uniform=params.add_uniform,
                       random_seed=params.seed)
 
 
@@ -53,7 +54,22 @@ def _rank_deficient_init(o, res, slot, w):
     else:
         return False
     counts = np.bincount(lab, minlength=3)
-    return bool(((counts[:2] > 0) & (counts[:2] <= w)).any())
+    if ((counts[:2] > 0) & (counts[:2] <= w)).any():
+        return True
+    # a component that collapsed onto a (numerically) singular covariance during EM: whether the
+    # Cholesky pivot comes out as +1e-12 or -1e-12 is rounding noise in every implementation
+    covs = []
+    if o.fit is not None:
+        covs += [o.fit.dists[0].cov, o.fit.dists[1].cov]
+    if slot is not None and res.cov is not None:
+        covs += [res.cov[slot][0], res.cov[slot][1]]
+    for cv in covs:
+        if not np.isfinite(cv).all():
+            return True
+        ev = np.linalg.eigvalsh((cv + cv.T) / 2)
+        if ev.min() < 1e-9 * ev.max():
+            return True
+    return False
 
 
 def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
@@ -120,8 +136,8 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
             if not np.array_equal(res.labels[s, :nrows], fit.init_pred):
                 errs['labels'].append((key, int((res.labels[s, :nrows] != fit.init_pred).sum()), nrows))
                 continue
-            if not (np.array_equal(res.box[s, :, 0], fit.dists[2].lo)
-                    and np.array_equal(res.box[s, :, 1], fit.dists[2].hi)):
+            if params.add_uniform and not (np.array_equal(res.box[s, :, 0], fit.dists[2].lo)
+                                           and np.array_equal(res.box[s, :, 1], fit.dists[2].hi)):
                 errs['box'].append(key)
             if res.iters[s] != fit.iterations:
                 errs['iters'].append((key, int(res.iters[s]), fit.iterations))
@@ -130,13 +146,14 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
                   and np.allclose(res.mu[s, 1], fit.dists[1].mu, rtol=PARAM_RTOL, atol=0)
                   and np.allclose(res.cov[s, 0], fit.dists[0].cov, rtol=PARAM_RTOL, atol=1e-6)
                   and np.allclose(res.cov[s, 1], fit.dists[1].cov, rtol=PARAM_RTOL, atol=1e-6)
-                  and np.allclose(res.cw[s], fit.combined_weights, rtol=PARAM_RTOL, atol=0))
+                  and np.allclose(res.cw[s][:len(fit.combined_weights)], fit.combined_weights, rtol=PARAM_RTOL, atol=0)
+                  and (params.add_uniform or res.cw[s][2] == 0))
             if not ok:
                 errs['params'].append((key, res.mu[s].tolist(), fit.dists[0].mu.tolist(), fit.dists[1].mu.tolist()))
                 continue
             preds = np.concatenate([fit.cntrl_preds, fit.treat_preds])
             sizes = np.array([(ob_rows > 0) for ob_rows in res.preds[s].sum(axis=1)])
-            got = res.preds[s][sizes]
+            got = res.preds[s][sizes][:, :preds.shape[1]]
             if got.shape != preds.shape or not np.array_equal(got, preds):
                 errs['preds'].append((key, got.tolist(), preds.tolist()))
                 continue
@@ -228,3 +245,11 @@ def test_no_gmm_mode(ks_path):
     feats = synth.make_dataset(18, 2, 40, 25, 2, 2, planted_frac=0.2)
     out = compare(feats, 4, 2, window_size=3, gmm=False)
     assert (out['res'].status == N.ST_KS_ONLY).sum() == out['windows'] and out['res'].n_fitted == 0
+
+
+def test_no_uniform_two_component_model(ks_path):
+    '''--no-uniform (stats.py:170, 472, 500-502): no MAD outliers, two components, 2-column homogeneity tables'''
+    feats = synth.make_dataset(19, 4, 50, [28, 33, 30, 26], 2, 2, planted_frac=0.25)
+    out = compare(feats, 4, 2, window_size=3, add_uniform=False)
+    assert out['fitted'] > 20
+    assert (out['res'].preds[:, :, 2] == 0).all() and (out['res'].cw[:, 2] == 0).all()

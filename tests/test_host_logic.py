@@ -163,8 +163,9 @@ def test_options_mirror_the_reference_cli():
                      output_sm_preds_fn='s.json', random_seed='17')
     assert o5.min_read_depth == 10 and o5.generate_sm_preds and o5.random_seed == 17
     import click
-    for kw in (dict(covariance_type='diag'), dict(add_uniform=False), dict(outlier_method='dbscan'),
-               dict(window_size=4)):
+    assert not GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='x',
+                           add_uniform=False).engine_params().add_uniform
+    for kw in (dict(covariance_type='diag'), dict(outlier_method='dbscan'), dict(window_size=4)):
         with pytest.raises(click.UsageError):
             GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='x', **kw)
 

@@ -106,3 +106,21 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     b.max_reads = 400
     p.max_fit_depth = 1000
     assert lib.yc_smem_bytes(C.byref(b), C.byref(p), out) == 0 and max(out) < 232448
+
+
+def test_two_component_gtest_matches_scipy():
+    '''--no-uniform: R x 2 homogeneity tables get Yates' correction when they are 2 x 2 (dof 1)'''
+    lib = N.lib()
+    rng = np.random.default_rng(3)
+    for t in range(400):
+        rc, rt = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        pr = np.zeros((rc + rt, 3))
+        pr[:, :2] = np.round(rng.uniform(0, 60, (rc + rt, 2)) * (rng.uniform(size=(rc + rt, 2)) > 0.1))
+        if t % 25 == 0:
+            pr[:] = 0
+        with np.errstate(all='ignore'):
+            het, hom, pv = yo.gmm_g_test(pr[:rc, :2], pr[rc:, :2], 0.05)
+            fs = yo.calculate_fractional_stats(pr[:rc, :2], pr[rc:, :2])
+        out = np.zeros(8)
+        lib.yc_gtest_fractions2_host(_pd(np.ascontiguousarray(pr)), rc, rt, 0.05, _pd(out))
+        np.testing.assert_allclose(out, [het, hom, pv, *fs], rtol=1e-12, atol=1e-300, equal_nan=True)

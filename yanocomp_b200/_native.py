@@ -42,6 +42,7 @@ class Params(C.Structure):
     _fields_ = [
         ('window_size', C.c_int32), ('min_read_depth', C.c_int32),
         ('max_fit_depth', C.c_int32), ('gmm', C.c_int32),
+        ('add_uniform', C.c_int32), ('reserved0', C.c_int32),
         ('min_ks', C.c_double), ('fdr_threshold', C.c_double),
         ('outlier_factor', C.c_double), ('seed', C.c_uint64),
     ]
@@ -74,6 +75,7 @@ _PROTOTYPES = {
     'yc_kolmogorov_sf_host': (C.c_double, [C.c_double]),
     'yc_chi2_sf_1dof_host': (C.c_double, [C.c_double]),
     'yc_gtest_fractions_host': (None, [_P(C.c_double), C.c_int32, C.c_int32, C.c_double, _P(C.c_double)]),
+    'yc_gtest_fractions2_host': (None, [_P(C.c_double), C.c_int32, C.c_int32, C.c_double, _P(C.c_double)]),
     'yc_position_key_host': (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_int64]),
     'yc_mix64_host': (C.c_uint64, [C.c_uint64]),
     'yc_first_right_singular_vector_device': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -200,6 +200,9 @@ double yc_chi2_sf_1dof_host(double g) { return yc::chi2_sf_1dof(g); }
 void yc_gtest_fractions_host(const double *preds, int32_t nrow_c, int32_t nrow_t, double thr, double *out8) {
     yc::gtest_fractions(preds, nrow_c, nrow_t, thr, out8);
 }
+void yc_gtest_fractions2_host(const double *preds, int32_t nrow_c, int32_t nrow_t, double thr, double *out8) {
+    yc::gtest_fractions(preds, nrow_c, nrow_t, thr, out8, 2);
+}
 uint64_t yc_position_key_host(uint64_t seed, uint64_t fkey, int64_t pos) {
     return yc::position_key(seed, fkey, pos);
 }

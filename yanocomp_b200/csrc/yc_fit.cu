@@ -284,7 +284,16 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         if (tid == 0) status[g] = YC_ST_FIT_FAILED;
         return;
     }
-    // ---------------- distances to the centroids, MAD outliers (stats.py:114-122, A1)
+    // ---------------- nearest-centroid labels; MAD outliers unless --no-uniform (stats.py:114-122, A1)
+    int n_out = 0;
+    if (!p.add_uniform) {
+        for (int i = tid; i < n; i += YC_BLOCK) {
+            double x[W];
+            load_row<W>(c, i, x);
+            lab[i] = (int8_t)(sqdist<W>(x, best + W) < sqdist<W>(x, best));
+        }
+        __syncthreads();
+    } else {
     const int P = next_pow2(n);
     for (int i = tid; i < P; i += YC_BLOCK) {
         double dmin = INFINITY;
@@ -316,7 +325,6 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     const double mad = (n & 1) ? sortbuf[n >> 1] : mul_rn(add_rn(sortbuf[(n >> 1) - 1], sortbuf[n >> 1]), 0.5);
     const double thr = mul_rn(p.outlier_factor, mad);
     __syncthreads();
-    int n_out = 0;
     for (int i = tid; i < n; i += YC_BLOCK) {
         double x[W];
         load_row<W>(c, i, x);
@@ -324,6 +332,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         if ((d1 < d0 ? d1 : d0) > thr) { lab[i] = 2; ++n_out; }
     }
     n_out = block_sum_i(n_out, ired);          // also orders the lab[] writes
+    }
     if (labels_out) for (int i = tid; i < n && i < max_fit_rows; i += YC_BLOCK)
         labels_out[(size_t)slot * max_fit_rows + i] = lab[i];
 
@@ -373,7 +382,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         for (int j = 0; j < W; ++j) {
             lo[j] = block_min1(lo[j], red);
             hi[j] = block_max1(hi[j], red);
-            box_ok &= hi[j] > lo[j];
+            if (p.add_uniform) box_ok &= hi[j] > lo[j];
             if (tid == 0) { out.box[((size_t)slot * W + j) * 2] = lo[j]; out.box[((size_t)slot * W + j) * 2 + 1] = hi[j]; }
         }
         if (tid == 0) par[2] = box_ok ? 1.0 : 0.0;
@@ -387,10 +396,10 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         if (lane == 0) {
             double *lw = out.logw + ((size_t)slot * R + s) * 3;
             if (e > a) {
-                const double den = (double)(e - a) + 1.5;
+                const double den = (double)(e - a) + (p.add_uniform ? 1.5 : 1.0);
                 lw[0] = log(((double)k0 + 0.5) / den);
                 lw[1] = log(((double)k1 + 0.5) / den);
-                lw[2] = log(((double)k2 + 0.5) / den);
+                lw[2] = p.add_uniform ? log(((double)k2 + 0.5) / den) : -INFINITY;
             } else { lw[0] = lw[1] = lw[2] = 0.0; }
         }
     }
@@ -485,7 +494,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 }
                 const double l0 = par->cst[0] - 0.5 * q0 + par->logw[s][0];
                 const double l1 = par->cst[1] - 0.5 * q1 + par->logw[s][1];
-                const double l2 = inside ? par->ulogp + par->logw[s][2] : -INFINITY;
+                const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[s][2] : -INFINITY;
                 const double m = fmax(fmax(l0, l1), l2);
                 const double e0 = exp(l0 - m), e1 = exp(l1 - m), e2 = exp(l2 - m);
                 const double se = e0 + e1 + e2;
@@ -566,9 +575,10 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 for (int w2 = 0; w2 < YC_NWARPS; ++w2)
                     for (int k = 0; k < 3; ++k) v[k] += wsum[(w2 * YC_MAX_SAMPLES + s) * 3 + k];
                 if (v[0] + v[1] + v[2] != 0.0) {
-                    v[0] += 0.5; v[1] += 0.5; v[2] += 0.5;
-                    const double t = v[0] + v[1] + v[2];
-                    for (int k = 0; k < 3; ++k) par->logw[s][k] = log(v[k] / t);
+                    const int ncomp = p.add_uniform ? 3 : 2;
+                    double t = 0.0;
+                    for (int k = 0; k < ncomp; ++k) { v[k] += 0.5; t += v[k]; }
+                    for (int k = 0; k < 3; ++k) par->logw[s][k] = k < ncomp ? log(v[k] / t) : -INFINITY;
                 }
             }
         }
@@ -637,7 +647,7 @@ gtest_smpred_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             } else { po[0] = po[1] = po[2] = 0.0; }
         }
         double st[8];
-        gtest_fractions(pr, rows_c, rows_t, p.fdr_threshold, st);
+        gtest_fractions(pr, rows_c, rows_t, p.fdr_threshold, st, p.add_uniform ? 3 : 2);
         for (int k = 0; k < 8; ++k) out.stats[(size_t)slot * 8 + k] = st[k];
         long long off = -1;
         if (post != nullptr && st[2] < p.fdr_threshold) {
@@ -694,7 +704,7 @@ gtest_smpred_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             }
             const double l0 = par->cst[0] - 0.5 * q0 + par->logw[0][0];
             const double l1 = par->cst[1] - 0.5 * q1 + par->logw[0][1];
-            const double l2 = inside ? par->ulogp + par->logw[0][2] : -INFINITY;
+            const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[0][2] : -INFINITY;
             const double mx = fmax(fmax(l0, l1), l2);
             const double e0 = exp(l0 - mx), e1 = exp(l1 - mx), e2 = exp(l2 - mx);
             const double inv = 1.0 / (e0 + e1 + e2);

@@ -276,7 +276,17 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     }
     if (!have_best) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
 
-    // ---- MAD outliers (stats.py:114-122, A1)
+    // ---- nearest-centroid labels; MAD outliers unless --no-uniform (stats.py:114-122, A1)
+    int n_out = 0;
+    if (!p.add_uniform) {
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) {
+            double x[W];
+            fw_row<W>(xs, cap, i, x);
+            lab[i] = (int8_t)(sqdist<W>(x, best + W) < sqdist<W>(x, best));
+        }
+        __syncwarp();
+    } else {
     int P = 32;
     while (P < n) P <<= 1;
 #pragma unroll 1
@@ -320,7 +330,6 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     const double mad = (n & 1) ? wsel[1] : mul_rn(add_rn(wsel[0], wsel[1]), 0.5);
     const double thr = mul_rn(p.outlier_factor, mad);
     __syncwarp();
-    int n_out = 0;
 #pragma unroll 1
     for (int i = lane; i < n; i += 32) {
         double x[W];
@@ -330,6 +339,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     }
     n_out = warp_sum_i(n_out);
     __syncwarp();
+    }
     if (labels_out)
         for (int i = lane; i < n && i < max_fit_rows; i += 32) labels_out[(size_t)slot * max_fit_rows + i] = lab[i];
 
@@ -402,7 +412,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 #pragma unroll
         for (int j = 0; j < W; ++j) {
             lo[j] = warp_min(lo[j]); hi[j] = warp_max(hi[j]);
-            ok_all &= hi[j] > lo[j];
+            if (p.add_uniform) ok_all &= hi[j] > lo[j];
             if (lane == 0) { out.box[((size_t)slot * W + j) * 2] = lo[j]; out.box[((size_t)slot * W + j) * 2 + 1] = hi[j]; }
         }
     }
@@ -418,7 +428,8 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             double v = 0.0;
             if (e > a) {
                 const int kk = lane == 0 ? k0 : (lane == 1 ? k1 : (e - a) - k0 - k1);
-                v = log(((double)kk + 0.5) / ((double)(e - a) + 1.5));
+                v = log(((double)kk + 0.5) / ((double)(e - a) + (p.add_uniform ? 1.5 : 1.0)));
+                if (lane == 2 && !p.add_uniform) v = -INFINITY;       // two-component model
             }
             out.logw[((size_t)slot * R + s) * 3 + lane] = v;
         }
@@ -562,6 +573,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     const int *fstart = c.fstart;
     load_model<W>(par, out, slot, lane, out.logw + (size_t)slot * R * 3, R * 3);
     bool failed = par->ok == 0;
+    const bool uni = p.add_uniform != 0;
 
     double carry[NS];                                   // lanes 0/1: summaries kept when S0 < 1e-7 (A3)
 #pragma unroll
@@ -604,7 +616,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 }
                 const double l0 = c0 - 0.5 * q0 + par->logw[s][0];
                 const double l1 = c1 - 0.5 * q1 + par->logw[s][1];
-                const double l2 = inside ? ul + par->logw[s][2] : -INFINITY;
+                const double l2 = (inside && uni) ? ul + par->logw[s][2] : -INFINITY;
                 // exp(l_max - l_max) = 1 exactly: only the two non-maximal terms need an exp
                 const double m = fmax(fmax(l0, l1), l2);
                 const bool m0 = l0 == m, m1 = !m0 && l1 == m;
@@ -670,10 +682,11 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             const int ns = fstart[s + 1] - fstart[s];
             if (ns > 0) {
                 const double t0 = wtmp[2 * s], t1 = wtmp[2 * s + 1];
-                const double t2 = fmax((double)ns - t0 - t1, 0.0);
+                const double t2 = uni ? fmax((double)ns - t0 - t1, 0.0) : 0.0;
                 if (t0 + t1 + t2 != 0.0) {
                     const double vk = (k == 0 ? t0 : (k == 1 ? t1 : t2)) + 0.5;
-                    par->logw[s][k] = log(vk / ((t0 + 0.5) + (t1 + 0.5) + (t2 + 0.5)));
+                    const double den = (t0 + 0.5) + (t1 + 0.5) + (uni ? t2 + 0.5 : 0.0);
+                    par->logw[s][k] = (k == 2 && !uni) ? -INFINITY : log(vk / den);
                 }
             }
         }
@@ -749,7 +762,7 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             } else { po[0] = po[1] = po[2] = 0.0; }
         }
         double st8[8];
-        gtest_fractions(pr, rows_c, rows_t, p.fdr_threshold, st8);
+        gtest_fractions(pr, rows_c, rows_t, p.fdr_threshold, st8, p.add_uniform ? 3 : 2);
 #pragma unroll 1
         for (int k = 0; k < 8; ++k) out.stats[(size_t)slot * 8 + k] = st8[k];
         if (post != nullptr && st8[2] < p.fdr_threshold) {
@@ -789,7 +802,7 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         const double l0 = par->cst[0] - 0.5 * q0 + par->logw[0][0];
         const double l1 = par->cst[1] - 0.5 * q1 + par->logw[0][1];
-        const double l2 = inside ? par->ulogp + par->logw[0][2] : -INFINITY;
+        const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[0][2] : -INFINITY;
         const double mx = fmax(fmax(l0, l1), l2);
         const double e0 = exp(l0 - mx), e1 = exp(l1 - mx), e2 = exp(l2 - mx);
         const double inv = 1.0 / (e0 + e1 + e2);

@@ -61,16 +61,17 @@ YC_HD double xlogy(double x, double y) { return x == 0.0 ? 0.0 : x * log(y); }
 // alpha the reference passes (stats.py:354, alpha = 1 - ci/100 in floating point)
 #define YC_Z_CI95 1.959963984540054
 
-// G statistic of an nrow x ncol table without continuity correction
-// (scipy.stats.chi2_contingency(lambda_='log-likelihood'), dof != 1);
-// zero expected cell or dof 0 -> 0.0  (two_cond_g_test, stats.py:302-313).
+// G statistic of the first `ncol` columns of an nrow x 3 table (row stride 3), as
+// scipy.stats.chi2_contingency(lambda_='log-likelihood') computes it: zero expected cell or
+// dof 0 -> 0.0 (two_cond_g_test, stats.py:302-313); dof 1 (2 x 2, only with --no-uniform) gets
+// Yates' continuity correction of magnitude min(0.5, |E - O|).
 YC_HD_COLD double g_stat_table(const double *obs, int nrow, int ncol) {
     double rs[YC_MAX_SAMPLES], cs[YC_NCOMP] = {0.0, 0.0, 0.0}, tot = 0.0;
     _Pragma("unroll 1")
     for (int i = 0; i < nrow; ++i) {
         rs[i] = 0.0;
         _Pragma("unroll 1")
-        for (int j = 0; j < ncol; ++j) { rs[i] += obs[i * ncol + j]; cs[j] += obs[i * ncol + j]; }
+        for (int j = 0; j < ncol; ++j) { rs[i] += obs[i * 3 + j]; cs[j] += obs[i * 3 + j]; }
         tot += rs[i];
     }
     if (!(tot > 0.0)) return 0.0;
@@ -78,15 +79,22 @@ YC_HD_COLD double g_stat_table(const double *obs, int nrow, int ncol) {
     for (int i = 0; i < nrow; ++i) if (rs[i] == 0.0) return 0.0;
     _Pragma("unroll 1")
     for (int j = 0; j < ncol; ++j) if (cs[j] == 0.0) return 0.0;
-    if ((nrow - 1) * (ncol - 1) == 0) return 0.0;
+    const int dof = (nrow - 1) * (ncol - 1);
+    if (dof == 0) return 0.0;
     double g = 0.0;
     _Pragma("unroll 1")
-    for (int i = 0; i < nrow; ++i)
+    for (int i = 0; i < nrow; ++i) {
         _Pragma("unroll 1")
         for (int j = 0; j < ncol; ++j) {
             const double e = rs[i] * cs[j] / tot;
-            g += 2.0 * xlogy(obs[i * ncol + j], obs[i * ncol + j] / e);
+            double o = obs[i * 3 + j];
+            if (dof == 1) {
+                const double diff = e - o;
+                o += fmin(0.5, fabs(diff)) * (diff > 0.0 ? 1.0 : (diff < 0.0 ? -1.0 : 0.0));
+            }
+            g += 2.0 * xlogy(o, o / e);
         }
+    }
     return g;
 }
 
@@ -94,7 +102,8 @@ YC_HD_COLD double g_stat_table(const double *obs, int nrow, int ncol) {
 // preds: [nrow_c + nrow_t][3] rounded counts of the PRESENT samples, control
 // rows first.  gmm_g_test (stats.py:316-338) + calculate_fractional_stats
 // (stats.py:341-355).
-YC_HD_COLD void gtest_fractions(const double *preds, int nrow_c, int nrow_t, double thr, double *out) {
+YC_HD_COLD void gtest_fractions(const double *preds, int nrow_c, int nrow_t, double thr, double *out,
+                                int ncomp = 3) {
     const double nan_ = nan("");
     double c[3] = {0, 0, 0}, t[3] = {0, 0, 0};
     _Pragma("unroll 1")
@@ -125,7 +134,7 @@ YC_HD_COLD void gtest_fractions(const double *preds, int nrow_c, int nrow_t, dou
     }
     double hom;
     if (p < thr) {
-        hom = g_stat_table(preds, nrow_c, 3) + g_stat_table(preds + nrow_c * 3, nrow_t, 3);
+        hom = g_stat_table(preds, nrow_c, ncomp) + g_stat_table(preds + nrow_c * 3, nrow_t, ncomp);
         if (hom >= het) p = 1.0;
     } else {
         hom = nan_;

@@ -25,6 +25,7 @@ class EngineParams:
     fdr_threshold: float = 0.05
     outlier_factor: float = 0.5
     gmm: bool = True
+    add_uniform: bool = True
     generate_sm_preds: bool = False
     seed: int = 0
 
@@ -34,7 +35,7 @@ class EngineParams:
 
     def struct(self):
         return N.Params(window_size=self.window_size, min_read_depth=self.min_read_depth,
-                        max_fit_depth=self.max_fit_depth, gmm=int(self.gmm),
+                        max_fit_depth=self.max_fit_depth, gmm=int(self.gmm), add_uniform=int(self.add_uniform),
                         min_ks=self.min_ks, fdr_threshold=self.fdr_threshold,
                         outlier_factor=self.outlier_factor, seed=int(self.seed) & ((1 << 64) - 1))
 

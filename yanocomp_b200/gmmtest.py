@@ -79,8 +79,6 @@ class GMMTestOpts:
         if self.gmm:
             if self.covariance_type != 'full':
                 raise click.UsageError('--covariance-type diag is not implemented in yanocomp_b200')
-            if not self.add_uniform:
-                raise click.UsageError('--no-uniform is not implemented in yanocomp_b200')
             if self.outlier_method != 'mad':
                 raise click.UsageError('--outlier-method dbscan is not implemented in yanocomp_b200')
         if self.window_size % 2 == 0 or not 1 <= self.window_size <= N.YC_MAX_WINDOW:
@@ -92,7 +90,8 @@ class GMMTestOpts:
             window_size=self.window_size, min_read_depth=self.min_read_depth,
             max_fit_depth=self.max_fit_depth, min_ks=self.min_ks,
             fdr_threshold=self.fdr_threshold, outlier_factor=self.outlier_factor,
-            gmm=self.gmm, generate_sm_preds=self.generate_sm_preds and self.gmm,
+            gmm=self.gmm, add_uniform=self.add_uniform,
+            generate_sm_preds=self.generate_sm_preds and self.gmm,
             seed=self.random_seed)
 
 
@@ -164,7 +163,8 @@ def _batch_records(host, res, opts):
         if off >= 0 and res.post is not None:
             n_all = int(res.nall_fit[s])
             pos_sm = _position_sm_preds(f, c, kmers, opts, n_cntrl,
-                                        format_model(mu, res.cov[s], res.box[s], res.cw[s]),
+                                        format_model(mu, res.cov[s], res.box[s] if opts.add_uniform else None,
+                                                     res.cw[s]),
                                         res.post[off:off + n_all].copy())
         elif off == -2:
             raise RuntimeError('single-molecule posterior buffer overflow (internal sizing error)')

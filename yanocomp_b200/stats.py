@@ -33,13 +33,17 @@ def benjamini_hochberg(p):
 def format_model(mu, cov, box, cw):
     '''JSON-serialisable GMM parameters (reference stats.py:382-419)'''
     w = np.asarray(cw, dtype=np.float64)
-    w = w / w.sum()
-    return {
+    model = {
         'unmod': {'mu': mu[0].tolist(), 'cov': cov[0].tolist()},
         'mod': {'mu': mu[1].tolist(), 'cov': cov[1].tolist()},
-        'outlier': {'bounds': [[float(lo), float(hi)] for lo, hi in box]},
-        'weights': np.exp(np.log(w)).tolist(),
     }
+    if box is not None:
+        model['outlier'] = {'bounds': [[float(lo), float(hi)] for lo, hi in box]}
+    else:
+        w = w[:2]                                   # --no-uniform: two components
+    w = w / w.sum()
+    model['weights'] = np.exp(np.log(w)).tolist()
+    return model
 
 
 def format_sm_preds(preds, outlier, events, reps, read_ids):
