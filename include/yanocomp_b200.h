@@ -48,6 +48,10 @@ extern "C" {
 #define YC_MAX_SAMPLES  16     /* replicates over both conditions */
 #define YC_NCOMP        3      /* two Gaussians + uniform outlier component */
 
+/* yc_batch_t.flags: every ld[f] and x_off[f] is a multiple of 8 elements and the padding
+ * elements events[x_off + c*ld + r], n_reads <= r < ld, are NaN -> rows can be read 16 bytes at a time */
+#define YC_BATCH_ROWS_ALIGNED 1
+
 /* error codes (negative; positive values are cudaError_t) */
 #define YC_OK            0
 #define YC_EINVAL       -1     /* bad argument (see yc_last_error) */
@@ -69,7 +73,7 @@ typedef struct yc_batch {
     int32_t  n_cntrl;            /* Rc: samples [0,Rc) are control */
     int32_t  max_reads;          /* max over features of n_reads (sizes shared memory) */
     int32_t  max_cond_reads;     /* max over features of max(control rows, treatment rows) */
-    int32_t  reserved0;
+    int32_t  flags;              /* YC_BATCH_* */
     int64_t  total_cols;         /* sum of n_cols = number of candidate positions */
     const uint16_t *events;      /* IEEE binary16 bits, layout above */
     const int64_t  *x_off;       /* [F]   element offset of each feature matrix */

@@ -29,7 +29,7 @@ class Batch(C.Structure):
     _fields_ = [
         ('n_features', C.c_int32), ('n_samples', C.c_int32),
         ('n_cntrl', C.c_int32), ('max_reads', C.c_int32),
-        ('max_cond_reads', C.c_int32), ('reserved0', C.c_int32),
+        ('max_cond_reads', C.c_int32), ('flags', C.c_int32),
         ('total_cols', C.c_int64),
         ('events', C.c_void_p), ('x_off', C.c_void_p), ('n_cols', C.c_void_p),
         ('n_reads', C.c_void_p), ('ld', C.c_void_p), ('col_off', C.c_void_p),

@@ -201,6 +201,7 @@ class DeviceBatch:
         self.struct = N.Batch(
             n_features=F, n_samples=host.n_samples, n_cntrl=host.n_cntrl,
             max_reads=host.max_reads, max_cond_reads=host.max_cond_reads, total_cols=host.total_cols,
+            flags=1,        # YC_BATCH_ROWS_ALIGNED: ld is a multiple of 8 and the padding is NaN (HostBatch)
             events=self.events.data_ptr(), x_off=self.x_off.data_ptr(),
             n_cols=self.n_cols.data_ptr(), n_reads=self.n_reads.data_ptr(),
             ld=self.ld.data_ptr(), col_off=self.col_off.data_ptr(),
