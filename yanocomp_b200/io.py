@@ -71,12 +71,14 @@ def _clean_events(d, gene_id):
     '''
     e = d[f'{gene_id}/events'][:]
     key = (e['read_idx'].astype(np.int64) << 32) | e['pos'].astype(np.int64)
-    _, first = np.unique(key, return_index=True)
-    if len(first) != len(e):
-        e = e[np.sort(first)]
-    dur = e['duration'].astype(np.float64)
-    with np.errstate(divide='ignore', invalid='ignore'):
-        keep = np.log10(dur) <= 0
+    if len(key) > 1 and not (key[1:] > key[:-1]).all():
+        # prep writes events sorted by (read, pos) without repeats; only otherwise pay for a sort
+        _, first = np.unique(key, return_index=True)
+        if len(first) != len(e):
+            e = e[np.sort(first)]
+    dur = e['duration'].astype(np.float32)
+    keep = dur <= 1.0                      # log10(duration) <= 0; NaN and negative durations compare False / drop
+    keep &= dur >= 0.0
     if not keep.all():
         e = e[keep]
     r_ids = d[f'{gene_id}/read_ids'][:]
@@ -85,12 +87,34 @@ def _clean_events(d, gene_id):
     return e, r_ids.astype('U32')
 
 
+def _dense_rank(values, size):
+    '''(sorted unique values, rank of every value) for small non-negative integers, without sorting'''
+    present = np.zeros(size, dtype=bool)
+    present[values] = True
+    uniq = np.flatnonzero(present)
+    rank = np.cumsum(present, dtype=np.int64) - 1
+    return uniq, rank[values]
+
+
 def _sample_block(e, r_ids):
-    '''(sorted unique read ids, sorted positions, row index, col index, means) of one sample'''
-    ids = r_ids[e['read_idx']]
-    uniq_ids, row = np.unique(ids, return_inverse=True)
-    positions, col = np.unique(e['pos'].astype(np.int64), return_inverse=True)
-    return uniq_ids, positions, row, col, e['mean']
+    '''(read ids sorted as strings, sorted positions, row index, col index, means) of one sample'''
+    read_idx = e['read_idx'].astype(np.int64)
+    used, inv = _dense_rank(read_idx, len(r_ids))
+    ids_used = r_ids[used]
+    order = np.argsort(ids_used, kind='stable')          # unstack() sorts the rows by read id string (io.py:329-332)
+    if len(ids_used) > 1 and (ids_used[order][1:] == ids_used[order][:-1]).any():
+        raise ValueError('read ids are not unique after truncation to 32 characters')
+    rank = np.empty(len(used), dtype=np.int64)
+    rank[order] = np.arange(len(used))
+    pos = e['pos'].astype(np.int64)
+    p0 = int(pos.min()) if len(pos) else 0
+    span = int(pos.max()) - p0 + 1 if len(pos) else 0
+    if span <= 8 * max(len(pos), 1) + 1024:
+        upos, col = _dense_rank(pos - p0, span)
+        upos = upos + p0
+    else:                                                # very sparse coordinates: fall back to a sort
+        upos, col = np.unique(pos, return_inverse=True)
+    return ids_used[order], upos, rank[inv], col, e['mean']
 
 
 def _build_feature(feature_id, chrom, strand, blocks, n_samples, kmers):
