@@ -257,3 +257,31 @@ def test_no_uniform_two_component_model(ks_path):
     out = compare(feats, 4, 2, window_size=3, add_uniform=False)
     assert out['fitted'] > 20
     assert (out['res'].preds[:, :, 2] == 0).all() and (out['res'].cw[:, 2] == 0).all()
+
+
+@pytest.mark.parametrize('seed', [101, 102, 103, 104])
+def test_randomised_ragged_batches(seed, ks_path):
+    '''random replicate counts, sample sizes (some empty), dropout, strands, window sizes and gaps'''
+    rng = np.random.default_rng(seed)
+    n_c, n_t = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    R = n_c + n_t
+    w = int(rng.choice([1, 3, 5]))
+    feats = []
+    for i in range(5):
+        sizes = [int(rng.integers(0, 45)) if rng.random() < 0.15 else int(rng.integers(2 * w + 4, 60)) for _ in range(R)]
+        if sum(sizes[:n_c]) == 0:
+            sizes[0] = 20
+        if sum(sizes[n_c:]) == 0:
+            sizes[n_c] = 20
+        f = synth.make_feature(rng, f'RND{seed}_{i}', int(rng.integers(8, 40)), sizes, n_c, n_t,
+                               planted_frac=0.3, dropout=float(rng.choice([0.0, 0.05, 0.3])),
+                               strand=str(rng.choice(['+', '-'])), pos0=int(rng.integers(0, 5000)))
+        if rng.random() < 0.5 and f.n_cols > 12:
+            keep = np.ones(f.n_cols, dtype=bool)
+            keep[rng.integers(3, f.n_cols - 3, size=2)] = False
+            f = type(f)(feature_id=f.feature_id, chrom='.', strand=f.strand, pos0=0, X=f.X[keep].copy(),
+                        samp_start=f.samp_start, kmers=f.kmers, positions=f.positions[keep])
+        feats.append(f)
+    out = compare(feats, R, n_c, window_size=w, max_fit_discordance=0.02,
+                  max_fit_depth=int(rng.choice([1000, 1000, 40])))
+    assert out['windows'] >= 0
