@@ -190,20 +190,34 @@ def test_chunk(opts, gene_ids):
     chunk_res, chunk_sm = [], {}
 
     def batches():
-        '''packed batches of ~BATCH_EVENT_BYTES, decoded by `processes` host threads'''
+        '''
+        Packed batches of ~BATCH_EVENT_BYTES, decoded by `processes` host threads.  Shallow features
+        (<= 1024 reads, no sub-sampling possible) and deep ones go to separate batches: the kernels
+        are chosen per batch, and one deep gene must not push thousands of shallow ones off the
+        warp-per-position path (include/yanocomp_b200.h, yc_gmm_fit_batch).
+        '''
+        n_cntrl = len(opts.cntrl_hdf5_fns)
+
+        def shallow(f):
+            split = int(f.samp_start[n_cntrl])
+            return f.n_reads <= 1024 and max(split, f.n_reads - split) <= opts.max_fit_depth
+
         with hdf5_list(opts.cntrl_hdf5_fns) as cntrl_h5, hdf5_list(opts.treat_hdf5_fns) as treat_h5:
-            pending, nbytes = [], 0
+            pending = {True: [], False: []}
+            nbytes = {True: 0, False: 0}
             with ThreadPoolExecutor(max(1, opts.processes)) as pool:
                 loaded = pool.map(lambda gid: load_gene_features(gid, cntrl_h5, treat_h5, by_t), list(gene_ids))
                 for feats in loaded:
                     for f in feats:
-                        pending.append(f)
-                        nbytes += f.X.nbytes
-                    if nbytes >= BATCH_EVENT_BYTES:
-                        yield HostBatch(pending, R, len(opts.cntrl_hdf5_fns))
-                        pending, nbytes = [], 0
-                if pending:
-                    yield HostBatch(pending, R, len(opts.cntrl_hdf5_fns))
+                        k = shallow(f)
+                        pending[k].append(f)
+                        nbytes[k] += f.X.nbytes
+                        if nbytes[k] >= BATCH_EVENT_BYTES:
+                            yield HostBatch(pending[k], R, n_cntrl)
+                            pending[k], nbytes[k] = [], 0
+                for k in (True, False):
+                    if pending[k]:
+                        yield HostBatch(pending[k], R, n_cntrl)
 
     # upload of batch k+1 overlaps the kernels of batch k (engine.run_pipelined)
     for host, res in engine.run_pipelined(batches()):
