@@ -469,6 +469,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         double mu0[W], mu1[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) { mu0[j] = par->mu[0][j]; mu1[j] = par->mu[1][j]; }
+        double seprod = 1.0;
         for (int base = wid * 32; base < n; base += YC_NWARPS * 32) {
             const int i = base + lane;
             const bool valid = i < n;
@@ -500,7 +501,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 const double se = e0 + e1 + e2;
                 const double inv = 1.0 / se;
                 r0 = e0 * inv; r1 = e1 * inv; r2 = e2 * inv;
-                acc[2 * NS] += m + log(se);
+                acc[2 * NS] += m; seprod *= se;            // one log per thread: log prod se_i, 1 <= se_i <= 3
                 acc[0] += r0; acc[NS] += r1;
                 int q = 1 + W;
 #pragma unroll
@@ -523,6 +524,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 }
             }
         }
+        acc[2 * NS] += log(seprod);
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
             const double t = warp_sum(acc[q]);

@@ -16,6 +16,7 @@
 //    stays inside the 32 KB instruction cache.
 // Eligibility (dispatcher): w <= 5, <= 1024 reads per feature, no sub-sampling
 // possible (reads per condition <= max_fit_depth).
+#include <algorithm>
 #include <type_traits>
 #include "yc_fit_common.cuh"
 #include "yc_stats.cuh"
@@ -26,22 +27,27 @@ struct FwSmem {
     int xs_off, srow_off, lab_off, buf_off, par_off, mask_off, cnt_off, fstart_off, wtmp_off, red_off, total;
 };
 
-__host__ __device__ inline FwSmem fw_layout(int W, int R, int cap) {
+// which: 0 = init (sort buffer, labels, 2 NS reduction rows), 1 = EM (responsibilities, 2 NS + 1 + 2 R
+// reduction rows), 2 = G-test / posteriors (rows and the parameter block only)
+__host__ __device__ inline FwSmem fw_layout(int W, int R, int cap, int which) {
     FwSmem s;
     int P = 32;
     while (P < cap) P <<= 1;
+    const int NS = 1 + W + W * (W + 1) / 2;
+    const int buf_n = which == 0 ? P : (which == 1 ? 2 * cap : 0);
+    const int red_rows = which == 0 ? 2 * NS : (which == 1 ? 2 * NS + 1 + 2 * R : 1);
     int o = 0;
-    s.buf_off = o;    o += (P > 2 * cap ? P : 2 * cap) * (int)sizeof(double);   // MAD sort buffer / EM responsibilities
+    s.buf_off = o;    o += buf_n * (int)sizeof(double);                         // MAD sort buffer / EM responsibilities
     s.par_off = o;    o += (4 * W * W + 4 * W + 3 * YC_MAX_SAMPLES + 8) * (int)sizeof(double);
     s.wtmp_off = o;   o += 2 * YC_MAX_SAMPLES * (int)sizeof(double);
-    s.red_off = o;    o += (2 * (1 + W + W * (W + 1) / 2) + 1) * 33 * (int)sizeof(double);
+    s.red_off = o;    o += red_rows * 33 * (int)sizeof(double);
     s.mask_off = o;   o += ((cap + 31) / 32 + 1) * (int)sizeof(uint32_t);
     s.cnt_off = o;    o += (YC_MAX_SAMPLES + 2) * (int)sizeof(int);
     s.fstart_off = o; o += (YC_MAX_SAMPLES + 2) * (int)sizeof(int);
     s.xs_off = o;     o += W * cap * (int)sizeof(uint16_t);
     o = (o + 3) & ~3;
     s.srow_off = o;   o += cap;
-    s.lab_off = o;    o += cap;
+    s.lab_off = o;    o += which == 0 ? cap : 0;
     s.total = (o + 15) & ~15;
     return s;
 }
@@ -75,10 +81,11 @@ __device__ __forceinline__ void warp_sum_smem(double (&v)[K], double *red, int l
     __syncwarp();
 #pragma unroll 1
     for (int q = lane; q < K; q += 32) {
-        double t = 0.0;
-#pragma unroll 8
-        for (int l2 = 0; l2 < 32; ++l2) t += red[q * 33 + l2];
-        red[q * 33 + 32] = t;
+        const double *rq = red + q * 33;
+        double ta = 0.0, tb = 0.0, tc = 0.0, td = 0.0;             // four interleaved chains: latency / 4
+#pragma unroll
+        for (int l2 = 0; l2 < 32; l2 += 4) { ta += rq[l2]; tb += rq[l2 + 1]; tc += rq[l2 + 2]; td += rq[l2 + 3]; }
+        red[q * 33 + 32] = (ta + tb) + (tc + td);
     }
     __syncwarp();
 #pragma unroll
@@ -181,14 +188,17 @@ __device__ __noinline__ bool fw_front(const yc_batch_t &b, const yc_params_t &p,
 // ===========================================================================
 // Kernel 2a (warp): k-means++ x3, MAD outliers, ML Gaussians, weights, box
 // ===========================================================================
+#ifndef YC_FW_INIT_MINBLOCKS
+#define YC_FW_INIT_MINBLOCKS 20
+#endif
 template <int W>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, YC_FW_INIT_MINBLOCKS)
 init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                  const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
                  uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = b.n_samples, lane = threadIdx.x;
-    const FwSmem L = fw_layout(W, R, cap);
+    const FwSmem L = fw_layout(W, R, cap, 0);
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
     const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
@@ -199,6 +209,20 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     double *buf = c.buf, *red = c.red;
     int8_t *lab = c.lab;
     const uint64_t pkey = c.pkey;
+
+    // column totals of the fit rows (exact), so that Lloyd only accumulates one cluster
+    double sumx[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) sumx[j] = 0.0;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {
+        double x[W];
+        fw_row<W>(xs, cap, i, x);
+#pragma unroll
+        for (int j = 0; j < W; ++j) sumx[j] += x[j];
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) sumx[j] = warp_sum(sumx[j]);
 
     // ---- k-means++ x3 + Lloyd  (assumption A2)
     double best[2 * W], best_total = INFINITY;
@@ -236,34 +260,49 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         int iteration = 0;
         double improvement = INFINITY, last = INFINITY, total = INFINITY;
-        double acc[2 * W + 3];
+        double acc[W + 1];                                   // column sums of cluster 1, total distance
+        int n1 = 0;
         bool have_sums = false;
 #pragma unroll 1
         while (improvement > 0.5 && iteration < 101) {
             if (have_sums) {
+                // centroid = cluster sum / cluster size.  Cluster 0's sums are the column totals minus
+                // cluster 1's (sums of binary16 values: exact either way).  Lane q divides coordinate q
+                // (one IEEE division per lane instead of 2W per lane), the quotients are broadcast.
+                const int n0 = n - n1;
+                double num = 0.0;
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    if (acc[2 * W + 1 + k] > 0.0)
+                for (int q = 0; q < 2 * W; ++q) {
+                    const double v = q < W ? sub_rn(sumx[q < W ? q : 0], acc[q < W ? q : 0]) : acc[q < W ? 0 : q - W];
+                    if (lane == q) num = v;
+                }
+                const int den = lane < W ? n0 : n1;
+                double mine = 0.0;
+                if (lane < 2 * W && den > 0) mine = div_rn(num, (double)den);
 #pragma unroll
-                        for (int j = 0; j < W; ++j) cen[k * W + j] = div_rn(acc[k * W + j], acc[2 * W + 1 + k]);
+                for (int q = 0; q < 2 * W; ++q) {
+                    const double v = __shfl_sync(YC_FULL, mine, q);
+                    if ((q < W ? n0 : n1) > 0) cen[q] = v;   // an empty cluster keeps its centroid (A2)
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 2 * W + 3; ++k) acc[k] = 0.0;
+            for (int k = 0; k <= W; ++k) acc[k] = 0.0;
+            n1 = 0;
 #pragma unroll 1
             for (int i = lane; i < n; i += 32) {
                 double x[W];
                 fw_row<W>(xs, cap, i, x);
                 const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
                 const bool k = d1 < d0;
-                acc[2 * W] += k ? d1 : d0;
-                acc[2 * W + 1] += k ? 0.0 : 1.0;
-                acc[2 * W + 2] += k ? 1.0 : 0.0;
+                acc[W] += k ? d1 : d0;
+                n1 += k;
 #pragma unroll
-                for (int j = 0; j < W; ++j) { acc[j] += k ? 0.0 : x[j]; acc[W + j] += k ? x[j] : 0.0; }
+                for (int j = 0; j < W; ++j) acc[j] += k ? x[j] : 0.0;
             }
-            warp_sum_smem<2 * W + 3>(acc, red, lane);
+            warp_sum_smem<W + 1>(acc, red, lane);
+            n1 = warp_sum_i(n1);
             have_sums = true;
-            total = acc[2 * W];
+            total = acc[W];
             if (iteration > 0) improvement = last - total;
             ++iteration;
             last = total;
@@ -548,7 +587,7 @@ __device__ __noinline__ void load_model(EmPar<W> *par, const yc_fit_out_t &out, 
 }
 
 #ifndef YC_FW_MINBLOCKS
-#define YC_FW_MINBLOCKS 1
+#define YC_FW_MINBLOCKS 16
 #endif
 
 template <int W>
@@ -557,7 +596,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                const int32_t *__restrict__ fit_list, const yc_fit_out_t out, uint8_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = b.n_samples, lane = threadIdx.x;
-    const FwSmem L = fw_layout(W, R, cap);
+    const FwSmem L = fw_layout(W, R, cap, 1);
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT, NP = 2 * NS + 1;
     const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
@@ -585,7 +624,9 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         // ---- E-step (GeneralMixtureModel.summarize, A6) in two passes over the rows so that neither
         //      needs both the model (24 doubles) and the 2 NS + 1 accumulators in registers at once:
         //      pass 1 writes the responsibilities and the log-likelihood, pass 2 the sufficient statistics.
-        double llsum = 0.0;
+        // log-likelihood = sum_i (m_i + log se_i): the logs are taken once per lane from the running
+        // product of the se_i (1 <= se_i <= 3 and at most cap/32 <= 32 rows per lane: no overflow)
+        double llsum = 0.0, seprod = 1.0;
         {
             double mu0[W], mu1[W], li0[NT], li1[NT], blo[W], bhi[W];
 #pragma unroll
@@ -624,18 +665,32 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
                 const double se = e0 + e1 + e2, inv = 1.0 / se;
                 rb0[i] = e0 * inv; rb1[i] = e1 * inv;
-                llsum += m + log(se);
+                llsum += m; seprod *= se;
             }
         }
+        llsum += log(seprod);
         double acc[NP];
 #pragma unroll
         for (int q = 0; q < NP; ++q) acc[q] = 0.0;
         acc[2 * NS] = llsum;
+        // per-sample responsibility sums (gmm.summaries) ride along: fit rows are pooled in sample
+        // order, so a lane sees its samples in ascending order and flushes a running pair of sums
+        // into its own column of red rows NP + 2 s, NP + 2 s + 1 whenever the sample changes
+#pragma unroll 1
+        for (int q = 0; q < 2 * R; ++q) red[(NP + q) * 33 + lane] = 0.0;
+        int cur = -1;
+        double t0 = 0.0, t1 = 0.0;
 #pragma unroll 2
         for (int i = lane; i < n; i += 32) {
             double x[W];
             fw_row<W>(xs, cap, i, x);
             const double r0 = rb0[i], r1 = rb1[i];
+            const int s = srow[i];
+            if (s != cur) {
+                if (cur >= 0) { red[(NP + 2 * cur) * 33 + lane] = t0; red[(NP + 2 * cur + 1) * 33 + lane] = t1; }
+                cur = s; t0 = 0.0; t1 = 0.0;
+            }
+            t0 += r0; t1 += r1;
             acc[0] += r0; acc[NS] += r1;
             int qq = 1 + W;
 #pragma unroll
@@ -646,16 +701,18 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 for (int bb = a; bb < W; ++bb) { acc[qq] = fma(xa0, x[bb], acc[qq]); acc[NS + qq] = fma(xa1, x[bb], acc[NS + qq]); ++qq; }
             }
         }
-        // per-lane partial sums -> totals in red[q*33 + 32]
+        if (cur >= 0) { red[(NP + 2 * cur) * 33 + lane] = t0; red[(NP + 2 * cur + 1) * 33 + lane] = t1; }
+        // per-lane partial sums -> totals in red[q*33 + 32]; four interleaved chains per total
 #pragma unroll
         for (int q = 0; q < NP; ++q) red[q * 33 + lane] = acc[q];
         __syncwarp();
 #pragma unroll 1
-        for (int q = lane; q < NP; q += 32) {
-            double t = 0.0;
-#pragma unroll 8
-            for (int l2 = 0; l2 < 32; ++l2) t += red[q * 33 + l2];
-            red[q * 33 + 32] = t;
+        for (int q = lane; q < NP + 2 * R; q += 32) {
+            const double *rq = red + q * 33;
+            double ta = 0.0, tb = 0.0, tc = 0.0, td = 0.0;
+#pragma unroll
+            for (int l2 = 0; l2 < 32; l2 += 4) { ta += rq[l2]; tb += rq[l2 + 1]; tc += rq[l2 + 2]; td += rq[l2 + 3]; }
+            red[q * 33 + 32] = (ta + tb) + (tc + td);
         }
         __syncwarp();
         const double ll = red[2 * NS * 33 + 32];
@@ -664,28 +721,18 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         last = ll;
         if (!isfinite(ll)) { failed = true; break; }                     // assumption A5
         if (!(improvement > 0.1 && iteration < 1001)) break;             // last E-step's summaries discarded
-        // ---- per-sample responsibility sums -> weights (stats.py:206-211); the uniform
-        //      component's sum is n_s - sum r0 - sum r1 (responsibilities sum to one)
+        // ---- weights from the per-sample sums (stats.py:206-211), one lane per (sample, component);
+        //      the uniform component's sum is n_s - sum r0 - sum r1 (responsibilities sum to one)
 #pragma unroll 1
-        for (int s = 0; s < R; ++s) {
-            const int a = fstart[s], e = fstart[s + 1];
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll 1
-            for (int i = a + lane; i < e; i += 32) { t0 += rb0[i]; t1 += rb1[i]; }
-            t0 = warp_sum(t0); t1 = warp_sum(t1);
-            if (lane == 0) { wtmp[2 * s] = t0; wtmp[2 * s + 1] = t1; }
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int q = lane; q < 3 * R; q += 32) {        // one lane per (sample, component): logs in parallel
+        for (int q = lane; q < 3 * R; q += 32) {
             const int s = q / 3, k = q - 3 * s;
             const int ns = fstart[s + 1] - fstart[s];
             if (ns > 0) {
-                const double t0 = wtmp[2 * s], t1 = wtmp[2 * s + 1];
-                const double t2 = uni ? fmax((double)ns - t0 - t1, 0.0) : 0.0;
-                if (t0 + t1 + t2 != 0.0) {
-                    const double vk = (k == 0 ? t0 : (k == 1 ? t1 : t2)) + 0.5;
-                    const double den = (t0 + 0.5) + (t1 + 0.5) + (uni ? t2 + 0.5 : 0.0);
+                const double t0s = red[(NP + 2 * s) * 33 + 32], t1s = red[(NP + 2 * s + 1) * 33 + 32];
+                const double t2s = uni ? fmax((double)ns - t0s - t1s, 0.0) : 0.0;
+                if (t0s + t1s + t2s != 0.0) {
+                    const double vk = (k == 0 ? t0s : (k == 1 ? t1s : t2s)) + 0.5;
+                    const double den = (t0s + 0.5) + (t1s + 0.5) + (uni ? t2s + 0.5 : 0.0);
                     par->logw[s][k] = (k == 2 && !uni) ? -INFINITY : log(vk / den);
                 }
             }
@@ -696,29 +743,28 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         __syncwarp();
         failed = par->ok == 0;
     }
-    // ---- results (fit_multisamp_gmm, stats.py:250-253)
+    // ---- results (fit_multisamp_gmm, stats.py:250-253): size-weighted mean of the sample weights,
+    //      one lane per (sample, component) for the exponentials
     if (lane == 0) {
         out.iters[slot] = iteration;
         out.loglik[slot] = last;
-        if (failed) status[g] = YC_ST_FIT_FAILED;
-        else {
-            status[g] = YC_ST_TESTED;
-            double cw[3] = {0.0, 0.0, 0.0}, tot = 0.0;
-#pragma unroll 1
-            for (int s = 0; s < R; ++s) {
-                const double ns = (double)(fstart[s + 1] - fstart[s]);
-                if (ns > 0.0) {
-#pragma unroll 1
-                    for (int k = 0; k < 3; ++k) cw[k] += exp(par->logw[s][k]) * ns;
-                    tot += ns;
-                }
-            }
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) out.cw[(size_t)slot * 3 + k] = cw[k] / tot;
-        }
+        status[g] = failed ? YC_ST_FIT_FAILED : YC_ST_TESTED;
     }
     if (failed) return;
     __syncwarp();
+#pragma unroll 1
+    for (int q = lane; q < 3 * R; q += 32) {
+        const int s = q / 3, k = q - 3 * s;
+        const double ns = (double)(fstart[s + 1] - fstart[s]);
+        red[q] = ns > 0.0 ? exp(par->logw[s][k]) * ns : 0.0;
+    }
+    __syncwarp();
+    if (lane < 3) {
+        double cwk = 0.0;
+#pragma unroll 1
+        for (int s = 0; s < R; ++s) cwk += red[3 * s + lane];
+        out.cw[(size_t)slot * 3 + lane] = cwk / (double)n;                // n = sum of the present samples' sizes
+    }
     for (int i = lane; i < 2 * W; i += 32) out.mu[(size_t)slot * 2 * W + i] = par->mu[i / W][i % W];
     for (int i = lane; i < 2 * W * W; i += 32) out.cov[(size_t)slot * 2 * W * W + i] = par->cov[i / (W * W)][i % (W * W)];
     for (int i = lane; i < R * 3; i += 32) out.logw[(size_t)slot * R * 3 + i] = par->logw[i / 3][i % 3];
@@ -735,7 +781,7 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                   const long long post_capacity, unsigned long long *__restrict__ post_cursor) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = b.n_samples, Rc = b.n_cntrl, lane = threadIdx.x;
-    const FwSmem L = fw_layout(W, R, cap);
+    const FwSmem L = fw_layout(W, R, cap, 2);
     const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
     if (status[g] != YC_ST_TESTED) { if (lane == 0) out.post_off[slot] = -1; return; }
@@ -823,8 +869,12 @@ bool fit_warp_eligible(const yc_batch_t &b, const yc_params_t &p) {
     return p.window_size <= 5 && b.max_reads <= 1024 && b.max_cond_reads <= p.max_fit_depth && b.max_cond_reads > 0;
 }
 
-int fit_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p) {
-    return fw_layout(p.window_size, b.n_samples, fw_cap(b)).total;
+static int fw_smem(const yc_batch_t &b, const yc_params_t &p, int which) {
+    return fw_layout(p.window_size, b.n_samples, fw_cap(b), which).total;
+}
+
+int fit_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p) {       // the largest of the three kernels
+    return std::max(fw_smem(b, p, 0), std::max(fw_smem(b, p, 1), fw_smem(b, p, 2)));
 }
 
 template <typename F>
@@ -840,7 +890,7 @@ static int dispatch_w135(int W, F &&f) {
 int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
                        const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st) {
     if (n_fit <= 0) return 0;
-    const int cap = fw_cap(b), smem = fit_warp_smem_bytes(b, p);
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 0);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(init_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -853,7 +903,7 @@ int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t 
 int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
                      const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
     if (n_fit <= 0) return 0;
-    const int cap = fw_cap(b), smem = fit_warp_smem_bytes(b, p);
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 1);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(em_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -867,7 +917,7 @@ int gtest_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t
                         const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
                         int64_t *post_cursor, cudaStream_t st) {
     if (n_fit <= 0) return 0;
-    const int cap = fw_cap(b), smem = fit_warp_smem_bytes(b, p);
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 2);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(gtest_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -35,7 +35,7 @@ struct KwSmem {
 __host__ __device__ inline KwSmem kw_layout(int W, int R, int max_reads, int P) {
     KwSmem s;
     int o = 0;
-    s.sort_off = o; o += 2 * P * (int)sizeof(double);
+    s.sort_off = o; o += (2 * P + P / 8 + 2) * (int)sizeof(double);     // + 1 pad per 16 (register-sort write-back)
     s.tab_off = o;  o += 2 * (P + 1) * (int)sizeof(double);
     s.gt_off = o;   o += 32 * (2 * W * W + 2 * W) * (int)sizeof(double);
     s.v_off = o;    o += 32 * W * (int)sizeof(double);
@@ -65,6 +65,118 @@ __device__ __noinline__ void warp_bitonic(double *a, int P, int nseg, int lane) 
             __syncwarp();
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Register-resident sort + ECDF difference (round-1 profile: the shared-memory bitonic sort was
+// 35 % of this kernel's instructions and the per-element binary searches another 10 %).
+//
+// Both samples (each padded with +inf to P = 16 E values) sit in a[0..P) and a[P..2P).  Lane l
+// loads E of them -- lanes 0-15 the control sample, lanes 16-31 the treatment sample -- and the
+// warp sorts both halves at once with a bitonic network in the "mirror" formulation (first step
+// of every merge compares i with i ^ (k-1), the rest i with i ^ j): the lower index always keeps
+// the minimum, so there is no direction flag, strides below E are register-to-register DMNMX
+// pairs and strides >= E one 64-bit shuffle + one DMNMX per value.  The sorted values go back to
+// shared memory (index i at i + i/16: conflict-free 64-bit stores for the blocked layout), and
+// every lane then walks ITS E consecutive sorted values: the count in the own sample is the
+// index of the last equal value + 1, the count in the other sample comes from one binary search
+// for the first value and a linear advance for the rest (counts are monotone).
+// Returns max |c1/n1 - c2/n2| over the pooled points (np.searchsorted side='right' semantics),
+// with the same separately rounded operations as before: tabA[c] = c / n1, tabB[c] = c / n2.
+#define YC_KPAD(i) ((i) + ((i) >> 4))
+
+// compare-exchange of two finite-or-inf doubles (no NaNs reach the sort): one DSETP + selects,
+// instead of the NaN-aware fmin / fmax sequences
+__device__ __forceinline__ void cmpx(double &lo, double &hi) {
+    const bool sw = lo > hi;
+    const double a = sw ? hi : lo, b = sw ? lo : hi;
+    lo = a; hi = b;
+}
+// the lower lane of a pair keeps the smaller value, the upper lane the larger one
+__device__ __forceinline__ double keep_side(double mine, double other, bool lower) {
+    const bool take = (other < mine) == lower;          // equal values: either copy will do
+    return take ? other : mine;
+}
+
+template <int E>
+__device__ __noinline__ double ks_sort_ecdf(double *a, const double *tabA, const double *tabB,
+                                            int n1, int n2, int lane) {
+    constexpr int P = 16 * E;
+    const int half = lane >> 4, l16 = lane & 15;
+    double v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = a[half * P + e * 16 + l16];      // any assignment will do before the sort
+    __syncwarp();
+#pragma unroll
+    for (int k = 2; k <= P; k <<= 1) {
+        // first step of the merge: partner i ^ (k - 1)
+        if (k <= E) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int o = e ^ (k - 1);
+                if (e < o) cmpx(v[e], v[o]);
+            }
+        } else {
+            const int lm = k / E - 1;                                    // partner lane, values mirrored inside the lane
+            const bool lower = (lane & (k / (2 * E))) == 0;
+            double t[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) t[e] = __shfl_xor_sync(YC_FULL, v[E - 1 - e], lm);
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = keep_side(v[e], t[e], lower);
+        }
+        // remaining steps: partner i ^ j
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            if (j < E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if ((e & j) == 0) cmpx(v[e], v[e | j]);
+            } else {
+                const int lm = j / E;
+                const bool lower = (lane & lm) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double t = __shfl_xor_sync(YC_FULL, v[e], lm);
+                    v[e] = keep_side(v[e], t, lower);
+                }
+            }
+        }
+    }
+    // sorted: global index i = lane * E + e (control sample 0..P-1, treatment sample P..2P-1)
+#pragma unroll
+    for (int e = 0; e < E; ++e) a[YC_KPAD(lane * E + e)] = v[e];
+    __syncwarp();
+    const int own_base = half * P, oth_base = P - own_base;
+    const int n_own = half ? n2 : n1, n_oth = half ? n1 : n2;
+    const int i0 = l16 * E;
+    double dmax = 0.0;
+    if (i0 < n_own) {
+        int co;                                                          // values <= v in the other sample
+        {
+            int lo = 0, hi = n_oth;
+            const double v0 = v[0];
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a[YC_KPAD(oth_base + mid)] <= v0) lo = mid + 1; else hi = mid;
+            }
+            co = lo;
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int i = i0 + e;
+            if (i < n_own) {
+                const double x = v[e];
+                int cs = i + 1;                                          // values <= x in the own sample
+                while (cs < n_own && a[YC_KPAD(own_base + cs)] == x) ++cs;
+                if (e > 0) while (co < n_oth && a[YC_KPAD(oth_base + co)] <= x) ++co;
+                const int c1 = half ? co : cs, c2 = half ? cs : co;
+                dmax = fmax(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
+            }
+        }
+    }
+    __syncwarp();
+    return warp_max(dmax);
 }
 
 // warp-local window scan: per-column non-null masks and the complete-row mask go to shared
@@ -250,7 +362,7 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
         }
         if (n1 != tab_n1) { for (int i = lane; i <= n1; i += 32) tabA[i] = div_rn((double)i, (double)n1); tab_n1 = n1; }
         if (n2 != tab_n2) { for (int i = lane; i <= n2; i += 32) tabB[i] = div_rn((double)i, (double)n2); tab_n2 = n2; }
-        const int Pq = next_pow2(max(n1, n2));
+        const int Pq = max(32, next_pow2(max(n1, n2)));
         for (int i = lane; i < 2 * Pq; i += 32) sortbuf[i] = INFINITY;
         __syncwarp();
         int ca = 0, cb = 0;
@@ -269,27 +381,36 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
             ca += __popc(ma); cb += __popc(mb);
         }
         __syncwarp();
-        warp_bitonic(sortbuf, Pq, 2, lane);
-        const double *A = sortbuf, *B = sortbuf + Pq;
         double dmax = 0.0;
-        for (int i = lane; i < n1 + n2; i += 32) {
-            // ECDF counts at pooled point v: in its own (sorted) sample the count is the index of the
-            // last element equal to v plus one; only the other sample needs a binary search
-            int c1, c2;
-            if (i < n1) {
-                const double v = A[i];
-                int e = i + 1;
-                while (e < n1 && A[e] == v) ++e;
-                c1 = e; c2 = upper_bound(B, n2, v);
-            } else {
-                const double v = B[i - n1];
-                int e = i - n1 + 1;
-                while (e < n2 && B[e] == v) ++e;
-                c2 = e; c1 = upper_bound(A, n1, v);
+        if (Pq <= 256) {
+            // sort + ECDF difference in registers (2 Pq / 32 values per lane)
+            switch (Pq) {
+                case 32:  dmax = ks_sort_ecdf<2>(sortbuf, tabA, tabB, n1, n2, lane); break;
+                case 64:  dmax = ks_sort_ecdf<4>(sortbuf, tabA, tabB, n1, n2, lane); break;
+                case 128: dmax = ks_sort_ecdf<8>(sortbuf, tabA, tabB, n1, n2, lane); break;
+                default:  dmax = ks_sort_ecdf<16>(sortbuf, tabA, tabB, n1, n2, lane); break;
             }
-            dmax = fmax(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
+        } else {
+            // deep positions (> 256 reads per condition): shared-memory sort, one binary search per value
+            warp_bitonic(sortbuf, Pq, 2, lane);
+            const double *A = sortbuf, *B = sortbuf + Pq;
+            for (int i = lane; i < n1 + n2; i += 32) {
+                int c1, c2;
+                if (i < n1) {
+                    const double v = A[i];
+                    int e = i + 1;
+                    while (e < n1 && A[e] == v) ++e;
+                    c1 = e; c2 = upper_bound(B, n2, v);
+                } else {
+                    const double v = B[i - n1];
+                    int e = i - n1 + 1;
+                    while (e < n2 && B[e] == v) ++e;
+                    c2 = e; c1 = upper_bound(A, n1, v);
+                }
+                dmax = fmax(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
+            }
+            dmax = warp_max(dmax);
         }
-        dmax = warp_max(dmax);
         if (lane == q) my_d = dmax;
         __syncwarp();
     }
