@@ -119,6 +119,8 @@ typedef struct yc_fit_out {
 
 const char *yc_version(void);
 const char *yc_last_error(void);
+/* number of kernels this library has launched in this process (monotonic; callers take differences) */
+uint64_t    yc_kernel_launches(void);
 
 /* how many bytes of dynamic shared memory the kernels need for this batch
  * (so a caller can reject a batch up front); returns YC_ECAPACITY if any

@@ -61,6 +61,7 @@ _P = C.POINTER
 _PROTOTYPES = {
     'yc_version': (C.c_char_p, []),
     'yc_last_error': (C.c_char_p, []),
+    'yc_kernel_launches': (C.c_uint64, []),
     'yc_smem_bytes': (C.c_int, [_P(Batch), _P(Params), _P(C.c_int64)]),
     'yc_fill_col_feature': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'yc_ks_batch': (C.c_int, [_P(Batch), _P(Params)] + [C.c_void_p] * 8),

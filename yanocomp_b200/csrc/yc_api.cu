@@ -1,4 +1,5 @@
 // extern "C" surface of libyanocomp_b200.so (see include/yanocomp_b200.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -89,12 +90,15 @@ __global__ void svd_v1_kernel(const double *__restrict__ G, const double *__rest
 
 namespace yc {
 int ks_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }
 
 extern "C" {
 
 const char *yc_version(void) { return "yanocomp_b200 0.1.0 (sm_100a)"; }
 const char *yc_last_error(void) { return g_err; }
+uint64_t yc_kernel_launches(void) { return (uint64_t)yc::g_launches.load(std::memory_order_relaxed); }
 
 int yc_smem_bytes(const yc_batch_t *b, const yc_params_t *p, int64_t out[4]) {
     if (int e = check_common(b, p)) return e;
@@ -113,6 +117,7 @@ int yc_fill_col_feature(int32_t n_features, const int64_t *col_off, int32_t *col
     if (n_features <= 0) return 0;
     const int grid = n_features < 148 * 8 ? n_features : 148 * 8;
     fill_col_feature_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n_features, col_off, col_feature);
+    yc::count_launches(1);
     return cuda_fail((int)cudaGetLastError(), "yc_fill_col_feature");
 }
 

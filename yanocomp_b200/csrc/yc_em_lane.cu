@@ -24,6 +24,7 @@
 //    stay in step: read phase (all lanes), then end-of-iteration phase
 //    (M-step for the lanes that continue, store + reload for those that stop).
 #include "yc_fit_common.cuh"
+#include "yc_internal.h"
 #include "yc_stats.cuh"
 
 namespace yc {
@@ -374,6 +375,7 @@ int em_lane_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *f
         if (lanes > n_fit) lanes = n_fit;
         const int grid = (int)((lanes + 127) / 128);
         kernel<<<grid, 128, 0, st>>>(b, p, fit_list, n_fit, out, status, counters[dev]);
+        count_launches(1);
         return (int)cudaGetLastError();
     };
     switch (p.window_size) {

@@ -16,6 +16,7 @@
 // is written with separately rounded operations to reproduce the oracle bit
 // for bit; EM runs in FP64 with fused multiply-adds.
 #include "yc_common.cuh"
+#include "yc_internal.h"
 #include "yc_stats.cuh"
 #include "yc_fit_common.cuh"
 
@@ -754,6 +755,7 @@ int init_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_
         cudaError_t e = cudaFuncSetAttribute(gmm_init_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         gmm_init_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
+        count_launches(1);
         return (int)cudaGetLastError();
     });
 }
@@ -768,6 +770,7 @@ int em_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_li
         cudaError_t e = cudaFuncSetAttribute(gmm_em_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         gmm_em_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, out, status);
+        count_launches(1);
         return (int)cudaGetLastError();
     });
 }
@@ -785,6 +788,7 @@ int gtest_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit
         gtest_smpred_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(
             b, p, cap, fit_list, out, status, post, (long long)post_capacity,
             reinterpret_cast<unsigned long long *>(post_cursor));
+        count_launches(1);
         return (int)cudaGetLastError();
     });
 }

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <type_traits>
 #include "yc_fit_common.cuh"
+#include "yc_internal.h"
 #include "yc_stats.cuh"
 
 namespace yc {
@@ -479,6 +480,25 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 // ===========================================================================
 // Kernel 2b (warp): EM
 // ===========================================================================
+// inertia of the M-step before E-step `iteration` (stats.py:202): 1 - 0.99 (2 + iteration)^-0.001,
+// tabulated on the host (the same libm pow the reference's Python float power calls) instead of
+// a pow() per position and iteration on two lanes
+__constant__ double c_em_step[1008];
+
+static int upload_em_steps() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 64 && done[dev]) return 0;
+    double h[1008];
+    for (int it = 0; it < 1008; ++it) h[it] = 1.0 - (0.99 * pow(2.0 + (double)it, -1e-3));
+    e = cudaMemcpyToSymbol(c_em_step, h, sizeof(h));
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 64) done[dev] = true;
+    return 0;
+}
+
 // M-step of one shared Gaussian (reference stats.py:202-205 via pomegranate from_summaries,
 // assumptions A3/A4).  One lane per component runs it, so it is written for latency: everything
 // in registers, fully unrolled for the small W of this path, reciprocals instead of divisions,
@@ -586,6 +606,13 @@ __device__ __noinline__ void load_model(EmPar<W> *par, const yc_fit_out_t &out, 
     __syncwarp();
 }
 
+#ifndef YC_EM_UNROLL1
+#define YC_EM_UNROLL1 1
+#endif
+#ifndef YC_EM_UNROLL2
+#define YC_EM_UNROLL2 1
+#endif
+constexpr int kEmUnroll1 = YC_EM_UNROLL1, kEmUnroll2 = YC_EM_UNROLL2;
 #ifndef YC_FW_MINBLOCKS
 #define YC_FW_MINBLOCKS 16
 #endif
@@ -639,7 +666,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                     for (int bb = 0; bb <= a; ++bb) { li0[q] = par->linv[0][a * W + bb]; li1[q] = par->linv[1][a * W + bb]; ++q; }
             }
             const double c0 = par->cst[0], c1 = par->cst[1], ul = par->ulogp;
-#pragma unroll 2
+#pragma unroll kEmUnroll1
             for (int i = lane; i < n; i += 32) {
                 double x[W];
                 fw_row<W>(xs, cap, i, x);
@@ -680,7 +707,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         for (int q = 0; q < 2 * R; ++q) red[(NP + q) * 33 + lane] = 0.0;
         int cur = -1;
         double t0 = 0.0, t1 = 0.0;
-#pragma unroll 2
+#pragma unroll kEmUnroll2
         for (int i = lane; i < n; i += 32) {
             double x[W];
             fw_row<W>(xs, cap, i, x);
@@ -738,8 +765,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             }
         }
         // ---- M-step of the shared Gaussians: lane k owns component k (stats.py:202-205, A3/A4)
-        const double step = 1.0 - (0.99 * pow(2.0 + (double)iteration, -1e-3));
-        if (lane < 2) em_mstep<W>(par, lane, red, carry, step);
+        if (lane < 2) em_mstep<W>(par, lane, red, carry, c_em_step[iteration]);
         __syncwarp();
         failed = par->ok == 0;
     }
@@ -896,6 +922,7 @@ int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t 
         cudaError_t e = cudaFuncSetAttribute(init_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         init_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
+        count_launches(1);
         return (int)cudaGetLastError();
     });
 }
@@ -903,12 +930,14 @@ int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t 
 int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
                      const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
     if (n_fit <= 0) return 0;
+    if (int e = upload_em_steps()) return e;
     const int cap = fw_cap(b), smem = fw_smem(b, p, 1);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(em_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         em_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status);
+        count_launches(1);
         return (int)cudaGetLastError();
     });
 }
@@ -924,6 +953,7 @@ int gtest_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t
         if (e != cudaSuccess) return (int)e;
         gtest_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, post, (long long)post_capacity,
                                                        reinterpret_cast<unsigned long long *>(post_cursor));
+        count_launches(1);
         return (int)cudaGetLastError();
     });
 }

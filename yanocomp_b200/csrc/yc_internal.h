@@ -4,6 +4,8 @@
 #include "../../include/yanocomp_b200.h"
 
 namespace yc {
+// kernel launches made by this library in this process (yc_kernel_launches in the C ABI)
+void count_launches(int n);
 int ks_sort_cap(const yc_batch_t &b, const yc_params_t &p);
 int ks_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
 int ks_dispatch(const yc_batch_t &b, const yc_params_t &p,

@@ -15,6 +15,7 @@
 // bit-exact as long as the ORDER of the projections is right; the projections
 // are computed in FP64 and only their order is used.
 #include "yc_common.cuh"
+#include "yc_internal.h"
 #include "yc_stats.cuh"
 #include "yc_svdsign.cuh"
 
@@ -242,6 +243,7 @@ static int launch_ks(const yc_batch_t &b, const yc_params_t &p, int sort_cap, in
     if (e != cudaSuccess) return (int)e;
     ks_kernel<W><<<(unsigned)b.total_cols, YC_BLOCK, smem, st>>>(
         b, p, sort_cap, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count);
+    count_launches(1);
     return (int)cudaGetLastError();
 }
 

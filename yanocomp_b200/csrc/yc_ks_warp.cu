@@ -21,33 +21,13 @@
 // Eligibility (checked by the dispatcher): w <= 5, reads per feature <= 1024
 // and no sub-sampling possible (reads per condition <= max_fit_depth).
 #include "yc_common.cuh"
+#include "yc_internal.h"
 #include "yc_stats.cuh"
 #include "yc_svdsign.cuh"
 
 namespace yc {
 
 #define YC_KW_WARPS 4
-
-struct KwSmem {
-    int sort_off, gt_off, v_off, st_off, mask_off, cnt_off, ridx_off, wc_off, cm_off, tab_off, per_warp;
-};
-
-__host__ __device__ inline KwSmem kw_layout(int W, int R, int max_reads, int P) {
-    KwSmem s;
-    int o = 0;
-    s.sort_off = o; o += (2 * P + P / 8 + 2) * (int)sizeof(double);     // + 1 pad per 16 (register-sort write-back)
-    s.tab_off = o;  o += 2 * (P + 1) * (int)sizeof(double);
-    s.gt_off = o;   o += 32 * (2 * W * W + 2 * W) * (int)sizeof(double);
-    s.v_off = o;    o += 32 * W * (int)sizeof(double);
-    s.wc_off = o;   o += 32 * W * (int)sizeof(void *);
-    s.st_off = o;   o += 32 * 8 * (int)sizeof(int);
-    s.mask_off = o; o += 32 * ((max_reads + 31) / 32) * (int)sizeof(uint32_t);
-    s.cnt_off = o;  o += (W + 1) * R * (int)sizeof(int);
-    s.cm_off = o;   o += W * ((max_reads + 31) / 32) * (int)sizeof(uint32_t);
-    s.ridx_off = o; o += 16 * (int)sizeof(int);
-    s.per_warp = (o + 15) & ~15;
-    return s;
-}
 
 __device__ __noinline__ void warp_bitonic(double *a, int P, int nseg, int lane) {
     const int pairs = (P * nseg) >> 1;
@@ -107,41 +87,41 @@ __device__ __noinline__ double ks_sort_ecdf(double *a, const double *tabA, const
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = a[half * P + e * 16 + l16];      // any assignment will do before the sort
     __syncwarp();
+    // 1. every lane sorts its own E values (static network, registers only)
 #pragma unroll
-    for (int k = 2; k <= P; k <<= 1) {
-        // first step of the merge: partner i ^ (k - 1)
-        if (k <= E) {
+    for (int k = 2; k <= E; k <<= 1) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int o = e ^ (k - 1);
-                if (e < o) cmpx(v[e], v[o]);
-            }
-        } else {
-            const int lm = k / E - 1;                                    // partner lane, values mirrored inside the lane
-            const bool lower = (lane & (k / (2 * E))) == 0;
+        for (int e = 0; e < E; ++e) { const int o = e ^ (k - 1); if (e < o) cmpx(v[e], v[o]); }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1)
+#pragma unroll
+            for (int e = 0; e < E; ++e) if ((e & j) == 0) cmpx(v[e], v[e | j]);
+    }
+    // 2. merges across lanes, k = 2E .. P.  Rolled loops with run-time lane masks: the body is the
+    //    same code for every k, which keeps the routine inside the instruction cache.
+#pragma unroll 1
+    for (int kl = 2; kl <= 16; kl <<= 1) {                              // kl = k / E
+        {   // first step of the merge: partner i ^ (k - 1) = lane ^ (kl - 1), values mirrored inside the lane
+            const bool lower = (lane & (kl >> 1)) == 0;
             double t[E];
 #pragma unroll
-            for (int e = 0; e < E; ++e) t[e] = __shfl_xor_sync(YC_FULL, v[E - 1 - e], lm);
+            for (int e = 0; e < E; ++e) t[e] = __shfl_xor_sync(YC_FULL, v[E - 1 - e], kl - 1);
 #pragma unroll
             for (int e = 0; e < E; ++e) v[e] = keep_side(v[e], t[e], lower);
         }
-        // remaining steps: partner i ^ j
+#pragma unroll 1
+        for (int jl = kl >> 2; jl > 0; jl >>= 1) {                      // partner i ^ j, j = jl * E >= E
+            const bool lower = (lane & jl) == 0;
 #pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
-            if (j < E) {
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if ((e & j) == 0) cmpx(v[e], v[e | j]);
-            } else {
-                const int lm = j / E;
-                const bool lower = (lane & lm) == 0;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const double t = __shfl_xor_sync(YC_FULL, v[e], lm);
-                    v[e] = keep_side(v[e], t, lower);
-                }
+            for (int e = 0; e < E; ++e) {
+                const double t = __shfl_xor_sync(YC_FULL, v[e], jl);
+                v[e] = keep_side(v[e], t, lower);
             }
         }
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1)                            // partner i ^ j inside the lane
+#pragma unroll
+            for (int e = 0; e < E; ++e) if ((e & j) == 0) cmpx(v[e], v[e | j]);
     }
     // sorted: global index i = lane * E + e (control sample 0..P-1, treatment sample P..2P-1)
 #pragma unroll
@@ -215,48 +195,62 @@ __device__ __forceinline__ void warp_window_scan(const Window<W> &w, int R, uint
     }
 }
 
+// transient status between the three kernels: passed the filters, moments stored, D pending
+#define YC_ST_KS_PENDING 7
+
+// ---------------------------------------------------------------------------
+// Kernel 1a: window filters + exact moments.  One CTA = 32 adjacent columns, warp w takes columns
+// w, w + 4, ... (adjacent columns share w-1 rows: L1 reuse inside the CTA).  Per position, all
+// 32 lanes: complete-row mask, depth counters, raw moments -> means, population stds,
+// G = Z^T Z, the first W rows of Z.  Staged in shared memory and written transposed
+// (scr[k * ncol + i]) so that kernels 1b / 1c read them coalesced.
+// ---------------------------------------------------------------------------
+struct KmSmem { int gt_off, st_off, mask_off, cm_off, cnt_off, ridx_off, total; };
+
+__host__ __device__ inline KmSmem km_layout(int W, int R, int max_reads) {
+    KmSmem s;
+    const int nw = (max_reads + 31) / 32;
+    int o = 0;
+    s.gt_off = o;   o += 32 * (2 * W * W + 2 * W) * (int)sizeof(double);
+    s.st_off = o;   o += 32 * 4 * (int)sizeof(int);
+    s.mask_off = o; o += YC_KW_WARPS * nw * (int)sizeof(uint32_t);
+    s.cm_off = o;   o += YC_KW_WARPS * W * nw * (int)sizeof(uint32_t);
+    s.cnt_off = o;  o += YC_KW_WARPS * (W + 1) * R * (int)sizeof(int);
+    s.ridx_off = o; o += YC_KW_WARPS * 16 * (int)sizeof(int);
+    s.total = (o + 15) & ~15;
+    return s;
+}
+
 template <int W>
 __global__ void __launch_bounds__(YC_KW_WARPS * 32)
-ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
-               double *__restrict__ ks_stat, double *__restrict__ ks_pval,
-               int32_t *__restrict__ n_c_out, int32_t *__restrict__ n_t_out,
-               uint8_t *__restrict__ status, int32_t *__restrict__ fit_list,
-               int32_t *__restrict__ fit_count) {
+ks_moments_kernel(const yc_batch_t b, const yc_params_t p, const int64_t c0, const int ncol,
+                  double *__restrict__ scr, int32_t *__restrict__ n_c_out, int32_t *__restrict__ n_t_out,
+                  uint8_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = b.n_samples, Rc = b.n_cntrl;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const KwSmem L = kw_layout(W, R, b.max_reads, P);
-    unsigned char *base_ptr = smem_raw + (size_t)wid * L.per_warp;
-    double *sortbuf = reinterpret_cast<double *>(base_ptr + L.sort_off);
-    double *gt = reinterpret_cast<double *>(base_ptr + L.gt_off);
-    double *vbuf = reinterpret_cast<double *>(base_ptr + L.v_off);
-    const uint16_t **wcache = reinterpret_cast<const uint16_t **>(base_ptr + L.wc_off);
-    int *st = reinterpret_cast<int *>(base_ptr + L.st_off);       // [32][8]: state, n_c, n_t, n_reads, split
-    uint32_t *masks = reinterpret_cast<uint32_t *>(base_ptr + L.mask_off);
-    int *cnt = reinterpret_cast<int *>(base_ptr + L.cnt_off);
-    int *ridx = reinterpret_cast<int *>(base_ptr + L.ridx_off);
-    uint32_t *colmask = reinterpret_cast<uint32_t *>(base_ptr + L.cm_off);
-    double *tabA = reinterpret_cast<double *>(base_ptr + L.tab_off), *tabB = tabA + (P + 1);
     const int nwords_max = (b.max_reads + 31) / 32;
+    const KmSmem L = km_layout(W, R, b.max_reads);
+    double *gt = reinterpret_cast<double *>(smem_raw + L.gt_off);
+    int *st = reinterpret_cast<int *>(smem_raw + L.st_off);            // [32][4]: state, n_c, n_t
+    uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + L.mask_off) + wid * nwords_max;
+    uint32_t *colmask = reinterpret_cast<uint32_t *>(smem_raw + L.cm_off) + wid * W * nwords_max;
+    int *cnt = reinterpret_cast<int *>(smem_raw + L.cnt_off) + wid * (W + 1) * R;
+    int *ridx = reinterpret_cast<int *>(smem_raw + L.ridx_off) + wid * 16;
     constexpr int NT = W * (W + 1) / 2, GT = 2 * W * W + 2 * W;
+    const int i0 = blockIdx.x * 32;                                     // first column of the CTA inside the chunk
 
-    const int64_t g0 = ((int64_t)blockIdx.x * YC_KW_WARPS + wid) * 32;
-    if (g0 >= b.total_cols) return;                 // no block-level synchronisation anywhere below
-
-    // ------------------------------------------------------------ phase 1
-    for (int q = 0; q < 32; ++q) {
-        const int64_t g = g0 + q;
-        int state = 0, n_c = 0, n_t = 0, n = 0, split = 0;    // state 0: not a window
+#pragma unroll 1
+    for (int q = wid; q < 32; q += YC_KW_WARPS) {
+        const int64_t g = c0 + i0 + q;
+        int state = 0, n_c = 0, n_t = 0;                                // state 0: not a window
         Window<W> w;
-        if (g < b.total_cols && window_setup<W>(b, p, g, w)) {
-            n = w.n_reads;
-            split = w.samp_start[Rc];
-            uint32_t *mask = masks + q * nwords_max;
+        if (i0 + q < ncol && window_setup<W>(b, p, g, w)) {
+            const int n = w.n_reads;
             warp_window_scan<W>(w, R, mask, colmask, nwords_max, cnt, lane);
             __syncwarp();
-            if (window_depth_ok<W>(w, R, Rc, p.min_read_depth, cnt, n_c, n_t)) {
-                state = (n_c == 0 || n_t == 0) ? 1 : 2;       // 1: degenerate
-            }
+            if (window_depth_ok<W>(w, R, Rc, p.min_read_depth, cnt, n_c, n_t))
+                state = (n_c == 0 || n_t == 0) ? 1 : 2;                 // 1: degenerate
             if (state == 2) {
                 const int ntot = n_c + n_t;
                 // one pass: exact raw first and second moments (binary16 inputs: every partial sum is an
@@ -293,7 +287,7 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
 #pragma unroll
                     for (int a = 0; a < W; ++a) {
                         sig[a] = sqrt(cm[k] / (double)ntot);
-                        if (!(sig[a] > 0.0)) state = 1;          // constant column (assumption A9)
+                        if (!(sig[a] > 0.0)) state = 1;                  // constant column (assumption A9)
                         k += W - a;
                     }
                 }
@@ -306,20 +300,29 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
                         for (; found < W; ++found) ridx[found] = -1;
                     }
                     __syncwarp();
-                    double *slot = gt + q * GT;                 // G[W*W], T[W*W], mu[W], sig[W]
-                    if (lane == 0) {
-                        int k = 0;
+                    double *slot = gt + q * GT;                         // G[W*W], T[W*W], mu[W], sig[W]
+                    // G = C / (sig sig^T): lane k divides upper-triangle entry k (one division per lane)
+                    {
+                        double num = 0.0, den = 1.0;
+                        int ia = 0, ib = 0, k = 0;
+#pragma unroll
                         for (int a = 0; a < W; ++a)
+#pragma unroll
                             for (int c2 = a; c2 < W; ++c2) {
-                                const double gv = cm[k++] / (sig[a] * sig[c2]);
-                                slot[a * W + c2] = gv; slot[c2 * W + a] = gv;
+                                if (lane == k) { num = cm[k]; den = sig[a] * sig[c2]; ia = a * W + c2; ib = c2 * W + a; }
+                                ++k;
                             }
-                        for (int a = 0; a < W; ++a) { slot[2 * W * W + a] = mu[a]; slot[2 * W * W + W + a] = sig[a]; }
+                        if (lane < NT) { const double gv = num / den; slot[ia] = gv; slot[ib] = gv; }
+                    }
+                    if (lane < W) {
+                        double muj = 0.0, sigj = 1.0;
+#pragma unroll
+                        for (int jj = 0; jj < W; ++jj) if (jj == lane) { muj = mu[jj]; sigj = sig[jj]; }
+                        slot[2 * W * W + lane] = muj; slot[2 * W * W + W + lane] = sigj;
                     }
                     if (lane < W * W) {
                         const int k = lane / W, j = lane % W;
                         const int r = ridx[k];
-                        // mu / sig are identical in every lane; select without dynamic indexing
                         double muj = 0.0, sigj = 1.0;
 #pragma unroll
                         for (int jj = 0; jj < W; ++jj) if (jj == j) { muj = mu[jj]; sigj = sig[jj]; }
@@ -330,35 +333,102 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
                     }
                 }
             }
-#pragma unroll
-            for (int j = 0; j < W; ++j) if (lane == j) wcache[q * W + j] = w.col[j];
         }
-        if (lane == 0) { int *s = st + q * 8; s[0] = state; s[1] = n_c; s[2] = n_t; s[3] = n; s[4] = split; }
+        if (lane == 0) { int *s4 = st + q * 4; s4[0] = state; s4[1] = state ? n_c : 0; s4[2] = state ? n_t : 0; }
         __syncwarp();
     }
-    // ------------------------------------------------------------ phase 2
-    if (st[lane * 8] == 2) {
-        const double *slot = gt + lane * GT;
-        lapack::first_right_singular_vector<W>(slot, slot + W * W, vbuf + lane * W);
+    __syncthreads();
+    // coalesced write-out: per-column bookkeeping, then the moment block transposed
+    if (wid == 0 && i0 + lane < ncol) {
+        const int64_t g = c0 + i0 + lane;
+        const int state = st[lane * 4];
+        n_c_out[g] = st[lane * 4 + 1]; n_t_out[g] = st[lane * 4 + 2];
+        status[g] = state == 0 ? YC_ST_NOT_A_WINDOW : (state == 1 ? YC_ST_DEGENERATE : YC_ST_KS_PENDING);
     }
-    __syncwarp();
-    // ------------------------------------------------------------ phase 3
+    for (int idx = threadIdx.x; idx < 32 * GT; idx += YC_KW_WARPS * 32) {
+        const int k = idx >> 5, q = idx & 31;
+        if (i0 + q < ncol && st[q * 4] == 2) scr[(size_t)k * ncol + i0 + q] = gt[q * GT + k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Kernel 1b: one THREAD per position replays dgesdd on (G, T) -> first right singular vector with
+// numpy's sign; stores c_j = v_j / sig_j over the mean rows (only the ORDER of the projections
+// enters D, and sum_j x_j c_j differs from the standardised projection by a constant).
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(64)
+ks_axis_kernel(const int64_t c0, const int ncol, double *__restrict__ scr, const uint8_t *__restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncol || status[c0 + i] != YC_ST_KS_PENDING) return;
+    double GT_[2 * W * W], v[W];
+#pragma unroll
+    for (int k = 0; k < 2 * W * W; ++k) GT_[k] = scr[(size_t)k * ncol + i];
+    lapack::first_right_singular_vector<W>(GT_, GT_ + W * W, v);
+#pragma unroll
+    for (int j = 0; j < W; ++j) scr[(size_t)(2 * W * W + j) * ncol + i] = v[j] / scr[(size_t)(2 * W * W + W + j) * ncol + i];
+}
+
+// ---------------------------------------------------------------------------
+// Kernel 1c: projections, sort, D, p-value, gate.  A warp owns 32 adjacent columns: per pending
+// position all lanes project the complete rows (recognised on the fly: no NaN in the W values),
+// append them per condition (ballot prefix), sort and difference the ECDFs; then lane q
+// finalises position q (Kolmogorov p-value, gate, coalesced stores, one atomic per warp).
+// ---------------------------------------------------------------------------
+struct KdSmem { int sort_off, tab_off, per_warp; };
+
+__host__ __device__ inline KdSmem kd_layout(int P) {
+    KdSmem s;
+    int o = 0;
+    s.sort_off = o; o += (2 * P + P / 8 + 2) * (int)sizeof(double);     // + 1 pad per 16 (register-sort write-back)
+    s.tab_off = o;  o += 2 * (P + 1) * (int)sizeof(double);
+    s.per_warp = (o + 15) & ~15;
+    return s;
+}
+
+template <int W>
+__global__ void __launch_bounds__(YC_KW_WARPS * 32)
+ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t c0, const int ncol,
+            const double *__restrict__ scr,
+            double *__restrict__ ks_stat, double *__restrict__ ks_pval,
+            const int32_t *__restrict__ n_c_in, const int32_t *__restrict__ n_t_in,
+            uint8_t *__restrict__ status, int32_t *__restrict__ fit_list, int32_t *__restrict__ fit_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Rc = b.n_cntrl;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const KdSmem L = kd_layout(P);
+    unsigned char *base_ptr = smem_raw + (size_t)wid * L.per_warp;
+    double *sortbuf = reinterpret_cast<double *>(base_ptr + L.sort_off);
+    double *tabA = reinterpret_cast<double *>(base_ptr + L.tab_off), *tabB = tabA + (P + 1);
+    const int i0 = (blockIdx.x * YC_KW_WARPS + wid) * 32;
+    if (i0 >= ncol) return;                                              // no block-level synchronisation below
+    const bool mine = i0 + lane < ncol;
+    const int64_t g = c0 + i0 + lane;
+    const int my_state = mine ? (int)status[g] : YC_ST_NOT_A_WINDOW;
+    const int my_n1 = mine ? n_c_in[g] : 0, my_n2 = mine ? n_t_in[g] : 0;
     double my_d = 0.0;
-    int tab_n1 = -1, tab_n2 = -1;           // ECDF ratio tables c/n1, c/n2 (IEEE divisions), rebuilt when n changes
-    for (int q = 0; q < 32; ++q) {
-        const int *s = st + q * 8;
-        if (s[0] != 2) continue;                                // warp-uniform
-        const int n1 = s[1], n2 = s[2], n = s[3], split = s[4];
-        const uint32_t *mask = masks + q * nwords_max;
-        const double *slot = gt + q * GT;
-        // Only the ORDER of the projections y = sum_j z_j v_j enters D, and
-        // sum_j x_j (v_j / sig_j) differs from y by a constant: no centring, no division per read.
-        double cj[W];
+    int tab_n1 = -1, tab_n2 = -1;            // ECDF ratio tables c/n1, c/n2 (IEEE divisions), rebuilt when n changes
+    const uint32_t pending = __ballot_sync(YC_FULL, my_state == YC_ST_KS_PENDING);
+#pragma unroll 1
+    for (uint32_t todo = pending; todo; todo &= todo - 1) {
+        const int q = __ffs(todo) - 1;
+        const int n1 = __shfl_sync(YC_FULL, my_n1, q), n2 = __shfl_sync(YC_FULL, my_n2, q);
+        const int64_t gq = c0 + i0 + q;
+        // window columns of position gq (validated by kernel 1a)
+        const int f = b.col_feature[gq];
+        const int c = (int)(gq - b.col_off[f]);
+        const int n = b.n_reads[f];
+        const int split = b.samp_start[(size_t)f * (b.n_samples + 1) + Rc];
+        const int64_t ld = b.ld[f];
+        const uint16_t *fbase = b.events + b.x_off[f];
+        const bool rev = b.reverse[f] != 0;
         const uint16_t *col[W];
+        double cj[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            cj[j] = vbuf[q * W + j] / slot[2 * W * W + W + j];
-            col[j] = wcache[q * W + j];
+            const int cc = rev ? (c + W / 2 - j) : (c - W / 2 + j);
+            col[j] = fbase + (int64_t)cc * ld;
+            cj[j] = scr[(size_t)(2 * W * W + j) * ncol + i0 + q];
         }
         if (n1 != tab_n1) { for (int i = lane; i <= n1; i += 32) tabA[i] = div_rn((double)i, (double)n1); tab_n1 = n1; }
         if (n2 != tab_n2) { for (int i = lane; i <= n2; i += 32) tabB[i] = div_rn((double)i, (double)n2); tab_n2 = n2; }
@@ -369,12 +439,16 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
         const uint32_t lt = (1u << lane) - 1u;
         for (int base = 0; base < n; base += 32) {
             const int r = base + lane;
-            const bool bit = r < n && ((mask[r >> 5] >> (r & 31)) & 1u);
+            bool bit = r < n;
             const bool cond = r >= split;
             double y = 0.0;
             if (bit) {
 #pragma unroll
-                for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(col[j] + r)), cj[j], y);
+                for (int j = 0; j < W; ++j) {
+                    const uint16_t h = __ldg(col[j] + r);
+                    bit &= !h_isnan(h);
+                    y = fma(h2d(h), cj[j], y);
+                }
             }
             const uint32_t ma = __ballot_sync(YC_FULL, bit && !cond), mb = __ballot_sync(YC_FULL, bit && cond);
             if (bit) sortbuf[cond ? Pq + cb + __popc(mb & lt) : ca + __popc(ma & lt)] = y;
@@ -414,26 +488,22 @@ ks_warp_kernel(const yc_batch_t b, const yc_params_t p, const int P,
         if (lane == q) my_d = dmax;
         __syncwarp();
     }
-    // ------------------------------------------------------------ phase 4
-    const int64_t g = g0 + lane;
+    // ---- lane q finalises position q
     bool gated = false;
-    if (g < b.total_cols) {
-        const int *s = st + lane * 8;
-        const int state = s[0], n1 = s[1], n2 = s[2];
+    if (mine) {
         double d = nan(""), pv = nan("");
-        uint8_t code = YC_ST_NOT_A_WINDOW;
-        if (state == 1) code = YC_ST_DEGENERATE;
-        else if (state == 2) {
+        uint8_t code = (uint8_t)my_state;
+        if (my_state == YC_ST_KS_PENDING) {
             d = my_d;
+            const int n1 = my_n1, n2 = my_n2;
             const double en = __dsqrt_rn(div_rn((double)((int64_t)n1 * (int64_t)n2), (double)(n1 + n2)));
             pv = kolmogorov_sf(mul_rn(add_rn(add_rn(en, 0.12), div_rn(0.11, en)), d));
             if (!p.gmm) code = YC_ST_KS_ONLY;
             else if (d >= p.min_ks && pv < p.fdr_threshold) { code = YC_ST_GATED; gated = true; }
             else code = YC_ST_KS_FILTERED;
+            status[g] = code;
         }
         ks_stat[g] = d; ks_pval[g] = pv;
-        n_c_out[g] = state ? n1 : 0; n_t_out[g] = state ? n2 : 0;
-        status[g] = code;
     }
     const uint32_t gm = __ballot_sync(YC_FULL, gated);
     if (gm) {
@@ -456,22 +526,53 @@ bool ks_warp_eligible(const yc_batch_t &b, const yc_params_t &p) {
 }
 
 int ks_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p) {
-    return kw_layout(p.window_size, b.n_samples, b.max_reads, kw_sort_cap(b)).per_warp * YC_KW_WARPS;
+    const int a = km_layout(p.window_size, b.n_samples, b.max_reads).total;
+    const int d = kd_layout(kw_sort_cap(b)).per_warp * YC_KW_WARPS;
+    return a > d ? a : d;
 }
+
+// Stream-ordered scratch for the moment blocks: (2 W^2 + 2 W) doubles per column of a chunk.
+// Chunks bound the scratch for very large batches; the pool keeps the memory between calls.
+static const int64_t KW_CHUNK = 1 << 21;
 
 template <int W>
 static int launch_kw(const yc_batch_t &b, const yc_params_t &p, double *ks_stat, double *ks_pval,
                      int32_t *n_c, int32_t *n_t, uint8_t *status, int32_t *fit_list, int32_t *fit_count,
                      cudaStream_t st) {
+    constexpr int GT = 2 * W * W + 2 * W;
+    static bool pool_ready = false;
+    if (!pool_ready) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_ready = true;
+    }
     const int P = kw_sort_cap(b);
-    const int smem = kw_layout(W, b.n_samples, b.max_reads, P).per_warp * YC_KW_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(ks_warp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem_m = km_layout(W, b.n_samples, b.max_reads).total;
+    const int smem_d = kd_layout(P).per_warp * YC_KW_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(ks_moments_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m);
     if (e != cudaSuccess) return (int)e;
-    const int64_t groups = (b.total_cols + 31) / 32;
-    const unsigned grid = (unsigned)((groups + YC_KW_WARPS - 1) / YC_KW_WARPS);
-    ks_warp_kernel<W><<<grid, YC_KW_WARPS * 32, smem, st>>>(b, p, P, ks_stat, ks_pval, n_c, n_t, status,
-                                                            fit_list, fit_count);
-    return (int)cudaGetLastError();
+    e = cudaFuncSetAttribute(ks_d_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t chunk = b.total_cols < KW_CHUNK ? b.total_cols : KW_CHUNK;
+    double *scr = nullptr;
+    e = cudaMallocAsync(reinterpret_cast<void **>(&scr), (size_t)chunk * GT * sizeof(double), st);
+    if (e != cudaSuccess) return (int)e;
+    for (int64_t c0 = 0; c0 < b.total_cols; c0 += chunk) {
+        const int ncol = (int)(b.total_cols - c0 < chunk ? b.total_cols - c0 : chunk);
+        ks_moments_kernel<W><<<(ncol + 31) / 32, YC_KW_WARPS * 32, smem_m, st>>>(b, p, c0, ncol, scr, n_c, n_t, status);
+        count_launches(1);
+        ks_axis_kernel<W><<<(ncol + 63) / 64, 64, 0, st>>>(c0, ncol, scr, status);
+        count_launches(1);
+        ks_d_kernel<W><<<(ncol + 32 * YC_KW_WARPS - 1) / (32 * YC_KW_WARPS), YC_KW_WARPS * 32, smem_d, st>>>(
+            b, p, P, c0, ncol, scr, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count);
+        count_launches(1);
+    }
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(scr, st);
+    return (int)(e != cudaSuccess ? e : e2);
 }
 
 int ks_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, double *ks_stat, double *ks_pval,

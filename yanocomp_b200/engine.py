@@ -165,11 +165,10 @@ class Engine:
         status = torch.empty(n, dtype=torch.uint8, device=d)
         fit_list = torch.empty(n, dtype=i32, device=d)
         fit_count = torch.empty(1, dtype=i32, device=d)
-        launches = 0
+        launches0 = lib.yc_kernel_launches()
         N.check(timed('ks', lambda: lib.yc_ks_batch(
             b, ps, ks_stat.data_ptr(), ks_pval.data_ptr(), n_c.data_ptr(), n_t.data_ptr(),
             status.data_ptr(), fit_list.data_ptr(), fit_count.data_ptr(), stream)))
-        launches += 1 if dev.host.total_cols else 0
         n_fit = int(fit_count.item()) if (p.gmm and dev.host.total_cols) else 0   # 4-byte D2H + sync
         m = max(n_fit, 1)
         out_t = dict(
@@ -211,7 +210,7 @@ class Engine:
             N.check(timed('gtest_smpred', lambda: lib.yc_gtest_smpred_batch(
                 b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
                 post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
-            launches += 3
+        launches = int(lib.yc_kernel_launches() - launches0)   # counted by the library at every <<< >>>
         if not fetch:
             return dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
                         fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
