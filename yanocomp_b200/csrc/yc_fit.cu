@@ -498,7 +498,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 const double l1 = par->cst[1] - 0.5 * q1 + par->logw[s][1];
                 const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[s][2] : -INFINITY;
                 const double m = fmax(fmax(l0, l1), l2);
-                const double e0 = exp(l0 - m), e1 = exp(l1 - m), e2 = exp(l2 - m);
+                const double e0 = exp_nonpos(l0 - m), e1 = exp_nonpos(l1 - m), e2 = exp_nonpos(l2 - m);
                 const double se = e0 + e1 + e2;
                 const double inv = 1.0 / se;
                 r0 = e0 * inv; r1 = e1 * inv; r2 = e2 * inv;
@@ -709,7 +709,7 @@ gtest_smpred_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             const double l1 = par->cst[1] - 0.5 * q1 + par->logw[0][1];
             const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[0][2] : -INFINITY;
             const double mx = fmax(fmax(l0, l1), l2);
-            const double e0 = exp(l0 - mx), e1 = exp(l1 - mx), e2 = exp(l2 - mx);
+            const double e0 = exp_nonpos(l0 - mx), e1 = exp_nonpos(l1 - mx), e2 = exp_nonpos(l2 - mx);
             const double inv = 1.0 / (e0 + e1 + e2);
             post[2 * (off + rank)] = e1 * inv;
             post[2 * (off + rank) + 1] = e2 * inv;

@@ -688,7 +688,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 // exp(l_max - l_max) = 1 exactly: only the two non-maximal terms need an exp
                 const double m = fmax(fmax(l0, l1), l2);
                 const bool m0 = l0 == m, m1 = !m0 && l1 == m;
-                const double ea = exp((m0 ? l1 : l0) - m), eb = exp(((m0 || m1) ? l2 : l1) - m);
+                const double ea = exp_nonpos((m0 ? l1 : l0) - m), eb = exp_nonpos(((m0 || m1) ? l2 : l1) - m);
                 const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
                 const double se = e0 + e1 + e2, inv = 1.0 / se;
                 rb0[i] = e0 * inv; rb1[i] = e1 * inv;
@@ -876,7 +876,7 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         const double l1 = par->cst[1] - 0.5 * q1 + par->logw[0][1];
         const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[0][2] : -INFINITY;
         const double mx = fmax(fmax(l0, l1), l2);
-        const double e0 = exp(l0 - mx), e1 = exp(l1 - mx), e2 = exp(l2 - mx);
+        const double e0 = exp_nonpos(l0 - mx), e1 = exp_nonpos(l1 - mx), e2 = exp_nonpos(l2 - mx);
         const double inv = 1.0 / (e0 + e1 + e2);
         post[2 * (off + i)] = e1 * inv;
         post[2 * (off + i) + 1] = e2 * inv;
