@@ -17,6 +17,7 @@
 // Eligibility (dispatcher): w <= 5, <= 1024 reads per feature, no sub-sampling
 // possible (reads per condition <= max_fit_depth).
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "yc_fit_common.cuh"
 #include "yc_internal.h"
@@ -77,16 +78,32 @@ __device__ __forceinline__ void fw_row(const uint16_t *xs, int cap, int i, doubl
 // 32 loads + K broadcast loads instead of 10*K shuffles, and compact code.
 template <int K>
 __device__ __forceinline__ void warp_sum_smem(double (&v)[K], double *red, int lane) {
+    // G lanes share one total: each adds 32 / G of the per-lane partials, then log2 G shuffle steps
+    constexpr int KP = K <= 1 ? 1 : (K <= 2 ? 2 : (K <= 4 ? 4 : (K <= 8 ? 8 : (K <= 16 ? 16 : 32))));
+    constexpr int G = 32 / KP, CH = 32 / G;
 #pragma unroll
     for (int q = 0; q < K; ++q) red[q * 33 + lane] = v[q];
     __syncwarp();
-#pragma unroll 1
-    for (int q = lane; q < K; q += 32) {
-        const double *rq = red + q * 33;
-        double ta = 0.0, tb = 0.0, tc = 0.0, td = 0.0;             // four interleaved chains: latency / 4
+    if (K <= 16) {
+        const int q = lane / G, part = lane % G;
+        double t = 0.0;
+        if (q < K) {
+            const double *rq = red + q * 33 + part * CH;
 #pragma unroll
-        for (int l2 = 0; l2 < 32; l2 += 4) { ta += rq[l2]; tb += rq[l2 + 1]; tc += rq[l2 + 2]; td += rq[l2 + 3]; }
-        red[q * 33 + 32] = (ta + tb) + (tc + td);
+            for (int i = 0; i < CH; ++i) t += rq[i];
+        }
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(YC_FULL, t, o);
+        if (q < K && part == 0) red[q * 33 + 32] = t;
+    } else {
+#pragma unroll 1
+        for (int q = lane; q < K; q += 32) {
+            const double *rq = red + q * 33;
+            double ta = 0.0, tb = 0.0, tc = 0.0, td = 0.0;             // four interleaved chains: latency / 4
+#pragma unroll
+            for (int l2 = 0; l2 < 32; l2 += 4) { ta += rq[l2]; tb += rq[l2 + 1]; tc += rq[l2 + 2]; td += rq[l2 + 3]; }
+            red[q * 33 + 32] = (ta + tb) + (tc + td);
+        }
     }
     __syncwarp();
 #pragma unroll
@@ -109,6 +126,30 @@ __device__ __noinline__ void warp_bitonic1(double *a, int P, int lane) {
             }
             __syncwarp();
         }
+    }
+}
+
+// ascending sort of buf[0..P), P a power of two >= 32: in registers (P / 32 values per lane) up to
+// P = 512, by the shared-memory network beyond
+template <int E>
+__device__ __noinline__ void warp_sort_buf_regs(double *buf, int lane) {
+    double v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = buf[e * 32 + lane];              // any assignment will do before the sort
+    __syncwarp();
+    warp_sort_regs<E>(v, lane, 32);
+#pragma unroll
+    for (int e = 0; e < E; ++e) buf[lane * E + e] = v[e];
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_sort_buf(double *buf, int P, int lane) {
+    switch (P) {
+        case 32:  warp_sort_buf_regs<1>(buf, lane); break;
+        case 64:  warp_sort_buf_regs<2>(buf, lane); break;
+        case 128: warp_sort_buf_regs<4>(buf, lane); break;
+        case 256: warp_sort_buf_regs<8>(buf, lane); break;
+        case 512: warp_sort_buf_regs<16>(buf, lane); break;
+        default:  warp_bitonic1(buf, P, lane); break;
     }
 }
 
@@ -342,7 +383,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         buf[i] = dmin;
     }
     __syncwarp();
-    warp_bitonic1(buf, P, lane);
+    warp_sort_buf(buf, P, lane);
     const double med = (n & 1) ? buf[n >> 1] : mul_rn(add_rn(buf[(n >> 1) - 1], buf[n >> 1]), 0.5);
     // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are
     // V-shaped, i.e. two ascending runs (left of the median walked outwards, right of it), so the
@@ -931,7 +972,8 @@ int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *f
                      const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
     if (n_fit <= 0) return 0;
     if (int e = upload_em_steps()) return e;
-    const int cap = fw_cap(b), smem = fw_smem(b, p, 1);
+    const char *xs_ = getenv("YC_EM_EXTRA_SMEM");                    // occupancy experiments only
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 1) + (xs_ ? atoi(xs_) : 0);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(em_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

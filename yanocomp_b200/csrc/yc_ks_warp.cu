@@ -65,19 +65,6 @@ __device__ __noinline__ void warp_bitonic(double *a, int P, int nseg, int lane) 
 // with the same separately rounded operations as before: tabA[c] = c / n1, tabB[c] = c / n2.
 #define YC_KPAD(i) ((i) + ((i) >> 4))
 
-// compare-exchange of two finite-or-inf doubles (no NaNs reach the sort): one DSETP + selects,
-// instead of the NaN-aware fmin / fmax sequences
-__device__ __forceinline__ void cmpx(double &lo, double &hi) {
-    const bool sw = lo > hi;
-    const double a = sw ? hi : lo, b = sw ? lo : hi;
-    lo = a; hi = b;
-}
-// the lower lane of a pair keeps the smaller value, the upper lane the larger one
-__device__ __forceinline__ double keep_side(double mine, double other, bool lower) {
-    const bool take = (other < mine) == lower;          // equal values: either copy will do
-    return take ? other : mine;
-}
-
 template <int E>
 __device__ __noinline__ double ks_sort_ecdf(double *a, const double *tabA, const double *tabB,
                                             int n1, int n2, int lane) {
@@ -87,42 +74,7 @@ __device__ __noinline__ double ks_sort_ecdf(double *a, const double *tabA, const
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = a[half * P + e * 16 + l16];      // any assignment will do before the sort
     __syncwarp();
-    // 1. every lane sorts its own E values (static network, registers only)
-#pragma unroll
-    for (int k = 2; k <= E; k <<= 1) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) { const int o = e ^ (k - 1); if (e < o) cmpx(v[e], v[o]); }
-#pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1)
-#pragma unroll
-            for (int e = 0; e < E; ++e) if ((e & j) == 0) cmpx(v[e], v[e | j]);
-    }
-    // 2. merges across lanes, k = 2E .. P.  Rolled loops with run-time lane masks: the body is the
-    //    same code for every k, which keeps the routine inside the instruction cache.
-#pragma unroll 1
-    for (int kl = 2; kl <= 16; kl <<= 1) {                              // kl = k / E
-        {   // first step of the merge: partner i ^ (k - 1) = lane ^ (kl - 1), values mirrored inside the lane
-            const bool lower = (lane & (kl >> 1)) == 0;
-            double t[E];
-#pragma unroll
-            for (int e = 0; e < E; ++e) t[e] = __shfl_xor_sync(YC_FULL, v[E - 1 - e], kl - 1);
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = keep_side(v[e], t[e], lower);
-        }
-#pragma unroll 1
-        for (int jl = kl >> 2; jl > 0; jl >>= 1) {                      // partner i ^ j, j = jl * E >= E
-            const bool lower = (lane & jl) == 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const double t = __shfl_xor_sync(YC_FULL, v[e], jl);
-                v[e] = keep_side(v[e], t, lower);
-            }
-        }
-#pragma unroll
-        for (int j = E >> 1; j > 0; j >>= 1)                            // partner i ^ j inside the lane
-#pragma unroll
-            for (int e = 0; e < E; ++e) if ((e & j) == 0) cmpx(v[e], v[e | j]);
-    }
+    warp_sort_regs<E>(v, lane, 16);                                      // two segments of 16 lanes each
     // sorted: global index i = lane * E + e (control sample 0..P-1, treatment sample P..2P-1)
 #pragma unroll
     for (int e = 0; e < E; ++e) a[YC_KPAD(lane * E + e)] = v[e];
