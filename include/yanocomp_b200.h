@@ -140,8 +140,9 @@ int yc_fill_col_feature(int32_t n_features, const int64_t *col_off,
  *   ks_stat, ks_pval [total_cols]; n_c, n_t [total_cols] = complete-window rows
  *   per condition (before sub-sampling); status [total_cols];
  *   fit_list [total_cols] receives the global column index of every position
- *   that passed the gate (unordered), *fit_count their number (device int32,
- *   zeroed by the call).
+ *   that passed the gate, in ascending order (an ordered compaction pass, so
+ *   the slot order of the fit outputs is deterministic), *fit_count their
+ *   number (device int32).
  */
 int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
                 double *ks_stat, double *ks_pval, int32_t *n_c, int32_t *n_t,

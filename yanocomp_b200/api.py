@@ -24,13 +24,16 @@ def test_host_batch(host: HostBatch, params: EngineParams, engine: Engine = None
 
 
 def test_host_batch_pipelined(host: HostBatch, params: EngineParams, engine: Engine = None,
-                              fetch='records', chunks=4):
+                              fetch='records', chunks=4, growth=2.5):
     '''
-    Same as test_host_batch with the batch cut into `chunks` feature ranges (views, no copy) whose
-    host->device copies overlap the kernels of the previous range.  Returns [(sub-batch, result)].
+    Same as test_host_batch with the batch cut into `chunks` feature ranges (views, no copy) that go
+    through the engine's three-stage pipeline: the host->device copy of a range overlaps the kernels
+    of the previous ones, the device->host copy of its results those of the next.  The ranges grow
+    geometrically (`growth`), because only the first upload cannot be hidden.
+    Returns [(sub-batch, result)].
     '''
     eng = engine or Engine(params)
-    return list(eng.run_pipelined(host.split(chunks), fetch=fetch, keep_results=True))
+    return list(eng.run_pipelined(host.split(chunks, growth), fetch=fetch, keep_results=True))
 
 
 def tested_table(host: HostBatch, res: BatchResult, gmm=True):

@@ -100,6 +100,12 @@ class HostBatch:
             self.feature_key[i] = feature_key(f.feature_id)
             self.reverse[i] = f.strand == '-'
         self.total_cols = int(self.col_off[-1])
+        if pin:
+            # the per-feature / per-column tables travel with every upload: pinned, so that the copies
+            # of a pipelined upload are all asynchronous
+            for name in ('n_cols', 'n_reads', 'ld', 'x_off', 'col_off', 'samp_start', 'feature_key',
+                         'col_pos', 'reverse'):
+                setattr(self, name, self._pinned_copy(getattr(self, name)))
         self.max_reads = int(self.n_reads.max()) if F else 0
         split = self.samp_start[:, n_cntrl] if F else np.zeros(0, dtype=np.int32)
         self.max_cond_reads = int(max(split.max(), (self.n_reads - split).max())) if F else 0
@@ -126,20 +132,37 @@ class HostBatch:
         v.max_cond_reads = int(max(split.max(), (v.n_reads - split).max())) if f1 > f0 else 0
         return v
 
-    def split(self, k):
-        '''at most k views with balanced event bytes (for host->device / compute pipelining)'''
+    def split(self, k, growth=1.0):
+        '''
+        At most k views for host->device / compute pipelining.  growth = 1: balanced event bytes;
+        growth > 1: every view is `growth` times the previous one, so the first upload (which nothing
+        can hide) is short and the later, larger ones hide behind the kernels of their predecessors.
+        '''
         F = self.n_features
         if k <= 1 or F < 2:
             return [self]
         sizes = self.n_cols.astype(np.int64) * self.ld
         cum = np.cumsum(sizes)
+        w = np.power(float(growth), np.arange(k))
+        targets = np.cumsum(w) / w.sum()
         cuts = [0]
-        for j in range(1, k):
-            c = int(np.searchsorted(cum, cum[-1] * j / k, side='left')) + 1
+        for j in range(k - 1):
+            c = int(np.searchsorted(cum, cum[-1] * targets[j], side='left')) + 1
             if cuts[-1] < c < F:
                 cuts.append(c)
         cuts.append(F)
         return [self.view(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
+
+    @staticmethod
+    def _pinned_copy(a):
+        import torch
+        if not torch.cuda.is_available() or a.size == 0:
+            return a
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].view(np.int64) if a.dtype == np.uint64 else a[:0]).dtype,
+                        pin_memory=True)
+        out = t.numpy().view(a.dtype)
+        out[...] = a
+        return out
 
     @staticmethod
     def _alloc_events(total, pin):
@@ -169,6 +192,14 @@ class HostBatch:
 
 class DeviceBatch:
     '''a HostBatch resident in HBM + the ctypes struct the kernels take'''
+
+    _TENSORS = ('events', 'x_off', 'n_cols', 'n_reads', 'ld', 'col_off', 'samp_start', 'feature_key',
+                'col_pos', 'reverse', 'col_feature')
+
+    def record_stream(self, stream):
+        '''the buffers were allocated on another stream than the one whose kernels read them'''
+        for name in self._TENSORS:
+            getattr(self, name).record_stream(stream)
 
     def __init__(self, host, device=None, stream=None):
         import torch

@@ -79,6 +79,99 @@ __global__ void fill_col_feature_kernel(int n_features, const int64_t *__restric
     }
 }
 
+// ---- ordered compaction of the gated positions: fit_list = ascending global columns with
+// status == YC_ST_GATED, *fit_count = their number.  Three small launches (per-block counts,
+// one-block exclusive scan, ordered scatter) instead of an atomic append + a sort: the slot
+// order of the fit outputs is deterministic and needs no host-side pass.
+constexpr int CG_THREADS = 256, CG_ITEMS = 8, CG_TILE = CG_THREADS * CG_ITEMS;
+
+__global__ void __launch_bounds__(CG_THREADS)
+compact_count_kernel(const uint8_t *__restrict__ status, long long n, int *__restrict__ block_cnt) {
+    __shared__ int wsum[CG_THREADS / 32];
+    const long long base = (long long)blockIdx.x * CG_TILE;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < CG_ITEMS; ++i) {
+        const long long g = base + i * CG_THREADS + threadIdx.x;
+        c += (g < n && status[g] == YC_ST_GATED);
+    }
+    c = yc::warp_sum_i(c);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < CG_THREADS / 32; ++w) t += wsum[w];
+        block_cnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(int *__restrict__ block_cnt, int nb, int32_t *__restrict__ fit_count) {
+    __shared__ int wtot[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < nb ? block_cnt[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(YC_FULL, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wtot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int t = wtot[lane], s = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(YC_FULL, s, o); if (lane >= o) s += u; }
+            wtot[lane] = s - t;                                          // exclusive offsets of the warps
+        }
+        __syncthreads();
+        const int excl = carry_s + wtot[wid] + inc - v;
+        if (i < nb) block_cnt[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;                     // running total after this tile
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *fit_count = carry_s;
+}
+
+__global__ void __launch_bounds__(CG_THREADS)
+compact_scatter_kernel(const uint8_t *__restrict__ status, long long n, const int *__restrict__ block_off,
+                       int32_t *__restrict__ fit_list) {
+    __shared__ int wcnt[CG_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * CG_TILE;
+    int run = block_off[blockIdx.x];
+    for (int i = 0; i < CG_ITEMS; ++i) {
+        const long long g = base + i * CG_THREADS + threadIdx.x;
+        const bool hit = g < n && status[g] == YC_ST_GATED;
+        const uint32_t m = __ballot_sync(YC_FULL, hit);
+        if (lane == 0) wcnt[wid] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < CG_THREADS / 32; ++w) { const int c = wcnt[w]; if (w < wid) before += c; total += c; }
+        if (hit) fit_list[run + before + __popc(m & ((1u << lane) - 1u))] = (int32_t)g;
+        run += total;
+        __syncthreads();
+    }
+}
+
+int compact_gated(const uint8_t *status, long long n, int32_t *fit_list, int32_t *fit_count, cudaStream_t st) {
+    const int nb = (int)((n + CG_TILE - 1) / CG_TILE);
+    int *block_cnt = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&block_cnt), (size_t)nb * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    compact_count_kernel<<<nb, CG_THREADS, 0, st>>>(status, n, block_cnt);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(block_cnt, nb, fit_count);
+    compact_scatter_kernel<<<nb, CG_THREADS, 0, st>>>(status, n, block_cnt, fit_list);
+    yc::count_launches(3);
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(block_cnt, st);
+    return (int)(e != cudaSuccess ? e : e2);
+}
+
 template <int D>
 __global__ void svd_v1_kernel(const double *__restrict__ G, const double *__restrict__ T,
                               double *__restrict__ v, int count) {
@@ -135,12 +228,16 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
     // YC_KS_PATH=cta forces the general kernel (used by the tests to cover both).
     const char *force = getenv("YC_KS_PATH");
     const bool want_cta = force && strcmp(force, "cta") == 0;
-    if (!want_cta && yc::ks_warp_eligible(*b, *p) && yc::ks_warp_smem_bytes(*b, *p) <= smem_limit())
-        return cuda_fail(yc::ks_warp_dispatch(*b, *p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st),
-                         "yc_ks_batch (warp path)");
-    if (int e = check_smem(yc::ks_smem_bytes(*b, *p), "yc_ks_batch")) return e;
-    return cuda_fail(yc::ks_dispatch(*b, *p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st),
-                     "yc_ks_batch");
+    if (!want_cta && yc::ks_warp_eligible(*b, *p) && yc::ks_warp_smem_bytes(*b, *p) <= smem_limit()) {
+        if (int e = cuda_fail(yc::ks_warp_dispatch(*b, *p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st),
+                              "yc_ks_batch (warp path)")) return e;
+    } else {
+        if (int e = check_smem(yc::ks_smem_bytes(*b, *p), "yc_ks_batch")) return e;
+        if (int e = cuda_fail(yc::ks_dispatch(*b, *p, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count, st),
+                              "yc_ks_batch")) return e;
+    }
+    if (!p->gmm) return 0;                                              // --no-gmm: nothing is gated
+    return cuda_fail(compact_gated(status, b->total_cols, fit_list, fit_count, st), "yc_ks_batch (compaction)");
 }
 
 int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,

@@ -228,8 +228,7 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
         uint8_t st;
         if (!p.gmm) st = YC_ST_KS_ONLY;
         else if (dmax >= p.min_ks && pv < p.fdr_threshold) {
-            st = YC_ST_GATED;
-            fit_list[atomicAdd(fit_count, 1)] = (int32_t)g;
+            st = YC_ST_GATED;                 // fit_list is built afterwards by compact_gated (ordered)
         } else st = YC_ST_KS_FILTERED;
         status[g] = st;
     }

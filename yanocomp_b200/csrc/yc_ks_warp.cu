@@ -457,13 +457,7 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
         }
         ks_stat[g] = d; ks_pval[g] = pv;
     }
-    const uint32_t gm = __ballot_sync(YC_FULL, gated);
-    if (gm) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(fit_count, __popc(gm));
-        base = __shfl_sync(YC_FULL, base, 0);
-        if (gated) fit_list[base + __popc(gm & ((1u << lane) - 1u))] = (int32_t)g;
-    }
+    (void)gated; (void)fit_list; (void)fit_count;    // fit_list is built afterwards by compact_gated (ordered)
 }
 
 static int kw_sort_cap(const yc_batch_t &b) {

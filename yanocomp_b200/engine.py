@@ -95,6 +95,7 @@ class Engine:
         self.params = params
         self._stages = {}               # pinned device->host staging buffers (one per pipeline slot)
         self._copy_stream = None
+        self._fetch_stream = None
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
     def upload(self, host: HostBatch) -> DeviceBatch:
@@ -102,34 +103,51 @@ class Engine:
 
     def run_pipelined(self, hosts, fetch='records', keep_results=False, **kw):
         '''
-        Yield (host batch, BatchResult) for every batch of the iterable `hosts`, uploading batch k+1
-        on a copy stream while the kernels of batch k run: the host->device copy (PCIe, ~55 GB/s)
-        hides behind the compute.  `hosts` is consumed lazily with one batch of look-ahead.  A result
-        stays valid until the batch after the next one has run (two staging buffers), or for ever
-        with keep_results=True (one staging buffer per batch).
+        Yield (host batch, BatchResult) for every batch of the iterable `hosts` as a three-stage
+        software pipeline, so that neither the PCIe copies nor the host's two synchronisation
+        points leave the GPU idle:
+          A(k)  host->device copy on the copy stream, KS kernels, gated-position count -> pinned int
+          B(k)  wait for that count only (KS of batch k+1 is already queued behind it), size the
+                outputs, launch init / EM / G-test, gather the result rows
+          C(k)  device->host copy of the result rows on the fetch stream, wait for it
+        issued in the order A0 A1 B0 | A2 B1 C0 | A3 B2 C1 | ...  `hosts` is consumed lazily with two
+        batches of look-ahead.  A result stays valid until three more batches have been fetched
+        (staging buffers rotate), or for ever with keep_results=True (one staging buffer per batch).
         '''
         it = iter(hosts)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
+            self._fetch_stream = torch.cuda.Stream(self.device)
         compute = torch.cuda.current_stream(self.device)
 
-        def up():
+        def stage_a():
             h = next(it, None)
             if h is None:
                 return None
-            self._copy_stream.wait_stream(compute)          # buffers freed by earlier batches are safe to reuse
             with torch.cuda.stream(self._copy_stream):
                 dev = self.upload(h)
-                return h, dev, self._copy_stream.record_event()
-
-        nxt = up()
-        i = 0
-        while nxt is not None:
-            h, dev, ready = nxt
-            nxt = up()
+                dev.record_stream(compute)                   # inputs are allocated on the copy stream, read on compute
+                ready = self._copy_stream.record_event()
             compute.wait_event(ready)
-            yield h, self.run(dev, fetch=fetch, stage_key=i if keep_results else i % 2, **kw)
-            i += 1
+            return h, self._launch_ks(dev, **kw)
+
+        a_q, b_q = [], []                                    # batches that finished stage A / stage B
+        i = 0
+        nxt = stage_a()
+        while nxt is not None or a_q or b_q:
+            if nxt is not None:
+                a_q.append(nxt)
+                if len(a_q) < 2 and not b_q:
+                    nxt = stage_a()                          # prologue: A0 A1 before B0
+                    continue
+            if a_q:
+                h, ctx = a_q.pop(0)
+                b_q.append((h, self._launch_fit(ctx, fetch)))
+            if len(b_q) > 1 or (not a_q and nxt is None):
+                h, ctx = b_q.pop(0)
+                yield h, self._fetch_result(ctx, i if keep_results else i % 4)
+                i += 1
+            nxt = stage_a() if nxt is not None else None
 
     def run(self, dev: DeviceBatch, want_labels=False, fetch='full', events=None, stage_key=0):
         '''
@@ -139,6 +157,14 @@ class Engine:
         (a list) receives (kernel name, start event, end event) per launch so
         that bench.py can time each kernel on the launching stream.
         '''
+        ctx = self._launch_ks(dev, want_labels=want_labels, events=events)
+        ctx = self._launch_fit(ctx, fetch)
+        if not fetch:
+            return ctx['device']
+        return self._fetch_result(ctx, stage_key)
+
+    # ---- stage A: KS kernels + asynchronous count of the gated positions
+    def _launch_ks(self, dev: DeviceBatch, want_labels=False, events=None):
         def timed(name, call):
             if events is None:
                 return call()
@@ -151,25 +177,38 @@ class Engine:
             return r
 
         lib, p = self.lib, self.params
-        ps = p.struct()
-        b = dev.struct
         d = self.device
         n = max(dev.host.total_cols, 1)
+        stream = torch.cuda.current_stream(d).cuda_stream
+        f64, i32 = torch.float64, torch.int32
+        t = dict(
+            ks_stat=torch.empty(n, dtype=f64, device=d), ks_pval=torch.empty(n, dtype=f64, device=d),
+            n_c=torch.empty(n, dtype=i32, device=d), n_t=torch.empty(n, dtype=i32, device=d),
+            status=torch.empty(n, dtype=torch.uint8, device=d),
+            fit_list=torch.empty(n, dtype=i32, device=d), fit_count=torch.empty(1, dtype=i32, device=d))
+        launches0 = lib.yc_kernel_launches()
+        ps = p.struct()
+        N.check(timed('ks', lambda: lib.yc_ks_batch(
+            dev.struct, ps, t['ks_stat'].data_ptr(), t['ks_pval'].data_ptr(), t['n_c'].data_ptr(),
+            t['n_t'].data_ptr(), t['status'].data_ptr(), t['fit_list'].data_ptr(), t['fit_count'].data_ptr(),
+            stream)))
+        counts = torch.empty(2, dtype=torch.int64, pin_memory=True)     # [n_fit, posterior reads written]
+        counts.zero_()
+        cnt32 = counts.view(torch.int32)
+        cnt32[:1].copy_(t['fit_count'], non_blocking=True)
+        return dict(dev=dev, t=t, ps=ps, timed=timed, want_labels=want_labels, launches0=launches0,
+                    counts=counts, counted=torch.cuda.current_stream(d).record_event())
+
+    # ---- stage B: size the outputs from the count, fit kernels, gather of the result rows
+    def _launch_fit(self, ctx, fetch):
+        lib, p, d = self.lib, self.params, self.device
+        dev, t, ps, timed = ctx['dev'], ctx['t'], ctx['ps'], ctx['timed']
         w, R = p.window_size, dev.host.n_samples
         stream = torch.cuda.current_stream(d).cuda_stream
         f64, i32 = torch.float64, torch.int32
-        ks_stat = torch.empty(n, dtype=f64, device=d)
-        ks_pval = torch.empty(n, dtype=f64, device=d)
-        n_c = torch.empty(n, dtype=i32, device=d)
-        n_t = torch.empty(n, dtype=i32, device=d)
-        status = torch.empty(n, dtype=torch.uint8, device=d)
-        fit_list = torch.empty(n, dtype=i32, device=d)
-        fit_count = torch.empty(1, dtype=i32, device=d)
-        launches0 = lib.yc_kernel_launches()
-        N.check(timed('ks', lambda: lib.yc_ks_batch(
-            b, ps, ks_stat.data_ptr(), ks_pval.data_ptr(), n_c.data_ptr(), n_t.data_ptr(),
-            status.data_ptr(), fit_list.data_ptr(), fit_count.data_ptr(), stream)))
-        n_fit = int(fit_count.item()) if (p.gmm and dev.host.total_cols) else 0   # 4-byte D2H + sync
+        status, fit_list, n_c, n_t = t['status'], t['fit_list'], t['n_c'], t['n_t']
+        ctx['counted'].synchronize()                                     # the 4-byte count only
+        n_fit = int(ctx['counts'].view(torch.int32)[0]) if (p.gmm and dev.host.total_cols) else 0
         m = max(n_fit, 1)
         out_t = dict(
             mu=torch.empty(m * 2 * w, dtype=f64, device=d),
@@ -188,11 +227,11 @@ class Engine:
         max_fit_rows = 0
         post = None
         post_cursor = torch.zeros(1, dtype=torch.int64, device=d)
+        b = dev.struct
+        ks_stat, ks_pval = t['ks_stat'], t['ks_pval']
+        want_labels = ctx['want_labels']
         if n_fit:
-            fl = fit_list[:n_fit]
-            # deterministic slot order: sort the gated positions by global column
-            fl, _ = torch.sort(fl)
-            fit_list[:n_fit] = fl
+            # fit_list arrives in ascending column order (ordered compaction inside yc_ks_batch)
             if want_labels:
                 max_fit_rows = int(min(dev.host.max_reads, R * p.max_fit_depth))
                 labels = torch.full((n_fit, max_fit_rows), -1, dtype=torch.int8, device=d)
@@ -210,14 +249,15 @@ class Engine:
             N.check(timed('gtest_smpred', lambda: lib.yc_gtest_smpred_batch(
                 b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
                 post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
-        launches = int(lib.yc_kernel_launches() - launches0)   # counted by the library at every <<< >>>
+        launches = int(lib.yc_kernel_launches() - ctx['launches0'])   # counted by the library at every <<< >>>
+        ctx.update(n_fit=n_fit, launches=launches)
         if not fetch:
-            return dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
-                        fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
-                        labels=labels, launches=launches, **out_t)
+            ctx['device'] = dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
+                                 fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
+                                 labels=labels, launches=launches, **out_t)
+            return ctx
         nc = dev.host.total_cols
         level = 'full' if fetch is True else fetch
-        used = int(post_cursor.item()) if post is not None else 0
         fl = fit_list[:n_fit]
         fli = fl.long()
         cov = out_t['cov'][:n_fit * 2 * w * w].view(n_fit, 2, w, w)
@@ -232,16 +272,33 @@ class Engine:
             want.update(nall_fit=(n_c[fli] + n_t[fli]), cov=cov,
                         box=out_t['box'][:n_fit * w * 2].view(n_fit, w, 2),
                         cw=out_t['cw'][:n_fit * 3].view(n_fit, 3), post_off=out_t['post_off'][:n_fit])
-            if post is not None:
-                want['post'] = post[:used * 2].view(used, 2)
         if level == 'full':
             want.update(n_c=n_c[:nc], n_t=n_t[:nc],
                         logw=out_t['logw'][:n_fit * R * 3].view(n_fit, R, 3), iters=out_t['iters'][:n_fit],
                         loglik=out_t['loglik'][:n_fit], preds=out_t['preds'][:n_fit * R * 3].view(n_fit, R, 3))
             if labels is not None:
                 want['labels'] = labels
-        host, d2h = self._fetch(want, stage_key)
-        return BatchResult(launches=launches, d2h_bytes=d2h, **host)
+        if post is not None:
+            ctx['counts'][1:].copy_(post_cursor, non_blocking=True)     # posterior reads written
+        ctx.update(want=want, post=post, done=torch.cuda.current_stream(d).record_event())
+        return ctx
+
+    # ---- stage C: result rows -> pinned staging buffer on the fetch stream
+    def _fetch_result(self, ctx, stage_key=0):
+        d = self.device
+        want, post = ctx['want'], ctx['post']
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(d)
+            self._fetch_stream = torch.cuda.Stream(d)
+        fs = self._fetch_stream
+        if post is not None:
+            ctx['done'].synchronize()                                    # needs the number of posterior rows
+            used = int(ctx['counts'][1])
+            want['post'] = post[:used * 2].view(used, 2)
+        fs.wait_event(ctx['done'])
+        with torch.cuda.stream(fs):
+            host, d2h = self._fetch(want, stage_key)
+        return BatchResult(launches=ctx['launches'], d2h_bytes=d2h, **host)
 
     def _fetch(self, tensors, stage_key=0):
         '''device tensors -> numpy views of one pinned staging buffer (async copies, one sync)'''
