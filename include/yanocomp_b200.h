@@ -48,6 +48,11 @@ extern "C" {
 #define YC_MAX_SAMPLES  16     /* replicates over both conditions */
 #define YC_NCOMP        3      /* two Gaussians + uniform outlier component */
 
+#define YC_COV_FULL        0   /* MultivariateGaussianDistribution                  stats.py:148-152 */
+#define YC_COV_DIAG        1   /* IndependentComponentsDistribution of Normals      stats.py:153-166 */
+#define YC_OUTLIER_MAD     0   /* distance-to-centroid MAD rule                     stats.py:116-120 */
+#define YC_OUTLIER_DBSCAN  1   /* sklearn DBSCAN(eps, min_samples = n/4) noise      stats.py:91-104 */
+
 /* yc_batch_t.flags: every ld[f] and x_off[f] is a multiple of 8 elements and the padding
  * elements events[x_off + c*ld + r], n_reads <= r < ld, are NaN -> rows can be read 16 bytes at a time */
 #define YC_BATCH_ROWS_ALIGNED 1
@@ -94,11 +99,14 @@ typedef struct yc_params {
     int32_t  max_fit_depth;      /* -d, gmmtest.py:304-305 */
     int32_t  gmm;                /* --gmm/--no-gmm, gmmtest.py:310-311 */
     int32_t  add_uniform;        /* -u/--add-uniform / --no-uniform, gmmtest.py:290-292 (1 = 3-component GMM) */
-    int32_t  reserved0;
+    int32_t  covariance_type;    /* -C, gmmtest.py:286-289: YC_COV_FULL / YC_COV_DIAG */
     double   min_ks;             /* -k, gmmtest.py:306-307 */
     double   fdr_threshold;      /* -f, gmmtest.py:308-309 */
     double   outlier_factor;     /* -e, gmmtest.py:296-298 */
     uint64_t seed;               /* --random-seed, gmmtest.py:315 */
+    double   dbscan_eps;         /* -E, gmmtest.py:299-300 */
+    int32_t  outlier_method;     /* -D, gmmtest.py:293-295: YC_OUTLIER_MAD / YC_OUTLIER_DBSCAN */
+    int32_t  reserved1;
 } yc_params_t;
 
 /* fitted model + test results of one gated position (slot-indexed SoA) */

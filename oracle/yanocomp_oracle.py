@@ -71,6 +71,20 @@ ASSUMPTIONS = {
     'A8': 'statsmodels Table2x2(shift_zeros=True): +0.5 on every cell if any '
           'cell is 0; log odds = ln f00 - ln f01 - ln f10 + ln f11; CI = '
           'lor -/+ norm.ppf(1-alpha/2) * sqrt(sum 1/f)',
+    'A10': '--covariance-type diag: IndependentComponentsDistribution of '
+           'NormalDistribution(mean, std): log density -log(sigma sqrt(2 pi)) '
+           '- (x-mu)^2 / (2 sigma^2) per column (sigma = 0 gives +inf); '
+           'summaries sum w, sum w x, sum w x^2; from_summaries(inertia) is '
+           'skipped (summaries kept) when sum w < 1e-8, else mu = S1/S0, '
+           'sigma = sqrt(S2/S0 - S1^2/S0^2) (min_std 0) and BOTH mu and sigma '
+           'are blended old*inertia + new*(1-inertia); a non-finite likelihood '
+           'is a failed fit as in A5',
+    'A11': '--outlier-method dbscan: sklearn DBSCAN(eps, min_samples = '
+           '0.25 n as a float, euclidean): a point is a core point when at '
+           'least min_samples points (itself included) lie within eps, and an '
+           'outlier (label -1) when it is neither a core point nor within eps '
+           'of one (recent scikit-learn rejects a float min_samples; the '
+           'pinned environment of the reference accepted it)',
     'A9': 'a window whose pooled data has a constant column makes '
           'np.linalg.svd raise inside the reference (stats.py:26, outside any '
           'try block) and abort the run; here the position is skipped',
@@ -295,6 +309,55 @@ class MVNormal:
         self.clear()
 
 
+class DiagNormal:
+    '''A10: pm.IndependentComponentsDistribution([pm.NormalDistribution(mu_j, sigma_j)])  (stats.py:153-166)'''
+
+    def __init__(self, mu, sigma):
+        self.mu = np.array(mu, dtype=np.float64)
+        self.sigma = np.array(sigma, dtype=np.float64)
+        self.d = self.mu.shape[0]
+        self.clear()
+
+    @classmethod
+    def from_samples(cls, X):
+        '''stats.py:155-166: N(0, 1) per column for an empty cluster, else column mean / population std'''
+        d = X.shape[1]
+        if len(X) == 0:
+            return cls(np.zeros(d), np.ones(d))
+        return cls(X.mean(axis=0), X.std(axis=0))
+
+    @property
+    def cov(self):
+        '''the evident intent of stats.py:395-412 (np.diag(std ** 2); the reference raises there)'''
+        return np.diag(self.sigma ** 2)
+
+    def clear(self):
+        self.s0 = np.zeros(self.d)
+        self.s1 = np.zeros(self.d)
+        self.s2 = np.zeros(self.d)
+
+    def log_probability(self, X):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            log_norm = -np.log(self.sigma * math.sqrt(2.0 * math.pi))
+            inv2 = np.where(self.sigma > 0, 1.0 / (2.0 * self.sigma ** 2), 0.0)
+            return np.sum(log_norm - (X - self.mu) ** 2 * inv2, axis=1)
+
+    def summarize(self, X, w):
+        self.s0 += float(np.sum(w))
+        self.s1 += w.dot(X)
+        self.s2 += w.dot(X * X)
+
+    def from_summaries(self, inertia):
+        if self.s0[0] < 1e-8:
+            return
+        mu = self.s1 / self.s0
+        with np.errstate(invalid='ignore'):
+            sigma = np.sqrt(self.s2 / self.s0 - self.s1 ** 2.0 / self.s0 ** 2.0)
+        self.mu = self.mu * inertia + mu * (1.0 - inertia)
+        self.sigma = self.sigma * inertia + sigma * (1.0 - inertia)
+        self.clear()
+
+
 class UniformBox:
     '''A5: IndependentComponentsDistribution of UniformDistributions'''
 
@@ -407,26 +470,55 @@ def median_absolute_deviation(arr):
     return np.median(np.abs(arr - np.median(arr)))
 
 
-def kmeans_init_clusters(X, pkey, outlier_factor=0.5, detect_outliers=True):
-    '''stats.py:81-124, `mad` branch (detect_outliers=False: --no-uniform, stats.py:115)'''
-    centroids = kmeans_fit(X, pkey)
+def dbscan_outliers(X, eps=5.0, min_samples=None):
+    '''A11: DBSCAN(eps, min_samples='auto' -> 0.25 n).fit_predict(X) == -1  (stats.py:91-99)'''
+    n = len(X)
+    if min_samples is None:
+        min_samples = 0.25 * n
+    near = _sqdist(X, X) <= eps * eps                      # exact for binary16 inputs; sqrt is monotone
+    core = near.sum(axis=1) >= min_samples
+    return ~core & ~near[:, core].any(axis=1)
+
+
+def kmeans_init_clusters(X, pkey, outlier_factor=0.5, detect_outliers='mad', dbscan_eps=5.0):
+    '''stats.py:81-124; detect_outliers in (None, 'mad', 'dbscan') as position_stats passes it (stats.py:472)'''
+    if detect_outliers is True:
+        detect_outliers = 'mad'
+    elif detect_outliers is False:
+        detect_outliers = None
+    outlier_mask = None
+    X_fit = X
+    if detect_outliers == 'dbscan':
+        outlier_mask = dbscan_outliers(X, dbscan_eps)
+        if outlier_mask.all():
+            return np.full(len(X), N_COMPONENTS, dtype=np.int64)
+        X_fit = X[~outlier_mask]                           # stats.py:104
+    centroids = kmeans_fit(X_fit, pkey)
     d2 = _sqdist(X, centroids)                                     # A1
     init_pred = np.argmin(d2, axis=1)
-    if not detect_outliers:
+    if detect_outliers is None:
         return init_pred
-    dists = np.min(d2, axis=1)
-    mad = median_absolute_deviation(dists)
-    init_pred[dists > outlier_factor * mad] = N_COMPONENTS
+    if detect_outliers == 'mad':
+        dists = np.min(d2, axis=1)
+        mad = median_absolute_deviation(dists)
+        outlier_mask = dists > outlier_factor * mad
+    init_pred[outlier_mask] = N_COMPONENTS
     return init_pred
 
 
-def initialise_gmms(samples, pkey, outlier_factor=0.5, pseudocount=0.5, add_uniform=True):
-    '''stats.py:127-191 (full covariance; MAD outliers + uniform component unless --no-uniform)'''
+def initialise_gmms(samples, pkey, outlier_factor=0.5, pseudocount=0.5, add_uniform=True,
+                    covariance='full', outlier_method='mad', dbscan_eps=5.0):
+    '''stats.py:127-191: full / diag covariance; MAD or DBSCAN outliers + uniform component unless --no-uniform'''
     sizes = [len(s) for s in samples]
     pooled = np.concatenate(samples)
-    init_pred = kmeans_init_clusters(pooled, pkey, outlier_factor, add_uniform)
-    dists = [MVNormal.from_samples(pooled[init_pred == i])
-             for i in range(N_COMPONENTS)]
+    init_pred = kmeans_init_clusters(pooled, pkey, outlier_factor,
+                                     outlier_method if add_uniform else None, dbscan_eps)
+    if covariance == 'full':
+        dists = [MVNormal.from_samples(pooled[init_pred == i]) for i in range(N_COMPONENTS)]
+    elif covariance == 'diag':
+        dists = [DiagNormal.from_samples(pooled[init_pred == i]) for i in range(N_COMPONENTS)]
+    else:
+        raise ValueError('Only full and diag covariances are supported')
     ncomp = N_COMPONENTS + int(add_uniform)
     per_samp = np.array_split(init_pred, np.cumsum(sizes)[:-1])
     weights = [(np.bincount(p, minlength=ncomp) + pseudocount)
@@ -480,7 +572,8 @@ class GMMFit:
 
 
 def fit_gmm(cntrl, treat, pkey, outlier_factor=0.5, max_fit_depth=1000,
-            sample_ids=None, sample_rows=None, add_uniform=True):
+            sample_ids=None, sample_rows=None, add_uniform=True,
+            covariance='full', outlier_method='mad', dbscan_eps=5.0):
     '''
     stats.py:228-299 (`full`, `mad`); cntrl / treat are lists of (n_s, d).
     sample_ids[s] = packed sample index (selects the sub-sampling stream),
@@ -500,7 +593,9 @@ def fit_gmm(cntrl, treat, pkey, outlier_factor=0.5, max_fit_depth=1000,
         samples.append(samp if idx is None else samp[idx])
     trace = []
     with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
-        gmms, dists, init_pred = initialise_gmms(samples, pkey, outlier_factor, add_uniform=add_uniform)
+        gmms, dists, init_pred = initialise_gmms(samples, pkey, outlier_factor, add_uniform=add_uniform,
+                                                 covariance=covariance, outlier_method=outlier_method,
+                                                 dbscan_eps=dbscan_eps)
         iters = em(samples, gmms, dists, trace=trace)
     if not all(np.isfinite(trace)):
         raise FitError('non-finite likelihood')                       # A5
@@ -576,6 +671,9 @@ class Options:
     fdr_threshold: float = 0.05
     outlier_factor: float = 0.5
     add_uniform: bool = True
+    covariance_type: str = 'full'
+    outlier_method: str = 'mad'
+    dbscan_eps: float = 5.0
     gmm: bool = True
     generate_sm_preds: bool = False
     test_level: str = 'gene'
@@ -691,15 +789,17 @@ def position_stats(cntrl, treat, kmers, opts, pkey, n_cntrl_files=None):
     sample_ids = [rep - 1 for rep in c_reps] + [n_cntrl_files + rep - 1 for rep in t_reps]
     try:
         fit = fit_gmm(cntrl_fit, treat_fit, pkey, opts.outlier_factor,
-                      opts.max_fit_depth, sample_ids, c_rows + t_rows, opts.add_uniform)
+                      opts.max_fit_depth, sample_ids, c_rows + t_rows, opts.add_uniform,
+                      opts.covariance_type, opts.outlier_method, opts.dbscan_eps)
     except np.linalg.LinAlgError:
         r.status = ST_FIT_FAILED
         return r
     r.status = ST_TESTED
     r.fit = fit
     r.dist1_means, r.dist2_means = fit.dists[0].mu, fit.dists[1].mu
-    r.dist1_stds = np.sqrt(np.diagonal(fit.dists[0].cov))
-    r.dist2_stds = np.sqrt(np.diagonal(fit.dists[1].cov))
+    # stats.py:277-291: sqrt of the covariance diagonal (full) / the NormalDistribution sigmas (diag)
+    r.dist1_stds, r.dist2_stds = [d.sigma if isinstance(d, DiagNormal) else np.sqrt(np.diagonal(d.cov))
+                                  for d in fit.dists[:2]]
     r.g_stat, r.hom_g_stat, r.p_val = gmm_g_test(
         fit.cntrl_preds, fit.treat_preds, opts.fdr_threshold)
     (r.cntrl_frac_mod, r.treat_frac_mod, r.log_odds,

@@ -35,7 +35,8 @@ def _oracle_opts(params):
                       max_fit_depth=params.max_fit_depth, min_ks=params.min_ks,
                       fdr_threshold=params.fdr_threshold, outlier_factor=params.outlier_factor,
                       gmm=params.gmm, generate_sm_preds=params.generate_sm_preds,
-                      add_uniform=params.add_uniform,
+                      add_uniform=params.add_uniform, covariance_type=params.covariance_type,
+                      outlier_method=params.outlier_method, dbscan_eps=params.dbscan_eps,
                       random_seed=params.seed)
 
 
@@ -257,6 +258,40 @@ def test_no_uniform_two_component_model(ks_path):
     out = compare(feats, 4, 2, window_size=3, add_uniform=False)
     assert out['fitted'] > 20
     assert (out['res'].preds[:, :, 2] == 0).all() and (out['res'].cw[:, 2] == 0).all()
+
+
+@pytest.mark.parametrize('w', [3, 5])
+def test_diag_covariance(w):
+    '''-C diag (stats.py:153-166, 281-291): independent Normals per column, sigma blended in the M-step (A10)'''
+    feats = synth.make_dataset(21 + w, 4, 50, [28, 33, 30, 26], 2, 2, planted_frac=0.25)
+    out = compare(feats, 4, 2, window_size=w, covariance_type='diag', max_fit_discordance=0.02)
+    assert out['fitted'] > 10
+    cov = out['res'].cov
+    off = ~np.eye(w, dtype=bool)
+    assert (cov[:, :, off] == 0).all()                # diagonal covariances come back as diag(sigma^2)
+
+
+@pytest.mark.parametrize('eps', [5.0, 3.0, 0.5])
+def test_dbscan_outliers(eps):
+    '''-D dbscan (stats.py:91-104, A11): core / border / noise rows, k-means on the inliers only; with a tiny eps
+    every row is noise and all labels are 2 (stats.py:100-101)'''
+    feats = synth.make_dataset(31, 4, 50, [28, 33, 30, 26], 2, 2, planted_frac=0.25, outlier_frac=0.06)
+    out = compare(feats, 4, 2, window_size=3, outlier_method='dbscan', dbscan_eps=eps, max_fit_discordance=0.02)
+    assert out['res'].n_fitted > 10
+    lab = out['res'].labels
+    if eps == 0.5:
+        assert ((lab == 2) | (lab == -1)).all()
+    else:
+        assert (lab == 2).any() and (lab == 0).any()
+
+
+def test_diag_dbscan_no_uniform_combinations():
+    feats = synth.make_dataset(41, 3, 40, [30, 24, 36, 31], 2, 2, planted_frac=0.3, outlier_frac=0.05)
+    compare(feats, 4, 2, window_size=3, covariance_type='diag', outlier_method='dbscan', max_fit_discordance=0.02)
+    # --no-uniform disables outlier detection whatever -D says (stats.py:472)
+    out = compare(feats, 4, 2, window_size=3, covariance_type='diag', outlier_method='dbscan', add_uniform=False,
+                  max_fit_discordance=0.02)
+    assert (out['res'].labels != 2).all()
 
 
 @pytest.mark.parametrize('seed', [101, 102, 103, 104])

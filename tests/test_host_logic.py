@@ -165,7 +165,12 @@ def test_options_mirror_the_reference_cli():
     import click
     assert not GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='x',
                            add_uniform=False).engine_params().add_uniform
-    for kw in (dict(covariance_type='diag'), dict(outlier_method='dbscan'), dict(window_size=4)):
+    ep = GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='x', covariance_type='diag',
+                     outlier_method='dbscan', dbscan_eps=3.5).engine_params()
+    assert (ep.covariance_type, ep.outlier_method, ep.dbscan_eps) == ('diag', 'dbscan', 3.5)
+    ps = ep.struct()
+    assert (ps.covariance_type, ps.outlier_method, ps.dbscan_eps) == (1, 1, 3.5)
+    for kw in (dict(covariance_type='tied'), dict(outlier_method='lof'), dict(window_size=4)):
         with pytest.raises(click.UsageError):
             GMMTestOpts(cntrl_hdf5_fns=('a',), treat_hdf5_fns=('b',), output_bed_fn='x', **kw)
 

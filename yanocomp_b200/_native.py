@@ -17,6 +17,8 @@ YC_MAX_SAMPLES = 16
 ST_NOT_A_WINDOW, ST_KS_FILTERED, ST_TESTED, ST_FIT_FAILED, ST_DEGENERATE, ST_KS_ONLY, ST_GATED = range(7)
 
 YC_EINVAL, YC_ECAPACITY, YC_ENOGPU = -1, -2, -3
+YC_COV_FULL, YC_COV_DIAG = 0, 1
+YC_OUTLIER_MAD, YC_OUTLIER_DBSCAN = 0, 1
 
 
 class YcError(RuntimeError):
@@ -42,9 +44,10 @@ class Params(C.Structure):
     _fields_ = [
         ('window_size', C.c_int32), ('min_read_depth', C.c_int32),
         ('max_fit_depth', C.c_int32), ('gmm', C.c_int32),
-        ('add_uniform', C.c_int32), ('reserved0', C.c_int32),
+        ('add_uniform', C.c_int32), ('covariance_type', C.c_int32),
         ('min_ks', C.c_double), ('fdr_threshold', C.c_double),
         ('outlier_factor', C.c_double), ('seed', C.c_uint64),
+        ('dbscan_eps', C.c_double), ('outlier_method', C.c_int32), ('reserved1', C.c_int32),
     ]
 
 

@@ -39,6 +39,12 @@ int check_common(const yc_batch_t *b, const yc_params_t *p) {
     if (p->max_fit_depth < 1) return fail(YC_EINVAL, "max_fit_depth must be >= 1");
     if (p->min_read_depth < 1) return fail(YC_EINVAL, "min_read_depth must be >= 1");
     if (b->total_cols > 0x7fffffffll) return fail(YC_EINVAL, "more than 2^31-1 candidate positions in one batch");
+    if (p->covariance_type != YC_COV_FULL && p->covariance_type != YC_COV_DIAG)
+        return fail(YC_EINVAL, "covariance_type=%d (only full and diag covariances are supported)", p->covariance_type);
+    if (p->outlier_method != YC_OUTLIER_MAD && p->outlier_method != YC_OUTLIER_DBSCAN)
+        return fail(YC_EINVAL, "outlier_method=%d", p->outlier_method);
+    if (p->outlier_method == YC_OUTLIER_DBSCAN && !(p->dbscan_eps > 0.0))
+        return fail(YC_EINVAL, "dbscan_eps must be positive");
     return 0;
 }
 
@@ -68,6 +74,8 @@ int check_smem(int need, const char *kernel) {
 bool use_warp_fit(const yc_batch_t &b, const yc_params_t &p) {
     const char *force = getenv("YC_FIT_PATH");
     if (force && strcmp(force, "cta") == 0) return false;
+    // the non-default model branches (diag covariance, DBSCAN outliers) live in the general kernels only
+    if (p.covariance_type != YC_COV_FULL || (p.outlier_method != YC_OUTLIER_MAD && p.add_uniform)) return false;
     return yc::fit_warp_eligible(b, p) && yc::fit_warp_smem_bytes(b, p) <= smem_limit();
 }
 

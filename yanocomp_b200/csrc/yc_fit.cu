@@ -175,6 +175,25 @@ __device__ __forceinline__ void load_row(const FitCtx<W> &c, int i, double (&x)[
     for (int j = 0; j < W; ++j) x[j] = h2d(c.xs[j * c.cap + i]);
 }
 
+// Row index of the k-th row (0-based, pooled order) whose label is not 2 -- the mapping from an
+// index into X[~outlier_mask] (stats.py:104) back to the fit rows.  Every thread owns the
+// contiguous chunk [i0c, i1c); scratch: YC_NWARPS + 1 ints.  All threads return the row.
+__device__ __forceinline__ int nth_inlier(const int8_t *lab, int i0c, int i1c, int k, int *scratch) {
+    int loc = 0;
+    for (int i = i0c; i < i1c; ++i) loc += lab[i] != 2;
+    int total;
+    const int before = block_excl_scan_i(loc, scratch, total);
+    if (k >= before && k < before + loc) {
+        int seen = before;
+        for (int i = i0c; i < i1c; ++i)
+            if (lab[i] != 2) { if (seen == k) { scratch[YC_NWARPS] = i; break; } ++seen; }
+    }
+    __syncthreads();
+    const int row = scratch[YC_NWARPS];
+    __syncthreads();
+    return row;
+}
+
 // ---------------------------------------------------------------------------
 // Kernel 2a
 // ---------------------------------------------------------------------------
@@ -204,16 +223,57 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     const int n = c.n;
     const uint64_t pkey = c.w.pkey;
 
-    // ---------------- k-means++ x3 + Lloyd  (assumption A2)
+    // ---------------- --outlier-method dbscan (stats.py:91-104, assumption A11): a row is an outlier when it
+    // is neither a core point (>= n/4 rows within eps, itself included) nor within eps of one.  Squared
+    // distances of binary16 rows are exact in FP64, so `d2 <= eps^2` is the comparison sklearn makes.
+    const bool db = p.add_uniform && p.outlier_method == YC_OUTLIER_DBSCAN;
+    int n_in = n;                                          // rows k-means is fitted on
+    if (db) {
+        const double eps2 = mul_rn(p.dbscan_eps, p.dbscan_eps), min_samples = mul_rn(0.25, (double)n);
+        for (int i = tid; i < n; i += YC_BLOCK) {
+            double x[W];
+            load_row<W>(c, i, x);
+            int cnt = 0;
+            for (int j = 0; j < n; ++j) {
+                double y[W];
+                load_row<W>(c, j, y);
+                cnt += sqdist<W>(x, y) <= eps2;
+            }
+            lab[i] = (double)cnt >= min_samples ? 0 : 3;   // 0: core point, 3: not core (resolved below)
+        }
+        __syncthreads();
+        int noise = 0;
+        for (int i = tid; i < n; i += YC_BLOCK) {
+            if (lab[i] == 3) {
+                double x[W];
+                load_row<W>(c, i, x);
+                bool reach = false;
+                for (int j = 0; j < n && !reach; ++j) {
+                    if (lab[j] == 0) {                     // lab[j] of other non-core rows may turn 1 meanwhile: never 0
+                        double y[W];
+                        load_row<W>(c, j, y);
+                        reach = sqdist<W>(x, y) <= eps2;
+                    }
+                }
+                lab[i] = reach ? 1 : 2;                    // 1: border point (inlier), 2: outlier
+                noise += !reach;
+            }
+        }
+        noise = block_sum_i(noise, ired);                  // also orders the lab[] writes
+        n_in = n - noise;
+    }
+
+    // ---------------- k-means++ x3 + Lloyd on the inliers  (assumption A2)
     double best[2 * W], best_total = INFINITY;
     bool have_best = false;
     const int C = (n + YC_BLOCK - 1) / YC_BLOCK;
     const int i0c = min(tid * C, n), i1c = min(i0c + C, n);
-    for (int restart = 0; restart < 3; ++restart) {
+    for (int restart = 0; restart < 3 && n_in > 0; ++restart) {
         double cen[2 * W];
         {
             const double u0 = rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 0);
-            const int i0 = min((int)(u0 * (double)n), n - 1);
+            int i0 = min((int)(u0 * (double)n_in), n_in - 1);
+            if (db) i0 = nth_inlier(lab, i0c, i1c, i0, ired);
             double x[W];
             load_row<W>(c, i0, x);
 #pragma unroll
@@ -221,7 +281,10 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         {   // second centre: D^2 sampling through the cumulative sum
             double loc = 0.0;
-            for (int i = i0c; i < i1c; ++i) { double x[W]; load_row<W>(c, i, x); loc = add_rn(loc, sqdist<W>(x, cen)); }
+            for (int i = i0c; i < i1c; ++i) {
+                if (db && lab[i] == 2) continue;
+                double x[W]; load_row<W>(c, i, x); loc = add_rn(loc, sqdist<W>(x, cen));
+            }
             // exclusive scan of the chunk sums over the CTA
             double inc = loc;
 #pragma unroll
@@ -236,9 +299,13 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             const double u1 = rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 1);
             const double target = mul_rn(u1, total);
             int below = 0;
-            for (int i = i0c; i < i1c; ++i) { double x[W]; load_row<W>(c, i, x); run = add_rn(run, sqdist<W>(x, cen)); below += (run <= target); }
+            for (int i = i0c; i < i1c; ++i) {
+                if (db && lab[i] == 2) continue;
+                double x[W]; load_row<W>(c, i, x); run = add_rn(run, sqdist<W>(x, cen)); below += (run <= target);
+            }
             below = block_sum_i(below, ired);
-            const int i1 = min(below, n - 1);
+            int i1 = min(below, n_in - 1);
+            if (db) i1 = nth_inlier(lab, i0c, i1c, i1, ired);
             double x[W];
             load_row<W>(c, i1, x);
 #pragma unroll
@@ -259,6 +326,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 #pragma unroll
             for (int k = 0; k < 2 * W + 3; ++k) acc[k] = 0.0;
             for (int i = tid; i < n; i += YC_BLOCK) {
+                if (db && lab[i] == 2) continue;
                 double x[W];
                 load_row<W>(c, i, x);
                 const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
@@ -281,13 +349,25 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             for (int j = 0; j < 2 * W; ++j) best[j] = cen[j];
         }
     }
-    if (!have_best) {
+    if (!have_best && n_in > 0) {
         if (tid == 0) status[g] = YC_ST_FIT_FAILED;
         return;
     }
-    // ---------------- nearest-centroid labels; MAD outliers unless --no-uniform (stats.py:114-122, A1)
+    // ---------------- nearest-centroid labels; outliers: MAD rule (stats.py:114-122, A1), the DBSCAN
+    // mask (stats.py:122), or none with --no-uniform
     int n_out = 0;
-    if (!p.add_uniform) {
+    if (db) {
+        n_out = n - n_in;
+        if (n_in > 0) {                                    // every row an outlier: all labels stay 2 (stats.py:100-101)
+            for (int i = tid; i < n; i += YC_BLOCK) {
+                if (lab[i] == 2) continue;
+                double x[W];
+                load_row<W>(c, i, x);
+                lab[i] = (int8_t)(sqdist<W>(x, best + W) < sqdist<W>(x, best));
+            }
+        }
+        __syncthreads();
+    } else if (!p.add_uniform) {
         for (int i = tid; i < n; i += YC_BLOCK) {
             double x[W];
             load_row<W>(c, i, x);
@@ -337,7 +417,8 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     if (labels_out) for (int i = tid; i < n && i < max_fit_rows; i += YC_BLOCK)
         labels_out[(size_t)slot * max_fit_rows + i] = lab[i];
 
-    // ---------------- ML Gaussians per label (stats.py:148-152)
+    // ---------------- ML Gaussians per label (stats.py:148-152; diag: column mean / population std,
+    // N(0, 1) per column for an empty cluster, stats.py:153-166)
     for (int k = 0; k < 2; ++k) {
         double S[NS];
 #pragma unroll
@@ -357,7 +438,30 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             }
         }
         block_sum<NS>(S, red);
-        if (tid == k * 32) {
+        if (p.covariance_type == YC_COV_DIAG) {
+            // numpy's .std(): sqrt(mean((x - mean)^2)) from the deviations (exactly 0 for a constant column)
+            double mean[W], dev[W];
+#pragma unroll
+            for (int a = 0; a < W; ++a) { mean[a] = S[0] > 0.0 ? div_rn(S[1 + a], S[0]) : 0.0; dev[a] = 0.0; }
+            for (int i = tid; i < n; i += YC_BLOCK) {
+                if (lab[i] == k) {
+                    double x[W];
+                    load_row<W>(c, i, x);
+#pragma unroll
+                    for (int a = 0; a < W; ++a) { const double t = sub_rn(x[a], mean[a]); dev[a] += t * t; }
+                }
+            }
+            block_sum<W>(dev, red);
+            if (tid == k * 32) {
+                for (int a = 0; a < W; ++a) {
+                    const double sg = S[0] > 0.0 ? sqrt(dev[a] / S[0]) : 1.0;
+                    out.mu[((size_t)slot * 2 + k) * W + a] = mean[a];
+                    for (int c2 = 0; c2 < W; ++c2)
+                        out.cov[((size_t)slot * 2 + k) * W * W + a * W + c2] = (a == c2) ? sg * sg : 0.0;
+                }
+                par[k] = 1.0;                  // no factorisation to fail: sigma = 0 shows up as a non-finite likelihood
+            }
+        } else if (tid == k * 32) {
             double mu[W], cov[W * W];
             const bool ok = ml_gaussian<W>(S, mu, cov);
             for (int a = 0; a < W; ++a) out.mu[((size_t)slot * 2 + k) * W + a] = mu[a];
@@ -552,7 +656,27 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 for (int w2 = 0; w2 < YC_NWARPS; ++w2) t += part[w2 * NP + k * NS + q];
                 S[q] = t;
             }
-            if (S[0] < 1e-7) {                                           // A3: skipped, summaries kept
+            if (p.covariance_type == YC_COV_DIAG) {
+                // NormalDistribution.from_summaries per column (A10): skipped below 1e-8, mean AND sigma blended
+                if (S[0] < 1e-8) {
+                    for (int q = 0; q < NS; ++q) carry[k * NS + q] = S[q];
+                } else {
+                    for (int q = 0; q < NS; ++q) carry[k * NS + q] = 0.0;
+                    double logdet = 0.0;
+                    for (int a = 0; a < W; ++a) {
+                        const double s2 = S[1 + W + a * W - a * (a - 1) / 2];
+                        const double m_new = S[1 + a] / S[0];
+                        const double sg_new = sqrt(s2 / S[0] - (S[1 + a] * S[1 + a]) / (S[0] * S[0]));
+                        const double sg = sqrt(par->cov[k][a * W + a]) * step + sg_new * (1.0 - step);
+                        par->mu[k][a] = par->mu[k][a] * step + m_new * (1.0 - step);
+                        for (int c2 = 0; c2 < W; ++c2) { par->cov[k][a * W + c2] = 0.0; par->linv[k][a * W + c2] = 0.0; }
+                        par->cov[k][a * W + a] = sg * sg;
+                        par->linv[k][a * W + a] = 1.0 / sg;
+                        logdet += 2.0 * log(sg);
+                    }
+                    par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+                }
+            } else if (S[0] < 1e-7) {                                    // A3: skipped, summaries kept
                 for (int q = 0; q < NS; ++q) carry[k * NS + q] = S[q];
             } else {
                 for (int q = 0; q < NS; ++q) carry[k * NS + q] = 0.0;

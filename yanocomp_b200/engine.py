@@ -26,6 +26,9 @@ class EngineParams:
     outlier_factor: float = 0.5
     gmm: bool = True
     add_uniform: bool = True
+    covariance_type: str = 'full'        # -C full | diag
+    outlier_method: str = 'mad'          # -D mad | dbscan
+    dbscan_eps: float = 5.0
     generate_sm_preds: bool = False
     seed: int = 0
 
@@ -36,6 +39,9 @@ class EngineParams:
     def struct(self):
         return N.Params(window_size=self.window_size, min_read_depth=self.min_read_depth,
                         max_fit_depth=self.max_fit_depth, gmm=int(self.gmm), add_uniform=int(self.add_uniform),
+                        covariance_type={'full': N.YC_COV_FULL, 'diag': N.YC_COV_DIAG}[self.covariance_type],
+                        outlier_method={'mad': N.YC_OUTLIER_MAD, 'dbscan': N.YC_OUTLIER_DBSCAN}[self.outlier_method],
+                        dbscan_eps=float(self.dbscan_eps),
                         min_ks=self.min_ks, fdr_threshold=self.fdr_threshold,
                         outlier_factor=self.outlier_factor, seed=int(self.seed) & ((1 << 64) - 1))
 

@@ -75,14 +75,12 @@ class GMMTestOpts:
         self.check_supported()
 
     def check_supported(self):
-        '''non-default model branches the kernels do not implement yet'''
-        if self.gmm:
-            if self.covariance_type != 'full':
-                raise click.UsageError('--covariance-type diag is not implemented in yanocomp_b200')
-            if self.outlier_method != 'mad':
-                raise click.UsageError('--outlier-method dbscan is not implemented in yanocomp_b200')
         if self.window_size % 2 == 0 or not 1 <= self.window_size <= N.YC_MAX_WINDOW:
             raise click.UsageError(f'--window-size must be odd and <= {N.YC_MAX_WINDOW}')
+        if self.covariance_type not in ('full', 'diag'):
+            raise click.UsageError('Only full and diag covariances are supported')      # stats.py:167-168
+        if self.outlier_method not in ('mad', 'dbscan'):
+            raise click.UsageError('--outlier-method must be mad or dbscan')
 
     def engine_params(self):
         from .engine import EngineParams
@@ -90,7 +88,8 @@ class GMMTestOpts:
             window_size=self.window_size, min_read_depth=self.min_read_depth,
             max_fit_depth=self.max_fit_depth, min_ks=self.min_ks,
             fdr_threshold=self.fdr_threshold, outlier_factor=self.outlier_factor,
-            gmm=self.gmm, add_uniform=self.add_uniform,
+            gmm=self.gmm, add_uniform=self.add_uniform, covariance_type=self.covariance_type,
+            outlier_method=self.outlier_method, dbscan_eps=self.dbscan_eps,
             generate_sm_preds=self.generate_sm_preds and self.gmm,
             seed=self.random_seed)
 
