@@ -95,7 +95,7 @@ def run_reference(args, cfg, opts_kw):
     if rank != 0:
         return
     cores = min(host_cores(), 64)
-    n_feat = max(3 * cores, 8)      # three features (~1500 positions, ~10 s) per core per step
+    n_feat = max(8 * cores, 8)      # eight features (~4000 positions, ~10 s of CPU work) per core per step
     ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
@@ -309,7 +309,7 @@ def run_gpu(args, cfg, opts_kw):
     em_name = 'gmm_em'
     em_ms = kavg.get(em_name, float('inf'))
     traffic = None
-    tfn = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    tfn = os.path.join(ROOT, 'profiles', 'r01c_traffic.json')
     if os.path.exists(tfn) and args.config == 2 and not args.features:
         with open(tfn) as fh:
             traffic = json.load(fh).get(dom)        # ncu --set full capture of the same workload
@@ -326,7 +326,7 @@ def run_gpu(args, cfg, opts_kw):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = min(host_cores(), 64)
-        n_feat = max(3 * cores, 8)
+        n_feat = max(8 * cores, 8)          # ~10 s of CPU work per core
         ctx = mp.get_context('spawn')
         with ctx.Pool(cores) as pool:
             v, pos, fit, wall = cpu_sample(cfg, n_feat, cores, 777, opts_kw, pool)

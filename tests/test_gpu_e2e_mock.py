@@ -18,8 +18,11 @@ GENES = {'GENE_A': (1000, 40, ['TX_A1', 'TX_A2']), 'GENE_B': (50, 30, ['TX_B1'])
 MOD = {'GENE_A': {1010: 9.0, 1011: -7.0, 1012: 8.0, 1025: -9.0, 1026: 9.0}, 'GENE_B': {60: 10.0, 61: 9.0, 62: -8.0}}
 
 
-@pytest.mark.parametrize('level,strand', [('gene', '+'), ('transcript', '-')])
-def test_parallel_test_matches_oracle(level, strand, monkeypatch):
+@pytest.mark.parametrize('level,strand,extra', [
+    ('gene', '+', {}), ('transcript', '-', {}),
+    ('gene', '+', dict(covariance_type='diag', outlier_method='dbscan', dbscan_eps=6.0)),      # -C diag -D dbscan -E 6
+])
+def test_parallel_test_matches_oracle(level, strand, extra, monkeypatch):
     rng = np.random.default_rng(7)
     files = {}
     for i in range(4):
@@ -33,9 +36,9 @@ def test_parallel_test_matches_oracle(level, strand, monkeypatch):
     monkeypatch.setattr(G, 'hdf5_list', fake_hdf5_list)
     opts = G.GMMTestOpts(cntrl_hdf5_fns=('file0', 'file1'), treat_hdf5_fns=('file2', 'file3'),
                          output_bed_fn='x.bed', output_sm_preds_fn='x.json', test_level=level,
-                         random_seed=3, processes=2)
+                         random_seed=3, processes=2, **extra)
     res, sm = G.parallel_test(opts)
-    o_opts = yo.Options(window_size=3, generate_sm_preds=True, test_level=level, random_seed=3)
+    o_opts = yo.Options(window_size=3, generate_sm_preds=True, test_level=level, random_seed=3, **extra)
     recs, everything = yo.test_features([files['file0'], files['file1']], [files['file2'], files['file3']], o_opts)
     ref = {(r['gene_id'], r['pos']): r for r in recs}
     got = {(r.gene_id, r.pos): r for r in res.itertuples(index=False)}

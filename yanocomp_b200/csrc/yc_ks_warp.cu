@@ -338,8 +338,11 @@ __host__ __device__ inline KdSmem kd_layout(int P) {
     return s;
 }
 
+#ifndef YC_KD_MINBLOCKS
+#define YC_KD_MINBLOCKS 8
+#endif
 template <int W>
-__global__ void __launch_bounds__(YC_KW_WARPS * 32)
+__global__ void __launch_bounds__(YC_KW_WARPS * 32, YC_KD_MINBLOCKS)
 ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t c0, const int ncol,
             const double *__restrict__ scr,
             double *__restrict__ ks_stat, double *__restrict__ ks_pval,
