@@ -26,7 +26,7 @@
 namespace yc {
 
 struct FwSmem {
-    int xs_off, srow_off, lab_off, buf_off, par_off, mask_off, cnt_off, fstart_off, wtmp_off, red_off, total;
+    int xs_off, srow_off, lab_off, buf_off, par_off, mask_off, cnt_off, fstart_off, wtmp_off, carry_off, red_off, total;
 };
 
 // which: 0 = init (sort buffer, labels, 2 NS reduction rows), 1 = EM (responsibilities, 2 NS + 1 + 2 R
@@ -42,6 +42,7 @@ __host__ __device__ inline FwSmem fw_layout(int W, int R, int cap, int which) {
     s.buf_off = o;    o += buf_n * (int)sizeof(double);                         // MAD sort buffer / EM responsibilities
     s.par_off = o;    o += (4 * W * W + 4 * W + 3 * YC_MAX_SAMPLES + 8) * (int)sizeof(double);
     s.wtmp_off = o;   o += 2 * YC_MAX_SAMPLES * (int)sizeof(double);
+    s.carry_off = o;  o += (which == 1 ? 2 * NS : 0) * (int)sizeof(double);          // EM: summaries kept when S0 < 1e-7
     s.red_off = o;    o += red_rows * 33 * (int)sizeof(double);
     s.mask_off = o;   o += ((cap + 31) / 32 + 1) * (int)sizeof(uint32_t);
     s.cnt_off = o;    o += (YC_MAX_SAMPLES + 2) * (int)sizeof(int);
@@ -591,9 +592,8 @@ __device__ __noinline__ void em_mstep(EmPar<W> *par, int k, const double *red, d
             if (i == j) {
                 ok &= (sacc > 0.0) && isfinite(sacc);
                 prod *= sacc;
-                const double d = sqrt(sacc);
-                Lp[i * (i + 1) / 2 + i] = d;
-                rinv[i] = 1.0 / d;
+                rinv[i] = rsqrt(sacc);                                   // one reciprocal square root instead of sqrt + division
+                Lp[i * (i + 1) / 2 + i] = sacc * rinv[i];
             } else {
                 Lp[i * (i + 1) / 2 + j] = sacc * rinv[j];
             }
@@ -682,9 +682,9 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     bool failed = par->ok == 0;
     const bool uni = p.add_uniform != 0;
 
-    double carry[NS];                                   // lanes 0/1: summaries kept when S0 < 1e-7 (A3)
-#pragma unroll
-    for (int q = 0; q < NS; ++q) carry[q] = 0.0;
+    double *carry = reinterpret_cast<double *>(smem_raw + L.carry_off);   // [2][NS]: summaries kept when S0 < 1e-7 (A3)
+    for (int q = lane; q < 2 * NS; q += 32) carry[q] = 0.0;
+    __syncwarp();
     int iteration = 0;
     double improvement = INFINITY, last = 0.0;
 #pragma unroll 1
@@ -789,24 +789,28 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         last = ll;
         if (!isfinite(ll)) { failed = true; break; }                     // assumption A5
         if (!(improvement > 0.1 && iteration < 1001)) break;             // last E-step's summaries discarded
-        // ---- weights from the per-sample sums (stats.py:206-211), one lane per (sample, component);
-        //      the uniform component's sum is n_s - sum r0 - sum r1 (responsibilities sum to one)
+        // ---- M-step of the shared Gaussians on lanes 0 / 1 (stats.py:202-205, A3/A4) and, in the same
+        //      divergent region so that the two serial chains can interleave, the weights from the per-sample
+        //      sums on the lanes above (stats.py:206-211; one lane per (sample, component); the uniform
+        //      component's sum is n_s - sum r0 - sum r1: responsibilities sum to one)
+        if (lane < 2) {
+            em_mstep<W>(par, lane, red, carry + lane * NS, c_em_step[iteration]);
+        } else {
 #pragma unroll 1
-        for (int q = lane; q < 3 * R; q += 32) {
-            const int s = q / 3, k = q - 3 * s;
-            const int ns = fstart[s + 1] - fstart[s];
-            if (ns > 0) {
-                const double t0s = red[(NP + 2 * s) * 33 + 32], t1s = red[(NP + 2 * s + 1) * 33 + 32];
-                const double t2s = uni ? fmax((double)ns - t0s - t1s, 0.0) : 0.0;
-                if (t0s + t1s + t2s != 0.0) {
-                    const double vk = (k == 0 ? t0s : (k == 1 ? t1s : t2s)) + 0.5;
-                    const double den = (t0s + 0.5) + (t1s + 0.5) + (uni ? t2s + 0.5 : 0.0);
-                    par->logw[s][k] = (k == 2 && !uni) ? -INFINITY : log(vk / den);
+            for (int q = lane - 2; q < 3 * R; q += 30) {
+                const int s = q / 3, k = q - 3 * s;
+                const int ns = fstart[s + 1] - fstart[s];
+                if (ns > 0) {
+                    const double t0s = red[(NP + 2 * s) * 33 + 32], t1s = red[(NP + 2 * s + 1) * 33 + 32];
+                    const double t2s = uni ? fmax((double)ns - t0s - t1s, 0.0) : 0.0;
+                    if (t0s + t1s + t2s != 0.0) {
+                        const double vk = (k == 0 ? t0s : (k == 1 ? t1s : t2s)) + 0.5;
+                        const double den = (t0s + 0.5) + (t1s + 0.5) + (uni ? t2s + 0.5 : 0.0);
+                        par->logw[s][k] = (k == 2 && !uni) ? -INFINITY : log(vk / den);
+                    }
                 }
             }
         }
-        // ---- M-step of the shared Gaussians: lane k owns component k (stats.py:202-205, A3/A4)
-        if (lane < 2) em_mstep<W>(par, lane, red, carry, c_em_step[iteration]);
         __syncwarp();
         failed = par->ok == 0;
     }
