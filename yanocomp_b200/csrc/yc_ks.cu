@@ -188,18 +188,17 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
     const int P = next_pow2(max(n1, n2));
     for (int i = tid; i < 2 * P; i += YC_BLOCK) sortbuf[i] = INFINITY;
     __syncthreads();
-    double vv[W];
+    // Only the ORDER of the projections y = sum_j z_j v_j enters D, and sum_j x_j (v_j / sig_j) differs from y
+    // by a constant: no centring, no division per read (the same arithmetic as ks_d_kernel, yc_ks_warp.cu)
+    double cj[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) vv[j] = misc[j];
+    for (int j = 0; j < W; ++j) cj[j] = misc[j] / sig[j];
     // ---- pass D: projections, appended per condition (order is irrelevant before the sort)
     for (int r = tid; r < n; r += YC_BLOCK) {
         if ((mask[r >> 5] >> (r & 31)) & 1u) {
             double y = 0.0;
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const double z = div_rn(sub_rn(h2d(__ldg(w.col[j] + r)), mu[j]), sig[j]);
-                y = fma(z, vv[j], y);
-            }
+            for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(w.col[j] + r)), cj[j], y);
             const int cond = r >= split;
             const int slot = atomicAdd(&icnt[cond], 1);
             sortbuf[cond * P + slot] = y;
