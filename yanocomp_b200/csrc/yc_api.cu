@@ -169,6 +169,7 @@ compact_scatter_kernel(const uint8_t *__restrict__ status, long long n, const in
 int compact_gated(const uint8_t *status, long long n, int32_t *fit_list, int32_t *fit_count, cudaStream_t st) {
     const int nb = (int)((n + CG_TILE - 1) / CG_TILE);
     int *block_cnt = nullptr;
+    yc::keep_pool_memory();
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&block_cnt), (size_t)nb * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     compact_count_kernel<<<nb, CG_THREADS, 0, st>>>(status, n, block_cnt);
@@ -193,6 +194,16 @@ namespace yc {
 int ks_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+void keep_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    done[dev] = true;
+}
 }
 
 extern "C" {

@@ -6,6 +6,9 @@
 namespace yc {
 // kernel launches made by this library in this process (yc_kernel_launches in the C ABI)
 void count_launches(int n);
+// the scratch of yc_ks_batch comes from the device's default memory pool (cudaMallocAsync); keep freed
+// memory in the pool instead of returning it to the driver at every synchronisation
+void keep_pool_memory();
 int ks_sort_cap(const yc_batch_t &b, const yc_params_t &p);
 int ks_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
 int ks_dispatch(const yc_batch_t &b, const yc_params_t &p,

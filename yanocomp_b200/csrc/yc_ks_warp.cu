@@ -489,15 +489,7 @@ static int launch_kw(const yc_batch_t &b, const yc_params_t &p, double *ks_stat,
                      int32_t *n_c, int32_t *n_t, uint8_t *status, int32_t *fit_list, int32_t *fit_count,
                      cudaStream_t st) {
     constexpr int GT = 2 * W * W + 2 * W;
-    static bool pool_ready = false;
-    if (!pool_ready) {
-        int dev = 0;
-        cudaMemPool_t pool;
-        unsigned long long keep = ~0ull;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        pool_ready = true;
-    }
+    keep_pool_memory();
     const int P = kw_sort_cap(b);
     const int smem_m = km_layout(W, b.n_samples, b.max_reads).total;
     const int smem_d = kd_layout(P).per_warp * YC_KW_WARPS;
