@@ -197,8 +197,11 @@ __device__ __forceinline__ int nth_inlier(const int8_t *lab, int i0c, int i1c, i
 // ---------------------------------------------------------------------------
 // Kernel 2a
 // ---------------------------------------------------------------------------
+#ifndef YC_INITC_MINBLOCKS
+#define YC_INITC_MINBLOCKS 1
+#endif
 template <int W>
-__global__ void __launch_bounds__(YC_BLOCK)
+__global__ void __launch_bounds__(YC_BLOCK, YC_INITC_MINBLOCKS)
 gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
                 uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows) {
@@ -263,6 +266,21 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         n_in = n - noise;
     }
 
+    // column totals of the rows k-means sees (exact), so that Lloyd accumulates one cluster only
+    double sumx[W];
+    {
+#pragma unroll
+        for (int j = 0; j < W; ++j) sumx[j] = 0.0;
+        for (int i = tid; i < n; i += YC_BLOCK) {
+            if (db && lab[i] == 2) continue;
+            double x[W];
+            load_row<W>(c, i, x);
+#pragma unroll
+            for (int j = 0; j < W; ++j) sumx[j] += x[j];
+        }
+        block_sum<W>(sumx, red);
+    }
+
     // ---------------- k-means++ x3 + Lloyd on the inliers  (assumption A2)
     double best[2 * W], best_total = INFINITY;
     bool have_best = false;
@@ -313,32 +331,34 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         int iteration = 0;
         double improvement = INFINITY, last = INFINITY, total = INFINITY;
-        double acc[2 * W + 3];
+        double acc[W + 2];                                   // column sums of cluster 1, total distance, size of cluster 1
         bool have_sums = false;
         while (improvement > 0.5 && iteration < 101) {
             if (have_sums) {
+                // cluster 0 = column totals - cluster 1 (sums of binary16 values: exact either way)
+                const double n1 = acc[W + 1], n0 = (double)n_in - n1;
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    if (acc[2 * W + 1 + k] > 0.0)
-#pragma unroll
-                        for (int j = 0; j < W; ++j) cen[k * W + j] = div_rn(acc[k * W + j], acc[2 * W + 1 + k]);
+                for (int j = 0; j < W; ++j) {
+                    if (n0 > 0.0) cen[j] = div_rn(sub_rn(sumx[j], acc[j]), n0);
+                    if (n1 > 0.0) cen[W + j] = div_rn(acc[j], n1);       // an empty cluster keeps its centroid (A2)
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 2 * W + 3; ++k) acc[k] = 0.0;
+            for (int k = 0; k < W + 2; ++k) acc[k] = 0.0;
             for (int i = tid; i < n; i += YC_BLOCK) {
                 if (db && lab[i] == 2) continue;
                 double x[W];
                 load_row<W>(c, i, x);
                 const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
-                const int k = d1 < d0;
-                acc[2 * W] += k ? d1 : d0;
-                acc[2 * W + 1 + k] += 1.0;
+                const bool k = d1 < d0;
+                acc[W] += k ? d1 : d0;
+                acc[W + 1] += k ? 1.0 : 0.0;
 #pragma unroll
-                for (int j = 0; j < W; ++j) { if (k) acc[W + j] += x[j]; else acc[j] += x[j]; }
+                for (int j = 0; j < W; ++j) acc[j] += k ? x[j] : 0.0;
             }
-            block_sum<2 * W + 3>(acc, red);
+            block_sum<W + 2>(acc, red);
             have_sums = true;
-            total = acc[2 * W];
+            total = acc[W];
             if (iteration > 0) improvement = last - total;
             ++iteration;
             last = total;
@@ -391,19 +411,29 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     bitonic_sort_segments(sortbuf, P, 1);
     const double med = (n & 1) ? sortbuf[n >> 1] : mul_rn(add_rn(sortbuf[(n >> 1) - 1], sortbuf[n >> 1]), 0.5);
     __syncthreads();
-    for (int i = tid; i < P; i += YC_BLOCK) {
-        double dv = INFINITY;
-        if (i < n) {
-            double x[W];
-            load_row<W>(c, i, x);
-            const double d0 = sqdist<W>(x, best), d1 = sqdist<W>(x, best + W);
-            dv = fabs(sub_rn(d1 < d0 ? d1 : d0, med));
+    // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are V-shaped,
+    // i.e. two ascending runs (left of the median walked outwards, right of it), so the order statistics of
+    // their union follow from merge ranks found by binary search (same selection as init_warp_kernel)
+    double *wsel = par + 4;
+    const int m_le = upper_bound(sortbuf, n, med);        // elements <= med form the left run
+    const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
+    for (int i = tid; i < n; i += YC_BLOCK) {
+        const double dv = fabs(sub_rn(sortbuf[i], med));
+        int rank;
+        if (i < m_le) {                                    // left run, index m_le-1-i; count right-run elements < dv
+            int lo = 0, hi = n - m_le;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(sortbuf[m_le + mid], med)) < dv) lo = mid + 1; else hi = mid; }
+            rank = (m_le - 1 - i) + lo;
+        } else {                                           // right run, index i-m_le; count left-run elements <= dv
+            int lo = 0, hi = m_le;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(sortbuf[m_le - 1 - mid], med)) <= dv) lo = mid + 1; else hi = mid; }
+            rank = (i - m_le) + lo;
         }
-        sortbuf[i] = dv;
+        if (rank == k_lo) wsel[0] = dv;
+        if (rank == k_hi) wsel[1] = dv;
     }
     __syncthreads();
-    bitonic_sort_segments(sortbuf, P, 1);
-    const double mad = (n & 1) ? sortbuf[n >> 1] : mul_rn(add_rn(sortbuf[(n >> 1) - 1], sortbuf[n >> 1]), 0.5);
+    const double mad = (n & 1) ? wsel[1] : mul_rn(add_rn(wsel[0], wsel[1]), 0.5);
     const double thr = mul_rn(p.outlier_factor, mad);
     __syncthreads();
     for (int i = tid; i < n; i += YC_BLOCK) {
@@ -515,8 +545,11 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 // ---------------------------------------------------------------------------
 // Kernel 2b
 // ---------------------------------------------------------------------------
+#ifndef YC_EMC_MINBLOCKS
+#define YC_EMC_MINBLOCKS 3
+#endif
 template <int W>
-__global__ void __launch_bounds__(YC_BLOCK)
+__global__ void __launch_bounds__(YC_BLOCK, YC_EMC_MINBLOCKS)
 gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
               const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
               uint8_t *__restrict__ status) {
