@@ -121,7 +121,8 @@ typedef struct yc_fit_out {
     /* yc_gtest_smpred_batch */
     double  *preds;     /* [n_fit*R*3]     np.round(weights*sizes)    stats.py:296 */
     double  *stats;     /* [n_fit*8]       g, hom_g, p, cntrl_frac, treat_frac,
-                                           log_odds, lower_ci, upper_ci  stats.py:316-355 */
+                                           log_odds, lower_ci, upper_ci  stats.py:316-355;
+                                           NaN for slots that were not tested */
     int64_t *post_off;  /* [n_fit]         offset (in reads) into `post`, -1 = none */
 } yc_fit_out_t;
 
@@ -197,6 +198,19 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p,
                           yc_fit_out_t *out, const uint8_t *status,
                           double *post, int64_t post_capacity,
                           int64_t *post_cursor, void *stream);
+
+/*
+ * Result rows in slot order (one launch): for every gated position its final
+ * status, KS D (GMMTestResults.ks_stat, stats.py:442), the complete-window
+ * read count and dist1_stds / dist2_stds = sqrt(diag(cov)) (stats.py:277-280),
+ * so that a caller fetches contiguous per-fit rows instead of gathering on the
+ * host.  stds [n_fit*2*w], the others [n_fit].
+ */
+int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, int32_t window_size,
+                       const uint8_t *status, const double *ks_stat,
+                       const int32_t *n_c, const int32_t *n_t, const double *cov,
+                       uint8_t *status_fit, double *ks_stat_fit, double *stds,
+                       int32_t *nall_fit, void *stream);
 
 /*
  * Kernels 2a + 2b + 3 back to back on one stream (convenience; same outputs

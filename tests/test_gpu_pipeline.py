@@ -45,3 +45,29 @@ def test_pipelined_equals_single_batch():
             seen += 1
         f0 += h.n_features
     assert seen == len(ref) > 20
+
+
+@pytest.mark.parametrize('growth', [1.0, 2.5])
+def test_streaming_pipeline_with_rotating_staging_buffers(growth):
+    '''engine.run_pipelined as test_chunk uses it: many batches, results consumed as they are yielded
+    (staging buffers rotate), in order, each equal to the same batch run on its own'''
+    from yanocomp_b200.engine import Engine, EngineParams
+    feats = synth.make_dataset(23, 14, 30, [20, 26, 24, 22], 2, 2, planted_frac=0.3)
+    host = HostBatch(feats, 4, 2)
+    params = EngineParams(window_size=3)
+    parts = host.split(7, growth)
+    assert 2 <= len(parts) <= 7 and sum(h.n_features for h in parts) == 14
+    eng = Engine(params)
+    got = []
+    for h, r in eng.run_pipelined(iter(parts), fetch='records'):
+        got.append((h, r.status.copy(), r.fit_list.copy(), r.stats.copy(), r.mu.copy(), r.launches))
+    assert [h for h, *_ in got] == parts                                   # yielded in submission order
+    solo = Engine(params)
+    for h, status, fit_list, stats, mu, launches in got:
+        one = solo.run(solo.upload(h), fetch='records')
+        np.testing.assert_array_equal(status, one.status)
+        np.testing.assert_array_equal(fit_list, one.fit_list)
+        assert np.all(np.diff(fit_list) > 0)                               # ordered compaction: ascending columns
+        np.testing.assert_array_equal(stats, one.stats)
+        np.testing.assert_array_equal(mu, one.mu)
+        assert launches == one.launches > 0

@@ -783,8 +783,9 @@ gtest_smpred_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     long long *soff = reinterpret_cast<long long *>(smem_raw + L.sel_off);
     const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
-    if (status[g] != YC_ST_TESTED) {
+    if (status[g] != YC_ST_TESTED) {                                     // failed fit: no row
         if (tid == 0) out.post_off[slot] = -1;
+        if (tid < 8) out.stats[(size_t)slot * 8 + tid] = nan("");
         return;
     }
     FitCtx<W> c;

@@ -855,7 +855,11 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     const FwSmem L = fw_layout(W, R, cap, 2);
     const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
-    if (status[g] != YC_ST_TESTED) { if (lane == 0) out.post_off[slot] = -1; return; }
+    if (status[g] != YC_ST_TESTED) {                                     // failed fit: no row
+        if (lane == 0) out.post_off[slot] = -1;
+        if (lane < 8) out.stats[(size_t)slot * 8 + lane] = nan("");
+        return;
+    }
     FwCtx<W> c;
     fw_front<W>(b, p, g, smem_raw, L, cap, lane, post != nullptr, c);
     const int n = c.n;

@@ -91,6 +91,29 @@ class BatchResult:
         return int(len(self.fit_list))
 
 
+_ALIGN = 256
+
+
+def _carve(specs, device=None, zero=False):
+    '''
+    One allocation for several arrays: specs = [(name, shape, torch dtype)].  Returns (arena, views,
+    extents) with extents[name] = (byte offset, byte length); every array starts on a 256-byte boundary.
+    device=None: layout only (arena is None).
+    '''
+    ext, off = {}, 0
+    for name, shape, dtype in specs:
+        nb = int(np.prod(shape, dtype=np.int64)) * torch.empty(0, dtype=dtype).element_size()
+        ext[name] = (off, nb)
+        off += (nb + _ALIGN - 1) // _ALIGN * _ALIGN
+    total = max(off, _ALIGN)
+    if device is None:
+        return None, None, ext, total
+    arena = (torch.zeros if zero else torch.empty)(total, dtype=torch.uint8, device=device)
+    views = {name: arena[ext[name][0]:ext[name][0] + ext[name][1]].view(dtype).view(shape)
+             for name, shape, dtype in specs}
+    return arena, views, ext, total
+
+
 class Engine:
     '''owns the per-device scratch and launches the kernels of one batch'''
 
@@ -187,11 +210,11 @@ class Engine:
         n = max(dev.host.total_cols, 1)
         stream = torch.cuda.current_stream(d).cuda_stream
         f64, i32 = torch.float64, torch.int32
-        t = dict(
-            ks_stat=torch.empty(n, dtype=f64, device=d), ks_pval=torch.empty(n, dtype=f64, device=d),
-            n_c=torch.empty(n, dtype=i32, device=d), n_t=torch.empty(n, dtype=i32, device=d),
-            status=torch.empty(n, dtype=torch.uint8, device=d),
-            fit_list=torch.empty(n, dtype=i32, device=d), fit_count=torch.empty(1, dtype=i32, device=d))
+        # per-column outputs in one arena, status and fit_list first: the host tail needs status[:n] and
+        # fit_list[:n_fit], which is then one contiguous device->host copy
+        specs = [('status', (n,), torch.uint8), ('fit_list', (n,), i32), ('ks_stat', (n,), f64),
+                 ('ks_pval', (n,), f64), ('n_c', (n,), i32), ('n_t', (n,), i32), ('fit_count', (1,), i32)]
+        col_arena, t, col_ext, _ = _carve(specs, d)
         launches0 = lib.yc_kernel_launches()
         ps = p.struct()
         N.check(timed('ks', lambda: lib.yc_ks_batch(
@@ -202,7 +225,8 @@ class Engine:
         counts.zero_()
         cnt32 = counts.view(torch.int32)
         cnt32[:1].copy_(t['fit_count'], non_blocking=True)
-        return dict(dev=dev, t=t, ps=ps, timed=timed, want_labels=want_labels, launches0=launches0,
+        return dict(dev=dev, t=t, col_arena=col_arena, col_ext=col_ext, ps=ps, timed=timed, want_labels=want_labels,
+                    launches=int(lib.yc_kernel_launches() - launches0),   # counted by the library at every <<< >>>
                     counts=counts, counted=torch.cuda.current_stream(d).record_event())
 
     # ---- stage B: size the outputs from the count, fit kernels, gather of the result rows
@@ -214,25 +238,23 @@ class Engine:
         f64, i32 = torch.float64, torch.int32
         status, fit_list, n_c, n_t = t['status'], t['fit_list'], t['n_c'], t['n_t']
         ctx['counted'].synchronize()                                     # the 4-byte count only
+        fit_launches0 = lib.yc_kernel_launches()
         n_fit = int(ctx['counts'].view(torch.int32)[0]) if (p.gmm and dev.host.total_cols) else 0
         m = max(n_fit, 1)
-        out_t = dict(
-            mu=torch.empty(m * 2 * w, dtype=f64, device=d),
-            cov=torch.empty(m * 2 * w * w, dtype=f64, device=d),
-            box=torch.empty(m * w * 2, dtype=f64, device=d),
-            logw=torch.empty(m * R * 3, dtype=f64, device=d),
-            cw=torch.zeros(m * 3, dtype=f64, device=d),
-            iters=torch.zeros(m, dtype=i32, device=d),
-            loglik=torch.zeros(m, dtype=f64, device=d),
-            preds=torch.zeros(m * R * 3, dtype=f64, device=d),
-            stats=torch.full((m * 8,), float('nan'), dtype=f64, device=d),
-            post_off=torch.full((m,), -1, dtype=torch.int64, device=d),
-        )
-        out = N.FitOut(**{k: v.data_ptr() for k, v in out_t.items()})
+        # per-fit outputs in one zero-filled arena (one memset instead of a fill per array), ordered so that
+        # each fetch level is a prefix: records | + sm-preds | + full
+        specs = [('status_fit', (m,), torch.uint8), ('ks_stat_fit', (m,), f64), ('mu', (m, 2, w), f64),
+                 ('stds', (m, 2, w), f64), ('stats', (m, 8), f64),
+                 ('nall_fit', (m,), i32), ('cov', (m, 2, w, w), f64), ('box', (m, w, 2), f64),
+                 ('cw', (m, 3), f64), ('post_off', (m,), torch.int64),
+                 ('logw', (m, R, 3), f64), ('iters', (m,), i32), ('loglik', (m,), f64), ('preds', (m, R, 3), f64)]
+        fit_arena, out_t, fit_ext, fit_total = _carve(specs, d, zero=True)
+        out = N.FitOut(**{k: out_t[k].data_ptr() for k in ('mu', 'cov', 'box', 'logw', 'cw', 'iters', 'loglik',
+                                                            'preds', 'stats', 'post_off')})
         labels = None
         max_fit_rows = 0
         post = None
-        post_cursor = torch.zeros(1, dtype=torch.int64, device=d)
+        post_cursor = torch.empty(1, dtype=torch.int64, device=d)       # zeroed by yc_gtest_smpred_batch
         b = dev.struct
         ks_stat, ks_pval = t['ks_stat'], t['ks_pval']
         want_labels = ctx['want_labels']
@@ -255,72 +277,96 @@ class Engine:
             N.check(timed('gtest_smpred', lambda: lib.yc_gtest_smpred_batch(
                 b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
                 post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
-        launches = int(lib.yc_kernel_launches() - ctx['launches0'])   # counted by the library at every <<< >>>
+            # the per-fit rows the host tail reads, gathered on the device in slot order
+            N.check(lib.yc_gather_fit_rows(
+                fit_list.data_ptr(), n_fit, w, status.data_ptr(), ks_stat.data_ptr(), n_c.data_ptr(), n_t.data_ptr(),
+                out_t['cov'].data_ptr(), out_t['status_fit'].data_ptr(), out_t['ks_stat_fit'].data_ptr(),
+                out_t['stds'].data_ptr(), out_t['nall_fit'].data_ptr(), stream))
+        launches = ctx['launches'] + int(lib.yc_kernel_launches() - fit_launches0)
         ctx.update(n_fit=n_fit, launches=launches)
         if not fetch:
+            dev_out = {k: v for k, v in out_t.items() if k not in ('status_fit', 'ks_stat_fit', 'stds', 'nall_fit')}
+            flat = {k: dev_out[k].reshape(-1) for k in dev_out}
             ctx['device'] = dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
                                  fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
-                                 labels=labels, launches=launches, **out_t)
+                                 labels=labels, launches=launches, **flat)
             return ctx
-        nc = dev.host.total_cols
         level = 'full' if fetch is True else fetch
-        fl = fit_list[:n_fit]
-        fli = fl.long()
-        cov = out_t['cov'][:n_fit * 2 * w * w].view(n_fit, 2, w, w)
-        want = dict(
-            status=status[:nc], fit_list=fl, status_fit=status[fli], ks_stat_fit=ks_stat[fli],
-            mu=out_t['mu'][:n_fit * 2 * w].view(n_fit, 2, w),
-            stds=torch.sqrt(torch.diagonal(cov, dim1=2, dim2=3)).contiguous(),
-            stats=out_t['stats'][:n_fit * 8].view(n_fit, 8))
-        if level == 'full' or not p.gmm:
-            want.update(ks_stat=ks_stat[:nc], ks_pval=ks_pval[:nc])
-        if level == 'full' or p.generate_sm_preds:
-            want.update(nall_fit=(n_c[fli] + n_t[fli]), cov=cov,
-                        box=out_t['box'][:n_fit * w * 2].view(n_fit, w, 2),
-                        cw=out_t['cw'][:n_fit * 3].view(n_fit, 3), post_off=out_t['post_off'][:n_fit])
-        if level == 'full':
-            want.update(n_c=n_c[:nc], n_t=n_t[:nc],
-                        logw=out_t['logw'][:n_fit * R * 3].view(n_fit, R, 3), iters=out_t['iters'][:n_fit],
-                        loglik=out_t['loglik'][:n_fit], preds=out_t['preds'][:n_fit * R * 3].view(n_fit, R, 3))
-            if labels is not None:
-                want['labels'] = labels
         if post is not None:
             ctx['counts'][1:].copy_(post_cursor, non_blocking=True)     # posterior reads written
-        ctx.update(want=want, post=post, done=torch.cuda.current_stream(d).record_event())
+        ctx.update(level=level, fit_arena=fit_arena, fit_ext=fit_ext, fit_specs=specs, out_t=out_t, labels=labels,
+                   post=post, done=torch.cuda.current_stream(d).record_event())
         return ctx
 
     # ---- stage C: result rows -> pinned staging buffer on the fetch stream
     def _fetch_result(self, ctx, stage_key=0):
-        d = self.device
-        want, post = ctx['want'], ctx['post']
+        '''
+        Device -> host with a handful of copies: the per-column arena prefix (status, fit_list[:n_fit]; the whole
+        arena for fetch='full' / --no-gmm), the per-fit arena prefix of the fetch level, and the posteriors /
+        labels when present.  The numpy results are views of one pinned staging buffer.
+        '''
+        d, p = self.device, self.params
+        dev, t, n_fit, level = ctx['dev'], ctx['t'], ctx['n_fit'], ctx['level']
+        nc = dev.host.total_cols
+        n = max(nc, 1)
+        w, R = p.window_size, dev.host.n_samples
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(d)
             self._fetch_stream = torch.cuda.Stream(d)
         fs = self._fetch_stream
+        post, labels = ctx['post'], ctx['labels']
+        used = 0
         if post is not None:
             ctx['done'].synchronize()                                    # needs the number of posterior rows
             used = int(ctx['counts'][1])
-            want['post'] = post[:used * 2].view(used, 2)
+        col_ext, fit_ext = ctx['col_ext'], ctx['fit_ext']
+        want_cols = level == 'full' or not p.gmm
+        col_bytes = (col_ext['n_t'][0] + col_ext['n_t'][1]) if want_cols else (col_ext['fit_list'][0] + 4 * n_fit)
+        last = 'preds' if level == 'full' else ('post_off' if p.generate_sm_preds else 'stats')
+        fit_bytes = fit_ext[last][0] + fit_ext[last][1]
+        chunks = [('cols', ctx['col_arena'], col_bytes), ('fits', ctx['fit_arena'], fit_bytes)]
+        if post is not None:
+            chunks.append(('post', post.view(torch.uint8), used * 16))
+        if labels is not None and level == 'full':
+            chunks.append(('labels', labels.view(torch.uint8).reshape(-1), labels.numel()))
+        offs, total = {}, 0
+        for name, _, nb in chunks:
+            offs[name] = total
+            total += (nb + _ALIGN - 1) // _ALIGN * _ALIGN
+        stage = self._stages.get(stage_key)
+        if stage is None or stage.numel() < total + _ALIGN:
+            stage = self._stages[stage_key] = torch.empty(int((total + _ALIGN) * 1.25), dtype=torch.uint8, pin_memory=True)
         fs.wait_event(ctx['done'])
         with torch.cuda.stream(fs):
-            host, d2h = self._fetch(want, stage_key)
-        return BatchResult(launches=ctx['launches'], d2h_bytes=d2h, **host)
+            for name, src, nb in chunks:
+                if nb:
+                    stage[offs[name]:offs[name] + nb].copy_(src[:nb], non_blocking=True)
+            fs.synchronize()
+        hs = stage.numpy()
 
-    def _fetch(self, tensors, stage_key=0):
-        '''device tensors -> numpy views of one pinned staging buffer (async copies, one sync)'''
-        align = 256
-        sizes = {k: t.numel() * t.element_size() for k, t in tensors.items()}
-        total = sum((v + align - 1) // align * align for v in sizes.values()) + align
-        stage = self._stages.get(stage_key)
-        if stage is None or stage.numel() < total:
-            stage = self._stages[stage_key] = torch.empty(int(total * 1.25), dtype=torch.uint8, pin_memory=True)
-        out, off = {}, 0
-        for k, t in tensors.items():
-            nb = sizes[k]
-            dst = stage[off:off + nb].view(t.dtype).view(t.shape)
-            if nb:
-                dst.copy_(t, non_blocking=True)
-            out[k] = dst
-            off += (nb + align - 1) // align * align
-        torch.cuda.current_stream(self.device).synchronize()
-        return {k: v.numpy() for k, v in out.items()}, sum(sizes.values())
+        def view(base, ext, name, shape, dtype, count=None):
+            off, nb = ext[name]
+            a = hs[base + off:base + off + nb].view(dtype)
+            a = a.reshape(shape) if count is None else a[:count]
+            return a
+
+        m = max(n_fit, 1)
+        c0, f0 = offs['cols'], offs['fits']
+        host = dict(status=view(c0, col_ext, 'status', None, np.uint8, nc),
+                    fit_list=view(c0, col_ext, 'fit_list', None, np.int32, n_fit))
+        if want_cols:
+            host.update(ks_stat=view(c0, col_ext, 'ks_stat', None, np.float64, nc),
+                        ks_pval=view(c0, col_ext, 'ks_pval', None, np.float64, nc))
+        if level == 'full':
+            host.update(n_c=view(c0, col_ext, 'n_c', None, np.int32, nc), n_t=view(c0, col_ext, 'n_t', None, np.int32, nc))
+        np_dtype = {torch.uint8: np.uint8, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}
+        for name, shape, dtype in ctx['fit_specs']:
+            host[name] = view(f0, fit_ext, name, shape, np_dtype[dtype])[:n_fit]
+            if name == last:
+                break
+        if post is not None:
+            host['post'] = hs[offs['post']:offs['post'] + used * 16].view(np.float64).reshape(used, 2)
+        if labels is not None and level == 'full':
+            host['labels'] = hs[offs['labels']:offs['labels'] + labels.numel()].view(np.int8).reshape(labels.shape)
+        d2h = sum(nb for _, _, nb in chunks)
+        return BatchResult(launches=ctx['launches'], d2h_bytes=d2h, **host)
