@@ -174,23 +174,19 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
     return dict(windows=n_windows, fitted=n_fit, res=res, ref=ref, host=host, errs=errs)
 
 
-@pytest.fixture(params=['warp', 'warp-emlane', 'cta'])
+@pytest.fixture(params=['warp', 'cta'])
 def ks_path(request, monkeypatch):
     '''
     Run every stage through both families of kernels: the warp-per-position fast paths
-    (yc_ks_warp.cu, yc_fit_warp.cu; 'warp-emlane' swaps in the experimental one-lane-per-position EM
-    kernel of yc_em_lane.cu) and the CTA-per-position general kernels (yc_ks.cu, yc_fit.cu).
+    (yc_ks_warp.cu, yc_fit_warp.cu) and the CTA-per-position general kernels (yc_ks.cu, yc_fit.cu).
     '''
     SPLIT_FIT['on'] = False
-    monkeypatch.delenv('YC_EM_PATH', raising=False)
     if request.param == 'cta':
         monkeypatch.setenv('YC_KS_PATH', 'cta')
         monkeypatch.setenv('YC_FIT_PATH', 'cta')
     else:
         monkeypatch.delenv('YC_KS_PATH', raising=False)
         monkeypatch.delenv('YC_FIT_PATH', raising=False)
-        if request.param == 'warp-emlane':       # experimental EM kernel: one lane per position
-            monkeypatch.setenv('YC_EM_PATH', 'lane')
     yield request.param
     SPLIT_FIT['on'] = False
 

@@ -296,17 +296,9 @@ int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fi
     if (int e = check_common(b, p)) return e;
     if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_em_batch: null pointer");
     if (n_fit <= 0) return 0;
-    if (use_warp_fit(*b, *p)) {
-        // default: one warp per position.  YC_EM_PATH=lane selects the experimental one-lane-per-position
-        // kernel (yc_em_lane.cu): correct, but measured slower on cfg2 (12.6 ms vs 8.0 ms: 255 registers
-        // -> 8 warps/SM, and ~3 positions per lane leave a long tail behind the slowest fits)
-        const char *em = getenv("YC_EM_PATH");
-        if (em && strcmp(em, "lane") == 0 && yc::em_lane_eligible(*b, *p))
-            return cuda_fail(yc::em_lane_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
-                             "yc_gmm_em_batch (lane path)");
+    if (use_warp_fit(*b, *p))
         return cuda_fail(yc::em_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
                          "yc_gmm_em_batch (warp path)");
-    }
     if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 1), "yc_gmm_em_batch")) return e;
     return cuda_fail(yc::em_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
                      "yc_gmm_em_batch");

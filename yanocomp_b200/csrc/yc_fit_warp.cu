@@ -37,7 +37,7 @@ __host__ __device__ inline FwSmem fw_layout(int W, int R, int cap, int which) {
     while (P < cap) P <<= 1;
     const int NS = 1 + W + W * (W + 1) / 2;
     const int buf_n = which == 0 ? P : (which == 1 ? 2 * cap : 0);
-    const int red_rows = which == 0 ? 2 * NS : (which == 1 ? 2 * NS + 1 + 2 * R : 1);
+    const int red_rows = which == 0 ? 2 * NS : (which == 1 ? 2 * NS + 1 + 2 * R : 3);
     int o = 0;
     s.buf_off = o;    o += buf_n * (int)sizeof(double);                         // MAD sort buffer / EM responsibilities
     s.par_off = o;    o += (4 * W * W + 4 * W + 3 * YC_MAX_SAMPLES + 8) * (int)sizeof(double);
@@ -830,6 +830,9 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         red[q] = ns > 0.0 ? exp(par->logw[s][k]) * ns : 0.0;
     }
     __syncwarp();
+    // the per-sample sizes (no sub-sampling on this path: fit rows = complete-window rows) travel to
+    // yc_gtest_smpred_batch in preds[.][s][0], which it overwrites with the rounded counts
+    for (int s2 = lane; s2 < R; s2 += 32) out.preds[((size_t)slot * R + s2) * 3] = (double)(fstart[s2 + 1] - fstart[s2]);
     if (lane < 3) {
         double cwk = 0.0;
 #pragma unroll 1
@@ -860,30 +863,52 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         if (lane < 8) out.stats[(size_t)slot * 8 + lane] = nan("");
         return;
     }
+    // The rows are only needed for the posteriors; without them the per-sample sizes come from the EM
+    // kernel (preds[.][s][0]) and the event data is not touched at all.
     FwCtx<W> c;
-    fw_front<W>(b, p, g, smem_raw, L, cap, lane, post != nullptr, c);
-    const int n = c.n;
+    int n = 0;
+    if (post != nullptr) { fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c); n = c.n; }
+    double *spr = reinterpret_cast<double *>(smem_raw + L.red_off);     // [3R] rounded counts, then [3R] compacted
+    double *cpr = spr + 3 * YC_MAX_SAMPLES;
+    // preds = np.round(weights * ORIGINAL sizes)  (stats.py:296): one lane per (sample, component)
+    {
+        int szq[(3 * YC_MAX_SAMPLES + 31) / 32];
+#pragma unroll
+        for (int h = 0; h < (3 * YC_MAX_SAMPLES + 31) / 32; ++h) {
+            const int q = lane + 32 * h;
+            szq[h] = 0;
+            if (q < 3 * R) {
+                const int s2 = q / 3;
+                szq[h] = post != nullptr ? c.fstart[s2 + 1] - c.fstart[s2]
+                                         : (int)out.preds[((size_t)slot * R + s2) * 3];
+            }
+        }
+        __syncwarp();                                                    // sizes read before the counts overwrite them
+#pragma unroll
+        for (int h = 0; h < (3 * YC_MAX_SAMPLES + 31) / 32; ++h) {
+            const int q = lane + 32 * h;
+            if (q < 3 * R) {
+                const double v = szq[h] > 0 ? rint(exp(out.logw[(size_t)slot * R * 3 + q]) * (double)szq[h]) : 0.0;
+                out.preds[(size_t)slot * R * 3 + q] = v;
+                spr[q] = szq[h] > 0 ? v : -1.0;                          // -1: sample without rows at this position
+            }
+        }
+    }
+    __syncwarp();
     long long off = -1;
     if (lane == 0) {
-        // preds = np.round(weights * ORIGINAL sizes)  (stats.py:296), present samples only
-        double pr[YC_MAX_SAMPLES * 3];
-        int rows_c = 0, rows_t = 0, q = 0;
+        int rows_c = 0, rows_t = 0, q = 0;                               // present samples only
 #pragma unroll 1
         for (int s = 0; s < R; ++s) {
-            const int sz = c.fstart[s + 1] - c.fstart[s];
-            double *po = out.preds + ((size_t)slot * R + s) * 3;
-            if (sz > 0) {
+            if (spr[3 * s] >= 0.0) {
 #pragma unroll 1
-                for (int k = 0; k < 3; ++k) {
-                    const double v = rint(exp(out.logw[((size_t)slot * R + s) * 3 + k]) * (double)sz);
-                    pr[q * 3 + k] = v; po[k] = v;
-                }
+                for (int k = 0; k < 3; ++k) cpr[q * 3 + k] = spr[3 * s + k];
                 ++q;
                 if (s < Rc) ++rows_c; else ++rows_t;
-            } else { po[0] = po[1] = po[2] = 0.0; }
+            }
         }
         double st8[8];
-        gtest_fractions(pr, rows_c, rows_t, p.fdr_threshold, st8, p.add_uniform ? 3 : 2);
+        gtest_fractions(cpr, rows_c, rows_t, p.fdr_threshold, st8, p.add_uniform ? 3 : 2);
 #pragma unroll 1
         for (int k = 0; k < 8; ++k) out.stats[(size_t)slot * 8 + k] = st8[k];
         if (post != nullptr && st8[2] < p.fdr_threshold) {

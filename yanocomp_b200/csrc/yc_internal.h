@@ -28,9 +28,6 @@ int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *f
 int gtest_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
                         const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
                         int64_t *post_cursor, cudaStream_t st);
-bool em_lane_eligible(const yc_batch_t &b, const yc_params_t &p);
-int em_lane_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                     const yc_fit_out_t &out, uint8_t *status, cudaStream_t st);
 int fit_cap(const yc_batch_t &b, const yc_params_t &p);
 int fit_smem_bytes(const yc_batch_t &b, const yc_params_t &p, int which);
 int init_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
