@@ -242,6 +242,15 @@ def test_subsampling_uses_the_shared_counter_based_stream():
     assert out['windows'] == 14
 
 
+@pytest.mark.parametrize('sizes', [[150, 140, 160, 130], [260, 250, 255, 245]])
+def test_deep_positions_on_the_warp_path(sizes):
+    '''300-500 reads per condition: the KS samples (512 slots each) and the MAD distances (1 024 slots) are
+    sorted in register chunks of 512 merged through shared memory (warp_sort_smem)'''
+    feats = synth.make_dataset(51, 2, 14, sizes, 2, 2, planted_frac=0.3)
+    out = compare(feats, 4, 2, window_size=3, min_ks=0.0, fdr_threshold=1.0, max_fit_discordance=0.05)
+    assert out['windows'] == 24 and out['fitted'] >= 12
+
+
 def test_no_gmm_mode(ks_path):
     feats = synth.make_dataset(18, 2, 40, 25, 2, 2, planted_frac=0.2)
     out = compare(feats, 4, 2, window_size=3, gmm=False)

@@ -112,26 +112,8 @@ __device__ __forceinline__ void warp_sum_smem(double (&v)[K], double *red, int l
     __syncwarp();
 }
 
-__device__ __noinline__ void warp_bitonic1(double *a, int P, int lane) {
-    const int pairs = P >> 1;
-#pragma unroll 1
-    for (int k = 2; k <= P; k <<= 1) {
-#pragma unroll 1
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 1
-            for (int t = lane; t < pairs; t += 32) {       // every lane owns one compare-exchange
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                const bool up = ((i & k) == 0);
-                const double x = a[i], y = a[l];
-                if ((x > y) == up) { a[i] = y; a[l] = x; }
-            }
-            __syncwarp();
-        }
-    }
-}
-
 // ascending sort of buf[0..P), P a power of two >= 32: in registers (P / 32 values per lane) up to
-// P = 512, by the shared-memory network beyond
+// P = 512, in register chunks of 512 merged through shared memory beyond (warp_sort_long, yc_common.cuh)
 template <int E>
 __device__ __noinline__ void warp_sort_buf_regs(double *buf, int lane) {
     double v[E];
@@ -143,14 +125,16 @@ __device__ __noinline__ void warp_sort_buf_regs(double *buf, int lane) {
     for (int e = 0; e < E; ++e) buf[lane * E + e] = v[e];
     __syncwarp();
 }
+template <bool LONG>
 __device__ __forceinline__ void warp_sort_buf(double *buf, int P, int lane) {
+    if (LONG) { if (P > 512) { warp_sort_long(buf, P, lane); return; } }
     switch (P) {
         case 32:  warp_sort_buf_regs<1>(buf, lane); break;
         case 64:  warp_sort_buf_regs<2>(buf, lane); break;
         case 128: warp_sort_buf_regs<4>(buf, lane); break;
         case 256: warp_sort_buf_regs<8>(buf, lane); break;
         case 512: warp_sort_buf_regs<16>(buf, lane); break;
-        default:  warp_bitonic1(buf, P, lane); break;
+        default:  break;                                    // P > 512: only in the LONG instantiation (above)
     }
 }
 
@@ -234,7 +218,9 @@ __device__ __noinline__ bool fw_front(const yc_batch_t &b, const yc_params_t &p,
 #ifndef YC_FW_INIT_MINBLOCKS
 #define YC_FW_INIT_MINBLOCKS 20
 #endif
-template <int W>
+// LONG: more than 512 fit rows per position -- a separate instantiation, because merely carrying the long
+// sort's code made the common kernel 4 % slower (3.49 -> 3.63 ms on cfg2)
+template <int W, bool LONG>
 __global__ void __launch_bounds__(32, YC_FW_INIT_MINBLOCKS)
 init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                  const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
@@ -384,7 +370,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         buf[i] = dmin;
     }
     __syncwarp();
-    warp_sort_buf(buf, P, lane);
+    warp_sort_buf<LONG>(buf, P, lane);
     const double med = (n & 1) ? buf[n >> 1] : mul_rn(add_rn(buf[(n >> 1) - 1], buf[n >> 1]), 0.5);
     // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are
     // V-shaped, i.e. two ascending runs (left of the median walked outwards, right of it), so the
@@ -993,9 +979,10 @@ int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t 
     const int cap = fw_cap(b), smem = fw_smem(b, p, 0);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
-        cudaError_t e = cudaFuncSetAttribute(init_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        auto kern = cap > 512 ? init_warp_kernel<W_, true> : init_warp_kernel<W_, false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        init_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
+        kern<<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
         count_launches(1);
         return (int)cudaGetLastError();
     });

@@ -29,24 +29,6 @@ namespace yc {
 
 #define YC_KW_WARPS 4
 
-__device__ __noinline__ void warp_bitonic(double *a, int P, int nseg, int lane) {
-    const int pairs = (P * nseg) >> 1;
-#pragma unroll 1
-    for (int k = 2; k <= P; k <<= 1) {
-#pragma unroll 1
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 1
-            for (int t = lane; t < pairs; t += 32) {       // every lane owns one compare-exchange
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                const bool up = (((i & (P - 1)) & k) == 0);
-                const double x = a[i], y = a[l];
-                if ((x > y) == up) { a[i] = y; a[l] = x; }
-            }
-            __syncwarp();
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------
 // Register-resident sort + ECDF difference (round-1 profile: the shared-memory bitonic sort was
 // 35 % of this kernel's instructions and the per-element binary searches another 10 %).
@@ -420,8 +402,10 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
                 default:  dmax = ks_sort_ecdf<16>(sortbuf, tabA, tabB, n1, n2, lane); break;
             }
         } else {
-            // deep positions (> 256 reads per condition): shared-memory sort, one binary search per value
-            warp_bitonic(sortbuf, Pq, 2, lane);
+            // deep positions (> 256 reads per condition): each sample sorted through registers in chunks of
+            // 512 (warp_sort_smem), one binary search per value
+            warp_sort_smem(sortbuf, Pq, lane);
+            warp_sort_smem(sortbuf + Pq, Pq, lane);
             const double *A = sortbuf, *B = sortbuf + Pq;
             for (int i = lane; i < n1 + n2; i += 32) {
                 int c1, c2;
