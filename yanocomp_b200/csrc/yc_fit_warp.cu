@@ -125,19 +125,6 @@ __device__ __noinline__ void warp_sort_buf_regs(double *buf, int lane) {
     for (int e = 0; e < E; ++e) buf[lane * E + e] = v[e];
     __syncwarp();
 }
-template <bool LONG>
-__device__ __forceinline__ void warp_sort_buf(double *buf, int P, int lane) {
-    if (LONG) { if (P > 512) { warp_sort_long(buf, P, lane); return; } }
-    switch (P) {
-        case 32:  warp_sort_buf_regs<1>(buf, lane); break;
-        case 64:  warp_sort_buf_regs<2>(buf, lane); break;
-        case 128: warp_sort_buf_regs<4>(buf, lane); break;
-        case 256: warp_sort_buf_regs<8>(buf, lane); break;
-        case 512: warp_sort_buf_regs<16>(buf, lane); break;
-        default:  break;                                    // P > 512: only in the LONG instantiation (above)
-    }
-}
-
 // complete-window rows of position g -> shared memory (binary16, pooled order), per-sample offsets
 template <int W>
 __device__ __noinline__ bool fw_front(const yc_batch_t &b, const yc_params_t &p, int64_t g,
@@ -218,9 +205,10 @@ __device__ __noinline__ bool fw_front(const yc_batch_t &b, const yc_params_t &p,
 #ifndef YC_FW_INIT_MINBLOCKS
 #define YC_FW_INIT_MINBLOCKS 20
 #endif
-// LONG: more than 512 fit rows per position -- a separate instantiation, because merely carrying the long
-// sort's code made the common kernel 4 % slower (3.49 -> 3.63 ms on cfg2)
-template <int W, bool LONG>
+// SE = slots per lane of the MAD sort (the batch's row capacity rounded up to a power of two, / 32), 0 = more
+// than 512 rows (warp_sort_long).  A template parameter because merely carrying the other sort variants' code
+// made the kernel slower (3.49 -> 3.63 ms on cfg2 with the long sort's 2 100 unexecuted instructions).
+template <int W, int SE>
 __global__ void __launch_bounds__(32, YC_FW_INIT_MINBLOCKS)
 init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                  const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
@@ -355,8 +343,8 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         __syncwarp();
     } else {
-    int P = 32;
-    while (P < n) P <<= 1;
+    int P = 32 * SE;                                   // fixed by the batch (padding = +inf)
+    if (SE == 0) { P = 1024; while (P < cap) P <<= 1; }
 #pragma unroll 1
     for (int i = lane; i < P; i += 32) {
         double dmin = INFINITY;
@@ -370,7 +358,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         buf[i] = dmin;
     }
     __syncwarp();
-    warp_sort_buf<LONG>(buf, P, lane);
+    if (SE > 0) warp_sort_buf_regs<(SE > 0 ? SE : 1)>(buf, lane); else warp_sort_long(buf, P, lane);
     const double med = (n & 1) ? buf[n >> 1] : mul_rn(add_rn(buf[(n >> 1) - 1], buf[n >> 1]), 0.5);
     // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are
     // V-shaped, i.e. two ascending runs (left of the median walked outwards, right of it), so the
@@ -979,7 +967,14 @@ int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t 
     const int cap = fw_cap(b), smem = fw_smem(b, p, 0);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
-        auto kern = cap > 512 ? init_warp_kernel<W_, true> : init_warp_kernel<W_, false>;
+        void (*kern)(const yc_batch_t, const yc_params_t, const int, const int32_t *, const yc_fit_out_t, uint8_t *,
+                     int8_t *, const int);
+        if (cap <= 32) kern = init_warp_kernel<W_, 1>;
+        else if (cap <= 64) kern = init_warp_kernel<W_, 2>;
+        else if (cap <= 128) kern = init_warp_kernel<W_, 4>;
+        else if (cap <= 256) kern = init_warp_kernel<W_, 8>;
+        else if (cap <= 512) kern = init_warp_kernel<W_, 16>;
+        else kern = init_warp_kernel<W_, 0>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         kern<<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);

@@ -323,7 +323,10 @@ __host__ __device__ inline KdSmem kd_layout(int P) {
 #ifndef YC_KD_MINBLOCKS
 #define YC_KD_MINBLOCKS 8
 #endif
-template <int W>
+// SE = values per lane of the register sort (2 P / 32 with P = the batch's per-condition capacity rounded up to
+// a power of two), 0 = more than 256 reads per condition.  A template parameter so that the kernel carries one
+// sort variant only (instruction footprint).
+template <int W, int SE>
 __global__ void __launch_bounds__(YC_KW_WARPS * 32, YC_KD_MINBLOCKS)
 ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t c0, const int ncol,
             const double *__restrict__ scr,
@@ -369,7 +372,7 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
         }
         if (n1 != tab_n1) { for (int i = lane; i <= n1; i += 32) tabA[i] = div_rn((double)i, (double)n1); tab_n1 = n1; }
         if (n2 != tab_n2) { for (int i = lane; i <= n2; i += 32) tabB[i] = div_rn((double)i, (double)n2); tab_n2 = n2; }
-        const int Pq = max(32, next_pow2(max(n1, n2)));
+        const int Pq = P;                                  // fixed by the batch (padding = +inf)
         for (int i = lane; i < 2 * Pq; i += 32) sortbuf[i] = INFINITY;
         __syncwarp();
         int ca = 0, cb = 0;
@@ -393,14 +396,9 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
         }
         __syncwarp();
         double dmax = 0.0;
-        if (Pq <= 256) {
+        if (SE > 0) {
             // sort + ECDF difference in registers (2 Pq / 32 values per lane)
-            switch (Pq) {
-                case 32:  dmax = ks_sort_ecdf<2>(sortbuf, tabA, tabB, n1, n2, lane); break;
-                case 64:  dmax = ks_sort_ecdf<4>(sortbuf, tabA, tabB, n1, n2, lane); break;
-                case 128: dmax = ks_sort_ecdf<8>(sortbuf, tabA, tabB, n1, n2, lane); break;
-                default:  dmax = ks_sort_ecdf<16>(sortbuf, tabA, tabB, n1, n2, lane); break;
-            }
+            dmax = ks_sort_ecdf<(SE > 0 ? SE : 2)>(sortbuf, tabA, tabB, n1, n2, lane);
         } else {
             // deep positions (> 256 reads per condition): each sample sorted through registers in chunks of
             // 512 (warp_sort_smem), one binary search per value
@@ -479,7 +477,16 @@ static int launch_kw(const yc_batch_t &b, const yc_params_t &p, double *ks_stat,
     const int smem_d = kd_layout(P).per_warp * YC_KW_WARPS;
     cudaError_t e = cudaFuncSetAttribute(ks_moments_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(ks_d_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+    void (*kd)(const yc_batch_t, const yc_params_t, const int, const int64_t, const int, const double *, double *, double *,
+               const int32_t *, const int32_t *, uint8_t *, int32_t *, int32_t *);
+    switch (P) {
+        case 32:  kd = ks_d_kernel<W, 2>; break;
+        case 64:  kd = ks_d_kernel<W, 4>; break;
+        case 128: kd = ks_d_kernel<W, 8>; break;
+        case 256: kd = ks_d_kernel<W, 16>; break;
+        default:  kd = ks_d_kernel<W, 0>; break;
+    }
+    e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
     if (e != cudaSuccess) return (int)e;
     const int64_t chunk = b.total_cols < KW_CHUNK ? b.total_cols : KW_CHUNK;
     double *scr = nullptr;
@@ -491,7 +498,7 @@ static int launch_kw(const yc_batch_t &b, const yc_params_t &p, double *ks_stat,
         count_launches(1);
         ks_axis_kernel<W><<<(ncol + 63) / 64, 64, 0, st>>>(c0, ncol, scr, status);
         count_launches(1);
-        ks_d_kernel<W><<<(ncol + 32 * YC_KW_WARPS - 1) / (32 * YC_KW_WARPS), YC_KW_WARPS * 32, smem_d, st>>>(
+        kd<<<(ncol + 32 * YC_KW_WARPS - 1) / (32 * YC_KW_WARPS), YC_KW_WARPS * 32, smem_d, st>>>(
             b, p, P, c0, ncol, scr, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count);
         count_launches(1);
     }
