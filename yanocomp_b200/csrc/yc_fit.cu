@@ -663,10 +663,10 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             }
         }
         acc[2 * NS] += log(seprod);
+        warp_sum_array<NP>(acc);
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            const double t = warp_sum(acc[q]);
-            if (lane == 0) part[wid * NP + q] = t;
+            if (lane == 0) part[wid * NP + q] = acc[q];
         }
         __syncthreads();
         // ---- bookkeeping of em(): likelihood, stop rule
@@ -696,6 +696,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 } else {
                     for (int q = 0; q < NS; ++q) carry[k * NS + q] = 0.0;
                     double logdet = 0.0;
+#pragma unroll 1
                     for (int a = 0; a < W; ++a) {
                         const double s2 = S[1 + W + a * W - a * (a - 1) / 2];
                         const double m_new = S[1 + a] / S[0];

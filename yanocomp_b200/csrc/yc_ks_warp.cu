@@ -205,14 +205,14 @@ ks_moments_kernel(const yc_batch_t b, const yc_params_t p, const int64_t c0, con
 #pragma unroll
                             for (int c2 = a; c2 < W; ++c2) cm[k++] += x[a] * x[c2];
                     }
-#pragma unroll
-                for (int j = 0; j < W; ++j) mu[j] = warp_sum(mu[j]);
+                warp_sum_array<W>(mu);
+                warp_sum_array<NT>(cm);
                 {
                     int k = 0;
 #pragma unroll
                     for (int a = 0; a < W; ++a)
 #pragma unroll
-                        for (int c2 = a; c2 < W; ++c2) { cm[k] = sub_rn(warp_sum(cm[k]), div_rn(mul_rn(mu[a], mu[c2]), (double)ntot)); ++k; }
+                        for (int c2 = a; c2 < W; ++c2) { cm[k] = sub_rn(cm[k], div_rn(mul_rn(mu[a], mu[c2]), (double)ntot)); ++k; }
                 }
 #pragma unroll
                 for (int j = 0; j < W; ++j) mu[j] = div_rn(mu[j], (double)ntot);
