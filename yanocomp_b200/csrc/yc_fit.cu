@@ -395,7 +395,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         __syncthreads();
     } else {
-    const int P = next_pow2(n);
+    const int P = max(32, next_pow2(n));
     for (int i = tid; i < P; i += YC_BLOCK) {
         double dmin = INFINITY;
         if (i < n) {
@@ -408,7 +408,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         sortbuf[i] = dmin;
     }
     __syncthreads();
-    bitonic_sort_segments(sortbuf, P, 1);
+    block_sort_segments_regs(sortbuf, P, 1);
     const double med = (n & 1) ? sortbuf[n >> 1] : mul_rn(add_rn(sortbuf[(n >> 1) - 1], sortbuf[n >> 1]), 0.5);
     __syncthreads();
     // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are V-shaped,

@@ -185,7 +185,7 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
         for (int a = 0; a < W; ++a) misc[a] = v[a];
         icnt[0] = 0; icnt[1] = 0;
     }
-    const int P = next_pow2(max(n1, n2));
+    const int P = max(32, next_pow2(max(n1, n2)));
     for (int i = tid; i < 2 * P; i += YC_BLOCK) sortbuf[i] = INFINITY;
     __syncthreads();
     // Only the ORDER of the projections y = sum_j z_j v_j enters D, and sum_j x_j (v_j / sig_j) differs from y
@@ -205,7 +205,7 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
         }
     }
     __syncthreads();
-    bitonic_sort_segments(sortbuf, P, 2);
+    block_sort_segments_regs(sortbuf, P, 2);
     // ---- D = max |F1 - F2| over the pooled points (stats.py:39-41)
     const double *A = sortbuf, *B = sortbuf + P;
     double dmax = 0.0;
