@@ -18,6 +18,7 @@
 #include "yc_internal.h"
 #include "yc_stats.cuh"
 #include "yc_svdsign.cuh"
+#include "yc_ks_axis.cuh"
 
 namespace yc {
 
@@ -40,27 +41,31 @@ __host__ __device__ inline KsSmem ks_smem_layout(int W, int R, int max_reads, in
     return s;
 }
 
+// The stage runs as three kernels, like the small-window path (yc_ks_warp.cu): the single-thread LAPACK axis
+// replay used to hold 127 threads at a barrier for 29 % of this kernel's time (profiles/r01_summary.md).
+//   ks_cta_moments_kernel  filters, sub-sampling, exact moments -> G, T, means, stds and the row mask to scratch
+//   ks_axis_kernel         one thread per position: axis with numpy's sign -> c_j = v_j / sigma_j   (yc_ks_axis.cuh)
+//   ks_cta_d_kernel        projections, sort, D, p-value, gate
 template <int W>
 __global__ void __launch_bounds__(YC_BLOCK)
-ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
-          double *__restrict__ ks_stat, double *__restrict__ ks_pval,
-          int32_t *__restrict__ n_c_out, int32_t *__restrict__ n_t_out,
-          uint8_t *__restrict__ status, int32_t *__restrict__ fit_list,
-          int32_t *__restrict__ fit_count) {
+ks_cta_moments_kernel(const yc_batch_t b, const yc_params_t p, const int64_t c0, const int ncol,
+                      double *__restrict__ scr, uint32_t *__restrict__ mask_scr, const int nwords_max,
+                      double *__restrict__ ks_stat, double *__restrict__ ks_pval,
+                      int32_t *__restrict__ n_c_out, int32_t *__restrict__ n_t_out, uint8_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = b.n_samples, Rc = b.n_cntrl;
-    const KsSmem L = ks_smem_layout(W, R, b.max_reads, sort_cap);
-    double *sortbuf = reinterpret_cast<double *>(smem_raw + L.sort_off);
+    const KsSmem L = ks_smem_layout(W, R, b.max_reads, 0);
     double *red = reinterpret_cast<double *>(smem_raw + L.red_off);
     unsigned long long *sel = reinterpret_cast<unsigned long long *>(smem_raw + L.sel_off);
     double *misc = reinterpret_cast<double *>(smem_raw + L.misc_off);
     uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + L.mask_off);
     int *cnt = reinterpret_cast<int *>(smem_raw + L.cnt_off);
     int *hist = reinterpret_cast<int *>(smem_raw + L.hist_off);
-    int *icnt = reinterpret_cast<int *>(misc + 12);     // two append cursors
+    int *ridx = reinterpret_cast<int *>(misc);            // first W selected rows
 
     const int tid = threadIdx.x;
-    const int64_t g = blockIdx.x;
+    const int i = blockIdx.x;                             // column inside the chunk
+    const int64_t g = c0 + i;
 
     Window<W> w;
     const bool in_range = window_setup<W>(b, p, g, w);
@@ -72,7 +77,7 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
         }
         return;
     }
-    for (int i = tid; i < (W + 1) * R; i += YC_BLOCK) cnt[i] = 0;
+    for (int q = tid; q < (W + 1) * R; q += YC_BLOCK) cnt[q] = 0;
     __syncthreads();
     window_scan<W>(w, R, mask, cnt);
     __syncthreads();
@@ -158,47 +163,104 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
         }
         return;
     }
-    // ---- first principal axis of the standardised data, oriented as LAPACK's dgesdd
-    // orients it (yc_svdsign.cuh): needs G = Z^T Z and the first W pooled rows of Z
+    // ---- hand-over to the axis kernel: G = Z^T Z, the first W selected rows of Z, means, stds; and the
+    //      row mask (after sub-sampling) for the D kernel
     if (tid == 0) {
-        // G and T live in shared memory: handing thread-local arrays to the (large) routine
-        // was observed to be miscompiled (the callee's zero-initialised workspace aliased T)
-        double *G = misc + 16, *T = misc + 16 + W * W;
-        double v[W];
-        int k = 0;
-        for (int a = 0; a < W; ++a)
-            for (int c2 = a; c2 < W; ++c2) {
-                const double gv = cm[k++] / (sig[a] * sig[c2]);
-                G[a * W + c2] = gv; G[c2 * W + a] = gv;
-            }
         int found = 0;
-        for (int r = 0; r < n && found < W; ++r) {
-            if ((mask[r >> 5] >> (r & 31)) & 1u) {
-#pragma unroll
-                for (int j = 0; j < W; ++j)
-                    T[found * W + j] = div_rn(sub_rn(h2d(__ldg(w.col[j] + r)), mu[j]), sig[j]);
-                ++found;
-            }
+        for (int wd = 0; wd * 32 < n && found < W; ++wd) {
+            uint32_t m = mask[wd];
+            while (m && found < W) { ridx[found++] = wd * 32 + __ffs(m) - 1; m &= m - 1; }
         }
-        for (; found < W; ++found) for (int j = 0; j < W; ++j) T[found * W + j] = 0.0;
-        lapack::first_right_singular_vector<W>(G, T, v);
-        for (int a = 0; a < W; ++a) misc[a] = v[a];
-        icnt[0] = 0; icnt[1] = 0;
+        for (; found < W; ++found) ridx[found] = -1;
+        status[g] = YC_ST_KS_PENDING;
+        n_c_out[g] = n_c; n_t_out[g] = n_t;
     }
-    const int P = max(32, next_pow2(max(n1, n2)));
-    for (int i = tid; i < 2 * P; i += YC_BLOCK) sortbuf[i] = INFINITY;
     __syncthreads();
+    {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < W; ++a)
+#pragma unroll
+            for (int c2 = a; c2 < W; ++c2) {
+                if (tid == k) {
+                    const double gv = cm[k] / (sig[a] * sig[c2]);
+                    scr[(size_t)(a * W + c2) * ncol + i] = gv;
+                    scr[(size_t)(c2 * W + a) * ncol + i] = gv;
+                }
+                ++k;
+            }
+    }
+    if (tid < W * W) {
+        const int k = tid / W, j = tid % W;
+        const int r = ridx[k];
+        double muj = 0.0, sigj = 1.0;
+        const uint16_t *cp = w.col[0];
+#pragma unroll
+        for (int jj = 0; jj < W; ++jj) if (jj == j) { muj = mu[jj]; sigj = sig[jj]; cp = w.col[jj]; }
+        scr[(size_t)(W * W + tid) * ncol + i] = r >= 0 ? div_rn(sub_rn(h2d(__ldg(cp + r)), muj), sigj) : 0.0;
+    }
+    if (tid < W) {
+        double muj = 0.0, sigj = 1.0;
+#pragma unroll
+        for (int jj = 0; jj < W; ++jj) if (jj == tid) { muj = mu[jj]; sigj = sig[jj]; }
+        scr[(size_t)(2 * W * W + tid) * ncol + i] = muj;
+        scr[(size_t)(2 * W * W + W + tid) * ncol + i] = sigj;
+    }
+    const int nwords = (n + 31) >> 5;
+    for (int wd = tid; wd < nwords; wd += YC_BLOCK) mask_scr[(size_t)i * nwords_max + wd] = mask[wd];
+}
+
+template <int W>
+__global__ void __launch_bounds__(YC_BLOCK)
+ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, const int64_t c0, const int ncol,
+                const double *__restrict__ scr, const uint32_t *__restrict__ mask_scr, const int nwords_max,
+                double *__restrict__ ks_stat, double *__restrict__ ks_pval,
+                const int32_t *__restrict__ n_c_in, const int32_t *__restrict__ n_t_in,
+                uint8_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Rc = b.n_cntrl;
+    const KsSmem L = ks_smem_layout(W, b.n_samples, b.max_reads, sort_cap);
+    double *sortbuf = reinterpret_cast<double *>(smem_raw + L.sort_off);
+    double *red = reinterpret_cast<double *>(smem_raw + L.red_off);
+    double *misc = reinterpret_cast<double *>(smem_raw + L.misc_off);
+    uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + L.mask_off);
+    int *icnt = reinterpret_cast<int *>(misc + 12);     // two append cursors
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x;
+    const int64_t g = c0 + i;
+    if (status[g] != YC_ST_KS_PENDING) return;
+    // window columns of position g (validated by the moments kernel)
+    const int f = b.col_feature[g];
+    const int c = (int)(g - b.col_off[f]);
+    const int n = b.n_reads[f];
+    const int split = b.samp_start[(size_t)f * (b.n_samples + 1) + Rc];
+    const int64_t ld = b.ld[f];
+    const uint16_t *fbase = b.events + b.x_off[f];
+    const bool rev = b.reverse[f] != 0;
+    const uint16_t *col[W];
     // Only the ORDER of the projections y = sum_j z_j v_j enters D, and sum_j x_j (v_j / sig_j) differs from y
     // by a constant: no centring, no division per read (the same arithmetic as ks_d_kernel, yc_ks_warp.cu)
     double cj[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) cj[j] = misc[j] / sig[j];
+    for (int j = 0; j < W; ++j) {
+        const int cc = rev ? (c + W / 2 - j) : (c - W / 2 + j);
+        col[j] = fbase + (int64_t)cc * ld;
+        cj[j] = scr[(size_t)(2 * W * W + j) * ncol + i];
+    }
+    const int n1 = min(n_c_in[g], p.max_fit_depth), n2 = min(n_t_in[g], p.max_fit_depth);
+    const int ntot = n1 + n2;
+    const int nwords = (n + 31) >> 5;
+    for (int wd = tid; wd < nwords; wd += YC_BLOCK) mask[wd] = mask_scr[(size_t)i * nwords_max + wd];
+    if (tid == 0) { icnt[0] = 0; icnt[1] = 0; }
+    const int P = max(32, next_pow2(max(n1, n2)));
+    for (int q = tid; q < 2 * P; q += YC_BLOCK) sortbuf[q] = INFINITY;
+    __syncthreads();
     // ---- pass D: projections, appended per condition (order is irrelevant before the sort)
     for (int r = tid; r < n; r += YC_BLOCK) {
         if ((mask[r >> 5] >> (r & 31)) & 1u) {
             double y = 0.0;
 #pragma unroll
-            for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(w.col[j] + r)), cj[j], y);
+            for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(col[j] + r)), cj[j], y);
             const int cond = r >= split;
             const int slot = atomicAdd(&icnt[cond], 1);
             sortbuf[cond * P + slot] = y;
@@ -210,8 +272,8 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
     const double *A = sortbuf, *B = sortbuf + P;
     double dmax = 0.0;
     const double fn1 = (double)n1, fn2 = (double)n2;
-    for (int i = tid; i < ntot; i += YC_BLOCK) {
-        const double v = (i < n1) ? A[i] : B[i - n1];
+    for (int q = tid; q < ntot; q += YC_BLOCK) {
+        const double v = (q < n1) ? A[q] : B[q - n1];
         const int c1 = upper_bound(A, n1, v), c2 = upper_bound(B, n2, v);
         const double df = fabs(sub_rn(div_rn((double)c1, fn1), div_rn((double)c2, fn2)));
         dmax = fmax(dmax, df);
@@ -223,7 +285,6 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
         const double arg = mul_rn(add_rn(add_rn(en, 0.12), div_rn(0.11, en)), dmax);
         const double pv = kolmogorov_sf(arg);
         ks_stat[g] = dmax; ks_pval[g] = pv;
-        n_c_out[g] = n_c; n_t_out[g] = n_t;
         uint8_t st;
         if (!p.gmm) st = YC_ST_KS_ONLY;
         else if (dmax >= p.min_ks && pv < p.fdr_threshold) {
@@ -233,16 +294,41 @@ ks_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap,
     }
 }
 
+// scratch per column of a chunk: the moment block (2 W^2 + 2 W doubles) + the row mask after sub-sampling
+static const int64_t KS_CTA_CHUNK = 1 << 18;
+
 template <int W>
-static int launch_ks(const yc_batch_t &b, const yc_params_t &p, int sort_cap, int smem,
+static int launch_ks(const yc_batch_t &b, const yc_params_t &p, int sort_cap, int smem_d,
                      double *ks_stat, double *ks_pval, int32_t *n_c, int32_t *n_t,
                      uint8_t *status, int32_t *fit_list, int32_t *fit_count, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(ks_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    (void)fit_list; (void)fit_count;
+    constexpr int GT = 2 * W * W + 2 * W;
+    keep_pool_memory();
+    const int smem_m = ks_smem_layout(W, b.n_samples, b.max_reads, 0).total;
+    cudaError_t e = cudaFuncSetAttribute(ks_cta_moments_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_m);
     if (e != cudaSuccess) return (int)e;
-    ks_kernel<W><<<(unsigned)b.total_cols, YC_BLOCK, smem, st>>>(
-        b, p, sort_cap, ks_stat, ks_pval, n_c, n_t, status, fit_list, fit_count);
-    count_launches(1);
-    return (int)cudaGetLastError();
+    e = cudaFuncSetAttribute(ks_cta_d_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+    if (e != cudaSuccess) return (int)e;
+    const int nwords_max = (b.max_reads + 31) / 32;
+    const int64_t chunk = b.total_cols < KS_CTA_CHUNK ? b.total_cols : KS_CTA_CHUNK;
+    const size_t scr_bytes = (size_t)chunk * GT * sizeof(double);
+    unsigned char *raw = nullptr;
+    e = cudaMallocAsync(reinterpret_cast<void **>(&raw), scr_bytes + (size_t)chunk * nwords_max * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    double *scr = reinterpret_cast<double *>(raw);
+    uint32_t *mask_scr = reinterpret_cast<uint32_t *>(raw + scr_bytes);
+    for (int64_t c0 = 0; c0 < b.total_cols; c0 += chunk) {
+        const int ncol = (int)(b.total_cols - c0 < chunk ? b.total_cols - c0 : chunk);
+        ks_cta_moments_kernel<W><<<ncol, YC_BLOCK, smem_m, st>>>(b, p, c0, ncol, scr, mask_scr, nwords_max,
+                                                                ks_stat, ks_pval, n_c, n_t, status);
+        ks_axis_kernel<W><<<(ncol + 63) / 64, 64, 0, st>>>(c0, ncol, scr, status);
+        ks_cta_d_kernel<W><<<ncol, YC_BLOCK, smem_d, st>>>(b, p, sort_cap, c0, ncol, scr, mask_scr, nwords_max,
+                                                          ks_stat, ks_pval, n_c, n_t, status);
+        count_launches(3);
+    }
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(raw, st);
+    return (int)(e != cudaSuccess ? e : e2);
 }
 
 int ks_sort_cap(const yc_batch_t &b, const yc_params_t &p) {

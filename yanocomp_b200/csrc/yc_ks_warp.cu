@@ -24,6 +24,7 @@
 #include "yc_internal.h"
 #include "yc_stats.cuh"
 #include "yc_svdsign.cuh"
+#include "yc_ks_axis.cuh"
 
 namespace yc {
 
@@ -129,8 +130,6 @@ __device__ __forceinline__ void warp_window_scan(const Window<W> &w, int R, uint
     }
 }
 
-// transient status between the three kernels: passed the filters, moments stored, D pending
-#define YC_ST_KS_PENDING 7
 
 // ---------------------------------------------------------------------------
 // Kernel 1a: window filters + exact moments.  One CTA = 32 adjacent columns, warp w takes columns
@@ -283,24 +282,6 @@ ks_moments_kernel(const yc_batch_t b, const yc_params_t p, const int64_t c0, con
         const int k = idx >> 5, q = idx & 31;
         if (i0 + q < ncol && st[q * 4] == 2) scr[(size_t)k * ncol + i0 + q] = gt[q * GT + k];
     }
-}
-
-// ---------------------------------------------------------------------------
-// Kernel 1b: one THREAD per position replays dgesdd on (G, T) -> first right singular vector with
-// numpy's sign; stores c_j = v_j / sig_j over the mean rows (only the ORDER of the projections
-// enters D, and sum_j x_j c_j differs from the standardised projection by a constant).
-// ---------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(64)
-ks_axis_kernel(const int64_t c0, const int ncol, double *__restrict__ scr, const uint8_t *__restrict__ status) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncol || status[c0 + i] != YC_ST_KS_PENDING) return;
-    double GT_[2 * W * W], v[W];
-#pragma unroll
-    for (int k = 0; k < 2 * W * W; ++k) GT_[k] = scr[(size_t)k * ncol + i];
-    lapack::first_right_singular_vector<W>(GT_, GT_ + W * W, v);
-#pragma unroll
-    for (int j = 0; j < W; ++j) scr[(size_t)(2 * W * W + j) * ncol + i] = v[j] / scr[(size_t)(2 * W * W + W + j) * ncol + i];
 }
 
 // ---------------------------------------------------------------------------
