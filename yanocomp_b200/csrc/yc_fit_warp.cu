@@ -36,8 +36,12 @@ __host__ __device__ inline FwSmem fw_layout(int W, int R, int cap, int which) {
     int P = 32;
     while (P < cap) P <<= 1;
     const int NS = 1 + W + W * (W + 1) / 2;
-    const int buf_n = which == 0 ? P : (which == 1 ? 2 * cap : 0);
-    const int red_rows = which == 0 ? 2 * NS : (which == 1 ? 2 * NS + 1 + 2 * R : 3);
+    // EM: the responsibilities (2 cap doubles, dead once the statistics pass has read them) and the main
+    // reduction rows (2 NS + 1 rows of 33, written after that pass) share one region; only the per-sample
+    // sums, flushed DURING the pass, get rows of their own
+    const int em_main = (2 * NS + 1) * 33;
+    const int buf_n = which == 0 ? P : (which == 1 ? (2 * cap > em_main ? 2 * cap : em_main) : 0);
+    const int red_rows = which == 0 ? 2 * NS : (which == 1 ? 2 * R : 3);
     int o = 0;
     s.buf_off = o;    o += buf_n * (int)sizeof(double);                         // MAD sort buffer / EM responsibilities
     s.par_off = o;    o += (4 * W * W + 4 * W + 3 * YC_MAX_SAMPLES + 8) * (int)sizeof(double);
@@ -656,7 +660,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     const uint16_t *xs = c.xs;
     const uint8_t *srow = c.srow;
     EmPar<W> *par = c.par;
-    double *red = c.red, *wtmp = c.wtmp;
+    double *red = c.buf, *ssum = c.red;                 // main reduction rows alias the responsibilities (fw_layout)
     double *rb0 = c.buf, *rb1 = c.buf + cap;            // responsibilities of components 0 / 1 per fit row
     const int *fstart = c.fstart;
     load_model<W>(par, out, slot, lane, out.logw + (size_t)slot * R * 3, R * 3);
@@ -726,7 +730,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         // order, so a lane sees its samples in ascending order and flushes a running pair of sums
         // into its own column of red rows NP + 2 s, NP + 2 s + 1 whenever the sample changes
 #pragma unroll 1
-        for (int q = 0; q < 2 * R; ++q) red[(NP + q) * 33 + lane] = 0.0;
+        for (int q = 0; q < 2 * R; ++q) ssum[q * 33 + lane] = 0.0;
         int cur = -1;
         double t0 = 0.0, t1 = 0.0;
 #pragma unroll kEmUnroll2
@@ -736,7 +740,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             const double r0 = rb0[i], r1 = rb1[i];
             const int s = srow[i];
             if (s != cur) {
-                if (cur >= 0) { red[(NP + 2 * cur) * 33 + lane] = t0; red[(NP + 2 * cur + 1) * 33 + lane] = t1; }
+                if (cur >= 0) { ssum[(2 * cur) * 33 + lane] = t0; ssum[(2 * cur + 1) * 33 + lane] = t1; }
                 cur = s; t0 = 0.0; t1 = 0.0;
             }
             t0 += r0; t1 += r1;
@@ -750,18 +754,19 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 for (int bb = a; bb < W; ++bb) { acc[qq] = fma(xa0, x[bb], acc[qq]); acc[NS + qq] = fma(xa1, x[bb], acc[NS + qq]); ++qq; }
             }
         }
-        if (cur >= 0) { red[(NP + 2 * cur) * 33 + lane] = t0; red[(NP + 2 * cur + 1) * 33 + lane] = t1; }
+        if (cur >= 0) { ssum[(2 * cur) * 33 + lane] = t0; ssum[(2 * cur + 1) * 33 + lane] = t1; }
+        __syncwarp();                                   // every lane has read its responsibilities: the region is free
         // per-lane partial sums -> totals in red[q*33 + 32]; four interleaved chains per total
 #pragma unroll
         for (int q = 0; q < NP; ++q) red[q * 33 + lane] = acc[q];
         __syncwarp();
 #pragma unroll 1
         for (int q = lane; q < NP + 2 * R; q += 32) {
-            const double *rq = red + q * 33;
+            double *rq = q < NP ? red + q * 33 : ssum + (q - NP) * 33;
             double ta = 0.0, tb = 0.0, tc = 0.0, td = 0.0;
 #pragma unroll
             for (int l2 = 0; l2 < 32; l2 += 4) { ta += rq[l2]; tb += rq[l2 + 1]; tc += rq[l2 + 2]; td += rq[l2 + 3]; }
-            red[q * 33 + 32] = (ta + tb) + (tc + td);
+            rq[32] = (ta + tb) + (tc + td);
         }
         __syncwarp();
         const double ll = red[2 * NS * 33 + 32];
@@ -782,7 +787,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 const int s = q / 3, k = q - 3 * s;
                 const int ns = fstart[s + 1] - fstart[s];
                 if (ns > 0) {
-                    const double t0s = red[(NP + 2 * s) * 33 + 32], t1s = red[(NP + 2 * s + 1) * 33 + 32];
+                    const double t0s = ssum[(2 * s) * 33 + 32], t1s = ssum[(2 * s + 1) * 33 + 32];
                     const double t2s = uni ? fmax((double)ns - t0s - t1s, 0.0) : 0.0;
                     if (t0s + t1s + t2s != 0.0) {
                         const double vk = (k == 0 ? t0s : (k == 1 ? t1s : t2s)) + 0.5;
