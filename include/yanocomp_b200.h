@@ -141,8 +141,11 @@ int yc_fill_col_feature(int32_t n_features, const int64_t *col_off,
                         int32_t *col_feature, void *stream);
 
 /*
- * Kernel 1 -- window filters + PCA + two-sample KS, one CTA per candidate
- * position.  Replaces, per position: get_valid_pos / get_valid_windows /
+ * Stage 1 -- window filters + PCA + two-sample KS over every candidate position
+ * (three kernels: moments, LAPACK axis replay one thread per position, sort + D;
+ * one warp or one CTA per position; then an ordered
+ * compaction of the gated positions).  Scratch comes stream-ordered from the
+ * device's memory pool and is returned before the call ends.  Replaces, per position: get_valid_pos / get_valid_windows /
  * index_pos_range / test_depth (gmmtest.py:24-61), subsample (stats.py:52-59),
  * pca_comp1 (stats.py:20-31), _ks_d / ks_2samp / pca_kstest (stats.py:34-73)
  * and the gate of position_stats (stats.py:460-465).
@@ -159,10 +162,11 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
                 void *stream);
 
 /*
- * Kernel 2a -- model initialisation, one CTA per gated position.  Replaces
+ * Stage 2a -- model initialisation, one warp or CTA per gated position.  Replaces
  * the per-replicate subsample of fit_gmm (stats.py:266-269),
- * kmeans_init_clusters (stats.py:81-124: pm.Kmeans k-means++ x3, MAD outlier
- * labelling) and initialise_gmms (stats.py:127-191).  Writes mu, cov, box,
+ * kmeans_init_clusters (stats.py:81-124: pm.Kmeans k-means++ x3, MAD or DBSCAN
+ * outlier labelling) and initialise_gmms (stats.py:127-191, full or diagonal
+ * covariance).  Writes mu, cov, box,
  * logw; status[g] becomes YC_ST_FIT_FAILED on a failed Cholesky / zero-width
  * box.  labels (optional, may be NULL): [n_fit*max_fit_rows] int8 initial labels
  * in pooled fit order, for parity tests.
@@ -173,19 +177,22 @@ int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p,
                       int8_t *labels, int32_t max_fit_rows, void *stream);
 
 /*
- * Kernel 2b -- multi-sample EM, one CTA per gated position.  Replaces em
+ * Stage 2b -- multi-sample EM, one warp or CTA per gated position.  Replaces em
  * (stats.py:194-225) and the pomegranate calls under it (from_summaries,
  * GeneralMixtureModel.summarize) plus the weight bookkeeping of
  * fit_multisamp_gmm (stats.py:250-253).  Updates mu, cov, logw in place,
  * writes cw, iters, loglik; status[g] = YC_ST_TESTED or YC_ST_FIT_FAILED.
+ * It also leaves every sample's complete-window row count in preds[.][s][0]
+ * for yc_gtest_smpred_batch, which replaces it with the rounded counts.
  */
 int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p,
                     const int32_t *fit_list, int32_t n_fit,
                     yc_fit_out_t *out, uint8_t *status, void *stream);
 
 /*
- * Kernel 3 -- per-sample modified-fraction counts, G-tests, log odds and the
- * single-molecule posteriors, one CTA per gated position.  Replaces the
+ * Stage 3 -- per-sample modified-fraction counts, G-tests, log odds and the
+ * single-molecule posteriors, one warp or CTA per gated position; call it after
+ * yc_gmm_em_batch on the same outputs.  Replaces the
  * rounding of fit_gmm (stats.py:296-297), gmm_g_test (stats.py:316-338),
  * calculate_fractional_stats (stats.py:341-355) and predict_proba
  * (stats.py:494-499).  When `post` is not NULL, positions with p < fdr
@@ -213,7 +220,7 @@ int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, int32_t window_si
                        int32_t *nall_fit, void *stream);
 
 /*
- * Kernels 2a + 2b + 3 back to back on one stream (convenience; same outputs
+ * Stages 2a + 2b + 3 back to back on one stream (convenience; same outputs
  * as the three calls above).
  *
  * Each of the three stages has two implementations chosen per batch: for
