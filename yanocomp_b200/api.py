@@ -24,12 +24,13 @@ def test_host_batch(host: HostBatch, params: EngineParams, engine: Engine = None
 
 
 def test_host_batch_pipelined(host: HostBatch, params: EngineParams, engine: Engine = None,
-                              fetch='records', chunks=4, growth=2.5):
+                              fetch='records', chunks=4, growth=1.0):
     '''
     Same as test_host_batch with the batch cut into `chunks` feature ranges (views, no copy) that go
     through the engine's three-stage pipeline: the host->device copy of a range overlaps the kernels
-    of the previous ones, the device->host copy of its results those of the next.  The ranges grow
-    geometrically (`growth`), because only the first upload cannot be hidden.
+    of the previous ones, the device->host copy of its results those of the next.  `growth` > 1 makes the
+    ranges grow geometrically (only the first upload cannot be hidden); equal ranges (the default) measured the
+    same on one GPU and better on eight, where the uploads of all ranks share the host (bench.py).
     Returns [(sub-batch, result)].
     '''
     eng = engine or Engine(params)
