@@ -206,22 +206,32 @@ ks_moments_kernel(const yc_batch_t b, const yc_params_t p, const int64_t c0, con
                     }
                 warp_sum_array<W>(mu);
                 warp_sum_array<NT>(cm);
+                // C_ab = S2_ab - (S1_a S1_b) / n, mean_j = S1_j / n, sig_a = sqrt(C_aa / n): the same IEEE operations
+                // as before, but one lane per quantity (every lane used to run all 12 divisions), then broadcast
                 {
+                    double num = 0.0, sub = 0.0;
                     int k = 0;
 #pragma unroll
                     for (int a = 0; a < W; ++a)
 #pragma unroll
-                        for (int c2 = a; c2 < W; ++c2) { cm[k] = sub_rn(cm[k], div_rn(mul_rn(mu[a], mu[c2]), (double)ntot)); ++k; }
-                }
+                        for (int c2 = a; c2 < W; ++c2) { if (lane == k) { num = mul_rn(mu[a], mu[c2]); sub = cm[k]; } ++k; }
 #pragma unroll
-                for (int j = 0; j < W; ++j) mu[j] = div_rn(mu[j], (double)ntot);
-                {
-                    int k = 0;
+                    for (int j = 0; j < W; ++j) if (lane == NT + j) num = mu[j];
+                    const double quo = div_rn(num, (double)ntot);
+                    const double mine = lane < NT ? sub_rn(sub, quo) : quo;
+#pragma unroll
+                    for (int k2 = 0; k2 < NT; ++k2) cm[k2] = __shfl_sync(YC_FULL, mine, k2);
+#pragma unroll
+                    for (int j = 0; j < W; ++j) mu[j] = __shfl_sync(YC_FULL, mine, NT + j);
+                    double sv = 1.0;
+                    k = 0;
+#pragma unroll
+                    for (int a = 0; a < W; ++a) { if (lane == a) sv = cm[k]; k += W - a; }
+                    sv = sqrt(sv / (double)ntot);
 #pragma unroll
                     for (int a = 0; a < W; ++a) {
-                        sig[a] = sqrt(cm[k] / (double)ntot);
+                        sig[a] = __shfl_sync(YC_FULL, sv, a);
                         if (!(sig[a] > 0.0)) state = 1;                  // constant column (assumption A9)
-                        k += W - a;
                     }
                 }
                 if (state == 2) {
