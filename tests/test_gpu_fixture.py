@@ -132,3 +132,20 @@ def test_cli_end_to_end_bed_and_json(tmp_path):
             np.testing.assert_allclose(a['model']['weights'], b['model']['weights'], rtol=1e-4)
             n += 1
     assert n > 20, n
+
+
+def test_cli_with_feature_cache_is_byte_identical(tmp_path):
+    '''--feature-cache: the cold run (fills the cache), the warm run (reads it) and a run without it write the
+    same BED and the same single-molecule JSON, byte for byte'''
+    from click.testing import CliRunner
+    from yanocomp_b200.cli import cli
+    outs = []
+    for name, extra in (('plain', []), ('cold', ['--feature-cache', str(tmp_path / 'cache')]),
+                        ('warm', ['--feature-cache', str(tmp_path / 'cache')])):
+        bed_fn, sm_fn = str(tmp_path / f'{name}.bed'), str(tmp_path / f'{name}.json')
+        r = CliRunner().invoke(cli, ['gmmtest', '-c', CNTRL, '-t', TREAT, '-o', bed_fn, '-s', sm_fn,
+                                     '--random-seed', '0'] + extra, catch_exceptions=False)
+        assert r.exit_code == 0, r.output
+        outs.append((open(bed_fn, 'rb').read(), open(sm_fn, 'rb').read()))
+    assert len(outs[0][0]) > 1000 and outs[0] == outs[1] == outs[2]
+    assert len(os.listdir(str(tmp_path / 'cache'))) == 1

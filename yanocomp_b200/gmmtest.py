@@ -22,7 +22,8 @@ import pandas as pd
 from . import _native as N
 from . import dist as ycdist
 from .batch import HostBatch
-from .io import (hdf5_list, get_shared_keys, load_model_priors, load_gene_features,
+from .io import (hdf5_list, get_shared_keys, load_model_priors, load_gene_features, load_gene_features_cached,
+                 FeatureCache,
                  save_gmmtest_results, save_sm_preds)
 from .stats import (benjamini_hochberg, assign_modified_distribution, format_model,
                     format_sm_preds)
@@ -62,6 +63,7 @@ class GMMTestOpts:
     processes: int = 1
     test_gene: tuple = ()
     random_seed: object = None
+    feature_cache: str = None          # --feature-cache DIR: packed features are kept there between runs (io.FeatureCache)
     generate_sm_preds: bool = dataclasses.field(init=False)
 
     def __post_init__(self):
@@ -201,11 +203,14 @@ def test_chunk(opts, gene_ids):
             split = int(f.samp_start[n_cntrl])
             return f.n_reads <= 1024 and max(split, f.n_reads - split) <= opts.max_fit_depth
 
+        cache = (FeatureCache(opts.feature_cache, opts.cntrl_hdf5_fns, opts.treat_hdf5_fns, by_t)
+                 if opts.feature_cache else None)
         with hdf5_list(opts.cntrl_hdf5_fns) as cntrl_h5, hdf5_list(opts.treat_hdf5_fns) as treat_h5:
             pending = {True: [], False: []}
             nbytes = {True: 0, False: 0}
             with ThreadPoolExecutor(max(1, opts.processes)) as pool:
-                loaded = pool.map(lambda gid: load_gene_features(gid, cntrl_h5, treat_h5, by_t), list(gene_ids))
+                loaded = pool.map(lambda gid: load_gene_features_cached(cache, gid, cntrl_h5, treat_h5, by_t),
+                                  list(gene_ids))
                 for feats in loaded:
                     for f in feats:
                         k = shallow(f)
@@ -329,6 +334,8 @@ def set_default_depth(ctx, param, val):
               help='Host threads used to decode HDF5 input (GPUs are selected with torchrun)')
 @click.option('--test-gene', required=False, default=None, hidden=True, multiple=True)
 @click.option('--random-seed', required=False, default=None, hidden=True)
+@click.option('--feature-cache', required=False, default=None, hidden=True,
+              help='Directory in which the packed per-gene features are cached between runs (not in the reference)')
 def gmm_test(**cli_kwargs):
     '''
     Differential RNA modifications using nanopore DRS signal level data

@@ -180,6 +180,73 @@ def load_gene_features(gene_id, cntrl_datasets, treat_datasets, by_transcript_id
     return feats
 
 
+class FeatureCache:
+    '''
+    On-disk cache of packed features: the second run over the same prep files skips the HDF5 decode
+    (zlib-bound, ~6 M events/s per thread) and the pivot and reads the binary16 matrices back at file-system
+    speed.  One uncompressed .npz per gene under `<root>/<key>/`, the key covering the format version, the test
+    level and every input file's path, size and mtime, so a changed input never meets a stale entry.
+    Opt-in (`--feature-cache DIR`); the reference has no counterpart.
+    '''
+    VERSION = 1
+
+    def __init__(self, root, cntrl_fns, treat_fns, by_transcript_ids):
+        import hashlib
+        h = hashlib.sha1(f'{self.VERSION}|{int(bool(by_transcript_ids))}'.encode())
+        for tag, fns in (('c', cntrl_fns), ('t', treat_fns)):
+            for fn in fns:
+                st = os.stat(fn)
+                h.update(f'|{tag}|{os.path.abspath(fn)}|{st.st_size}|{st.st_mtime_ns}'.encode())
+        self.dir = os.path.join(root, h.hexdigest()[:20])
+        os.makedirs(self.dir, exist_ok=True)
+
+    def _path(self, gene_id):
+        import hashlib
+        return os.path.join(self.dir, hashlib.sha1(str(gene_id).encode()).hexdigest()[:24] + '.npz')
+
+    def get(self, gene_id):
+        fn = self._path(gene_id)
+        if not os.path.exists(fn):
+            return None
+        feats = []
+        with np.load(fn, allow_pickle=False) as z:
+            if str(z['gene_id']) != str(gene_id):               # hash collision: treat as a miss
+                return None
+            for i in range(int(z['n'])):
+                kpos, kval = z[f'kpos{i}'], np.char.decode(z[f'kval{i}'], 'ascii')
+                meta = z[f'meta{i}'].tolist()
+                feats.append(Feature(
+                    feature_id=meta[0], chrom=meta[1], strand=meta[2], pos0=0, X=z[f'X{i}'],
+                    samp_start=z[f'samp_start{i}'], read_ids=np.char.decode(z[f'read_ids{i}'], 'ascii').tolist(),
+                    kmers=dict(zip(kpos.tolist(), kval.tolist())), positions=z[f'positions{i}']))
+        return feats
+
+    def put(self, gene_id, feats):
+        arrays = {'n': np.int64(len(feats)), 'gene_id': np.str_(gene_id)}
+        for i, f in enumerate(feats):
+            kpos = np.fromiter(f.kmers.keys(), dtype=np.int64, count=len(f.kmers))
+            arrays.update({
+                f'meta{i}': np.array([f.feature_id, f.chrom, f.strand]), f'X{i}': f.X,
+                f'samp_start{i}': np.asarray(f.samp_start, dtype=np.int32), f'positions{i}': f.positions,
+                f'read_ids{i}': np.char.encode(np.asarray(f.read_ids or [], dtype='U32'), 'ascii'),
+                f'kpos{i}': kpos, f'kval{i}': np.char.encode(np.asarray(list(f.kmers.values()), dtype='U16'), 'ascii')})
+        tmp = self._path(gene_id) + f'.{os.getpid()}.tmp.npz'
+        np.savez(tmp, **arrays)
+        os.replace(tmp, self._path(gene_id))                    # atomic: concurrent ranks never see a partial file
+
+
+def load_gene_features_cached(cache, gene_id, cntrl_datasets, treat_datasets, by_transcript_ids=False):
+    '''load_gene_features through a FeatureCache (None = no cache)'''
+    if cache is not None:
+        feats = cache.get(gene_id)
+        if feats is not None:
+            return feats
+    feats = load_gene_features(gene_id, cntrl_datasets, treat_datasets, by_transcript_ids)
+    if cache is not None:
+        cache.put(gene_id, feats)
+    return feats
+
+
 def load_model_priors(model_fn=None):
     '''
     Expected kmer current levels (reference io.py:352-362); returned as
