@@ -56,3 +56,21 @@ def test_feature_narrower_than_the_window():
     host, res = _run(feats, 4, 2, window_size=5)
     assert (res.status[:4] == N.ST_NOT_A_WINDOW).all()            # 4 columns cannot hold a window of 5
     assert (res.status[4:] != N.ST_NOT_A_WINDOW).sum() == 8       # 12 columns -> 8 windows
+
+
+@pytest.mark.parametrize('path', ['warp', 'cta'])
+def test_scratch_chunking_of_the_ks_stage(path, monkeypatch):
+    '''yc_ks_batch walks the columns in scratch-sized chunks (2 M / 256 k columns built in); with a 50-column chunk
+    the results must be those of the single-chunk run, bit for bit'''
+    if path == 'cta':
+        monkeypatch.setenv('YC_KS_PATH', 'cta')
+        monkeypatch.setenv('YC_FIT_PATH', 'cta')
+    feats = synth.make_dataset(77, 5, 37, [22, 28, 25, 24], 2, 2, planted_frac=0.25)
+    monkeypatch.delenv('YC_KS_CHUNK', raising=False)
+    _, one = _run(feats, 4, 2, window_size=3)
+    keep = {k: getattr(one, k).copy() for k in ('status', 'ks_stat', 'ks_pval', 'n_c', 'n_t', 'fit_list', 'mu', 'stats')}
+    monkeypatch.setenv('YC_KS_CHUNK', '50')                       # 185 columns -> 4 chunks, the last one partial
+    _, many = _run(feats, 4, 2, window_size=3)
+    for k, v in keep.items():
+        np.testing.assert_array_equal(getattr(many, k), v, err_msg=k)
+    assert many.launches > one.launches and one.n_fitted > 5

@@ -213,6 +213,11 @@ namespace yc {
 int ks_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+int64_t ks_chunk_override(int64_t builtin) {
+    const char *e = getenv("YC_KS_CHUNK");
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? (int64_t)v : builtin;
+}
 void keep_pool_memory() {
     static bool done[64] = {};
     int dev = 0;

@@ -9,6 +9,9 @@ void count_launches(int n);
 // the scratch of yc_ks_batch comes from the device's default memory pool (cudaMallocAsync); keep freed
 // memory in the pool instead of returning it to the driver at every synchronisation
 void keep_pool_memory();
+// columns per scratch chunk of yc_ks_batch: YC_KS_CHUNK in the environment overrides the built-in value
+// (tests use a tiny one to cover the multi-chunk path)
+int64_t ks_chunk_override(int64_t builtin);
 int ks_sort_cap(const yc_batch_t &b, const yc_params_t &p);
 int ks_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
 int ks_dispatch(const yc_batch_t &b, const yc_params_t &p,

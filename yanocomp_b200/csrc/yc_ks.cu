@@ -310,7 +310,8 @@ static int launch_ks(const yc_batch_t &b, const yc_params_t &p, int sort_cap, in
     e = cudaFuncSetAttribute(ks_cta_d_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
     if (e != cudaSuccess) return (int)e;
     const int nwords_max = (b.max_reads + 31) / 32;
-    const int64_t chunk = b.total_cols < KS_CTA_CHUNK ? b.total_cols : KS_CTA_CHUNK;
+    const int64_t cap_cols = ks_chunk_override(KS_CTA_CHUNK);
+    const int64_t chunk = b.total_cols < cap_cols ? b.total_cols : cap_cols;
     const size_t scr_bytes = (size_t)chunk * GT * sizeof(double);
     unsigned char *raw = nullptr;
     e = cudaMallocAsync(reinterpret_cast<void **>(&raw), scr_bytes + (size_t)chunk * nwords_max * sizeof(uint32_t), st);

@@ -479,7 +479,8 @@ static int launch_kw(const yc_batch_t &b, const yc_params_t &p, double *ks_stat,
     }
     e = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
     if (e != cudaSuccess) return (int)e;
-    const int64_t chunk = b.total_cols < KW_CHUNK ? b.total_cols : KW_CHUNK;
+    const int64_t cap_cols = ks_chunk_override(KW_CHUNK);
+    const int64_t chunk = b.total_cols < cap_cols ? b.total_cols : cap_cols;
     double *scr = nullptr;
     e = cudaMallocAsync(reinterpret_cast<void **>(&scr), (size_t)chunk * GT * sizeof(double), st);
     if (e != cudaSuccess) return (int)e;
