@@ -119,7 +119,7 @@ __device__ __forceinline__ void warp_sum_smem(double (&v)[K], double *red, int l
 // ascending sort of buf[0..P), P a power of two >= 32: in registers (P / 32 values per lane) up to
 // P = 512, in register chunks of 512 merged through shared memory beyond (warp_sort_long, yc_common.cuh)
 template <int E>
-__device__ __noinline__ void warp_sort_buf_regs(double *buf, int lane) {
+__device__ __forceinline__ void warp_sort_buf_regs(double *buf, int lane) {
     double v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = buf[e * 32 + lane];              // any assignment will do before the sort
@@ -131,7 +131,7 @@ __device__ __noinline__ void warp_sort_buf_regs(double *buf, int lane) {
 }
 // complete-window rows of position g -> shared memory (binary16, pooled order), per-sample offsets
 template <int W>
-__device__ __noinline__ bool fw_front(const yc_batch_t &b, const yc_params_t &p, int64_t g,
+__device__ __forceinline__ bool fw_front(const yc_batch_t &b, const yc_params_t &p, int64_t g,
                                       unsigned char *smem, const FwSmem &L, int cap, int lane, bool gather,
                                       FwCtx<W> &c) {
     const int R = b.n_samples;
@@ -532,7 +532,7 @@ static int upload_em_steps() {
 // one log for the determinant (log of the product of the Cholesky pivots).  Unlike the
 // initialisation (cholesky_inverse, bit-exact with the oracle) EM is compared with a tolerance.
 template <int W>
-__device__ __noinline__ void em_mstep(EmPar<W> *par, int k, const double *red, double *carry, double step) {
+__device__ __forceinline__ void em_mstep(EmPar<W> *par, int k, const double *red, double *carry, double step) {
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
     double S[NS];
 #pragma unroll
@@ -610,7 +610,7 @@ __device__ __noinline__ void em_mstep(EmPar<W> *par, int k, const double *red, d
 
 // model of slot -> shared memory parameter block (+ Cholesky factors, uniform log density)
 template <int W>
-__device__ __noinline__ void load_model(EmPar<W> *par, const yc_fit_out_t &out, int slot, int lane,
+__device__ __forceinline__ void load_model(EmPar<W> *par, const yc_fit_out_t &out, int slot, int lane,
                                         const double *logw_src, int n_logw) {
     for (int i = lane; i < 2 * W; i += 32) par->mu[i / W][i % W] = out.mu[(size_t)slot * 2 * W + i];
     for (int i = lane; i < 2 * W * W; i += 32) par->cov[i / (W * W)][i % (W * W)] = out.cov[(size_t)slot * 2 * W * W + i];
