@@ -640,7 +640,7 @@ __device__ __forceinline__ void load_model(EmPar<W> *par, const yc_fit_out_t &ou
 #endif
 constexpr int kEmUnroll1 = YC_EM_UNROLL1, kEmUnroll2 = YC_EM_UNROLL2;
 #ifndef YC_FW_MINBLOCKS
-#define YC_FW_MINBLOCKS 16
+#define YC_FW_MINBLOCKS 24
 #endif
 
 template <int W>
