@@ -712,8 +712,10 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 const double l1 = c1 - 0.5 * q1 + par->logw[s][1];
                 const double l2 = (inside && uni) ? ul + par->logw[s][2] : -INFINITY;
                 // exp(l_max - l_max) = 1 exactly: only the two non-maximal terms need an exp
-                const double m = fmax(fmax(l0, l1), l2);
-                const bool m0 = l0 == m, m1 = !m0 && l1 == m;
+                // arg-max by three comparisons (fmax is a NaN-aware multi-instruction sequence on doubles); a NaN
+                // makes every comparison false, m = l2, and the NaN still reaches the likelihood through ea / eb
+                const bool m0 = l0 >= l1 && l0 >= l2, m1 = !m0 && l1 >= l2;
+                const double m = m0 ? l0 : (m1 ? l1 : l2);
                 const double ea = exp_nonpos((m0 ? l1 : l0) - m), eb = exp_nonpos(((m0 || m1) ? l2 : l1) - m);
                 const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
                 const double se = e0 + e1 + e2, inv = 1.0 / se;
