@@ -473,7 +473,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 double x[W];
                 fw_row<W>(xs, cap, i, x);
 #pragma unroll
-                for (int j = 0; j < W; ++j) { lo[j] = fmin(lo[j], x[j]); hi[j] = fmax(hi[j], x[j]); }
+                for (int j = 0; j < W; ++j) { lo[j] = min_nn(lo[j], x[j]); hi[j] = max_nn(hi[j], x[j]); }
             }
         }
 #pragma unroll

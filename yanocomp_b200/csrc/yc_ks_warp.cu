@@ -86,7 +86,7 @@ __device__ __noinline__ double ks_sort_ecdf(double *a, const double *tabA, const
                 while (cs < n_own && a[YC_KPAD(own_base + cs)] == x) ++cs;
                 if (e > 0) while (co < n_oth && a[YC_KPAD(oth_base + co)] <= x) ++co;
                 const int c1 = half ? co : cs, c2 = half ? cs : co;
-                dmax = fmax(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
+                dmax = max_nn(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
             }
         }
     }
@@ -409,7 +409,7 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
                     while (e < n2 && B[e] == v) ++e;
                     c2 = e; c1 = upper_bound(A, n1, v);
                 }
-                dmax = fmax(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
+                dmax = max_nn(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
             }
             dmax = warp_max(dmax);
         }
