@@ -49,7 +49,7 @@ namespace yc {
 #define YC_KPAD(i) ((i) + ((i) >> 4))
 
 template <int E>
-__device__ __noinline__ double ks_sort_ecdf(double *a, const double *tabA, const double *tabB,
+__device__ __forceinline__ double ks_sort_ecdf(double *a, const double *tabA, const double *tabB,
                                             int n1, int n2, int lane) {
     constexpr int P = 16 * E;
     const int half = lane >> 4, l16 = lane & 15;
