@@ -634,8 +634,12 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 const double l0 = par->cst[0] - 0.5 * q0 + par->logw[s][0];
                 const double l1 = par->cst[1] - 0.5 * q1 + par->logw[s][1];
                 const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[s][2] : -INFINITY;
-                const double m = fmax(fmax(l0, l1), l2);
-                const double e0 = exp_nonpos(l0 - m), e1 = exp_nonpos(l1 - m), e2 = exp_nonpos(l2 - m);
+                // arg-max by comparisons; exp(l_max - l_max) = 1 exactly, so only the two other terms need an exp
+                // (the same evaluation as em_warp_kernel, yc_fit_warp.cu)
+                const bool m0 = l0 >= l1 && l0 >= l2, m1 = !m0 && l1 >= l2;
+                const double m = m0 ? l0 : (m1 ? l1 : l2);
+                const double ea = exp_nonpos((m0 ? l1 : l0) - m), eb = exp_nonpos(((m0 || m1) ? l2 : l1) - m);
+                const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
                 const double se = e0 + e1 + e2;
                 const double inv = 1.0 / se;
                 r0 = e0 * inv; r1 = e1 * inv; r2 = e2 * inv;
