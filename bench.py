@@ -310,7 +310,7 @@ def run_gpu(args, cfg, opts_kw):
     em_name = 'gmm_em'
     em_ms = kavg.get(em_name, float('inf'))
     traffic = None
-    tfn = os.path.join(ROOT, 'profiles', 'r01d_traffic.json')
+    tfn = os.path.join(ROOT, 'profiles', 'r01g_traffic.json')
     if os.path.exists(tfn) and args.config == 2 and not args.features:
         with open(tfn) as fh:
             traffic = json.load(fh).get(dom)        # ncu --set full capture of the same workload
