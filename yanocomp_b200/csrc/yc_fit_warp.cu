@@ -322,10 +322,15 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 fw_row<W>(xs, cap, i, x);
                 const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
                 const bool k = d1 < d0;
-                acc[W] += k ? d1 : d0;
-                n1 += k;
+                // predicated adds (the select form cost two FSEL per double on top of the DADD)
+                if (k) {
+                    acc[W] += d1;
+                    ++n1;
 #pragma unroll
-                for (int j = 0; j < W; ++j) acc[j] += k ? x[j] : 0.0;
+                    for (int j = 0; j < W; ++j) acc[j] += x[j];
+                } else {
+                    acc[W] += d0;
+                }
             }
             warp_sum_smem<W + 1>(acc, red, lane);
             n1 = warp_sum_i(n1);
