@@ -16,13 +16,13 @@ chunks = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 for _ in range(3):
     test_host_batch_pipelined(host, params, eng, chunks=chunks)
 torch.cuda.synchronize()
-for ch, gr in ((2, 1.0), (4, 1.0), (3, 3.0), (4, 2.5), (4, 2.0), (5, 2.0), (3, 4.0)):
+for ch, gr, fi in ((4, 1.0, 1.0), (4, 1.0, 0.5), (4, 1.0, 0.3), (5, 1.0, 0.3), (5, 1.0, 0.5), (3, 1.0, 0.4), (4, 1.3, 0.5)):
     for _ in range(2):
-        test_host_batch_pipelined(host, params, eng, chunks=ch, growth=gr)
+        test_host_batch_pipelined(host, params, eng, chunks=ch, growth=gr, first=fi)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(5):
-        test_host_batch_pipelined(host, params, eng, chunks=ch, growth=gr)
-    torch.cuda.synchronize(); print(f'chunks={ch} growth={gr}: {1e3*(time.perf_counter()-t0)/5:.2f} ms / step')
+        test_host_batch_pipelined(host, params, eng, chunks=ch, growth=gr, first=fi)
+    torch.cuda.synchronize(); print(f'chunks={ch} growth={gr} first={fi}: {1e3*(time.perf_counter()-t0)/5:.2f} ms / step')
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     test_host_batch_pipelined(host, params, eng, chunks=chunks)
     torch.cuda.synchronize()

@@ -24,7 +24,7 @@ def test_host_batch(host: HostBatch, params: EngineParams, engine: Engine = None
 
 
 def test_host_batch_pipelined(host: HostBatch, params: EngineParams, engine: Engine = None,
-                              fetch='records', chunks=4, growth=1.0):
+                              fetch='records', chunks=4, growth=1.0, first=1.0):
     '''
     Same as test_host_batch with the batch cut into `chunks` feature ranges (views, no copy) that go
     through the engine's three-stage pipeline: the host->device copy of a range overlaps the kernels
@@ -34,7 +34,7 @@ def test_host_batch_pipelined(host: HostBatch, params: EngineParams, engine: Eng
     Returns [(sub-batch, result)].
     '''
     eng = engine or Engine(params)
-    return list(eng.run_pipelined(host.split(chunks, growth), fetch=fetch, keep_results=True))
+    return list(eng.run_pipelined(host.split(chunks, growth, first), fetch=fetch, keep_results=True))
 
 
 def tested_table(host: HostBatch, res: BatchResult, gmm=True):

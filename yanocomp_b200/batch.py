@@ -132,7 +132,7 @@ class HostBatch:
         v.max_cond_reads = int(max(split.max(), (v.n_reads - split).max())) if f1 > f0 else 0
         return v
 
-    def split(self, k, growth=1.0):
+    def split(self, k, growth=1.0, first=1.0):
         '''
         At most k views for host->device / compute pipelining.  growth = 1: balanced event bytes;
         growth > 1: every view is `growth` times the previous one, so the first upload (which nothing
@@ -144,6 +144,7 @@ class HostBatch:
         sizes = self.n_cols.astype(np.int64) * self.ld
         cum = np.cumsum(sizes)
         w = np.power(float(growth), np.arange(k))
+        w[0] *= float(first)                 # a shorter first range: its upload is the one nothing can hide
         targets = np.cumsum(w) / w.sum()
         cuts = [0]
         for j in range(k - 1):
