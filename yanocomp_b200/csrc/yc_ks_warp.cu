@@ -311,6 +311,9 @@ __host__ __device__ inline KdSmem kd_layout(int P) {
     return s;
 }
 
+#ifndef YC_KD_MINBLOCKS_WIDE
+#define YC_KD_MINBLOCKS_WIDE 6      // 16 values per lane in the register sort (or the long path)
+#endif
 #ifndef YC_KD_MINBLOCKS
 #define YC_KD_MINBLOCKS 8
 #endif
@@ -318,7 +321,7 @@ __host__ __device__ inline KdSmem kd_layout(int P) {
 // a power of two), 0 = more than 256 reads per condition.  A template parameter so that the kernel carries one
 // sort variant only (instruction footprint).
 template <int W, int SE>
-__global__ void __launch_bounds__(YC_KW_WARPS * 32, YC_KD_MINBLOCKS)
+__global__ void __launch_bounds__(YC_KW_WARPS * 32, (SE >= 16 || SE == 0) ? YC_KD_MINBLOCKS_WIDE : YC_KD_MINBLOCKS)
 ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t c0, const int ncol,
             const double *__restrict__ scr,
             double *__restrict__ ks_stat, double *__restrict__ ks_pval,
