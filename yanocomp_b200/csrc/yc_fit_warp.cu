@@ -288,34 +288,37 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         int iteration = 0;
         double improvement = INFINITY, last = INFINITY, total = INFINITY;
-        double acc[W + 1];                                   // column sums of cluster 1, total distance
-        int n1 = 0;
+        double acc[W + 2];                                   // column sums of cluster 1, total distance, size of cluster 1
         bool have_sums = false;
+        double *cs = red + (W + 2) * 33;                     // the 2W centroid coordinates, kept in shared memory
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 2 * W; ++q) cs[q] = cen[q];
+        }
+        __syncwarp();
 #pragma unroll 1
         while (improvement > 0.5 && iteration < 101) {
             if (have_sums) {
-                // centroid = cluster sum / cluster size.  Cluster 0's sums are the column totals minus
-                // cluster 1's (sums of binary16 values: exact either way).  Lane q divides coordinate q
-                // (one IEEE division per lane instead of 2W per lane), the quotients are broadcast.
-                const int n0 = n - n1;
-                double num = 0.0;
+                // centroid = cluster sum / cluster size from the totals of the previous pass (still in `red`).
+                // Cluster 0's sums are the column totals minus cluster 1's (sums of binary16 values: exact either
+                // way).  Lane q divides coordinate q (one IEEE division per lane instead of 2W per lane) and stores
+                // it; an empty cluster keeps its centroid (A2).
+                if (lane < 2 * W) {
+                    const int j = lane < W ? lane : lane - W;
+                    const double s1 = red[j * 33 + 32], n1d = red[(W + 1) * 33 + 32];
+                    double sj = sumx[0];
 #pragma unroll
-                for (int q = 0; q < 2 * W; ++q) {
-                    const double v = q < W ? sub_rn(sumx[q < W ? q : 0], acc[q < W ? q : 0]) : acc[q < W ? 0 : q - W];
-                    if (lane == q) num = v;
+                    for (int jj = 1; jj < W; ++jj) if (j == jj) sj = sumx[jj];
+                    const double den = lane < W ? (double)n - n1d : n1d;
+                    const double num = lane < W ? sub_rn(sj, s1) : s1;
+                    if (den > 0.0) cs[lane] = div_rn(num, den);
                 }
-                const int den = lane < W ? n0 : n1;
-                double mine = 0.0;
-                if (lane < 2 * W && den > 0) mine = div_rn(num, (double)den);
+                __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 2 * W; ++q) {
-                    const double v = __shfl_sync(YC_FULL, mine, q);
-                    if ((q < W ? n0 : n1) > 0) cen[q] = v;   // an empty cluster keeps its centroid (A2)
-                }
+                for (int q = 0; q < 2 * W; ++q) cen[q] = cs[q];
             }
 #pragma unroll
-            for (int k = 0; k <= W; ++k) acc[k] = 0.0;
-            n1 = 0;
+            for (int k = 0; k < W + 2; ++k) acc[k] = 0.0;
 #pragma unroll 1
             for (int i = lane; i < n; i += 32) {
                 double x[W];
@@ -325,15 +328,14 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 // predicated adds (the select form cost two FSEL per double on top of the DADD)
                 if (k) {
                     acc[W] += d1;
-                    ++n1;
+                    acc[W + 1] += 1.0;
 #pragma unroll
                     for (int j = 0; j < W; ++j) acc[j] += x[j];
                 } else {
                     acc[W] += d0;
                 }
             }
-            warp_sum_smem<W + 1>(acc, red, lane);
-            n1 = warp_sum_i(n1);
+            warp_sum_smem<W + 2>(acc, red, lane);
             have_sums = true;
             total = acc[W];
             if (iteration > 0) improvement = last - total;
