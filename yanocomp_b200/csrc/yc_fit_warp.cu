@@ -665,7 +665,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     if (!fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c)) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
     const int n = c.n;
     const uint16_t *xs = c.xs;
-    const uint8_t *srow = c.srow;
+    uint8_t *srow = c.srow;
     EmPar<W> *par = c.par;
     double *red = c.buf, *ssum = c.red;                 // main reduction rows alias the responsibilities (fw_layout)
     double *rb0 = c.buf, *rb1 = c.buf + cap;            // responsibilities of components 0 / 1 per fit row
@@ -676,6 +676,17 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 
     double *carry = reinterpret_cast<double *>(smem_raw + L.carry_off);   // [2][NS]: summaries kept when S0 < 1e-7 (A3)
     for (int q = lane; q < 2 * NS; q += 32) carry[q] = 0.0;
+    // The uniform box does not move during EM (A5), so whether a row lies inside it (bounds inclusive) is decided
+    // once and kept in bit 7 of the row's sample byte instead of 2 W comparisons per row and E-step.
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) {
+        double x[W];
+        fw_row<W>(xs, cap, i, x);
+        bool in = true;
+#pragma unroll
+        for (int a = 0; a < W; ++a) in &= (x[a] >= par->lo[a]) && (x[a] <= par->hi[a]);
+        if (in) srow[i] |= 0x80;
+    }
     __syncwarp();
     int iteration = 0;
     double improvement = INFINITY, last = 0.0;
@@ -688,9 +699,9 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         // product of the se_i (1 <= se_i <= 3 and at most cap/32 <= 32 rows per lane: no overflow)
         double llsum = 0.0, seprod = 1.0;
         {
-            double mu0[W], mu1[W], li0[NT], li1[NT], blo[W], bhi[W];
+            double mu0[W], mu1[W], li0[NT], li1[NT];
 #pragma unroll
-            for (int j = 0; j < W; ++j) { mu0[j] = par->mu[0][j]; mu1[j] = par->mu[1][j]; blo[j] = par->lo[j]; bhi[j] = par->hi[j]; }
+            for (int j = 0; j < W; ++j) { mu0[j] = par->mu[0][j]; mu1[j] = par->mu[1][j]; }
             {
                 int q = 0;
 #pragma unroll
@@ -703,9 +714,9 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             for (int i = lane; i < n; i += 32) {
                 double x[W];
                 fw_row<W>(xs, cap, i, x);
-                const int s = srow[i];
+                const int sv = srow[i], s = sv & 0x7f;
+                const bool inside = (sv & 0x80) != 0;
                 double q0 = 0.0, q1 = 0.0;
-                bool inside = true;
                 int q = 0;
 #pragma unroll
                 for (int a = 0; a < W; ++a) {
@@ -713,7 +724,6 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 #pragma unroll
                     for (int bb = 0; bb <= a; ++bb) { y0 = fma(li0[q], x[bb] - mu0[bb], y0); y1 = fma(li1[q], x[bb] - mu1[bb], y1); ++q; }
                     q0 = fma(y0, y0, q0); q1 = fma(y1, y1, q1);
-                    inside &= (x[a] >= blo[a]) && (x[a] <= bhi[a]);
                 }
                 const double l0 = c0 - 0.5 * q0 + par->logw[s][0];
                 const double l1 = c1 - 0.5 * q1 + par->logw[s][1];
@@ -747,7 +757,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             double x[W];
             fw_row<W>(xs, cap, i, x);
             const double r0 = rb0[i], r1 = rb1[i];
-            const int s = srow[i];
+            const int s = srow[i] & 0x7f;
             if (s != cur) {
                 if (cur >= 0) { ssum[(2 * cur) * 33 + lane] = t0; ssum[(2 * cur + 1) * 33 + lane] = t1; }
                 cur = s; t0 = 0.0; t1 = 0.0;
