@@ -594,6 +594,17 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     }
     __syncthreads();
 
+    // the uniform box does not move during EM (A5): whether a row lies inside it (bounds inclusive) is decided once
+    // and kept in bit 7 of the row's sample byte
+    for (int i = tid; i < n; i += YC_BLOCK) {
+        double x[W];
+        load_row<W>(c, i, x);
+        bool in = true;
+#pragma unroll
+        for (int a = 0; a < W; ++a) in &= (x[a] >= par->lo[a]) && (x[a] <= par->hi[a]);
+        if (in) c.srow[i] |= 0x80;
+    }
+    __syncthreads();
     int iteration = 0;
     double improvement = INFINITY, last = 0.0;
     bool failed = par->ok == 0;
@@ -616,9 +627,10 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             if (valid) {
                 double x[W];
                 load_row<W>(c, i, x);
-                s = c.srow[i];
+                const int sv = c.srow[i];
+                s = sv & 0x7f;
+                const bool inside = (sv & 0x80) != 0;
                 double q0 = 0.0, q1 = 0.0;
-                bool inside = true;
 #pragma unroll
                 for (int a = 0; a < W; ++a) {
                     double y0 = 0.0, y1 = 0.0;
@@ -629,7 +641,6 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                     }
                     q0 = fma(y0, y0, q0);
                     q1 = fma(y1, y1, q1);
-                    inside &= (x[a] >= par->lo[a]) && (x[a] <= par->hi[a]);
                 }
                 const double l0 = par->cst[0] - 0.5 * q0 + par->logw[s][0];
                 const double l1 = par->cst[1] - 0.5 * q1 + par->logw[s][1];
@@ -656,7 +667,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             }
             // per-sample responsibility sums (gmm.summaries): a 32-row chunk spans few samples
             const int s_lo = __shfl_sync(YC_FULL, s, 0);
-            const int s_hi = c.srow[min(base + 31, n - 1)];
+            const int s_hi = c.srow[min(base + 31, n - 1)] & 0x7f;
             for (int ss = s_lo; ss <= s_hi; ++ss) {
                 const bool mine = valid && s == ss;
                 const double t0 = warp_sum(mine ? r0 : 0.0), t1 = warp_sum(mine ? r1 : 0.0), t2 = warp_sum(mine ? r2 : 0.0);
