@@ -741,10 +741,17 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             }
         }
         llsum += log(seprod);
+        // ---- bookkeeping of em() BEFORE the statistics pass: the summaries of the last E-step are discarded
+        //      (stats.py:224), so when this E-step ends the loop the second pass is not run at all
+        const double ll = warp_sum(llsum);
+        if (iteration > 0) improvement = ll - last;
+        ++iteration;
+        last = ll;
+        if (!isfinite(ll)) { failed = true; break; }                     // assumption A5
+        if (!(improvement > 0.1 && iteration < 1001)) break;
         double acc[NP];
 #pragma unroll
         for (int q = 0; q < NP; ++q) acc[q] = 0.0;
-        acc[2 * NS] = llsum;
         // per-sample responsibility sums (gmm.summaries) ride along: fit rows are pooled in sample
         // order, so a lane sees its samples in ascending order and flushes a running pair of sums
         // into its own column of red rows NP + 2 s, NP + 2 s + 1 whenever the sample changes
@@ -788,12 +795,6 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             rq[32] = (ta + tb) + (tc + td);
         }
         __syncwarp();
-        const double ll = red[2 * NS * 33 + 32];
-        if (iteration > 0) improvement = ll - last;
-        ++iteration;
-        last = ll;
-        if (!isfinite(ll)) { failed = true; break; }                     // assumption A5
-        if (!(improvement > 0.1 && iteration < 1001)) break;             // last E-step's summaries discarded
         // ---- M-step of the shared Gaussians on lanes 0 / 1 (stats.py:202-205, A3/A4) and, in the same
         //      divergent region so that the two serial chains can interleave, the weights from the per-sample
         //      sums on the lanes above (stats.py:206-211; one lane per (sample, component); the uniform
