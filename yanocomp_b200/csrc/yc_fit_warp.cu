@@ -733,7 +733,8 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 // makes every comparison false, m = l2, and the NaN still reaches the likelihood through ea / eb
                 const bool m0 = l0 >= l1 && l0 >= l2, m1 = !m0 && l1 >= l2;
                 const double m = m0 ? l0 : (m1 ? l1 : l2);
-                const double ea = exp_nonpos((m0 ? l1 : l0) - m), eb = exp_nonpos(((m0 || m1) ? l2 : l1) - m);
+                double ea, eb;
+                exp_nonpos2((m0 ? l1 : l0) - m, ((m0 || m1) ? l2 : l1) - m, ea, eb);
                 const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
                 const double se = e0 + e1 + e2, inv = 1.0 / se;
                 rb0[i] = e0 * inv; rb1[i] = e1 * inv;
