@@ -149,3 +149,31 @@ def test_cli_with_feature_cache_is_byte_identical(tmp_path):
         outs.append((open(bed_fn, 'rb').read(), open(sm_fn, 'rb').read()))
     assert len(outs[0][0]) > 1000 and outs[0] == outs[1] == outs[2]
     assert len(os.listdir(str(tmp_path / 'cache'))) == 1
+
+
+def test_prep_then_gmmtest_matches_the_hdf5_route(tmp_path):
+    '''eventalign -> `prep` -> packed files -> `gmmtest` writes the same BED and the same single-molecule
+    predictions as `gmmtest` on the reference's HDF5 fixtures those eventalign tables were regenerated from'''
+    import gzip
+    from click.testing import CliRunner
+    from yanocomp_b200.cli import cli
+    from test_prep import _fixture_to_eventalign
+    inputs = {'h5': (CNTRL, TREAT)}
+    packed_fns = []
+    for name, h5 in (('wt', CNTRL), ('mettl3', TREAT)):
+        _fixture_to_eventalign(h5, tmp_path / f'{name}.tsv')
+        r = CliRunner().invoke(cli, ['prep', '-e', str(tmp_path / f'{name}.tsv'), '-h', str(tmp_path / f'{name}.ycp')],
+                               catch_exceptions=False)
+        assert r.exit_code == 0, r.output
+        packed_fns.append(str(tmp_path / f'{name}.ycp'))
+    inputs['packed'] = tuple(packed_fns)
+    outs = {}
+    for name, (c, t) in inputs.items():
+        bed_fn, sm_fn = str(tmp_path / f'{name}.bed'), str(tmp_path / f'{name}.json.gz')
+        r = CliRunner().invoke(cli, ['gmmtest', '-c', c, '-t', t, '-o', bed_fn, '-s', sm_fn, '--random-seed', '0'],
+                               catch_exceptions=False)
+        assert r.exit_code == 0, r.output
+        outs[name] = (open(bed_fn, 'rb').read(), json.load(gzip.open(sm_fn, 'rt'))['single_molecule_predictions'])
+    assert len(outs['h5'][0]) > 1000
+    assert outs['h5'][0] == outs['packed'][0]
+    assert outs['h5'][1] == outs['packed'][1]

@@ -1,8 +1,7 @@
 '''
-`yanocomp` command group (reference yanocomp/cli.py).  Only `gmmtest` is
-provided: `prep` is the upstream text-parsing step and is out of scope
-(DESIGN.md section 8).  click_log is not a dependency here, so the
-`-v/--verbosity` option it provides is re-created by hand.
+`yanocomp` command group (reference yanocomp/cli.py): `prep` and `gmmtest`.
+click_log is not a dependency here, so the `-v/--verbosity` option it
+provides is re-created by hand.
 '''
 import logging
 
@@ -10,6 +9,7 @@ import click
 
 from . import dist as ycdist
 from .gmmtest import gmm_test
+from .prep import nanopolish_collapse
 
 
 def get_logger(name):
@@ -33,7 +33,7 @@ def _set_verbosity(ctx, param, value):
     return value
 
 
-@click.group(commands={'gmmtest': gmm_test})
+@click.group(commands={'prep': nanopolish_collapse, 'gmmtest': gmm_test})
 @click.option('-v', '--verbosity', default='INFO', metavar='LVL', expose_value=False,
               callback=_set_verbosity, is_eager=True,
               help='Either CRITICAL, ERROR, WARNING, INFO or DEBUG')

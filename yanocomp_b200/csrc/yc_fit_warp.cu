@@ -1020,8 +1020,7 @@ int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *f
                      const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
     if (n_fit <= 0) return 0;
     if (int e = upload_em_steps()) return e;
-    const char *xs_ = getenv("YC_EM_EXTRA_SMEM");                    // occupancy experiments only
-    const int cap = fw_cap(b), smem = fw_smem(b, p, 1) + (xs_ ? atoi(xs_) : 0);
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 1);
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(em_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

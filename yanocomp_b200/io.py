@@ -1,6 +1,7 @@
 '''
 I/O of the gmmtest path: prep-HDF5 -> packed ragged features, kmer model
-priors, BED and single-molecule JSON writers.
+priors, BED and single-molecule JSON writers; plus the text parsers and the
+packed writer of `prep` (reference yanocomp/io.py:18-243).
 
 This is the reworked gmmtest half of the reference's io.py
 (reference yanocomp/io.py:246-415).  Instead of one pandas read x position
@@ -13,11 +14,14 @@ import gzip
 import json
 import logging
 import os
+import re
+import sys
+from collections import OrderedDict
 from contextlib import contextmanager
 
 import numpy as np
 
-from . import h5lite
+from . import h5lite, packed
 from .batch import Feature
 
 logger = logging.getLogger('yanocomp')
@@ -29,13 +33,193 @@ DEFAULT_PRIORS_MODEL_FN = os.path.join(
 
 @contextmanager
 def hdf5_list(hdf5_fns):
-    '''context manager for a list of HDF5 files (reference io.py:246-256)'''
-    handles = [h5lite.File(fn, 'r') for fn in hdf5_fns]
+    '''
+    context manager for a list of event files (reference io.py:246-256): HDF5 written by the
+    reference's prep, or the packed container written by this package's prep, told apart by magic
+    '''
+    handles = []
+    try:
+        for fn in hdf5_fns:
+            handles.append(packed.File(fn, 'r') if packed.is_packed(fn) else h5lite.File(fn, 'r'))
+    except Exception:
+        for f in handles:
+            f.close()
+        raise
     try:
         yield handles
     finally:
         for f in handles:
             f.close()
+
+
+# ---------------------------------------------------------------- prep: text parsers and the packed writer
+
+def _open_text(fn):
+    if fn == '-':
+        return sys.stdin
+    return gzip.open(fn, 'rt') if os.path.splitext(fn)[1] == '.gz' else open(fn)
+
+
+def _open_bytes(fn):
+    if fn == '-':
+        return sys.stdin.buffer
+    return gzip.open(fn, 'rb') if os.path.splitext(fn)[1] == '.gz' else open(fn, 'rb')
+
+
+def parse_eventalign_summary(summary_fn):
+    '''read_index -> read_name of a nanopolish summary file (reference io.py:41-48)'''
+    import pyarrow as pa
+    from pyarrow import csv as pacsv
+    handle = _open_bytes(summary_fn)
+    try:
+        t = pacsv.read_csv(handle, parse_options=pacsv.ParseOptions(delimiter='\t', quote_char=False),
+                           convert_options=pacsv.ConvertOptions(
+                               include_columns=['read_index', 'read_name'], strings_can_be_null=False,
+                               column_types={'read_index': pa.string(), 'read_name': pa.string()}))
+    finally:
+        if handle is not sys.stdin.buffer:
+            handle.close()
+    return dict(zip(t['read_index'].to_pylist(), t['read_name'].to_pylist()))
+
+
+_EA_INT = ('position', 'start_idx', 'end_idx')
+_EA_FLOAT = ('event_level_mean', 'event_stdv', 'event_length')
+_EA_TEXT = ('contig', 'reference_kmer', 'read_name', 'read_index')
+
+
+def _codes(column):
+    '''(int64 codes, list of strings) of an arrow string column, codes in order of first appearance'''
+    d = column.dictionary_encode()
+    return d.indices.to_numpy(zero_copy_only=False).astype(np.int64), d.dictionary.to_pylist()
+
+
+def parse_eventalign(eventalign_fn, summary_fn=None, chunksize=1_000_000):
+    '''
+    nanopolish eventalign table as blocks of columns (reference io.py:51-85 yields one dict per
+    line).  Each block: integer codes + string tables for contig / kmer / read name, `pos` =
+    position + 2 (centre of the 5-mer), `points` = end_idx - start_idx.  The table is parsed by
+    Arrow's multi-threaded CSV reader, whose number conversion is correctly rounded, i.e. gives the
+    same doubles as Python's float().  `chunksize` is the approximate number of lines per block.
+    '''
+    import pyarrow as pa
+    from pyarrow import csv as pacsv
+    read_name_idx = parse_eventalign_summary(summary_fn) if summary_fn is not None else None
+    handle = _open_bytes(eventalign_fn)
+    try:
+        header = handle.readline().decode('ascii').rstrip('\r\n').split('\t')
+        source, skip = handle, 0
+        if eventalign_fn != '-':
+            # a path is opened by Arrow itself (native reads, gzip by extension) and the header line skipped
+            handle.close()
+            source, skip = eventalign_fn, 1
+        fieldnames = set(header)
+        if 'read_name' not in fieldnames and read_name_idx is None:
+            raise KeyError(
+                'nanopolish must be either run with --print-read-names option '
+                'or else a eventalign summary file must be provided')
+        if not fieldnames.issuperset(['start_idx', 'end_idx']):
+            raise KeyError(
+                'cannot find "start_idx" or "end_idx" fields, '
+                'nanopolish must be run with --signal-index option')
+        wanted = [c for c in header if c in _EA_INT or c in _EA_FLOAT or c in _EA_TEXT]
+        types = {c: (pa.int64() if c in _EA_INT else pa.float64() if c in _EA_FLOAT else pa.string()) for c in wanted}
+        block = int(min(max(int(chunksize) * 96, 1 << 14), 1 << 28))
+        try:
+            reader = pacsv.open_csv(
+                source, read_options=pacsv.ReadOptions(column_names=header, skip_rows=skip, block_size=block),
+                parse_options=pacsv.ParseOptions(delimiter='\t', quote_char=False),
+                convert_options=pacsv.ConvertOptions(include_columns=wanted, column_types=types,
+                                                     strings_can_be_null=False))
+        except pa.ArrowInvalid as e:
+            if 'Empty CSV' in str(e):                                # a header and nothing else
+                return
+            raise
+        for batch in reader:
+            if batch.num_rows == 0:
+                continue
+            t = {name: batch.column(i) for i, name in enumerate(batch.schema.names)}
+            if 'read_name' in t:
+                r_code, r_ids = _codes(t['read_name'])
+            else:
+                r_code, idx = _codes(t['read_index'])
+                r_ids = [read_name_idx[i] for i in idx]              # KeyError for an index the summary lacks
+            t_code, t_ids = _codes(t['contig'])
+            k_code, kmers = _codes(t['reference_kmer'])
+            num = lambda name: t[name].to_numpy(zero_copy_only=False)
+            yield {'t_code': t_code, 't_ids': t_ids, 'k_code': k_code, 'kmers': kmers, 'r_code': r_code, 'r_ids': r_ids,
+                   'pos': num('position') + 2, 'mean': num('event_level_mean'), 'std': num('event_stdv'),
+                   'duration': num('event_length'), 'points': num('end_idx') - num('start_idx')}
+    finally:
+        if handle is not sys.stdin.buffer:
+            handle.close()
+
+
+def parse_gtf_attrs(attrs):
+    return dict(re.findall(r'(\w+) \"(.+?)\"(?:;|$)', attrs))
+
+
+def read_gtf(gtf_fn, use_ftype):
+    '''(chrom, start0, end, ftype, strand, attrs) of the records of one feature type (reference io.py:98-117)'''
+    with _open_text(gtf_fn) as handle:
+        for line in handle:
+            if line.startswith('#'):
+                continue
+            f = line.rstrip('\r\n').split('\t')
+            if len(f) < 9 or f[2] != use_ftype:
+                continue
+            yield f[0], int(f[3]) - 1, int(f[4]), f[2], f[6], parse_gtf_attrs(f[8])
+
+
+def load_gtf_database(gtf_fn, mapped_to='transcript_id', parent_id='gene_id'):
+    '''transcript -> exon intervals (sorted, 0-based half-open) and their cumulative offsets (reference io.py:120-143)'''
+    gtf = {}
+    for chrom, start, end, ftype, strand, attrs in read_gtf(gtf_fn, 'exon'):
+        t = gtf.setdefault(attrs[mapped_to], {'gene_id': attrs[parent_id], 'chrom': chrom, 'strand': strand, 'invs': []})
+        t['invs'].append((start, end))
+    for t in gtf.values():
+        t['invs'].sort()
+        t['start'] = t['invs'][0][0]
+        t['invs_lns'] = [e - s for s, e in t['invs']]
+        t['ln'] = sum(t['invs_lns'])
+        t['inv_cs'] = [0] + np.cumsum(t['invs_lns'])[:-1].tolist()
+    return gtf
+
+
+def _index_in_arrival_order(index, codes, names):
+    '''incrementing_index (reference io.py:148-154) for a column of codes: returns the index of every row'''
+    uniq, first = np.unique(codes, return_index=True)
+    lut = np.empty(int(uniq.max()) + 1 if len(uniq) else 0, dtype=np.int64)
+    for c in uniq[np.argsort(first, kind='stable')].tolist():
+        lut[c] = index.setdefault(names[c], len(index))
+    return lut[codes]
+
+
+def save_events_to_packed(collapsed, out_fn):
+    '''
+    Writer of prep (reference save_events_to_hdf5, io.py:174-243): per-gene transcript / read indices
+    in order of first appearance, events as binary16 (EVENT_DTYPE), pos -> kmer with the last record
+    winning, chrom / strand attributes.  `collapsed` yields (gene_id, chrom, strand, columns).
+    '''
+    kmer_index, transcript_index, read_index, gene_attrs = {}, {}, {}, {}
+    with packed.Writer(out_fn) as o:
+        for gene_id, chrom, strand, rec in collapsed:
+            gene_attrs[gene_id] = (chrom, strand)
+            t_x = _index_in_arrival_order(transcript_index.setdefault(gene_id, OrderedDict()), rec['t_code'], rec['t_ids'])
+            r_x = _index_in_arrival_order(read_index.setdefault(gene_id, OrderedDict()), rec['r_code'], rec['r_ids'])
+            if len(t_x) and t_x.max() > 255:
+                raise OverflowError(f'{gene_id}: more than 256 transcripts (transcript_idx is uint8 in EVENT_DTYPE)')
+            if len(rec['pos']) and (rec['pos'].min() < 0 or rec['pos'].max() > 0xffffffff):
+                raise OverflowError(f'{gene_id}: position outside uint32')
+            data = np.empty(len(t_x), dtype=packed.EVENT_DTYPE)
+            data['transcript_idx'], data['read_idx'], data['pos'] = t_x, r_x, rec['pos']
+            with np.errstate(over='ignore'):
+                data['mean'], data['std'], data['duration'] = rec['mean'], rec['std'], rec['duration']
+            o.append_events(gene_id, data)
+            kmers = rec['kmers']
+            kmer_index.setdefault(gene_id, {}).update(zip(rec['pos'].tolist(), (kmers[k] for k in rec['k_code'].tolist())))
+        for gene_id, kmer_pos in kmer_index.items():
+            chrom, strand = gene_attrs[gene_id]
+            o.set_gene(gene_id, chrom, strand, kmer_pos.items(), read_index[gene_id].keys(), transcript_index[gene_id].keys())
 
 
 def get_shared_keys(hdf5_handles):
