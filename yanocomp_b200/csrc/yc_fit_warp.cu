@@ -16,6 +16,7 @@
 //    stays inside the 32 KB instruction cache.
 // Eligibility (dispatcher): w <= 5, <= 1024 reads per feature, no sub-sampling
 // possible (reads per condition <= max_fit_depth).
+#include <atomic>
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -520,16 +521,16 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 __constant__ double c_em_step[1008];
 
 static int upload_em_steps() {
-    static bool done[64] = {};
+    static std::atomic<bool> done[64];                                   // zero-initialised; callers may be on several threads
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    if (dev < 64 && done[dev]) return 0;
+    if (dev < 64 && done[dev].load(std::memory_order_acquire)) return 0;
     double h[1008];
     for (int it = 0; it < 1008; ++it) h[it] = 1.0 - (0.99 * pow(2.0 + (double)it, -1e-3));
     e = cudaMemcpyToSymbol(c_em_step, h, sizeof(h));
     if (e != cudaSuccess) return (int)e;
-    if (dev < 64) done[dev] = true;
+    if (dev < 64) done[dev].store(true, std::memory_order_release);
     return 0;
 }
 
