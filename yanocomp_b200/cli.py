@@ -33,11 +33,34 @@ def _set_verbosity(ctx, param, value):
     return value
 
 
+def _profile_until_exit():
+    '''hidden --profile flag of the reference (cli.py:36-50): cProfile over the whole process, top 50 by
+    cumulative time logged at DEBUG level on exit (host side only; kernels are profiled with ncu)'''
+    import atexit
+    import cProfile
+    import pstats
+    from io import StringIO
+    logger.debug('Running with profiler...')
+    prof = cProfile.Profile()
+    prof.enable()
+
+    @atexit.register
+    def print_profile_stats_on_exit():
+        prof.disable()
+        logger.debug('Profiling complete')
+        s = StringIO()
+        pstats.Stats(prof, stream=s).sort_stats('cumulative').print_stats(50)
+        logger.debug(s.getvalue())
+
+
 @click.group(commands={'prep': nanopolish_collapse, 'gmmtest': gmm_test})
 @click.option('-v', '--verbosity', default='INFO', metavar='LVL', expose_value=False,
               callback=_set_verbosity, is_eager=True,
               help='Either CRITICAL, ERROR, WARNING, INFO or DEBUG')
-def cli():
+@click.option('--profile', is_flag=True, hidden=True)
+def cli(profile):
+    if profile:
+        _profile_until_exit()
     world, _ = ycdist.init_from_env()
     if world > 1:
         import atexit
