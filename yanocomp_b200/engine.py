@@ -9,6 +9,8 @@ for device memory and streams only.
 '''
 import dataclasses
 
+import os
+
 import numpy as np
 import torch
 
@@ -125,6 +127,7 @@ class Engine:
         self._stages = {}               # pinned device->host staging buffers (one per pipeline slot)
         self._copy_stream = None
         self._fetch_stream = None
+        self._fit_stream = None
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
     def upload(self, host: HostBatch) -> DeviceBatch:
@@ -148,6 +151,13 @@ class Engine:
             self._copy_stream = torch.cuda.Stream(self.device)
             self._fetch_stream = torch.cuda.Stream(self.device)
         compute = torch.cuda.current_stream(self.device)
+        # the fit kernels of batch k go to their own stream, so that the long tail of its EM kernel (a few
+        # positions run hundreds of iterations) is filled by the KS kernels of batch k+1 on the compute stream
+        fit_stream = None
+        if os.environ.get('YC_FIT_STREAM', '1') != '0':
+            if self._fit_stream is None:
+                self._fit_stream = torch.cuda.Stream(self.device)
+            fit_stream = self._fit_stream
 
         def stage_a():
             h = next(it, None)
@@ -171,7 +181,13 @@ class Engine:
                     continue
             if a_q:
                 h, ctx = a_q.pop(0)
-                b_q.append((h, self._launch_fit(ctx, fetch)))
+                if fit_stream is not None:
+                    fit_stream.wait_event(ctx['counted'])    # KS of this batch has finished
+                    with torch.cuda.stream(fit_stream):
+                        ctx = self._launch_fit(ctx, fetch)
+                else:
+                    ctx = self._launch_fit(ctx, fetch)
+                b_q.append((h, ctx))
             if len(b_q) > 1 or (not a_q and nxt is None):
                 h, ctx = b_q.pop(0)
                 yield h, self._fetch_result(ctx, i if keep_results else i % 4)
