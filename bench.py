@@ -258,12 +258,13 @@ def run_gpu(args, cfg, opts_kw):
     #      of the previous one; every byte of input is copied host->device inside the timed region.
     CHUNKS = int(os.environ.get('YC_BENCH_CHUNKS', '4'))          # feature ranges of the pipelined public call
     GROWTH = float(os.environ.get('YC_BENCH_GROWTH', '1.0'))      # each range this many times the previous one
+    FIRST = float(os.environ.get('YC_BENCH_FIRST', '1.0'))        # relative size of the first range
     for _ in range(max(1, min(args.warmup, 2))):
-        parts = test_host_batch_pipelined(host, params, eng, chunks=CHUNKS, growth=GROWTH)
+        parts = test_host_batch_pipelined(host, params, eng, chunks=CHUNKS, growth=GROWTH, first=FIRST)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        parts = test_host_batch_pipelined(host, params, eng, chunks=CHUNKS, growth=GROWTH)
+        parts = test_host_batch_pipelined(host, params, eng, chunks=CHUNKS, growth=GROWTH, first=FIRST)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -344,7 +345,7 @@ def run_gpu(args, cfg, opts_kw):
                    'sharding': 'features (genes) split across ranks, no data-path collective'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e_max / args.steps,
                 'h2d_bytes_per_step': host.nbytes, 'd2h_bytes_per_step': d2h_bytes,
-                'tested_rows': int(n_rows), 'pipeline_chunks': CHUNKS, 'pipeline_growth': GROWTH,
+                'tested_rows': int(n_rows), 'pipeline_chunks': CHUNKS, 'pipeline_growth': GROWTH, 'pipeline_first': FIRST,
                 'bh_fdr_ms_not_included': bh_ms},
         'gpu_launches': launches,
         'clocks': sampler.summary(),
