@@ -156,7 +156,7 @@ class Engine:
         fit_stream = None
         if os.environ.get('YC_FIT_STREAM', '1') != '0':
             if self._fit_stream is None:
-                self._fit_stream = torch.cuda.Stream(self.device, priority=int(os.environ.get('YC_FIT_PRIO', '0')))
+                self._fit_stream = torch.cuda.Stream(self.device)
             fit_stream = self._fit_stream
 
         def stage_a():
