@@ -229,3 +229,39 @@ def test_gmmtest_loaders_read_both_formats_identically(tmp_path):
                     assert a.X.tobytes() == b.X.tobytes() and np.array_equal(a.positions, b.positions)
                     assert np.array_equal(a.samp_start, b.samp_start)
                     assert list(a.read_ids) == list(b.read_ids) and a.kmers == b.kmers
+
+
+def test_packed_container_edge_cases(tmp_path):
+    # header-only eventalign -> a valid, empty container
+    with open(tmp_path / 'empty.tsv', 'w') as f:
+        f.write('\t'.join(HEADER) + '\n')
+    _prep(['-e', tmp_path / 'empty.tsv', '-h', tmp_path / 'empty.ycp'])
+    with packed.File(tmp_path / 'empty.ycp') as f:
+        assert f.keys() == []
+        with pytest.raises(KeyError):
+            f['nothing/events']
+    # a file the writer never closed (no index footer) and a foreign file are refused loudly
+    data = open(tmp_path / 'empty.ycp', 'rb').read()
+    open(tmp_path / 'cut.ycp', 'wb').write(data[:-5])
+    with pytest.raises(packed.PackedFormatError):
+        packed.File(tmp_path / 'cut.ycp')
+    open(tmp_path / 'foreign.ycp', 'wb').write(b'not a packed file at all')
+    with pytest.raises(packed.PackedFormatError):
+        packed.File(tmp_path / 'foreign.ycp')
+    with pytest.raises(ValueError):
+        packed.File(tmp_path / 'empty.ycp', 'w')
+    # gene ids with a slash, several extents, read ids longer than the reference's 36-byte READ_DTYPE
+    ev = np.zeros(3, dtype=packed.EVENT_DTYPE)
+    ev['pos'] = [5, 6, 7]
+    with packed.Writer(tmp_path / 'w.ycp') as w:
+        w.append_events('a/b', ev[:2])
+        w.append_events('plain', ev)
+        w.append_events('a/b', ev[2:])
+        w.set_gene('a/b', 'chr1', '-', [(5, 'AAAAA'), (6, 'CCCCC'), (7, 'GGGGG')], ['r' * 40], ['t1'])
+        w.set_gene('plain', '.', '.', [(5, 'AAAAA')], ['r1'], ['plain'])
+    with packed.File(tmp_path / 'w.ycp') as f:
+        assert sorted(f.keys()) == ['a/b', 'plain'] and 'a/b' in f and 'zzz' not in f
+        assert f['a/b/events'][:]['pos'].tolist() == [5, 6, 7] and len(f['plain/events']) == 3
+        assert f['a/b'].attrs == {'chrom': 'chr1', 'strand': '-'}
+        assert f['a/b']['read_ids'][:].tolist() == [b'r' * 36]
+        assert f['/a/b/kmers'][:]['kmer'].tolist() == [b'AAAAA', b'CCCCC', b'GGGGG']

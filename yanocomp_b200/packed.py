@@ -171,7 +171,11 @@ class File:
         return list(self._genes.keys())
 
     def __contains__(self, key):
-        return key.strip('/').split('/')[0] in self._genes
+        try:
+            self[key]
+        except KeyError:
+            return False
+        return True
 
     def __getitem__(self, path):
         parts = path.strip('/').split('/')
