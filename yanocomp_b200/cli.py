@@ -33,24 +33,24 @@ def _set_verbosity(ctx, param, value):
     return value
 
 
+def _log_profile(prof, top=50):
+    import io
+    import pstats
+    prof.disable()
+    buf = io.StringIO()
+    pstats.Stats(prof, stream=buf).sort_stats('cumulative').print_stats(top)
+    logger.debug('Profiling complete\n%s', buf.getvalue())
+
+
 def _profile_until_exit():
-    '''hidden --profile flag of the reference (cli.py:36-50): cProfile over the whole process, top 50 by
-    cumulative time logged at DEBUG level on exit (host side only; kernels are profiled with ncu)'''
+    '''hidden --profile flag (reference cli.py:36-50): host-side cProfile over the whole process, the 50 entries
+    with the largest cumulative time logged at DEBUG level on exit; the kernels are profiled with ncu instead'''
     import atexit
     import cProfile
-    import pstats
-    from io import StringIO
-    logger.debug('Running with profiler...')
     prof = cProfile.Profile()
+    atexit.register(_log_profile, prof)
+    logger.debug('Running with profiler...')
     prof.enable()
-
-    @atexit.register
-    def print_profile_stats_on_exit():
-        prof.disable()
-        logger.debug('Profiling complete')
-        s = StringIO()
-        pstats.Stats(prof, stream=s).sort_stats('cumulative').print_stats(50)
-        logger.debug(s.getvalue())
 
 
 @click.group(commands={'prep': nanopolish_collapse, 'gmmtest': gmm_test})
