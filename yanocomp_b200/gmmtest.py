@@ -124,52 +124,81 @@ def _position_sm_preds(feat, c, kmers, opts, n_cntrl, model_json, post):
     }
 
 
+def _kmers_by_column(feat):
+    '''kmer of every column of a feature as one string array (cached on the feature; None = no kmer recorded)'''
+    kb = getattr(feat, '_kmers_by_column', None)
+    if kb is None:
+        get = feat.kmers.get
+        kb = np.array([get(p) for p in feat.positions.tolist()], dtype=object)
+        feat._kmers_by_column = kb
+    return kb
+
+
 def _batch_records(host, res, opts):
-    '''device results of one batch -> (records, sm_preds) in the reference's shapes'''
+    '''
+    Device results of one batch -> (records, sm_preds) in the reference's shapes
+    (GMMTestRecord tuples, reference gmmtest.py:120-136, 164-178).  The rows are assembled column
+    by column per feature (the gated positions arrive sorted by column, so a feature is a run) and
+    zipped into tuples at the end; only the positions that carry single-molecule predictions are
+    visited one by one.
+    '''
     w = opts.window_size
     centre = w // 2
     n_cntrl = host.n_cntrl
     records, sm = [], {}
     feats = host.features
-
-    def locate(g):
-        fi = int(np.searchsorted(host.col_off, g, side='right') - 1)
-        return fi, int(g - host.col_off[fi])
-
     if not opts.gmm:
-        for g in np.flatnonzero(res.status == N.ST_KS_ONLY):
-            fi, c = locate(g)
-            f = feats[fi]
-            pos = int(f.positions[c])
-            kmers = _window_kmers(f, pos, w, f.strand == '-')
-            records.append((f.chrom, pos, f.feature_id, f.strand, kmers[centre], kmers, centre,
-                            np.nan, np.nan, np.nan, float(res.ks_pval[g]), 1., np.nan, np.nan,
-                            np.nan, np.nan, None, None, None, None, float(res.ks_stat[g])))
-            sm.setdefault(f.feature_id, {})[pos] = None
+        cols = np.flatnonzero(res.status == N.ST_KS_ONLY)
+        slots = None
+    else:
+        slots = np.flatnonzero(np.asarray(res.status_fit) == N.ST_TESTED)     # others: LinAlgError path, dropped
+        cols = np.asarray(res.fit_list)[slots].astype(np.int64)
+    if len(cols) == 0:
         return records, sm
-    for s, g in enumerate(res.fit_list):
-        if res.status_fit[s] != N.ST_TESTED:
-            continue                                            # LinAlgError path: dropped
-        fi, c = locate(g)
-        f = feats[fi]
-        pos = int(f.positions[c])
-        kmers = _window_kmers(f, pos, w, f.strand == '-')
-        g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = res.stats[s].tolist()
-        mu, sd = res.mu[s], res.stds[s]
-        records.append((f.chrom, pos, f.feature_id, f.strand, kmers[centre], kmers, centre,
-                        lor, lo, hi, p_val, 1., c_frac, t_frac, g_stat, hom_g,
-                        mu[0].copy(), sd[0].copy(), mu[1].copy(), sd[1].copy(), float(res.ks_stat_fit[s])))
-        pos_sm = None
-        off = int(res.post_off[s]) if res.post_off is not None else -1
-        if off >= 0 and res.post is not None:
-            n_all = int(res.nall_fit[s])
-            pos_sm = _position_sm_preds(f, c, kmers, opts, n_cntrl,
-                                        format_model(mu, res.cov[s], res.box[s] if opts.add_uniform else None,
-                                                     res.cw[s]),
-                                        res.post[off:off + n_all].copy())
-        elif off == -2:
+    fidx = np.searchsorted(host.col_off, cols, side='right') - 1
+    run_starts = np.concatenate(([0], np.flatnonzero(np.diff(fidx)) + 1, [len(cols)]))
+    offs = np.arange(-centre, centre + 1)
+    nan = float('nan')
+    if slots is not None:
+        stats = np.asarray(res.stats)[slots]                                  # fancy indexing = copies: the
+        mu, sd = np.asarray(res.mu)[slots], np.asarray(res.stds)[slots]       # staging buffer is reused later
+        ks = np.asarray(res.ks_stat_fit)[slots].tolist()
+        g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = (stats[:, j].tolist() for j in range(8))
+        post_off = np.asarray(res.post_off)[slots] if res.post_off is not None else None
+        if post_off is not None and (post_off == -2).any():
             raise RuntimeError('single-molecule posterior buffer overflow (internal sizing error)')
-        sm.setdefault(f.feature_id, {})[pos] = pos_sm
+    else:
+        p_val, ks = res.ks_pval[cols].tolist(), res.ks_stat[cols].tolist()
+    for a, b in zip(run_starts[:-1].tolist(), run_starts[1:].tolist()):
+        f = feats[int(fidx[a])]
+        c = cols[a:b] - int(host.col_off[int(fidx[a])])
+        pos = f.positions[c].tolist()
+        win = _kmers_by_column(f)[c[:, None] + (-offs if f.strand == '-' else offs)]
+        if (win == None).any():                                               # noqa: E711 (elementwise)
+            raise KeyError(f'{f.feature_id}: no kmer recorded for a tested window')
+        win = win.astype(str)
+        n = b - a
+        head = (f.chrom, f.feature_id, f.strand)
+        if slots is None:
+            records.extend(
+                (head[0], p, head[1], head[2], km[centre], km, centre, nan, nan, nan, pv, 1., nan, nan, nan, nan,
+                 None, None, None, None, d)
+                for p, km, pv, d in zip(pos, win, p_val[a:b], ks[a:b]))
+            sm.setdefault(f.feature_id, {}).update(dict.fromkeys(pos))
+            continue
+        records.extend(zip(
+            [head[0]] * n, pos, [head[1]] * n, [head[2]] * n, win[:, centre].tolist(), win, [centre] * n,
+            lor[a:b], lo[a:b], hi[a:b], p_val[a:b], [1.] * n, c_frac[a:b], t_frac[a:b], g_stat[a:b], hom_g[a:b],
+            mu[a:b, 0], sd[a:b, 0], mu[a:b, 1], sd[a:b, 1], ks[a:b]))
+        fsm = sm.setdefault(f.feature_id, {})
+        fsm.update(dict.fromkeys(pos))
+        if post_off is not None and res.post is not None:
+            for i in np.flatnonzero(post_off[a:b] >= 0).tolist():
+                s = int(slots[a + i])
+                off = int(post_off[a + i])
+                model = format_model(mu[a + i], res.cov[s], res.box[s] if opts.add_uniform else None, res.cw[s])
+                fsm[pos[i]] = _position_sm_preds(f, int(c[i]), win[i], opts, n_cntrl, model,
+                                                 res.post[off:off + int(res.nall_fit[s])].copy())
     return records, sm
 
 
