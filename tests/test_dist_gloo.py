@@ -39,9 +39,13 @@ def _worker(rank, world, port, out_dir):
         recs.append(('.', 100 + i, g, '+', 'GGACT', km, 1, 0.1, 0., 0.2, p, 1., .5, .5, 1., 0.,
                      np.ones(3), np.ones(3), np.ones(3), np.ones(3), .3))
         sm[g] = {100 + i: {'rank': rank}}
+    from yanocomp_b200.gmmtest import Records
+    recs = Records(recs)                                  # what test_chunk returns: column blocks
     recs, sm = ycdist.gather_results(recs, sm)
     if rank == 0:
+        assert isinstance(recs, Records) and len(recs) == len(genes)
         res = _to_frame(recs)
+        assert _to_frame(list(recs)).to_csv() == res.to_csv()             # same frame from the tuples
         assert sorted(res.gene_id) == genes and sorted(sm) == genes
         res.sort_values('gene_id')[['gene_id', 'p_val', 'fdr']].to_csv(os.path.join(out_dir, 'w%d.csv' % world), index=False)
     else:

@@ -193,3 +193,34 @@ def test_oracle_bridge_roundtrip():
     c = ob.cond_events(f, 0, 2)
     assert c.X.shape == (17, 12) and c.rep.tolist() == [1] * 8 + [2] * 9
     np.testing.assert_array_equal(c.X.T, f.X[:, :17].astype(np.float64))
+
+
+def test_records_container_behaves_like_the_list_of_tuples():
+    import pickle
+    from yanocomp_b200.gmmtest import Records
+    rng = np.random.default_rng(11)
+    rows = _fake_records(40, rng)
+    rows[5] = rows[5][:10] + (np.nan,) + rows[5][11:]
+    ks_only = [r[:7] + (np.nan, np.nan, np.nan, r[10], 1., np.nan, np.nan, np.nan, np.nan, None, None, None, None, r[20])
+               for r in _fake_records(7, rng)]                                    # --no-gmm rows
+    recs = Records(rows[:25])
+    recs.extend(rows[25:])
+    other = Records(ks_only)
+    recs.extend(other)
+    assert len(recs) == 47 and len(recs.blocks) == 3 and len(Records()) == 0 and list(Records()) == []
+    everything = rows + ks_only
+    for got, want in zip(recs, everything):
+        assert len(got) == len(want) == len(COLUMNS)
+        for a, b in zip(got, want):
+            if isinstance(b, np.ndarray):
+                assert np.array_equal(a, b)
+            else:
+                assert a is b or a == b or (a != a and b != b)
+    assert recs[0][1] == rows[0][1] and recs[-1][2] == ks_only[-1][2] and recs[26][1] == rows[26][1]
+    assert [r[1] for r in recs[3:6]] == [r[1] for r in rows[3:6]]
+    with pytest.raises(IndexError):
+        recs[47]
+    back = pickle.loads(pickle.dumps(recs))
+    a, b, c = _to_frame(recs), _to_frame(back), _to_frame(everything)
+    assert a.to_csv() == b.to_csv() == c.to_csv() and a.dtypes.equals(c.dtypes) and len(a) == 46
+    assert list(_to_frame(Records()).columns) == COLUMNS and len(_to_frame(Records())) == 0

@@ -78,7 +78,9 @@ def gather_results(records, sm_preds):
     dist.gather_object((records, sm_preds), gathered, dst=0)
     if rank != 0:
         return [], {}
-    all_records, all_sm = [], {}
+    first = gathered[0][0]
+    all_records = type(first)() if hasattr(first, 'blocks') else []     # column blocks stay column blocks
+    all_sm = {}
     for recs, sm in gathered:
         all_records.extend(recs)
         for k, v in sm.items():

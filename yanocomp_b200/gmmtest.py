@@ -10,6 +10,7 @@ are packed into ragged device batches (`io.load_gene_features`,
 `batch.HostBatch`) and the whole KS -> GMM -> G-test -> posterior path runs in
 the CUDA kernels of libyanocomp_b200 (`engine.Engine`).
 '''
+import collections.abc
 import dataclasses
 import logging
 import os
@@ -38,6 +39,82 @@ RESULT_COLUMNS = ['kmer', 'kmers', 'centre', 'log_odds', 'log_odds_lower_ci', 'l
 COLUMNS = POS_COLUMNS + RESULT_COLUMNS
 
 BATCH_EVENT_BYTES = 1 << 30      # host->device granularity of test_chunk
+
+# columns whose cells are arrays of length window_size
+_ARRAY_COLUMNS = {'kmers', 'dist1_means', 'dist1_stds', 'dist2_means', 'dist2_stds'}
+
+
+class Records(collections.abc.Sequence):
+    '''
+    The list of GMMTestRecord tuples that `test_chunk` returns (reference gmmtest.py:120-136,
+    139-179), stored as column blocks.  It behaves like that list (len, iteration, indexing give
+    the 21-field tuples; it pickles; `extend` accepts tuples or other Records), but `_to_frame`
+    builds the DataFrame from the columns without ever creating one tuple per position.
+    A block = list of 21 columns (numpy arrays; 2-D for the array-valued fields, or None columns
+    stored as object arrays of None).
+    '''
+
+    def __init__(self, rows=()):
+        self.blocks = []
+        self.extend(rows)
+
+    def add_block(self, columns):
+        n = len(columns[1])
+        if n:
+            assert len(columns) == len(COLUMNS) and all(len(c) == n for c in columns)
+            self.blocks.append(list(columns))
+
+    def extend(self, rows):
+        if isinstance(rows, Records):
+            self.blocks.extend(rows.blocks)
+            return
+        rows = list(rows)
+        if rows:
+            cols = []
+            for name, col in zip(COLUMNS, zip(*rows)):
+                if name in _ARRAY_COLUMNS or name == 'kmer':
+                    a = np.empty(len(col), dtype=object)
+                    a[:] = list(col)
+                else:
+                    a = np.asarray(col)
+                cols.append(a)
+            self.add_block(cols)
+
+    def __len__(self):
+        return sum(len(b[1]) for b in self.blocks)
+
+    def __iter__(self):
+        for b in self.blocks:
+            yield from zip(*(c.tolist() if c.ndim == 1 and c.dtype != object else c for c in b))
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return list(self)[i]
+        if i < 0:
+            i += len(self)
+        for b in self.blocks:
+            n = len(b[1])
+            if i < n:
+                return tuple(c[i].item() if (c.ndim == 1 and c.dtype != object) else c[i] for c in b)
+            i -= n
+        raise IndexError('record index out of range')
+
+    def column(self, j):
+        '''column j over all blocks: 1-D array, or object array of row arrays for the array-valued fields'''
+        parts = []
+        for b in self.blocks:
+            c = b[j]
+            if c.ndim == 2:
+                o = np.empty(len(c), dtype=object)
+                o[:] = list(c)
+                c = o
+            parts.append(c)
+        if not parts:
+            return np.empty(0, dtype=object)
+        if len({p.dtype.kind for p in parts}) > 1:
+            parts = [p.astype(object) for p in parts]
+        return np.concatenate(parts)
+
 
 
 @dataclasses.dataclass
@@ -137,15 +214,15 @@ def _kmers_by_column(feat):
 def _batch_records(host, res, opts):
     '''
     Device results of one batch -> (records, sm_preds) in the reference's shapes
-    (GMMTestRecord tuples, reference gmmtest.py:120-136, 164-178).  The rows are assembled column
-    by column per feature (the gated positions arrive sorted by column, so a feature is a run) and
-    zipped into tuples at the end; only the positions that carry single-molecule predictions are
-    visited one by one.
+    (GMMTestRecord fields, reference gmmtest.py:120-136, 164-178).  The records are built as whole
+    columns (`Records`): feature attributes, positions and window kmers are gathers over the
+    batch's column index, the statistics are slices of the result rows.  Only the positions that
+    carry single-molecule predictions are visited one by one.
     '''
     w = opts.window_size
     centre = w // 2
     n_cntrl = host.n_cntrl
-    records, sm = [], {}
+    records, sm = Records(), {}
     feats = host.features
     if not opts.gmm:
         cols = np.flatnonzero(res.status == N.ST_KS_ONLY)
@@ -153,52 +230,57 @@ def _batch_records(host, res, opts):
     else:
         slots = np.flatnonzero(np.asarray(res.status_fit) == N.ST_TESTED)     # others: LinAlgError path, dropped
         cols = np.asarray(res.fit_list)[slots].astype(np.int64)
-    if len(cols) == 0:
+    n = len(cols)
+    if n == 0:
         return records, sm
     fidx = np.searchsorted(host.col_off, cols, side='right') - 1
-    run_starts = np.concatenate(([0], np.flatnonzero(np.diff(fidx)) + 1, [len(cols)]))
-    offs = np.arange(-centre, centre + 1)
-    nan = float('nan')
+    attrs = getattr(host, '_record_attrs', None)
+    if attrs is None:                                                         # per batch, shared by its ranges
+        obj = lambda values: np.array(list(values) + [None], dtype=object)[:-1]
+        attrs = host._record_attrs = (obj(f.chrom for f in feats), obj(f.feature_id for f in feats),
+                                      obj(f.strand for f in feats),
+                                      np.concatenate([_kmers_by_column(f) for f in feats]))
+    chrom, gene_id, strand, kmer_of_col = attrs
+    pos = np.asarray(host.col_pos)[cols].astype(np.int64)
+    step = np.where(np.asarray(host.reverse)[fidx] != 0, -1, 1)               # '-' strand: window read right to left
+    win = kmer_of_col[cols[:, None] + step[:, None] * np.arange(-centre, centre + 1)[None, :]]
+    if (win == None).any():                                                   # noqa: E711 (elementwise)
+        raise KeyError('no kmer recorded for a tested window')
+    win = win.astype(str)
+    nan_col = np.full(n, np.nan)
     if slots is not None:
         stats = np.asarray(res.stats)[slots]                                  # fancy indexing = copies: the
         mu, sd = np.asarray(res.mu)[slots], np.asarray(res.stds)[slots]       # staging buffer is reused later
-        ks = np.asarray(res.ks_stat_fit)[slots].tolist()
-        g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = (stats[:, j].tolist() for j in range(8))
+        g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = (np.ascontiguousarray(stats[:, j]) for j in range(8))
+        dists = [np.ascontiguousarray(mu[:, 0]), np.ascontiguousarray(sd[:, 0]),
+                 np.ascontiguousarray(mu[:, 1]), np.ascontiguousarray(sd[:, 1])]
+        ks = np.asarray(res.ks_stat_fit)[slots]
         post_off = np.asarray(res.post_off)[slots] if res.post_off is not None else None
         if post_off is not None and (post_off == -2).any():
             raise RuntimeError('single-molecule posterior buffer overflow (internal sizing error)')
     else:
-        p_val, ks = res.ks_pval[cols].tolist(), res.ks_stat[cols].tolist()
-    for a, b in zip(run_starts[:-1].tolist(), run_starts[1:].tolist()):
-        f = feats[int(fidx[a])]
-        c = cols[a:b] - int(host.col_off[int(fidx[a])])
-        pos = f.positions[c].tolist()
-        win = _kmers_by_column(f)[c[:, None] + (-offs if f.strand == '-' else offs)]
-        if (win == None).any():                                               # noqa: E711 (elementwise)
-            raise KeyError(f'{f.feature_id}: no kmer recorded for a tested window')
-        win = win.astype(str)
-        n = b - a
-        head = (f.chrom, f.feature_id, f.strand)
-        if slots is None:
-            records.extend(
-                (head[0], p, head[1], head[2], km[centre], km, centre, nan, nan, nan, pv, 1., nan, nan, nan, nan,
-                 None, None, None, None, d)
-                for p, km, pv, d in zip(pos, win, p_val[a:b], ks[a:b]))
-            sm.setdefault(f.feature_id, {}).update(dict.fromkeys(pos))
-            continue
-        records.extend(zip(
-            [head[0]] * n, pos, [head[1]] * n, [head[2]] * n, win[:, centre].tolist(), win, [centre] * n,
-            lor[a:b], lo[a:b], hi[a:b], p_val[a:b], [1.] * n, c_frac[a:b], t_frac[a:b], g_stat[a:b], hom_g[a:b],
-            mu[a:b, 0], sd[a:b, 0], mu[a:b, 1], sd[a:b, 1], ks[a:b]))
+        p_val, ks = np.asarray(res.ks_pval)[cols], np.asarray(res.ks_stat)[cols]
+        g_stat = hom_g = c_frac = t_frac = lor = lo = hi = nan_col
+        dists = [np.full(n, None, dtype=object)] * 4
+        post_off = None
+    records.add_block([chrom[fidx], pos, gene_id[fidx], strand[fidx], win[:, centre].astype(object), win,
+                       np.full(n, centre, dtype=np.int64), lor, lo, hi, p_val, np.ones(n), c_frac, t_frac,
+                       g_stat, hom_g] + dists + [ks])
+    # sm_preds[feature][pos]: None unless the position is significant and -s was asked for
+    run_starts = np.concatenate(([0], np.flatnonzero(np.diff(fidx)) + 1, [n])).tolist()
+    pos_list = pos.tolist()
+    for a, b in zip(run_starts[:-1], run_starts[1:]):
+        fi = int(fidx[a])
+        f = feats[fi]
         fsm = sm.setdefault(f.feature_id, {})
-        fsm.update(dict.fromkeys(pos))
+        fsm.update(dict.fromkeys(pos_list[a:b]))
         if post_off is not None and res.post is not None:
-            for i in np.flatnonzero(post_off[a:b] >= 0).tolist():
-                s = int(slots[a + i])
-                off = int(post_off[a + i])
-                model = format_model(mu[a + i], res.cov[s], res.box[s] if opts.add_uniform else None, res.cw[s])
-                fsm[pos[i]] = _position_sm_preds(f, int(c[i]), win[i], opts, n_cntrl, model,
-                                                 res.post[off:off + int(res.nall_fit[s])].copy())
+            for i in (np.flatnonzero(post_off[a:b] >= 0) + a).tolist():
+                s = int(slots[i])
+                off = int(post_off[i])
+                model = format_model(mu[i], res.cov[s], res.box[s] if opts.add_uniform else None, res.cw[s])
+                fsm[pos_list[i]] = _position_sm_preds(f, int(cols[i] - host.col_off[fi]), win[i], opts, n_cntrl, model,
+                                                      res.post[off:off + int(res.nall_fit[s])].copy())
     return records, sm
 
 
@@ -217,7 +299,7 @@ def test_chunk(opts, gene_ids):
     engine = Engine(opts.engine_params())
     by_t = opts.test_level == 'transcript'
     R = len(opts.cntrl_hdf5_fns) + len(opts.treat_hdf5_fns)
-    chunk_res, chunk_sm = [], {}
+    chunk_res, chunk_sm = Records(), {}
 
     def batches():
         '''
@@ -264,8 +346,16 @@ def test_chunk(opts, gene_ids):
 def _to_frame(records):
     # canonical row order (feature, position): the output must not depend on how genes were
     # sharded over ranks / batches (the reference's order depends on its pool scheduling)
-    records = sorted(records, key=lambda r: (r[2], r[1]))
-    res = pd.DataFrame(records, columns=COLUMNS)
+    if isinstance(records, Records):
+        cols = [records.column(j) for j in range(len(COLUMNS))]
+        if len(cols[1]):
+            codes = np.unique(cols[2].astype(str), return_inverse=True)[1]      # codepoint order, as Python's str
+            order = np.lexsort((cols[1].astype(np.int64), codes))               # stable, like sorted()
+            cols = [c[order] for c in cols]
+        res = pd.DataFrame(dict(zip(COLUMNS, cols)), columns=COLUMNS)
+    else:
+        records = sorted(records, key=lambda r: (r[2], r[1]))
+        res = pd.DataFrame(records, columns=COLUMNS)
     res.dropna(subset=['p_val'], inplace=True)            # reference gmmtest.py:221
     if len(res):
         res['fdr'] = benjamini_hochberg(res.p_val.values)  # multipletests(..., 'fdr_bh')
