@@ -453,31 +453,46 @@ def load_model_priors(model_fn=None):
     return model
 
 
+def _centre_values(cells, centre):
+    '''cell[centre] of every row of an array-valued column; NaN where the cell is None (--no-gmm)'''
+    if len(cells) and all(c is not None for c in cells):
+        try:
+            return np.asarray(cells, dtype=np.float64)[np.arange(len(cells)), centre].tolist()
+        except ValueError:                                    # ragged cells: fall through to the per-row pick
+            pass
+    return [float('nan') if c is None else float(c[k]) for c, k in zip(cells, centre.tolist())]
+
+
 def save_gmmtest_results(res, output_bed_fn):
-    '''main results as BED, byte-compatible with reference io.py:365-399'''
+    '''main results as BED, byte-compatible with reference io.py:365-399 (columns formatted as Python lists)'''
     res = res.sort_values(by=['chrom', 'pos'], kind='stable')
     logger.info(f'Writing output to {os.path.abspath(output_bed_fn)}')
+    col = {name: res[name].tolist() for name in (
+        'chrom', 'pos', 'gene_id', 'strand', 'kmer', 'log_odds', 'log_odds_lower_ci', 'log_odds_upper_ci', 'p_val',
+        'fdr', 'cntrl_frac_mod', 'treat_frac_mod', 'g_stat', 'hom_g_stat', 'ks_stat')}
+    centre = res['centre'].to_numpy(dtype=np.int64)
+    with np.errstate(divide='ignore'):
+        # int(round(min(-log10(fdr), 100))): rint is round-half-even like Python's round()
+        score = np.rint(np.minimum(-np.log10(res['fdr'].to_numpy(dtype=np.float64)), 100)).astype(np.int64).tolist()
+    mus1, sds1, mus2, sds2 = (_centre_values(res[name].tolist(), centre)
+                              for name in ('dist1_means', 'dist1_stds', 'dist2_means', 'dist2_stds'))
     with open(output_bed_fn, 'w') as bed:
-        for record in res.itertuples(index=False):
-            (chrom, pos, gene_id, strand, kmer, kmers, centre, log_odds, lb, ub, pval, fdr,
-             c_fm, t_fm, g_stat, hom_g_stat, unmod_mus, unmod_stds, mod_mus, mod_stds, ks) = record
-            try:
-                unmod_mu, unmod_std = unmod_mus[centre], unmod_stds[centre]
-                mod_mu, mod_std = mod_mus[centre], mod_stds[centre]
-            except TypeError:
-                unmod_mu = unmod_std = mod_mu = mod_std = np.nan      # --no-gmm
-            with np.errstate(divide='ignore'):
-                score = int(round(min(-np.log10(fdr), 100)))
-            bed.write(
-                f'{chrom:s}\t{pos - 2:d}\t{pos + 3:d}\t'
-                f'{gene_id}:{kmer}\t{score:d}\t{strand:s}\t'
-                f'{log_odds:.2f}[{lb:.2f},{ub:.2f}]\t'
-                f'{pval:.2g}\t{fdr:.2g}\t'
-                f'{c_fm:.2f}\t{t_fm:.2f}\t'
-                f'{g_stat:.2f}\t{hom_g_stat:.2f}\t'
-                f'{unmod_mu:.2f}\t{unmod_std:.2f}\t'
-                f'{mod_mu:.2f}\t{mod_std:.2f}\t'
-                f'{ks:.2f}\n')
+        bed.writelines(
+            f'{chrom:s}\t{pos - 2:d}\t{pos + 3:d}\t'
+            f'{gene_id}:{kmer}\t{sc:d}\t{strand:s}\t'
+            f'{log_odds:.2f}[{lb:.2f},{ub:.2f}]\t'
+            f'{pval:.2g}\t{fdr:.2g}\t'
+            f'{c_fm:.2f}\t{t_fm:.2f}\t'
+            f'{g_stat:.2f}\t{hom_g_stat:.2f}\t'
+            f'{unmod_mu:.2f}\t{unmod_std:.2f}\t'
+            f'{mod_mu:.2f}\t{mod_std:.2f}\t'
+            f'{ks:.2f}\n'
+            for (chrom, pos, gene_id, strand, kmer, log_odds, lb, ub, pval, fdr, c_fm, t_fm, g_stat, hom_g_stat, ks,
+                 sc, unmod_mu, unmod_std, mod_mu, mod_std)
+            in zip(*(col[k] for k in ('chrom', 'pos', 'gene_id', 'strand', 'kmer', 'log_odds', 'log_odds_lower_ci',
+                                      'log_odds_upper_ci', 'p_val', 'fdr', 'cntrl_frac_mod', 'treat_frac_mod',
+                                      'g_stat', 'hom_g_stat', 'ks_stat')),
+                   score, mus1, sds1, mus2, sds2))
 
 
 def save_sm_preds(sm_preds, cntrl_hdf5_fns, treat_hdf5_fns, output_json_fn):

@@ -91,37 +91,70 @@ def dist1_is_modified(kmers, dist1_means, dist2_means, kmer_shift_dirs):
     return s1 > s2
 
 
+def _stack(column):
+    '''(n, w) matrix of a DataFrame column whose cells are length-w arrays'''
+    return np.array(column.tolist())
+
+
 def assign_modified_distribution(results, sm_preds, model):
     '''
     Decide for every significant record which fitted component is the modified
     one and flip the record (and its single-molecule predictions) when it is
     dist1 (reference stats.py:557-599).  `results` is the DataFrame of
     gmmtest.parallel_test; modified in place and returned.
+
+    Evaluated on whole columns: the per-kmer medians of calculate_kmer_shift_directions
+    over a flattened (records x window) table, the vote of dist1_is_modified as w masked
+    column additions in window order (the same additions, in the same order, as the
+    per-record loop), the flip as masked column assignments.
     '''
-    if not len(results):
+    n = len(results)
+    if not n:
         return results, sm_preds
-    dirs = calculate_kmer_shift_directions(results, model)
-    for i in results.index:
-        kmers, m1, m2 = results.at[i, 'kmers'], results.at[i, 'dist1_means'], results.at[i, 'dist2_means']
-        if not dist1_is_modified(kmers, m1, m2, dirs):
-            continue
-        results.at[i, 'cntrl_frac_mod'] = 1 - results.at[i, 'cntrl_frac_mod']
-        results.at[i, 'treat_frac_mod'] = 1 - results.at[i, 'treat_frac_mod']
-        results.at[i, 'log_odds'] = np.negative(results.at[i, 'log_odds'])
-        lo, hi = results.at[i, 'log_odds_lower_ci'], results.at[i, 'log_odds_upper_ci']
-        results.at[i, 'log_odds_lower_ci'], results.at[i, 'log_odds_upper_ci'] = np.negative(hi), np.negative(lo)
-        results.at[i, 'dist1_means'], results.at[i, 'dist2_means'] = m2, m1
-        s1, s2 = results.at[i, 'dist1_stds'], results.at[i, 'dist2_stds']
-        results.at[i, 'dist1_stds'], results.at[i, 'dist2_stds'] = s2, s1
-        gene_id, pos = results.at[i, 'gene_id'], results.at[i, 'pos']
-        try:
-            pos_sm_preds = sm_preds[gene_id][pos]
-        except KeyError:
-            continue
-        m = pos_sm_preds['model']
-        m['unmod'], m['mod'] = m['mod'], m['unmod']
-        for cond in ('cntrl', 'treat'):
-            for rep_sm_preds in pos_sm_preds[cond].values():
-                rep_sm_preds['preds'] = [1 - (p + o) for p, o in
-                                         zip(rep_sm_preds['preds'], rep_sm_preds['outlier_preds'])]
+    kmers = _stack(results['kmers']).astype(str)
+    m1, m2 = _stack(results['dist1_means']).astype(np.float64), _stack(results['dist2_means']).astype(np.float64)
+    w = kmers.shape[1]
+    # ---- shift direction per kmer (stats.py:516-534)
+    uniq, code = np.unique(kmers.ravel(), return_inverse=True)
+    expected = np.array([model[k][0] for k in uniq.tolist()])[code]
+    lower = np.abs(np.minimum(m1, m2).ravel() - expected)
+    upper = np.abs(np.maximum(m1, m2).ravel() - expected)
+    order = np.argsort(code, kind='stable')
+    cuts = np.flatnonzero(np.diff(code[order])) + 1
+    dirs = np.array([1 if np.median(u) > np.median(lo) else 0
+                     for u, lo in zip(np.split(upper[order], cuts), np.split(lower[order], cuts))])
+    # ---- which records have dist1 as the modified component (stats.py:537-554)
+    d = m1 - m2
+    vote1 = dirs[code].reshape(n, w).astype(bool) ^ (d < 0)
+    s1, s2 = np.zeros(n), np.zeros(n)
+    for j in range(w):
+        ad = np.abs(d[:, j])
+        s1 = s1 + np.where(vote1[:, j], ad, 0.0)
+        s2 = s2 + np.where(vote1[:, j], 0.0, ad)
+    flip = s1 > s2
+    if not flip.any():
+        return results, sm_preds
+    # ---- flip them (stats.py:571-599)
+    idx = results.index[flip]
+    results.loc[idx, 'cntrl_frac_mod'] = 1 - results.loc[idx, 'cntrl_frac_mod'].to_numpy()
+    results.loc[idx, 'treat_frac_mod'] = 1 - results.loc[idx, 'treat_frac_mod'].to_numpy()
+    results.loc[idx, 'log_odds'] = np.negative(results.loc[idx, 'log_odds'].to_numpy())
+    lo, hi = results.loc[idx, 'log_odds_lower_ci'].to_numpy(), results.loc[idx, 'log_odds_upper_ci'].to_numpy()
+    results.loc[idx, 'log_odds_lower_ci'], results.loc[idx, 'log_odds_upper_ci'] = np.negative(hi), np.negative(lo)
+    for c1, c2 in (('dist1_means', 'dist2_means'), ('dist1_stds', 'dist2_stds')):
+        a, b = results[c1].to_numpy(dtype=object, copy=True), results[c2].to_numpy(dtype=object, copy=True)
+        a[flip], b[flip] = b[flip], a[flip].copy()
+        results[c1], results[c2] = a, b
+    if sm_preds:
+        for gene_id, pos in zip(results.loc[idx, 'gene_id'].tolist(), results.loc[idx, 'pos'].tolist()):
+            try:
+                pos_sm_preds = sm_preds[gene_id][pos]
+            except KeyError:
+                continue
+            m = pos_sm_preds['model']
+            m['unmod'], m['mod'] = m['mod'], m['unmod']
+            for cond in ('cntrl', 'treat'):
+                for rep_sm_preds in pos_sm_preds[cond].values():
+                    rep_sm_preds['preds'] = [1 - (p + o) for p, o in
+                                             zip(rep_sm_preds['preds'], rep_sm_preds['outlier_preds'])]
     return results, sm_preds
