@@ -47,8 +47,22 @@ def format_model(mu, cov, box, cw):
 
 
 def format_sm_preds(preds, outlier, events, reps, read_ids):
-    '''per-replicate read ids / events / predictions (reference stats.py:358-379)'''
+    '''
+    per-replicate read ids / events / predictions (reference stats.py:358-379).  The packed layout
+    keeps the reads of a replicate together, so a replicate is normally one slice of each list; reads
+    of one replicate scattered over several runs take the reference's read-by-read route.
+    '''
+    reps = list(reps)
+    n = len(reps)
     out = {}
+    if n:
+        r = np.asarray(reps)
+        starts = [0] + (np.flatnonzero(r[1:] != r[:-1]) + 1).tolist() + [n]
+        if len({reps[a] for a in starts[:-1]}) == len(starts) - 1:
+            for a, b in zip(starts[:-1], starts[1:]):
+                out[reps[a]] = {'read_ids': list(read_ids[a:b]), 'events': list(events[a:b]),
+                                'preds': list(preds[a:b]), 'outlier_preds': list(outlier[a:b])}
+            return out
     for r_id, rep, ev, p, o in zip(read_ids, reps, events, preds, outlier):
         entry = out.get(rep)
         if entry is None:
