@@ -224,3 +224,49 @@ def test_records_container_behaves_like_the_list_of_tuples():
     a, b, c = _to_frame(recs), _to_frame(back), _to_frame(everything)
     assert a.to_csv() == b.to_csv() == c.to_csv() and a.dtypes.equals(c.dtypes) and len(a) == 46
     assert list(_to_frame(Records()).columns) == COLUMNS and len(_to_frame(Records())) == 0
+
+
+def test_vectorised_assignment_equals_the_per_record_route(tmp_path):
+    '''assign_modified_distribution on whole columns vs the reference's record-by-record procedure
+    (stats.py:516-599) built from calculate_kmer_shift_directions / dist1_is_modified'''
+    import copy
+    from yanocomp_b200.gmmtest import Records
+    rng = np.random.default_rng(21)
+    model = ycio.load_model_priors()
+    res = _to_frame(Records(_fake_records(700, rng)))
+    sm = {}
+    for gene_id, pos in zip(res.gene_id.tolist()[::3], res.pos.tolist()[::3]):
+        sm.setdefault(gene_id, {})[pos] = {
+            'model': {'unmod': {'mu': [1.0]}, 'mod': {'mu': [2.0]}},
+            'cntrl': {1: {'preds': [0.2, 0.7], 'outlier_preds': [0.1, 0.0]}},
+            'treat': {1: {'preds': [0.5], 'outlier_preds': [0.25]}, 2: {'preds': [], 'outlier_preds': []}}}
+    want, want_sm = res.copy(), copy.deepcopy(sm)
+    dirs = ycstats.calculate_kmer_shift_directions(want, model)
+    n_flipped = 0
+    for i in want.index:
+        k, m1, m2 = want.at[i, 'kmers'], want.at[i, 'dist1_means'], want.at[i, 'dist2_means']
+        if not ycstats.dist1_is_modified(k, m1, m2, dirs):
+            continue
+        n_flipped += 1
+        for c in ('cntrl_frac_mod', 'treat_frac_mod'):
+            want.at[i, c] = 1 - want.at[i, c]
+        want.at[i, 'log_odds'] = -want.at[i, 'log_odds']
+        lo, hi = want.at[i, 'log_odds_lower_ci'], want.at[i, 'log_odds_upper_ci']
+        want.at[i, 'log_odds_lower_ci'], want.at[i, 'log_odds_upper_ci'] = -hi, -lo
+        want.at[i, 'dist1_means'], want.at[i, 'dist2_means'] = m2, m1
+        s1, s2 = want.at[i, 'dist1_stds'], want.at[i, 'dist2_stds']
+        want.at[i, 'dist1_stds'], want.at[i, 'dist2_stds'] = s2, s1
+        p = want_sm.get(want.at[i, 'gene_id'], {}).get(want.at[i, 'pos'])
+        if p is not None:
+            p['model']['unmod'], p['model']['mod'] = p['model']['mod'], p['model']['unmod']
+            for cond in ('cntrl', 'treat'):
+                for rep in p[cond].values():
+                    rep['preds'] = [1 - (a + b) for a, b in zip(rep['preds'], rep['outlier_preds'])]
+    assert 100 < n_flipped < 600
+    got, got_sm = ycstats.assign_modified_distribution(res, sm, model)
+    assert got.to_csv() == want.to_csv() and got.dtypes.equals(want.dtypes) and got_sm == want_sm
+    for c in ('dist1_means', 'dist1_stds', 'dist2_means', 'dist2_stds'):
+        assert all(np.array_equal(a, b) for a, b in zip(got[c], want[c]))
+    ycio.save_gmmtest_results(got, str(tmp_path / 'a.bed'))
+    ycio.save_gmmtest_results(want, str(tmp_path / 'b.bed'))
+    assert open(tmp_path / 'a.bed').read() == open(tmp_path / 'b.bed').read()
