@@ -124,16 +124,49 @@ def parse_eventalign(eventalign_fn, summary_fn=None, chunksize=1_000_000):
         wanted = [c for c in header if c in _EA_INT or c in _EA_FLOAT or c in _EA_TEXT]
         types = {c: (pa.int64() if c in _EA_INT else pa.float64() if c in _EA_FLOAT else pa.string()) for c in wanted}
         block = int(min(max(int(chunksize) * 96, 1 << 14), 1 << 28))
-        try:
-            reader = pacsv.open_csv(
-                source, read_options=pacsv.ReadOptions(column_names=header, skip_rows=skip, block_size=block),
-                parse_options=pacsv.ParseOptions(delimiter='\t', quote_char=False),
-                convert_options=pacsv.ConvertOptions(include_columns=wanted, column_types=types,
-                                                     strings_can_be_null=False))
-        except pa.ArrowInvalid as e:
-            if 'Empty CSV' in str(e):                                # a header and nothing else
-                return
-            raise
+        parse_options = pacsv.ParseOptions(delimiter='\t', quote_char=False)
+        convert_options = pacsv.ConvertOptions(include_columns=wanted, column_types=types, strings_can_be_null=False)
+
+        def windows():
+            '''an uncompressed file: memory-mapped and parsed in windows of ~chunksize lines cut at line ends, each
+            window by Arrow's multi-threaded reader (the streaming reader below parses its blocks one after the other)'''
+            import mmap
+            with open(eventalign_fn, 'rb') as fh:
+                size = os.fstat(fh.fileno()).st_size
+                if size == 0:
+                    return
+                mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+                try:
+                    lo = mm.find(b'\n') + 1                           # past the header line
+                    while 0 < lo < size:
+                        hi = size if lo + block >= size else mm.find(b'\n', lo + block) + 1
+                        if hi <= 0:
+                            hi = size
+                        view = memoryview(mm)[lo:hi]
+                        table = pacsv.read_csv(
+                            pa.BufferReader(pa.py_buffer(view)), parse_options=parse_options,
+                            convert_options=convert_options,
+                            read_options=pacsv.ReadOptions(column_names=header, use_threads=True))
+                        del view                                     # the parsed columns are copies
+                        yield from table.combine_chunks().to_batches()
+                        lo = hi
+                finally:
+                    try:
+                        mm.close()
+                    except BufferError:                              # a view still alive somewhere: left to the GC
+                        pass
+
+        if skip and os.path.splitext(eventalign_fn)[1] != '.gz':
+            reader = windows()
+        else:
+            try:
+                reader = pacsv.open_csv(
+                    source, read_options=pacsv.ReadOptions(column_names=header, skip_rows=skip, block_size=block),
+                    parse_options=parse_options, convert_options=convert_options)
+            except pa.ArrowInvalid as e:
+                if 'Empty CSV' in str(e):                            # a header and nothing else
+                    return
+                raise
         for batch in reader:
             if batch.num_rows == 0:
                 continue
