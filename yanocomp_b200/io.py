@@ -248,8 +248,15 @@ def save_events_to_packed(collapsed, out_fn):
             with np.errstate(over='ignore'):
                 data['mean'], data['std'], data['duration'] = rec['mean'], rec['std'], rec['duration']
             o.append_events(gene_id, data)
+            # kmer_index[gene][pos] = kmer for every record in turn (io.py:186): keys enter in order of first
+            # appearance, the last record of a position wins -> one dict update per distinct position
+            pos = rec['pos']
+            upos, first = np.unique(pos, return_index=True)
+            last = len(pos) - 1 - np.unique(pos[::-1], return_index=True)[1]
+            order = np.argsort(first, kind='stable')
             kmers = rec['kmers']
-            kmer_index.setdefault(gene_id, {}).update(zip(rec['pos'].tolist(), (kmers[k] for k in rec['k_code'].tolist())))
+            kmer_index.setdefault(gene_id, {}).update(
+                zip(upos[order].tolist(), [kmers[k] for k in rec['k_code'][last[order]].tolist()]))
         for gene_id, kmer_pos in kmer_index.items():
             chrom, strand = gene_attrs[gene_id]
             o.set_gene(gene_id, chrom, strand, kmer_pos.items(), read_index[gene_id].keys(), transcript_index[gene_id].keys())
