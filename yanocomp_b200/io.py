@@ -306,9 +306,7 @@ def _clean_events(d, gene_id):
     if not keep.all():
         e = e[keep]
     r_ids = d[f'{gene_id}/read_ids'][:]
-    if r_ids.dtype.kind == 'S':
-        r_ids = np.char.decode(r_ids, 'ascii')
-    return e, r_ids.astype('U32')
+    return e, r_ids.astype('U32')                         # ASCII bytes (or str) -> str cut to 32 characters
 
 
 def _dense_rank(values, size):

@@ -12,9 +12,12 @@ inflate, no chunk B-tree):
 
     bytes 0..7    magic  b'YCPACK01'
     ...           64-byte aligned blobs: raw little-endian EVENT_DTYPE rows, one blob per piece
-                  of a gene (a gene whose reads straddle parser chunks has several extents)
+                  of a gene (a gene whose reads straddle parser chunks has several extents);
+                  per gene one KMER_DTYPE blob and one blob of fixed 36-byte read ids
     index         UTF-8 JSON {'genes': {gene: {'chrom','strand','events':[[off,n],...],
-                  'kmers':[[pos,kmer],...],'read_ids':[...],'transcript_ids':[...]}}}
+                  'kmers':[off,n],'read_ids':[off,n],'transcript_ids':[...]}}}
+                  (only offsets and the few transcript names: its size does not grow with
+                  positions or reads)
     last 16 bytes <u8 index offset, <u8 index length
 '''
 import json
@@ -52,24 +55,35 @@ class Writer:
     def _entry(self, gene_id):
         g = self._genes.get(gene_id)
         if g is None:
-            g = self._genes[gene_id] = {'chrom': '.', 'strand': '.', 'events': [], 'kmers': [],
-                                        'read_ids': [], 'transcript_ids': []}
+            g = self._genes[gene_id] = {'chrom': '.', 'strand': '.', 'events': [], 'kmers': [0, 0],
+                                        'read_ids': [0, 0], 'transcript_ids': []}
         return g
 
-    def append_events(self, gene_id, events):
-        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+    def _blob(self, array):
         pad = (-self._f.tell()) % _ALIGN
         if pad:
             self._f.write(b'\0' * pad)
-        self._entry(gene_id)['events'].append([self._f.tell(), int(len(events))])
-        self._f.write(events.tobytes())
+        off = self._f.tell()
+        self._f.write(array.tobytes())
+        return [off, int(len(array))]
+
+    def append_events(self, gene_id, events):
+        events = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        self._entry(gene_id)['events'].append(self._blob(events))
 
     def set_gene(self, gene_id, chrom, strand, kmers, read_ids, transcript_ids):
         '''kmers: iterable of (pos, kmer); read / transcript ids in index order'''
         g = self._entry(gene_id)
         g['chrom'], g['strand'] = str(chrom), str(strand)
-        g['kmers'] = [[int(p), str(k)] for p, k in kmers]
-        g['read_ids'] = [str(r) for r in read_ids]
+        kmers = list(kmers)
+        km = np.empty(len(kmers), dtype=KMER_DTYPE)
+        if kmers:
+            pos, seq = zip(*kmers)
+            km['pos'], km['kmer'] = np.asarray(pos, dtype=np.int64), np.asarray(seq, dtype='S5')
+        g['kmers'] = self._blob(km)
+        # READ_DTYPE of the reference is a fixed 36-byte string: longer names are cut there as h5py does
+        g['read_ids'] = self._blob(np.asarray([str(r).encode('ascii')[:READ_ID_LEN] for r in read_ids],
+                                              dtype=f'S{READ_ID_LEN}'))
         g['transcript_ids'] = [str(t) for t in transcript_ids]
 
     def close(self):
@@ -127,10 +141,9 @@ class Group:
         if key == 'events':
             return _Dataset(lambda: self._f._events(m['events']))
         if key == 'kmers':
-            return _Dataset(lambda: np.array([(p, k.encode('ascii')) for p, k in m['kmers']], dtype=KMER_DTYPE))
+            return _Dataset(lambda: self._f._array(m['kmers'], KMER_DTYPE))
         if key == 'read_ids':
-            return _Dataset(lambda: np.array([r.encode('ascii')[:READ_ID_LEN] for r in m['read_ids']],
-                                             dtype=f'S{READ_ID_LEN}'))
+            return _Dataset(lambda: self._f._array(m['read_ids'], np.dtype(f'S{READ_ID_LEN}')))
         if key == 'transcript_ids':
             return _Dataset(lambda: np.array(m['transcript_ids'], dtype=object))
         raise KeyError(key)
@@ -160,6 +173,10 @@ class File:
         except Exception:
             self._fh.close()
             raise
+
+    def _array(self, extent, dtype):
+        off, n = extent
+        return np.frombuffer(self._mm, dtype=dtype, count=n, offset=off) if n else np.zeros(0, dtype=dtype)
 
     def _events(self, extents):
         parts = [np.frombuffer(self._mm, dtype=EVENT_DTYPE, count=n, offset=off) for off, n in extents if n]
