@@ -265,3 +265,21 @@ def test_packed_container_edge_cases(tmp_path):
         assert f['a/b'].attrs == {'chrom': 'chr1', 'strand': '-'}
         assert f['a/b']['read_ids'][:].tolist() == [b'r' * 36]
         assert f['/a/b/kmers'][:]['kmer'].tolist() == [b'AAAAA', b'CCCCC', b'GGGGG']
+
+
+def test_mixed_hdf5_and_packed_inputs(tmp_path):
+    '''control from the reference's HDF5, treatment from a packed file: same features as HDF5 + HDF5'''
+    c_h5 = os.path.join(GOLD, 'hek293t_wt.collapsed.hdf5')
+    t_h5 = os.path.join(GOLD, 'hek293t_mettl3.collapsed.hdf5')
+    _fixture_to_eventalign(t_h5, tmp_path / 't.tsv')
+    _prep(['-e', tmp_path / 't.tsv', '-h', tmp_path / 't.ycp'])
+    with hdf5_list([c_h5, t_h5]) as ref, hdf5_list([c_h5, str(tmp_path / 't.ycp')]) as mixed:
+        assert type(mixed[0]) is not type(mixed[1])
+        genes = sorted(get_shared_keys(ref))
+        assert genes == sorted(get_shared_keys(mixed)) and len(genes) >= 4
+        for g in genes:
+            for a, b in zip(load_gene_features(g, ref[:1], ref[1:]), load_gene_features(g, mixed[:1], mixed[1:])):
+                assert a.X.tobytes() == b.X.tobytes() and list(a.read_ids) == list(b.read_ids) and a.kmers == b.kmers
+    with pytest.raises(FileNotFoundError):
+        with hdf5_list([c_h5, str(tmp_path / 'missing.ycp')]):
+            pass
