@@ -270,3 +270,81 @@ def test_vectorised_assignment_equals_the_per_record_route(tmp_path):
     ycio.save_gmmtest_results(got, str(tmp_path / 'a.bed'))
     ycio.save_gmmtest_results(want, str(tmp_path / 'b.bed'))
     assert open(tmp_path / 'a.bed').read() == open(tmp_path / 'b.bed').read()
+
+
+def _expected_records(host, res, opts):
+    '''record-by-record construction of the GMMTestRecord tuples (reference gmmtest.py:156-178)'''
+    from yanocomp_b200 import _native as N
+    w = opts.window_size
+    h = w // 2
+    out, sm = [], {}
+    if opts.gmm:
+        todo = [(s, int(g)) for s, g in enumerate(res.fit_list) if res.status_fit[s] == N.ST_TESTED]
+    else:
+        todo = [(None, int(g)) for g in np.flatnonzero(res.status == N.ST_KS_ONLY)]
+    for s, g in todo:
+        fi = int(np.searchsorted(host.col_off, g, side='right') - 1)
+        f = host.features[fi]
+        pos = int(f.positions[g - host.col_off[fi]])
+        win = range(pos + h, pos - h - 1, -1) if f.strand == '-' else range(pos - h, pos + h + 1)
+        kmers = np.array([f.kmers[p] for p in win])
+        if opts.gmm:
+            g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = res.stats[s].tolist()
+            out.append((f.chrom, pos, f.feature_id, f.strand, kmers[h], kmers, h, lor, lo, hi, p_val, 1., c_frac, t_frac,
+                        g_stat, hom_g, res.mu[s, 0], res.stds[s, 0], res.mu[s, 1], res.stds[s, 1],
+                        float(res.ks_stat_fit[s])))
+        else:
+            out.append((f.chrom, pos, f.feature_id, f.strand, kmers[h], kmers, h, np.nan, np.nan, np.nan,
+                        float(res.ks_pval[g]), 1., np.nan, np.nan, np.nan, np.nan, None, None, None, None,
+                        float(res.ks_stat[g])))
+        sm.setdefault(f.feature_id, {})[pos] = None
+    return out, sm
+
+
+@pytest.mark.parametrize('gmm', [True, False])
+def test_batch_records_columns_equal_the_per_record_construction(gmm):
+    from yanocomp_b200 import _native as N
+    from yanocomp_b200.engine import BatchResult
+    from yanocomp_b200.gmmtest import Records, _batch_records
+    rng = np.random.default_rng(31)
+    feats = [synth.make_feature(rng, f'F{i:02d}', 40 + 7 * i, 6, 2, 2, strand='+-'[i % 2], pos0=100 + 13 * i)
+             for i in range(5)]
+    feats[3].chrom = 'chr7'
+    host = HostBatch(feats, 4, 2, pin=False)
+    nc, w = host.total_cols, 5
+    cols = np.sort(rng.choice(nc, nc // 3, replace=False)).astype(np.int64)
+    fi = np.searchsorted(host.col_off, cols, side='right') - 1
+    c = cols - host.col_off[fi]
+    cols = cols[(c >= 2) & (c < np.asarray(host.n_cols)[fi] - 2)]
+    n = len(cols)
+    opts = GMMTestOpts(cntrl_hdf5_fns=('a', 'b'), treat_hdf5_fns=('c', 'd'), output_bed_fn='x.bed', window_size=w, gmm=gmm)
+    if gmm:
+        status_fit = np.where(rng.random(n) < 0.15, N.ST_FIT_FAILED, N.ST_TESTED).astype(np.uint8)
+        stats = rng.normal(size=(n, 8))
+        stats[::7, 1] = np.nan                                       # hom_g is NaN when the first test is not significant
+        res = BatchResult(status=np.zeros(nc, np.uint8), fit_list=cols.astype(np.int32), status_fit=status_fit,
+                          ks_stat_fit=rng.random(n), mu=rng.normal(100, 5, (n, 2, w)), stds=rng.random((n, 2, w)),
+                          stats=stats, nall_fit=np.full(n, 24, np.int32), post_off=np.full(n, -1, np.int64))
+    else:
+        status = np.zeros(nc, np.uint8)
+        status[cols] = N.ST_KS_ONLY
+        res = BatchResult(status=status, fit_list=np.zeros(0, np.int32), status_fit=np.zeros(0, np.uint8),
+                          ks_stat_fit=np.zeros(0), mu=np.zeros((0, 2, w)), stds=np.zeros((0, 2, w)),
+                          stats=np.zeros((0, 8)), ks_stat=rng.random(nc), ks_pval=rng.random(nc))
+    got, got_sm = _batch_records(host, res, opts)
+    want, want_sm = _expected_records(host, res, opts)
+    assert isinstance(got, Records) and len(got) == len(want) > 20
+    assert got_sm == want_sm and [list(v) for v in got_sm.values()] == [list(v) for v in want_sm.values()]
+    for a, b in zip(got, want):
+        for x, y in zip(a, b):
+            if isinstance(y, np.ndarray):
+                assert np.array_equal(x, y) and x.dtype == y.dtype
+            else:
+                assert x is y or x == y or (x != x and y != y)
+    fa, fb = _to_frame(got), _to_frame(want)
+    assert fa.to_csv() == fb.to_csv() and fa.dtypes.equals(fb.dtypes)
+    # a buffer overflow flag from the kernels must not pass silently
+    if gmm:
+        res.post_off[np.flatnonzero(res.status_fit == N.ST_TESTED)[0]] = -2
+        with pytest.raises(RuntimeError, match='overflow'):
+            _batch_records(host, res, opts)
