@@ -348,3 +348,56 @@ def test_batch_records_columns_equal_the_per_record_construction(gmm):
         res.post_off[np.flatnonzero(res.status_fit == N.ST_TESTED)[0]] = -2
         with pytest.raises(RuntimeError, match='overflow'):
             _batch_records(host, res, opts)
+
+
+def test_batch_records_wires_single_molecule_predictions_to_the_right_slots():
+    '''posterior offsets / model rows are indexed by fit slot, records by tested row: check the wiring with
+    failed fits in between, against _position_sm_preds called with hand-picked arguments'''
+    from yanocomp_b200 import _native as N
+    from yanocomp_b200.engine import BatchResult
+    from yanocomp_b200.gmmtest import _batch_records, _position_sm_preds
+    rng = np.random.default_rng(41)
+    feats = [synth.make_feature(rng, f'F{i}', 30, 5, 2, 2, strand='+-'[i % 2]) for i in range(3)]
+    host = HostBatch(feats, 4, 2, pin=False)
+    w = 3
+    cols = np.array([3, 4, 10, 33, 40, 41, 65, 70], dtype=np.int32)           # columns of features 0, 1, 2
+    n = len(cols)
+    status_fit = np.full(n, N.ST_TESTED, np.uint8)
+    status_fit[[1, 4]] = N.ST_FIT_FAILED
+    n_all, post_off, off = np.zeros(n, np.int32), np.full(n, -1, np.int64), 0
+    for s in (0, 2, 3, 5, 7):                                                  # significant positions
+        fi = int(np.searchsorted(host.col_off, cols[s], side='right') - 1)
+        c = int(cols[s] - host.col_off[fi])
+        n_all[s] = int((~np.isnan(feats[fi].X[c - 1:c + 2]).any(axis=0)).sum())
+        post_off[s] = off
+        off += n_all[s]
+    post = rng.random((off, 2)) / 2
+    res = BatchResult(status=np.zeros(host.total_cols, np.uint8), fit_list=cols, status_fit=status_fit,
+                      ks_stat_fit=rng.random(n), mu=rng.normal(100, 5, (n, 2, w)), stds=rng.random((n, 2, w)),
+                      stats=rng.random((n, 8)), nall_fit=n_all, post_off=post_off, post=post,
+                      cov=rng.random((n, 2, w, w)), box=rng.random((n, w, 2)), cw=rng.dirichlet(np.ones(3), n))
+    opts = GMMTestOpts(cntrl_hdf5_fns=('a', 'b'), treat_hdf5_fns=('c', 'd'), output_bed_fn='x.bed',
+                       output_sm_preds_fn='x.json')
+    recs, sm = _batch_records(host, res, opts)
+    assert len(recs) == 6
+    seen = 0
+    for s in range(n):
+        fi = int(np.searchsorted(host.col_off, cols[s], side='right') - 1)
+        f, c = feats[fi], int(cols[s] - host.col_off[fi])
+        pos = int(f.positions[c])
+        if status_fit[s] != N.ST_TESTED:
+            assert pos not in sm[f.feature_id]
+            continue
+        if post_off[s] < 0:
+            assert sm[f.feature_id][pos] is None
+            continue
+        h = 1
+        win = range(pos + h, pos - h - 1, -1) if f.strand == '-' else range(pos - h, pos + h + 1)
+        kmers = np.array([f.kmers[p] for p in win])
+        want = _position_sm_preds(f, c, kmers, opts, 2, ycstats.format_model(res.mu[s], res.cov[s], res.box[s], res.cw[s]),
+                                  post[post_off[s]:post_off[s] + n_all[s]])
+        assert sm[f.feature_id][pos] == want
+        n_reads = sum(len(r['read_ids']) for cond in ('cntrl', 'treat') for r in want[cond].values())
+        assert n_reads == n_all[s] and want['kmers'] == kmers.tolist()
+        seen += 1
+    assert seen == 5
