@@ -247,6 +247,9 @@ def run_gpu(args, cfg, opts_kw):
     n_fit = int(out['fit_list'].numel())
     iters = out['iters'][:max(n_fit, 1)].double()
     mean_iters = float(iters.mean().item()) if n_fit else 0.0
+    iters_q = ([float(x) for x in torch.quantile(iters, torch.tensor([0.5, 0.9, 0.99, 0.999, 1.0], dtype=torch.float64,
+                                                                      device=iters.device)).tolist()] if n_fit else [])
+    iters_ge = {k: int((iters >= k).sum().item()) for k in (32, 64, 128, 256, 512, 1001)} if n_fit else {}
     sum_iters = float(iters.sum().item()) if n_fit else 0.0
     kms = {}
     for name, a, e in events:
@@ -340,7 +343,8 @@ def run_gpu(args, cfg, opts_kw):
         'warmup': args.warmup, 'ms_per_step': ms_resident_max / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': cfg['name'], 'per_gpu_positions_tested': n_tested, 'per_gpu_positions_fitted': n_fit,
-                   'mean_em_iterations': mean_iters, 'input_bytes_per_gpu': host.nbytes,
+                   'mean_em_iterations': mean_iters, 'em_iterations_p50_p90_p99_p999_max': iters_q,
+                   'em_fits_with_iterations_ge': iters_ge, 'input_bytes_per_gpu': host.nbytes,
                    'cache': 'inputs (%.0f MB) larger than the 126 MB L2; no flush' % (host.nbytes / 1e6),
                    'sharding': 'features (genes) split across ranks, no data-path collective'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e_max / args.steps,

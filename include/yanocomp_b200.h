@@ -208,16 +208,18 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p,
 
 /*
  * Result rows in slot order (one launch): for every gated position its final
- * status, KS D (GMMTestResults.ks_stat, stats.py:442), the complete-window
- * read count and dist1_stds / dist2_stds = sqrt(diag(cov)) (stats.py:277-280),
- * so that a caller fetches contiguous per-fit rows instead of gathering on the
- * host.  stds [n_fit*2*w], the others [n_fit].
+ * status, KS D (GMMTestResults.ks_stat, stats.py:442), the device KS p-value
+ * and the control / total complete-window read counts (what the host needs
+ * to re-decide a p-value that sits within YC_KS_P_GUARD of the threshold,
+ * stats.py:465) and dist1_stds / dist2_stds = sqrt(diag(cov))
+ * (stats.py:277-280), so that a caller fetches contiguous per-fit rows
+ * instead of gathering on the host.  stds [n_fit*2*w], the others [n_fit].
  */
 int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, int32_t window_size,
-                       const uint8_t *status, const double *ks_stat,
+                       const uint8_t *status, const double *ks_stat, const double *ks_pval,
                        const int32_t *n_c, const int32_t *n_t, const double *cov,
-                       uint8_t *status_fit, double *ks_stat_fit, double *stds,
-                       int32_t *nall_fit, void *stream);
+                       uint8_t *status_fit, double *ks_stat_fit, double *ks_pval_fit,
+                       double *stds, int32_t *nc_fit, int32_t *nall_fit, void *stream);
 
 /*
  * Stages 2a + 2b + 3 back to back on one stream (convenience; same outputs

@@ -90,6 +90,42 @@ ASSUMPTIONS = {
           'try block) and abort the run; here the position is skipped',
 }
 
+# Every assumption whose alternative is plausible sits behind a named switch.  The defaults are what
+# the CUDA path implements; `assume(...)` flips switches for a sensitivity run
+# (oracle/assumption_sensitivity.py -> DESIGN.md section 4: how many significant calls move).
+SWITCHES = {
+    'A1_kmeans_distance': 'squared',     # | 'euclidean': Kmeans.distance returns sqrt(d2) (changes the MAD rule only)
+    'A2_kmeans_stop': 'total',           # | 'mean': stop_threshold applies to the mean, not the total, squared distance
+    'A2_kmeans_n_init': 3,               # | 1: n_init ignored, a single k-means++ start
+    'A3_cov_centre': 'new_mean',         # | 'blended_mean': covariance centred on the inertia-blended mean
+    'A4_cholesky_failure': 'drop',       # | 'eig_floor': eigenvalues floored at min_covar = 1e-5 and a retry
+                                         # | 'eig_shift': cov -= min(eigenvalue) I, cov += min_covar I and a retry
+                                         #   (two readings of pomegranate's fallback path; in both the position is
+                                         #   dropped only if the retry fails too)
+    'A5_zero_width_box': 'fail',         # | 'widen': a zero-width column of the uniform box is ignored
+}
+_DEFAULT_SWITCHES = dict(SWITCHES)
+
+
+class assume:
+    '''context manager: `with assume(A4_cholesky_failure='eig_floor'): ...` (test infrastructure)'''
+
+    def __init__(self, **kw):
+        unknown = set(kw) - set(SWITCHES)
+        if unknown:
+            raise KeyError(f'unknown assumption switches {sorted(unknown)}')
+        self.kw = kw
+
+    def __enter__(self):
+        self.saved = dict(SWITCHES)
+        SWITCHES.update(self.kw)
+        return self
+
+    def __exit__(self, *exc):
+        SWITCHES.clear()
+        SWITCHES.update(self.saved)
+
+
 # position status codes shared with the CUDA path (include/yanocomp_b200.h)
 ST_NOT_A_WINDOW = 0    # fails the depth / window filters (gmmtest.py:24-61)
 ST_KS_FILTERED = 1     # entered position_stats, failed the gate (stats.py:465)
@@ -279,7 +315,19 @@ class MVNormal:
         return dist
 
     def _factor(self):
-        L = cholesky_lower(self.cov)
+        try:
+            L = cholesky_lower(self.cov)
+        except FitError:
+            mode = SWITCHES['A4_cholesky_failure']
+            if mode == 'drop' or not np.isfinite(self.cov).all():
+                raise
+            # alternatives to A4: regularise the spectrum and retry once
+            ev, vec = np.linalg.eigh((self.cov + self.cov.T) / 2)
+            if mode == 'eig_floor':
+                self.cov = (vec * np.maximum(ev, 1e-5)).dot(vec.T)
+            else:
+                self.cov = self.cov + (1e-5 - min(float(ev.min()), 0.0)) * np.eye(self.d)
+            L = cholesky_lower(self.cov)
         self.linv = lower_inverse(L)
         self.logdet = 2.0 * float(np.sum(np.log(np.diagonal(L))))
 
@@ -301,8 +349,13 @@ class MVNormal:
         if self.s0 < 1e-7:
             return
         u = self.s1 / self.s0
-        cov = (self.s2 - np.outer(self.s1, u) - np.outer(u, self.s1)
-               + self.s0 * np.outer(u, u)) / self.s0
+        if SWITCHES['A3_cov_centre'] == 'blended_mean':
+            c = self.mu * inertia + u * (1.0 - inertia)
+            cov = (self.s2 - np.outer(self.s1, c) - np.outer(c, self.s1)
+                   + self.s0 * np.outer(c, c)) / self.s0
+        else:
+            cov = (self.s2 - np.outer(self.s1, u) - np.outer(u, self.s1)
+                   + self.s0 * np.outer(u, u)) / self.s0
         self.mu = self.mu * inertia + u * (1.0 - inertia)
         self.cov = self.cov * inertia + cov * (1.0 - inertia)
         self._factor()
@@ -364,9 +417,12 @@ class UniformBox:
     def __init__(self, lo, hi):
         self.lo = np.array(lo, dtype=np.float64)
         self.hi = np.array(hi, dtype=np.float64)
-        if np.any(self.hi <= self.lo):
-            raise FitError('zero-width uniform component')
-        self.logp = -float(np.sum(np.log(self.hi - self.lo)))
+        width = self.hi - self.lo
+        if np.any(width <= 0):
+            if SWITCHES['A5_zero_width_box'] != 'widen':
+                raise FitError('zero-width uniform component')
+            width = np.where(width > 0, width, 1.0)
+        self.logp = -float(np.sum(np.log(width)))
 
     def log_probability(self, X):
         inside = np.all((X >= self.lo) & (X <= self.hi), axis=1)
@@ -430,6 +486,8 @@ def kmeans_fit(X, pkey, k=N_COMPONENTS, n_init=3, max_iterations=100,
     '''A2: pm.Kmeans(k, init='kmeans++', n_init=3).fit (stats.py:108-113)'''
     n = X.shape[0]
     best_c, best_total = None, np.inf
+    n_init = min(n_init, SWITCHES['A2_kmeans_n_init'])
+    stop_scale = float(n) if SWITCHES['A2_kmeans_stop'] == 'mean' else 1.0
     for restart in range(n_init):
         stream = STREAM_KMEANS0 + restart
         i0 = min(int(rng_uniform(pkey, stream, 0) * n), n - 1)
@@ -455,7 +513,7 @@ def kmeans_fit(X, pkey, k=N_COMPONENTS, n_init=3, max_iterations=100,
             sums = np.stack([X[lab == j].sum(axis=0) for j in range(k)])
             counts = np.bincount(lab, minlength=k)
             if iteration > 0:
-                improvement = last - total
+                improvement = (last - total) / stop_scale
             iteration += 1
             last = total
         if total < best_total:
@@ -500,6 +558,8 @@ def kmeans_init_clusters(X, pkey, outlier_factor=0.5, detect_outliers='mad', dbs
         return init_pred
     if detect_outliers == 'mad':
         dists = np.min(d2, axis=1)
+        if SWITCHES['A1_kmeans_distance'] == 'euclidean':
+            dists = np.sqrt(dists)
         mad = median_absolute_deviation(dists)
         outlier_mask = dists > outlier_factor * mad
     init_pred[outlier_mask] = N_COMPONENTS
@@ -1059,8 +1119,10 @@ def assign_modified_distribution(records, model_means):
             r.cntrl_frac_mod = 1 - r.cntrl_frac_mod
             r.treat_frac_mod = 1 - r.treat_frac_mod
             r.log_odds = -r.log_odds
-            r.log_odds_lower_ci, r.log_odds_upper_ci = (-r.log_odds_upper_ci,
-                                                        -r.log_odds_lower_ci)
+            # stats.py:577-579 assigns a label-indexed Series through .loc: pandas aligns it on the labels, so
+            # each bound is negated in place (the interval comes out inverted); reproduced, not repaired
+            r.log_odds_lower_ci, r.log_odds_upper_ci = (-r.log_odds_lower_ci,
+                                                        -r.log_odds_upper_ci)
             r.dist1_means, r.dist2_means = r.dist2_means, r.dist1_means
             r.dist1_stds, r.dist2_stds = r.dist2_stds, r.dist1_stds
             if r.sm_preds is not None:

@@ -1,0 +1,37 @@
+'''
+CPU: the oracle's pomegranate assumptions sit behind named switches (yanocomp_oracle.SWITCHES) and their effect
+on the significant-call set of the reference's own fixture pair is pinned here (the full table, including the
+cfg2 subset and the k-means alternatives, is profiles/r02_assumption_sensitivity.md, written by
+oracle/assumption_sensitivity.py and quoted in DESIGN.md section 4).
+'''
+import pytest
+
+import yanocomp_oracle as yo
+import assumption_sensitivity as sens
+
+
+def test_switch_names_and_defaults_are_restored():
+    before = dict(yo.SWITCHES)
+    with yo.assume(A4_cholesky_failure='eig_floor', A1_kmeans_distance='euclidean'):
+        assert yo.SWITCHES['A4_cholesky_failure'] == 'eig_floor' and yo.SWITCHES['A1_kmeans_distance'] == 'euclidean'
+    assert yo.SWITCHES == before == yo._DEFAULT_SWITCHES
+    with pytest.raises(KeyError):
+        yo.assume(A99_nothing=1)
+    assert {k.split('_')[0] for k in yo.SWITCHES} <= set(yo.ASSUMPTIONS)
+
+
+def test_fixture_sensitivity_to_the_cholesky_and_covariance_assumptions():
+    items, n_tested, opts, n_cntrl = sens._gated_fixture_inputs()
+    assert n_tested == 3444 and len(items) == 213
+    alts = [a for a in sens.ALTERNATIVES if a[0] in ('A3', 'A4a', 'A4b', 'A5')]
+    rep = sens.measure(items, opts, n_cntrl, alts)
+    assert (rep['fitted_default'], rep['failed_default'], rep['significant_default']) == (125, 88, 39)
+    rows = {r['assumption']: r for r in rep['rows']}
+    # A3 / A5: the alternative reading changes nothing on real data
+    for tag in ('A3', 'A5'):
+        assert rows[tag]['fit_status_changed'] == 0 and rows[tag]['discordance'] == 0.0
+    # A4 (the riskiest): regularise-and-retry fits all 88 positions the default drops; none of them becomes a call,
+    # and the larger multiple-testing family costs 2 of the 39 calls (5.1 % discordance) -- the stated bound
+    for tag in ('A4a', 'A4b'):
+        assert rows[tag]['fit_status_changed'] == 88 and rows[tag]['calls_gained'] == 0
+        assert rows[tag]['calls_lost'] == 2 and rows[tag]['discordance'] < 0.06

@@ -33,17 +33,13 @@ def test_cfg4_shape_subsampling_window5_posteriors():
     assert (res.n_c[tested] == 2000).all() and (res.n_t[tested] == 2000).all()      # before sub-sampling to 1 000
     k = res.ks_stat[tested] * 1000.0                                                # D = |c1 - c2| / 1000 after it
     assert np.abs(k - np.round(k)).max() < 1e-9
-    # posteriors of the significant positions: every complete-window read, probabilities in [0, 1]
+    # posteriors of the significant positions: every complete-window read (4 000, not the 1 000 / replicate the fit
+    # used); their VALUES are compared with the oracle's predict_proba inside compare() (rtol 1e-6)
     sig = np.flatnonzero(res.post_off >= 0)
-    assert len(sig) >= 1
+    assert len(sig) >= 1 and out['posteriors'] == len(sig) and not out['errs']['post']
     for s in sig:
         post = res.post[res.post_off[s]:res.post_off[s] + res.nall_fit[s]]
         assert len(post) == 4000 and (post >= 0).all() and (post.sum(axis=1) <= 1 + 1e-12).all()
-        o = out['ref'][feats[0].feature_id][int(feats[0].positions[int(res.fit_list[s])])]
-        if o.sm_preds is not None:
-            ref_p = np.concatenate([np.asarray(o.sm_preds[c][r]['preds']) for c in ('cntrl', 'treat')
-                                    for r in sorted(o.sm_preds[c])])
-            assert len(ref_p) == 4000
 
 
 def test_cfg5_shape_every_position_fitted():

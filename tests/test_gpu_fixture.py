@@ -45,7 +45,7 @@ def test_fixture_ks_bit_exact_and_fits():
         g = index[(str(feat), int(pos))]
         seen.add(g)
         assert res.ks_stat[g] == d, (feat, pos, res.ks_stat[g], d)                    # bit-exact
-        assert abs(res.ks_pval[g] - p) <= 4 * np.spacing(p), (feat, pos, res.ks_pval[g], p)
+        assert res.ks_pval[g] == p, (feat, pos, res.ks_pval[g], p)                    # SciPy's value, bit for bit
         gated_ref = st in (N.ST_TESTED, N.ST_FIT_FAILED)
         gated_gpu = res.status[g] in (N.ST_TESTED, N.ST_FIT_FAILED)
         n_gate_mismatch += gated_ref != gated_gpu
@@ -97,18 +97,14 @@ def test_cli_end_to_end_bed_and_json(tmp_path):
     assert r.exit_code == 0, r.output
     got = _parse_bed(open(bed_fn).read())
     ref = _parse_bed(open(os.path.join(GOLD, 'fixture_w3.bed')).read())
-    common = set(got) & set(ref)
-    # significant-call agreement: rank-deficient fits may flip a handful of calls
-    assert len(common) >= 0.9 * len(ref) and len(got) <= 1.1 * len(ref) + 1, (len(got), len(ref), len(common))
-    # The oracle tests 125 positions, the GPU path 123-125 (rank-deficient fits flip between
-    # "failed" and "fitted" on rounding noise), so BH-FDR (and the score derived from it) may move
-    # in the 2nd significant digit; every other column must be byte-identical.
-    def strip(f):
-        return f[:4] + f[5:8] + f[9:]
-    same = sum(strip(got[k]) == strip(ref[k]) for k in common)
-    assert same >= 0.95 * len(common), (same, len(common), [(got[k], ref[k]) for k in common if strip(got[k]) != strip(ref[k])][:3])
-    for k in common:
-        assert abs(float(got[k][8]) / float(ref[k][8]) - 1) < 0.1 and abs(int(got[k][4]) - int(ref[k][4])) <= 1
+    # Identical significant-call set and byte-identical BED lines (all 18 columns, BH-FDR and score included).
+    # KNOWN_EXCEPTIONS names every position allowed to differ and why; it is empty.
+    KNOWN_EXCEPTIONS = {}
+    diffs = {k: (got.get(k), ref.get(k)) for k in set(got) | set(ref) if got.get(k) != ref.get(k)}
+    for k, (a, b) in sorted(diffs.items()):
+        print('BED difference', k, a, b, KNOWN_EXCEPTIONS.get(k, 'UNEXPLAINED'))
+    assert len(ref) == 39
+    assert set(diffs) <= set(KNOWN_EXCEPTIONS), sorted(diffs)
     import gzip
     doc = json.load(gzip.open(sm_fn, 'rt'))
     gold = json.load(open(os.path.join(GOLD, 'fixture_w3_sm.json')))
@@ -119,16 +115,14 @@ def test_cli_end_to_end_bed_and_json(tmp_path):
         for pos in set(sm[gene]) & set(gsm[gene]):
             a, b = sm[gene][pos], gsm[gene][pos]
             assert a['kmers'] == b['kmers']
-            if f'{gene}:{a["kmers"][1]}' not in {k[0] for k in common if strip(got[k]) == strip(ref[k])}:
-                continue
             for cond in ('cntrl', 'treat'):
                 assert set(a[cond]) == set(b[cond])
                 for rep in a[cond]:
                     assert a[cond][rep]['read_ids'] == b[cond][rep]['read_ids']
                     assert a[cond][rep]['events'] == b[cond][rep]['events']
-                    np.testing.assert_allclose(a[cond][rep]['preds'], b[cond][rep]['preds'], rtol=1e-3, atol=1e-6)
+                    np.testing.assert_allclose(a[cond][rep]['preds'], b[cond][rep]['preds'], rtol=1e-6, atol=1e-9)
                     np.testing.assert_allclose(a[cond][rep]['outlier_preds'], b[cond][rep]['outlier_preds'],
-                                               rtol=1e-3, atol=1e-6)
+                                               rtol=1e-6, atol=1e-9)
             np.testing.assert_allclose(a['model']['weights'], b['model']['weights'], rtol=1e-4)
             n += 1
     assert n > 20, n

@@ -3,8 +3,8 @@ GPU, BASELINE.json configs[1] at FULL size (1 000 transcripts x 500 positions, 2
 100 reads / condition, window 3): the oracle needs ~10 minutes for this, so parity is checked
 through size-independent properties instead:
   * every interior column of a fully covered transcript is a window; edges are not;
-  * the KS p-value of all 498 000 positions equals scipy.special.kolmogorov of the device D to
-    <= 4 ulp, and the gate status is exactly (D >= min_ks and p < threshold) recomputed on the host;
+  * the KS p-value of all 498 000 positions equals scipy.special.kolmogorov of the device D bit for
+    bit, and the gate status is exactly (D >= min_ks and p < threshold) recomputed on the host;
   * D is a difference of count ratios: D * n1 * n2 is an integer (up to rounding);
   * results do not depend on the batch composition: reversing the feature order, or cutting the
     batch into pipelined chunks, reproduces every per-position number bit for bit;
@@ -44,8 +44,7 @@ def test_cfg2_full_size_properties():
     # p-values against SciPy on the device D
     en = np.sqrt(n1 * n2 / (n1 + n2))
     ref_p = special.kolmogorov((en + 0.12 + 0.11 / en) * d)
-    ulps = np.abs(p - ref_p) / np.spacing(ref_p)
-    assert ulps.max() <= 4, ulps.max()
+    assert np.array_equal(p, ref_p)                       # reported p-values are SciPy's own (engine._host_ks_pvalues)
     # the gate, recomputed on the host
     gate = (d >= params.min_ks) & (p < params.fdr_threshold)
     gated = np.isin(res.status[tested], (N.ST_TESTED, N.ST_FIT_FAILED))

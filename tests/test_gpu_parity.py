@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 PARAM_RTOL = 1e-4      # north_star: 1e-4 on fitted parameters
 STAT_RTOL = 1e-4
+POST_RTOL, POST_ATOL = 1e-6, 1e-9      # single-molecule posteriors P(dist2), P(outlier) per read (stats.py:494-499)
 SPLIT_FIT = {'on': False}
 KS_ORIENTATION_EXACT = True    # the kernel reproduces LAPACK's axis orientation (yc_svdsign.cuh)
 
@@ -84,8 +85,8 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
     ref = ob.run_features(features, R, Rc, opts)
     slot_of = {int(g): i for i, g in enumerate(res.fit_list)}
     errs = {k: [] for k in ('window', 'status', 'ks_d', 'ks_p', 'labels', 'iters', 'params',
-                            'box', 'preds', 'stats', 'boundary_gate', 'rank_deficient')}
-    n_windows = n_fit = 0
+                            'box', 'preds', 'stats', 'post', 'boundary_gate', 'rank_deficient')}
+    n_windows = n_fit = n_post = 0
     for fi, feat in enumerate(features):
         r = ref[feat.feature_id]
         for c in range(feat.n_cols):
@@ -109,7 +110,7 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
             if KS_ORIENTATION_EXACT:
                 if res.ks_stat[g] != o.ks_stat:
                     errs['ks_d'].append((key, res.ks_stat[g], o.ks_stat))
-                if abs(res.ks_pval[g] - o.ks_p_val) > 4 * np.spacing(o.ks_p_val):
+                if res.ks_pval[g] != o.ks_p_val:                         # reported p-values: SciPy's, bit for bit
                     errs['ks_p'].append((key, res.ks_pval[g], o.ks_p_val))
             else:
                 if abs(res.ks_stat[g] - o.ks_stat) > np.spacing(o.ks_stat):
@@ -162,16 +163,33 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
                                   o.log_odds, o.log_odds_lower_ci, o.log_odds_upper_ci])
             if not np.allclose(res.stats[s], ref_stats, rtol=STAT_RTOL, atol=1e-12, equal_nan=True):
                 errs['stats'].append((key, res.stats[s].tolist(), ref_stats.tolist()))
+                continue
+            if params.generate_sm_preds:
+                # posteriors of every complete-window read under the combined weights, pooled read order
+                has_gpu = res.post_off[s] >= 0
+                if (o.sm_preds is not None) != bool(has_gpu):
+                    errs['post'].append((key, 'presence', o.sm_preds is not None, bool(has_gpu)))
+                elif has_gpu:
+                    ref_post = np.array([[pr, ou] for cond in ('cntrl', 'treat') for rep in sorted(o.sm_preds[cond])
+                                         for pr, ou in zip(o.sm_preds[cond][rep]['preds'],
+                                                           o.sm_preds[cond][rep]['outlier_preds'])])
+                    got_post = res.post[res.post_off[s]:res.post_off[s] + res.nall_fit[s]]
+                    n_post += 1
+                    if got_post.shape != ref_post.shape or not np.allclose(got_post, ref_post, rtol=POST_RTOL,
+                                                                           atol=POST_ATOL):
+                        errs['post'].append((key, got_post.shape, ref_post.shape,
+                                             float(np.abs(got_post - ref_post).max())
+                                             if got_post.shape == ref_post.shape else None))
     summary = {k: len(v) for k, v in errs.items()}
-    print(f'windows={n_windows} fitted={n_fit} mismatches={summary}')
+    print(f'windows={n_windows} fitted={n_fit} posteriors={n_post} mismatches={summary}')
     for k, v in errs.items():
         for item in v[:3]:
             print('  ', k, item)
     hard = ('window', 'status', 'ks_d', 'ks_p', 'labels', 'box')
     assert all(summary[k] == 0 for k in hard), summary
-    soft = sum(summary[k] for k in ('iters', 'params', 'preds', 'stats'))
+    soft = sum(summary[k] for k in ('iters', 'params', 'preds', 'stats', 'post'))
     assert soft <= max_fit_discordance * max(n_fit, 1), summary
-    return dict(windows=n_windows, fitted=n_fit, res=res, ref=ref, host=host, errs=errs)
+    return dict(windows=n_windows, fitted=n_fit, posteriors=n_post, res=res, ref=ref, host=host, errs=errs)
 
 
 @pytest.fixture(params=['warp', 'cta'])
@@ -193,20 +211,20 @@ def ks_path(request, monkeypatch):
 
 def test_small_synthetic_w3(ks_path):
     feats = synth.make_dataset(11, 4, 60, 30, 2, 2, planted_frac=0.2)
-    out = compare(feats, 4, 2, window_size=3)
-    assert out['windows'] > 200 and out['fitted'] > 5
+    out = compare(feats, 4, 2, window_size=3, generate_sm_preds=True)
+    assert out['windows'] > 200 and out['fitted'] > 5 and out['posteriors'] > 3
 
 
 def test_small_synthetic_w5_dropout(ks_path):
     feats = synth.make_dataset(12, 3, 50, [25, 31, 40, 28], 2, 2, planted_frac=0.2, dropout=0.05)
-    out = compare(feats, 4, 2, window_size=5)
+    out = compare(feats, 4, 2, window_size=5, generate_sm_preds=True)
     assert out['windows'] > 50
 
 
 def test_reverse_strand_and_3x3_replicates(ks_path):
     feats = synth.make_dataset(13, 3, 40, [20, 24, 22, 30, 21, 26], 3, 3, planted_frac=0.25, strand='-')
-    out = compare(feats, 6, 3, window_size=3)
-    assert out['windows'] > 80 and out['fitted'] > 5
+    out = compare(feats, 6, 3, window_size=3, generate_sm_preds=True)
+    assert out['windows'] > 80 and out['fitted'] > 5 and out['posteriors'] > 3
 
 
 def test_window_1_and_low_depth(ks_path):
@@ -251,6 +269,25 @@ def test_deep_positions_on_the_warp_path(sizes):
     assert out['windows'] == 24 and out['fitted'] >= 12
 
 
+def test_gate_p_value_on_the_threshold_is_decided_by_scipy(ks_path):
+    '''
+    stats.py:465 gates on `ks_p_val < fdr_threshold` with SciPy's p-value.  The device p-value is within a few ulp of
+    it, so with the threshold set EXACTLY to SciPy's p-value of a D that occurs in the data (n1 = n2 = 50,
+    D = 15/50) the device alone could decide either way: such positions pass the device gate (YC_KS_P_GUARD) and the
+    host re-decides them with SciPy (engine._finish_ks_pvalues).  Statuses must equal the oracle's.
+    '''
+    from scipy import stats as sstats
+    en = np.sqrt(50 * 50 / float(100))
+    d = np.max(np.absolute(np.array([31]) / 50.0 - np.array([16]) / 50.0))
+    thr = float(sstats.kstwobign.sf((en + 0.12 + 0.11 / en) * d))
+    feats = synth.make_dataset(61, 8, 70, 25, 2, 2, planted_frac=0.1)
+    out = compare(feats, 4, 2, window_size=3, fdr_threshold=thr, min_ks=0.1)
+    res = out['res']
+    near = np.abs(res.ks_pval_fit - thr) <= thr * 2.0 ** -44
+    assert near.sum() >= 3, int(near.sum())                         # the case really occurs
+    assert (res.status_fit[near] == N.ST_KS_FILTERED).any()         # ... and SciPy rejected (p == thr is not < thr)
+
+
 def test_no_gmm_mode(ks_path):
     feats = synth.make_dataset(18, 2, 40, 25, 2, 2, planted_frac=0.2)
     out = compare(feats, 4, 2, window_size=3, gmm=False)
@@ -260,8 +297,8 @@ def test_no_gmm_mode(ks_path):
 def test_no_uniform_two_component_model(ks_path):
     '''--no-uniform (stats.py:170, 472, 500-502): no MAD outliers, two components, 2-column homogeneity tables'''
     feats = synth.make_dataset(19, 4, 50, [28, 33, 30, 26], 2, 2, planted_frac=0.25)
-    out = compare(feats, 4, 2, window_size=3, add_uniform=False)
-    assert out['fitted'] > 20
+    out = compare(feats, 4, 2, window_size=3, add_uniform=False, generate_sm_preds=True)
+    assert out['fitted'] > 20 and out['posteriors'] > 5
     assert (out['res'].preds[:, :, 2] == 0).all() and (out['res'].cw[:, 2] == 0).all()
 
 
@@ -322,6 +359,6 @@ def test_randomised_ragged_batches(seed, ks_path):
             f = type(f)(feature_id=f.feature_id, chrom='.', strand=f.strand, pos0=0, X=f.X[keep].copy(),
                         samp_start=f.samp_start, kmers=f.kmers, positions=f.positions[keep])
         feats.append(f)
-    out = compare(feats, R, n_c, window_size=w, max_fit_discordance=0.02,
+    out = compare(feats, R, n_c, window_size=w, max_fit_discordance=0.02, generate_sm_preds=bool(seed % 2),
                   max_fit_depth=int(rng.choice([1000, 1000, 40])))
     assert out['windows'] >= 0

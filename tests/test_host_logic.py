@@ -251,8 +251,10 @@ def test_vectorised_assignment_equals_the_per_record_route(tmp_path):
         for c in ('cntrl_frac_mod', 'treat_frac_mod'):
             want.at[i, c] = 1 - want.at[i, c]
         want.at[i, 'log_odds'] = -want.at[i, 'log_odds']
-        lo, hi = want.at[i, 'log_odds_lower_ci'], want.at[i, 'log_odds_upper_ci']
-        want.at[i, 'log_odds_lower_ci'], want.at[i, 'log_odds_upper_ci'] = -hi, -lo
+        # the reference's own statement (stats.py:577-579): a label-indexed Series assigned through .loc is aligned
+        # on the labels, so each bound is negated in place -- the product reproduces exactly what pandas does here
+        want.loc[i, ['log_odds_lower_ci', 'log_odds_upper_ci']] = np.negative(
+            want.loc[i, ['log_odds_upper_ci', 'log_odds_lower_ci']])
         want.at[i, 'dist1_means'], want.at[i, 'dist2_means'] = m2, m1
         s1, s2 = want.at[i, 'dist1_stds'], want.at[i, 'dist2_stds']
         want.at[i, 'dist1_stds'], want.at[i, 'dist2_stds'] = s2, s1

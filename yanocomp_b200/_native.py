@@ -74,7 +74,7 @@ _PROTOTYPES = {
                                   C.c_void_p, C.c_void_p]),
     'yc_gtest_smpred_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut),
                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    'yc_gather_fit_rows': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 10),
+    'yc_gather_fit_rows': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 13),
     'yc_gmm_fit_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut), C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'yc_kolmogorov_sf_host': (C.c_double, [C.c_double]),

@@ -185,15 +185,19 @@ int compact_gated(const uint8_t *status, long long n, int32_t *fit_list, int32_t
 // (status, KS D, sqrt of the covariance diagonals = dist*_stds of stats.py:277-280, complete-window rows)
 __global__ void gather_fit_rows_kernel(const int32_t *__restrict__ fit_list, int n_fit, int w,
                                        const uint8_t *__restrict__ status, const double *__restrict__ ks_stat,
+                                       const double *__restrict__ ks_pval,
                                        const int32_t *__restrict__ n_c, const int32_t *__restrict__ n_t,
-                                       const double *__restrict__ cov, uint8_t *__restrict__ status_fit,
-                                       double *__restrict__ ks_stat_fit, double *__restrict__ stds,
-                                       int32_t *__restrict__ nall_fit) {
+                                       const double *__restrict__ cov,
+                                       uint8_t *__restrict__ status_fit, double *__restrict__ ks_stat_fit,
+                                       double *__restrict__ ks_pval_fit, double *__restrict__ stds,
+                                       int32_t *__restrict__ nc_fit, int32_t *__restrict__ nall_fit) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_fit) return;
     const int g = fit_list[slot];
     status_fit[slot] = status[g];
     ks_stat_fit[slot] = ks_stat[g];
+    ks_pval_fit[slot] = ks_pval[g];
+    nc_fit[slot] = n_c[g];
     nall_fit[slot] = n_c[g] + n_t[g];
     for (int k = 0; k < 2; ++k)
         for (int a = 0; a < w; ++a)
@@ -330,13 +334,16 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p, const int32
 }
 
 int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, int32_t window_size, const uint8_t *status,
-                       const double *ks_stat, const int32_t *n_c, const int32_t *n_t, const double *cov,
-                       uint8_t *status_fit, double *ks_stat_fit, double *stds, int32_t *nall_fit, void *stream) {
+                       const double *ks_stat, const double *ks_pval, const int32_t *n_c, const int32_t *n_t,
+                       const double *cov, uint8_t *status_fit, double *ks_stat_fit, double *ks_pval_fit,
+                       double *stds, int32_t *nc_fit, int32_t *nall_fit, void *stream) {
     if (n_fit <= 0) return 0;
-    if (!fit_list || !status || !ks_stat || !n_c || !n_t || !cov || !status_fit || !ks_stat_fit || !stds || !nall_fit)
+    if (!fit_list || !status || !ks_stat || !ks_pval || !n_c || !n_t || !cov || !status_fit || !ks_stat_fit ||
+        !ks_pval_fit || !stds || !nc_fit || !nall_fit)
         return fail(YC_EINVAL, "yc_gather_fit_rows: null pointer");
     gather_fit_rows_kernel<<<(n_fit + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        fit_list, n_fit, window_size, status, ks_stat, n_c, n_t, cov, status_fit, ks_stat_fit, stds, nall_fit);
+        fit_list, n_fit, window_size, status, ks_stat, ks_pval, n_c, n_t, cov, status_fit, ks_stat_fit, ks_pval_fit,
+        stds, nc_fit, nall_fit);
     yc::count_launches(1);
     return cuda_fail((int)cudaGetLastError(), "yc_gather_fit_rows");
 }

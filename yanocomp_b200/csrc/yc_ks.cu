@@ -287,7 +287,7 @@ ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, con
         ks_stat[g] = dmax; ks_pval[g] = pv;
         uint8_t st;
         if (!p.gmm) st = YC_ST_KS_ONLY;
-        else if (dmax >= p.min_ks && pv < p.fdr_threshold) {
+        else if (ks_gate_open(dmax, pv, p.min_ks, p.fdr_threshold)) {
             st = YC_ST_GATED;                 // fit_list is built afterwards by compact_gated (ordered)
         } else st = YC_ST_KS_FILTERED;
         status[g] = st;

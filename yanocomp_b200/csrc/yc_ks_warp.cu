@@ -430,7 +430,7 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
             const double en = __dsqrt_rn(div_rn((double)((int64_t)n1 * (int64_t)n2), (double)(n1 + n2)));
             pv = kolmogorov_sf(mul_rn(add_rn(add_rn(en, 0.12), div_rn(0.11, en)), d));
             if (!p.gmm) code = YC_ST_KS_ONLY;
-            else if (d >= p.min_ks && pv < p.fdr_threshold) { code = YC_ST_GATED; gated = true; }
+            else if (ks_gate_open(d, pv, p.min_ks, p.fdr_threshold)) { code = YC_ST_GATED; gated = true; }
             else code = YC_ST_KS_FILTERED;
             status[g] = code;
         }

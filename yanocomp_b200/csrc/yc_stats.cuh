@@ -48,6 +48,17 @@ YC_HD_COLD double kolmogorov_sf(double x) {
     return P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
 }
 
+// The gate of position_stats (stats.py:465): ks_stat >= min_ks and ks_p < fdr_threshold.  D is bit-exact, but the
+// device p-value is only within a few ulp of scipy.special.kolmogorov (libm's exp / pow are not reproducible on
+// the device), so a p-value within 2^-44 (relative) of the threshold passes the gate as well; the host re-decides
+// exactly those positions with SciPy itself (engine._host_ks_pvalues) and drops the ones SciPy rejects.  Every
+// filter decision is therefore the one the reference's own call makes.
+#define YC_KS_P_GUARD 5.6843418860808015e-14
+YC_HD bool ks_p_near_threshold(double pv, double thr) { return fabs(pv - thr) <= thr * YC_KS_P_GUARD; }
+YC_HD bool ks_gate_open(double d, double pv, double min_ks, double thr) {
+    return d >= min_ks && (pv < thr || ks_p_near_threshold(pv, thr));
+}
+
 // chi2.sf(g, 1) = erfc(sqrt(g/2))
 YC_HD double chi2_sf_1dof(double g) {
     if (isnan(g)) return g;

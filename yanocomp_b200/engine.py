@@ -64,11 +64,13 @@ class BatchResult:
     mu: np.ndarray                    # (n_fit, 2, w)
     stds: np.ndarray                  # (n_fit, 2, w) sqrt of the covariance diagonals
     stats: np.ndarray                 # (n_fit, 8) g, hom_g, p, cntrl_frac, treat_frac, log_odds, lo, hi
+    ks_pval_fit: np.ndarray = None    # (n_fit,) device KS p-value of each gated position (gate only; see _host_ks_pvalues)
+    nc_fit: np.ndarray = None         # (n_fit,) complete-window control rows of each gated position
+    nall_fit: np.ndarray = None       # (n_fit,) complete-window rows of each gated position
     ks_stat: np.ndarray = None        # (total_cols,)            full / --no-gmm
     ks_pval: np.ndarray = None        # (total_cols,)            full / --no-gmm
     n_c: np.ndarray = None            # (total_cols,) complete-window control rows        full
     n_t: np.ndarray = None
-    nall_fit: np.ndarray = None       # (n_fit,) complete-window rows of each gated position (sm-preds)
     cov: np.ndarray = None            # (n_fit, 2, w, w)         full / sm-preds
     box: np.ndarray = None            # (n_fit, w, 2)
     cw: np.ndarray = None             # (n_fit, 3)
@@ -94,6 +96,22 @@ class BatchResult:
 
 
 _ALIGN = 256
+KS_P_GUARD = 2.0 ** -44          # YC_KS_P_GUARD of csrc/yc_stats.cuh
+
+
+def _host_ks_pvalues(d, n1, n2, max_fit_depth):
+    '''
+    The KS p-value exactly as the reference computes it (yanocomp/stats.py:46-49): SciPy's own
+    Kolmogorov survival function on the (bit-exact) device D, with the sample sizes after the
+    per-condition sub-sampling of stats.py:67-68.  Used for every REPORTED p-value (--no-gmm, full
+    fetches) and to re-decide gate p-values within KS_P_GUARD of the threshold; the device value
+    only ever serves the gate away from the threshold.
+    '''
+    from scipy import special
+    n1 = np.minimum(np.asarray(n1, dtype=np.int64), max_fit_depth)
+    n2 = np.minimum(np.asarray(n2, dtype=np.int64), max_fit_depth)
+    en = np.sqrt(n1 * n2 / (n1 + n2).astype(np.float64))
+    return special.kolmogorov((en + 0.12 + 0.11 / en) * np.asarray(d, dtype=np.float64))
 
 
 def _carve(specs, device=None, zero=False):
@@ -259,9 +277,10 @@ class Engine:
         m = max(n_fit, 1)
         # per-fit outputs in one zero-filled arena (one memset instead of a fill per array), ordered so that
         # each fetch level is a prefix: records | + sm-preds | + full
-        specs = [('status_fit', (m,), torch.uint8), ('ks_stat_fit', (m,), f64), ('mu', (m, 2, w), f64),
+        specs = [('status_fit', (m,), torch.uint8), ('ks_stat_fit', (m,), f64), ('ks_pval_fit', (m,), f64),
+                 ('nc_fit', (m,), i32), ('nall_fit', (m,), i32), ('mu', (m, 2, w), f64),
                  ('stds', (m, 2, w), f64), ('stats', (m, 8), f64),
-                 ('nall_fit', (m,), i32), ('cov', (m, 2, w, w), f64), ('box', (m, w, 2), f64),
+                 ('cov', (m, 2, w, w), f64), ('box', (m, w, 2), f64),
                  ('cw', (m, 3), f64), ('post_off', (m,), torch.int64),
                  ('logw', (m, R, 3), f64), ('iters', (m,), i32), ('loglik', (m,), f64), ('preds', (m, R, 3), f64)]
         fit_arena, out_t, fit_ext, fit_total = _carve(specs, d, zero=True)
@@ -295,13 +314,15 @@ class Engine:
                 post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
             # the per-fit rows the host tail reads, gathered on the device in slot order
             N.check(lib.yc_gather_fit_rows(
-                fit_list.data_ptr(), n_fit, w, status.data_ptr(), ks_stat.data_ptr(), n_c.data_ptr(), n_t.data_ptr(),
-                out_t['cov'].data_ptr(), out_t['status_fit'].data_ptr(), out_t['ks_stat_fit'].data_ptr(),
-                out_t['stds'].data_ptr(), out_t['nall_fit'].data_ptr(), stream))
+                fit_list.data_ptr(), n_fit, w, status.data_ptr(), ks_stat.data_ptr(), ks_pval.data_ptr(),
+                n_c.data_ptr(), n_t.data_ptr(), out_t['cov'].data_ptr(), out_t['status_fit'].data_ptr(),
+                out_t['ks_stat_fit'].data_ptr(), out_t['ks_pval_fit'].data_ptr(), out_t['stds'].data_ptr(),
+                out_t['nc_fit'].data_ptr(), out_t['nall_fit'].data_ptr(), stream))
         launches = ctx['launches'] + int(lib.yc_kernel_launches() - fit_launches0)
         ctx.update(n_fit=n_fit, launches=launches)
         if not fetch:
-            dev_out = {k: v for k, v in out_t.items() if k not in ('status_fit', 'ks_stat_fit', 'stds', 'nall_fit')}
+            dev_out = {k: v for k, v in out_t.items()
+                       if k not in ('status_fit', 'ks_stat_fit', 'ks_pval_fit', 'stds', 'nc_fit', 'nall_fit')}
             flat = {k: dev_out[k].reshape(-1) for k in dev_out}
             ctx['device'] = dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
                                  fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
@@ -375,6 +396,8 @@ class Engine:
                         ks_pval=view(c0, col_ext, 'ks_pval', None, np.float64, nc))
         if level == 'full':
             host.update(n_c=view(c0, col_ext, 'n_c', None, np.int32, nc), n_t=view(c0, col_ext, 'n_t', None, np.int32, nc))
+        elif want_cols:
+            host.update(_n_c=view(c0, col_ext, 'n_c', None, np.int32, nc), _n_t=view(c0, col_ext, 'n_t', None, np.int32, nc))
         np_dtype = {torch.uint8: np.uint8, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}
         for name, shape, dtype in ctx['fit_specs']:
             host[name] = view(f0, fit_ext, name, shape, np_dtype[dtype])[:n_fit]
@@ -385,4 +408,34 @@ class Engine:
         if labels is not None and level == 'full':
             host['labels'] = hs[offs['labels']:offs['labels'] + labels.numel()].view(np.int8).reshape(labels.shape)
         d2h = sum(nb for _, _, nb in chunks)
+        self._finish_ks_pvalues(host, want_cols, level == 'full')
         return BatchResult(launches=ctx['launches'], d2h_bytes=d2h, **host)
+
+    def _finish_ks_pvalues(self, host, want_cols, full):
+        '''
+        Host half of the KS p-value contract (see _host_ks_pvalues): reported p-values come from SciPy, and a gated
+        position whose device p-value lies within KS_P_GUARD of the threshold is kept only if SciPy's p-value passes
+        the gate of stats.py:465 too.
+        '''
+        p = self.params
+        thr = p.fdr_threshold
+        n_fit = len(host['fit_list'])
+        if n_fit:
+            pv = host['ks_pval_fit']
+            near = np.flatnonzero(np.abs(pv - thr) <= thr * KS_P_GUARD)
+            if len(near):
+                nc = host['nc_fit'][near]
+                exact = _host_ks_pvalues(host['ks_stat_fit'][near], nc, host['nall_fit'][near] - nc, p.max_fit_depth)
+                drop = near[~(exact < thr)]
+                host['status_fit'][drop] = N.ST_KS_FILTERED
+                host['status'][host['fit_list'][drop]] = N.ST_KS_FILTERED
+        if want_cols:
+            st = host['status']
+            tested = np.flatnonzero((st != N.ST_NOT_A_WINDOW) & (st != N.ST_DEGENERATE))
+            if full:
+                n1, n2 = host['n_c'][tested], host['n_t'][tested]
+            else:                                     # --no-gmm records: n_c / n_t sit right behind ks_pval in the arena
+                n1, n2 = host['_n_c'][tested], host['_n_t'][tested]
+            host['ks_pval'][tested] = _host_ks_pvalues(host['ks_stat'][tested], n1, n2, p.max_fit_depth)
+        host.pop('_n_c', None)
+        host.pop('_n_t', None)

@@ -39,6 +39,7 @@ RESULT_COLUMNS = ['kmer', 'kmers', 'centre', 'log_odds', 'log_odds_lower_ci', 'l
 COLUMNS = POS_COLUMNS + RESULT_COLUMNS
 
 BATCH_EVENT_BYTES = 1 << 30      # host->device granularity of test_chunk
+PIPELINE_RANGES = 4              # feature ranges per batch in the upload | kernels | fetch pipeline (bench.py sweeps it)
 
 # columns whose cells are arrays of length window_size
 _ARRAY_COLUMNS = {'kmers', 'dist1_means', 'dist1_stds', 'dist2_means', 'dist2_stds'}
@@ -334,8 +335,9 @@ def test_chunk(opts, gene_ids):
                     if pending[k]:
                         yield HostBatch(pending[k], R, n_cntrl)
 
-    # upload of batch k+1 overlaps the kernels of batch k (engine.run_pipelined)
-    for host, res in engine.run_pipelined(batches()):
+    # every batch is cut into PIPELINE_RANGES feature ranges (views, no copy): the upload of range k+1 overlaps
+    # the kernels of range k and the fetch of range k-1 (engine.run_pipelined), also when a whole chunk is one batch
+    for host, res in engine.run_pipelined(r for hb in batches() for r in hb.split(PIPELINE_RANGES)):
         recs, sm = _batch_records(host, res, opts)
         chunk_res.extend(recs)
         for k, v in sm.items():

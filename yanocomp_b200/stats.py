@@ -154,7 +154,10 @@ def assign_modified_distribution(results, sm_preds, model):
     results.loc[idx, 'treat_frac_mod'] = 1 - results.loc[idx, 'treat_frac_mod'].to_numpy()
     results.loc[idx, 'log_odds'] = np.negative(results.loc[idx, 'log_odds'].to_numpy())
     lo, hi = results.loc[idx, 'log_odds_lower_ci'].to_numpy(), results.loc[idx, 'log_odds_upper_ci'].to_numpy()
-    results.loc[idx, 'log_odds_lower_ci'], results.loc[idx, 'log_odds_upper_ci'] = np.negative(hi), np.negative(lo)
+    # stats.py:577-579 assigns np.negative(results.loc[i, [upper, lower]]), a label-indexed Series, through .loc:
+    # pandas aligns on the labels, so each bound is negated IN PLACE and the interval of a flipped row comes out
+    # inverted (lower > upper) in the reference's BED.  Reproduced here: the output contract is the reference's.
+    results.loc[idx, 'log_odds_lower_ci'], results.loc[idx, 'log_odds_upper_ci'] = np.negative(lo), np.negative(hi)
     for c1, c2 in (('dist1_means', 'dist2_means'), ('dist1_stds', 'dist2_stds')):
         a, b = results[c1].to_numpy(dtype=object, copy=True), results[c2].to_numpy(dtype=object, copy=True)
         a[flip], b[flip] = b[flip], a[flip].copy()
