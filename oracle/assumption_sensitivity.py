@@ -41,8 +41,9 @@ ALTERNATIVES = [
     ('A2a', 'k-means stop threshold on the mean, not the total, squared distance', dict(A2_kmeans_stop='mean')),
     ('A2b', 'a single k-means++ start (n_init ignored)', dict(A2_kmeans_n_init=1)),
     ('A3', 'covariance centred on the inertia-blended mean instead of the new ML mean', dict(A3_cov_centre='blended_mean')),
-    ('A4a', 'failed Cholesky: eigenvalues floored at 1e-5 and a retry, instead of dropping the position', dict(A4_cholesky_failure='eig_floor')),
-    ('A4b', 'failed Cholesky: covariance shifted by -min(eigenvalue) + 1e-5 on the diagonal and a retry', dict(A4_cholesky_failure='eig_shift')),
+    ('A4a', 'failed Cholesky: eigenvalues floored at 1e-5 and a retry, instead of dropping the position', dict(A4_cholesky_failure='eig_floor', A4_rank_deficient_init='noise')),
+    ('A4b', 'failed Cholesky: covariance shifted by -min(eigenvalue) + 1e-5 on the diagonal and a retry', dict(A4_cholesky_failure='eig_shift', A4_rank_deficient_init='noise')),
+    ('A4c', 'an initial cluster of 1..d rows is NOT failed up front: the sign of the rounding noise in its pivot decides', dict(A4_rank_deficient_init='noise')),
     ('A5', 'zero-width column of the uniform box ignored instead of failing the fit', dict(A5_zero_width_box='widen')),
     # not an assumption: the reference never seeds pomegranate's k-means++ (stats.py:108-113), so two runs of the
     # reference itself differ like two seeds do here -- the noise floor any parity statement has to live with

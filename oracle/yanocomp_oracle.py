@@ -59,7 +59,9 @@ ASSUMPTIONS = {
     'A4': 'a covariance whose Cholesky factorisation fails (non-positive or '
           'non-finite pivot) makes the reference raise LinAlgError (directly '
           'or through the complex-cast bug of stats.py:245-249): the position '
-          'is dropped',
+          'is dropped.  An initial cluster of 1..d rows has an exactly singular '
+          'covariance: its pivot is pure rounding noise in any implementation, '
+          'so the exact-arithmetic outcome (failure) is used',
     'A5': 'UniformDistribution: inclusive bounds, log density -log(hi-lo) '
           'inside and -inf outside; its min/max summaries cannot leave the '
           'initial box so the box is constant during EM; a zero-width box '
@@ -102,6 +104,8 @@ SWITCHES = {
                                          # | 'eig_shift': cov -= min(eigenvalue) I, cov += min_covar I and a retry
                                          #   (two readings of pomegranate's fallback path; in both the position is
                                          #   dropped only if the retry fails too)
+    'A4_rank_deficient_init': 'fail',    # | 'noise': an initial cluster of 1..d rows (exactly singular covariance) is
+                                         #   left to the sign of the rounding noise in the Cholesky pivot
     'A5_zero_width_box': 'fail',         # | 'widen': a zero-width column of the uniform box is ignored
 }
 _DEFAULT_SWITCHES = dict(SWITCHES)
@@ -309,6 +313,9 @@ class MVNormal:
     def from_samples(cls, X):
         '''blank N(0, I) then one fit at inertia 0 (stats.py:150)'''
         d = X.shape[1]
+        if 0 < len(X) <= d and SWITCHES['A4_rank_deficient_init'] == 'fail':
+            # 1..d rows: the ML covariance is exactly singular; whether LAPACK's pivot is +1e-13 or -1e-13 is noise
+            raise FitError('rank-deficient initial cluster')
         dist = cls(np.zeros(d), np.eye(d))
         dist.summarize(X, np.ones(len(X)))
         dist.from_summaries(0.0)

@@ -23,15 +23,17 @@ def test_switch_names_and_defaults_are_restored():
 def test_fixture_sensitivity_to_the_cholesky_and_covariance_assumptions():
     items, n_tested, opts, n_cntrl = sens._gated_fixture_inputs()
     assert n_tested == 3444 and len(items) == 213
-    alts = [a for a in sens.ALTERNATIVES if a[0] in ('A3', 'A4a', 'A4b', 'A5')]
+    alts = [a for a in sens.ALTERNATIVES if a[0] in ('A3', 'A4a', 'A4b', 'A4c', 'A5')]
     rep = sens.measure(items, opts, n_cntrl, alts)
-    assert (rep['fitted_default'], rep['failed_default'], rep['significant_default']) == (125, 88, 39)
+    assert (rep['fitted_default'], rep['failed_default'], rep['significant_default']) == (122, 91, 39)
     rows = {r['assumption']: r for r in rep['rows']}
     # A3 / A5: the alternative reading changes nothing on real data
     for tag in ('A3', 'A5'):
         assert rows[tag]['fit_status_changed'] == 0 and rows[tag]['discordance'] == 0.0
-    # A4 (the riskiest): regularise-and-retry fits all 88 positions the default drops; none of them becomes a call,
+    # A4 (the riskiest): regularise-and-retry fits all 91 positions the default drops; none of them becomes a call,
     # and the larger multiple-testing family costs 2 of the 39 calls (5.1 % discordance) -- the stated bound
     for tag in ('A4a', 'A4b'):
-        assert rows[tag]['fit_status_changed'] == 88 and rows[tag]['calls_gained'] == 0
+        assert rows[tag]['fit_status_changed'] == 91 and rows[tag]['calls_gained'] == 0
         assert rows[tag]['calls_lost'] == 2 and rows[tag]['discordance'] < 0.06
+    # A4c: leaving the 3 rank-deficient starts to the rounding noise of their pivots moves no call
+    assert rows['A4c']['fit_status_changed'] == 3 and rows['A4c']['discordance'] == 0.0

@@ -62,9 +62,7 @@ def test_fixture_ks_bit_exact_and_fits():
         g = index[(str(feat), int(pos))]
         s = slot_of[g]
         counts = gm['label_counts'][k]
-        if ((counts[:2] > 0) & (counts[:2] <= 3)).any():
-            n_skipped += 1          # singular initial covariance: rounding noise decides the outcome
-            continue
+        assert not ((counts[:2] > 0) & (counts[:2] <= 3)).any()     # rank-deficient starts fail on both sides (A4)
         if res.status[g] != N.ST_TESTED:
             n_status += 1
             continue
@@ -75,8 +73,12 @@ def test_fixture_ks_bit_exact_and_fits():
         np.testing.assert_allclose(res.cw[s], gm['cw'][k], rtol=1e-4)
         np.testing.assert_allclose(res.stats[s], gm['stats'][k], rtol=1e-4, atol=1e-12, equal_nan=True)
         n_cmp += 1
-    print(f'compared {n_cmp} fits, skipped {n_skipped} rank-deficient, status mismatches {n_status}')
-    assert n_status == 0 and n_cmp > 80
+    print(f'compared {n_cmp} fits, skipped {n_skipped}, status mismatches {n_status}')
+    assert n_status == 0 and n_skipped == 0 and n_cmp == len(gm['pos']) == 122
+    # ... and every gated position has the oracle's final status (fitted / dropped), 213 of them
+    assert len(gm['gated_pos']) == 213
+    for feat, pos, st in zip(gm['gated_feature'], gm['gated_pos'], gm['gated_status']):
+        assert res.status[index[(str(feat), int(pos))]] == st, (feat, pos)
 
 
 def _parse_bed(text):
