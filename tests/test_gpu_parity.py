@@ -65,6 +65,42 @@ def _rank_deficient_init(o, res, slot, w):
     return False
 
 
+def _soft_mismatch(o, fit, res, s, params, key):
+    '''first tolerance-level mismatch of fitted position `key` (slot s) as (category, detail), or None'''
+    if res.iters[s] != fit.iterations:
+        return 'iters', (key, int(res.iters[s]), fit.iterations)
+    ok = (np.allclose(res.mu[s, 0], fit.dists[0].mu, rtol=PARAM_RTOL, atol=0)
+          and np.allclose(res.mu[s, 1], fit.dists[1].mu, rtol=PARAM_RTOL, atol=0)
+          and np.allclose(res.cov[s, 0], fit.dists[0].cov, rtol=PARAM_RTOL, atol=1e-6)
+          and np.allclose(res.cov[s, 1], fit.dists[1].cov, rtol=PARAM_RTOL, atol=1e-6)
+          and np.allclose(res.cw[s][:len(fit.combined_weights)], fit.combined_weights, rtol=PARAM_RTOL, atol=0)
+          and (params.add_uniform or res.cw[s][2] == 0))
+    if not ok:
+        return 'params', (key, res.mu[s].tolist(), fit.dists[0].mu.tolist(), fit.dists[1].mu.tolist())
+    preds = np.concatenate([fit.cntrl_preds, fit.treat_preds])
+    sizes = np.array([(ob_rows > 0) for ob_rows in res.preds[s].sum(axis=1)])
+    got = res.preds[s][sizes][:, :preds.shape[1]]
+    if got.shape != preds.shape or not np.array_equal(got, preds):
+        return 'preds', (key, got.tolist(), preds.tolist())
+    ref_stats = np.array([o.g_stat, o.hom_g_stat, o.p_val, o.cntrl_frac_mod, o.treat_frac_mod,
+                          o.log_odds, o.log_odds_lower_ci, o.log_odds_upper_ci])
+    if not np.allclose(res.stats[s], ref_stats, rtol=STAT_RTOL, atol=1e-12, equal_nan=True):
+        return 'stats', (key, res.stats[s].tolist(), ref_stats.tolist())
+    if params.generate_sm_preds:
+        # posteriors of every complete-window read under the combined weights, pooled read order
+        has_gpu = res.post_off[s] >= 0
+        if (o.sm_preds is not None) != bool(has_gpu):
+            return 'post', (key, 'presence', o.sm_preds is not None, bool(has_gpu))
+        if has_gpu:
+            ref_post = np.array([[pr, ou] for cond in ('cntrl', 'treat') for rep in sorted(o.sm_preds[cond])
+                                 for pr, ou in zip(o.sm_preds[cond][rep]['preds'], o.sm_preds[cond][rep]['outlier_preds'])])
+            got_post = res.post[res.post_off[s]:res.post_off[s] + res.nall_fit[s]]
+            if got_post.shape != ref_post.shape or not np.allclose(got_post, ref_post, rtol=POST_RTOL, atol=POST_ATOL):
+                return 'post', (key, got_post.shape, ref_post.shape,
+                                float(np.abs(got_post - ref_post).max()) if got_post.shape == ref_post.shape else None)
+    return None
+
+
 def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
     '''
     Runs both paths and returns a report; hard (bit-exact) categories are
@@ -119,58 +155,27 @@ def compare(features, R, Rc, max_fit_discordance=0.0, **kw):
                 continue
             if o.status != yo.ST_TESTED:
                 continue
-            if _rank_deficient_init(o, res, slot_of.get(g), params.window_size):
-                errs['rank_deficient'].append(key)
-                continue
-            n_fit += 1
             s = slot_of[g]
             fit = o.fit
             nrows = len(fit.init_pred)
+            # hard: the initialisation is exact arithmetic
             if not np.array_equal(res.labels[s, :nrows], fit.init_pred):
                 errs['labels'].append((key, int((res.labels[s, :nrows] != fit.init_pred).sum()), nrows))
                 continue
             if params.add_uniform and not (np.array_equal(res.box[s, :, 0], fit.dists[2].lo)
                                            and np.array_equal(res.box[s, :, 1], fit.dists[2].hi)):
                 errs['box'].append(key)
-            if res.iters[s] != fit.iterations:
-                errs['iters'].append((key, int(res.iters[s]), fit.iterations))
-                continue
-            ok = (np.allclose(res.mu[s, 0], fit.dists[0].mu, rtol=PARAM_RTOL, atol=0)
-                  and np.allclose(res.mu[s, 1], fit.dists[1].mu, rtol=PARAM_RTOL, atol=0)
-                  and np.allclose(res.cov[s, 0], fit.dists[0].cov, rtol=PARAM_RTOL, atol=1e-6)
-                  and np.allclose(res.cov[s, 1], fit.dists[1].cov, rtol=PARAM_RTOL, atol=1e-6)
-                  and np.allclose(res.cw[s][:len(fit.combined_weights)], fit.combined_weights, rtol=PARAM_RTOL, atol=0)
-                  and (params.add_uniform or res.cw[s][2] == 0))
-            if not ok:
-                errs['params'].append((key, res.mu[s].tolist(), fit.dists[0].mu.tolist(), fit.dists[1].mu.tolist()))
-                continue
-            preds = np.concatenate([fit.cntrl_preds, fit.treat_preds])
-            sizes = np.array([(ob_rows > 0) for ob_rows in res.preds[s].sum(axis=1)])
-            got = res.preds[s][sizes][:, :preds.shape[1]]
-            if got.shape != preds.shape or not np.array_equal(got, preds):
-                errs['preds'].append((key, got.tolist(), preds.tolist()))
-                continue
-            ref_stats = np.array([o.g_stat, o.hom_g_stat, o.p_val, o.cntrl_frac_mod, o.treat_frac_mod,
-                                  o.log_odds, o.log_odds_lower_ci, o.log_odds_upper_ci])
-            if not np.allclose(res.stats[s], ref_stats, rtol=STAT_RTOL, atol=1e-12, equal_nan=True):
-                errs['stats'].append((key, res.stats[s].tolist(), ref_stats.tolist()))
-                continue
-            if params.generate_sm_preds:
-                # posteriors of every complete-window read under the combined weights, pooled read order
-                has_gpu = res.post_off[s] >= 0
-                if (o.sm_preds is not None) != bool(has_gpu):
-                    errs['post'].append((key, 'presence', o.sm_preds is not None, bool(has_gpu)))
-                elif has_gpu:
-                    ref_post = np.array([[pr, ou] for cond in ('cntrl', 'treat') for rep in sorted(o.sm_preds[cond])
-                                         for pr, ou in zip(o.sm_preds[cond][rep]['preds'],
-                                                           o.sm_preds[cond][rep]['outlier_preds'])])
-                    got_post = res.post[res.post_off[s]:res.post_off[s] + res.nall_fit[s]]
-                    n_post += 1
-                    if got_post.shape != ref_post.shape or not np.allclose(got_post, ref_post, rtol=POST_RTOL,
-                                                                           atol=POST_ATOL):
-                        errs['post'].append((key, got_post.shape, ref_post.shape,
-                                             float(np.abs(got_post - ref_post).max())
-                                             if got_post.shape == ref_post.shape else None))
+            # soft: EM and everything computed from it.  A mismatch on a fit whose component collapsed onto a
+            # numerically singular covariance is chaos, not a defect: counted apart and bounded below.
+            bad = _soft_mismatch(o, fit, res, s, params, key)
+            if bad is None:
+                n_fit += 1
+                n_post += bool(params.generate_sm_preds and res.post_off[s] >= 0)
+            elif _rank_deficient_init(o, res, s, params.window_size):
+                errs['rank_deficient'].append(key)
+            else:
+                n_fit += 1
+                errs[bad[0]].append(bad[1])
     summary = {k: len(v) for k, v in errs.items()}
     print(f'windows={n_windows} fitted={n_fit} posteriors={n_post} mismatches={summary}')
     for k, v in errs.items():

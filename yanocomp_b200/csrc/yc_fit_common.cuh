@@ -42,10 +42,6 @@ __device__ __noinline__ bool ml_gaussian(const double *S, double *mu, double *co
         for (int a = 0; a < W; ++a) { mu[a] = 0.0; for (int c2 = 0; c2 < W; ++c2) cov[a * W + c2] = (a == c2) ? 1.0 : 0.0; }
         return true;
     }
-    // A cluster of 1..W rows has an EXACTLY singular ML covariance: whether its Cholesky pivot comes out as +1e-13
-    // or -1e-13 is rounding noise (in LAPACK too), and EM started from such a matrix is chaotic.  The exact-arithmetic
-    // answer is used instead of the noise: the fit fails (assumption A4, oracle switch A4_rank_deficient_init).
-    if (s0 <= (double)W) return false;
     double u[W];
     #pragma unroll 1
     for (int a = 0; a < W; ++a) u[a] = div_rn(S[1 + a], s0);
@@ -63,6 +59,10 @@ __device__ __noinline__ bool ml_gaussian(const double *S, double *mu, double *co
     // inertia 0 blend: old*0 + new*1
     #pragma unroll 1
     for (int a = 0; a < W; ++a) mu[a] = u[a];
+    // A cluster of 1..W rows has an EXACTLY singular ML covariance: whether its Cholesky pivot comes out as +1e-13
+    // or -1e-13 is rounding noise (in LAPACK too), and EM started from such a matrix is chaotic.  The exact-arithmetic
+    // answer is used instead of the noise: the fit fails (assumption A4, oracle switch A4_rank_deficient_init).
+    if (s0 <= (double)W) return false;
     double linv[W * W], logdet;
     return cholesky_inverse<W>(cov, linv, logdet);
 }
