@@ -244,7 +244,8 @@ def run_gpu(args, cfg, opts_kw):
     ms_resident = start.elapsed_time(stop)
     launches = out['launches'] * args.steps
     n_tested = int((out['status'][:host.total_cols] != 0).sum().item())
-    n_fit = int(out['fit_list'].numel())
+    n_fit = int(out['fit_count'].item())                   # the count never left the device during the timed region
+    assert n_fit <= out['capacity'], (n_fit, out['capacity'])
     iters = out['iters'][:max(n_fit, 1)].double()
     mean_iters = float(iters.mean().item()) if n_fit else 0.0
     iters_q = ([float(x) for x in torch.quantile(iters, torch.tensor([0.5, 0.9, 0.99, 0.999, 1.0], dtype=torch.float64,

@@ -162,6 +162,16 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
                 void *stream);
 
 /*
+ * The fit stages take the gated positions as (fit_list, n_fit, fit_count):
+ * slots [0, min(n_fit, *fit_count)) are processed.  `fit_count` is the DEVICE
+ * counter yc_ks_batch wrote, so a caller can queue the three stages right behind
+ * yc_ks_batch without waiting for the count on the host: n_fit is then only an
+ * upper bound (the capacity of the slot-indexed outputs, at most total_cols).
+ * fit_count = NULL means "exactly n_fit slots".  The small-window kernels are
+ * persistent (every warp of the grid fetches the next slot from a device
+ * counter), so an upper bound costs nothing; the general kernels launch n_fit
+ * CTAs of which the surplus exits at once.
+ *
  * Stage 2a -- model initialisation, one warp or CTA per gated position.  Replaces
  * the per-replicate subsample of fit_gmm (stats.py:266-269),
  * kmeans_init_clusters (stats.py:81-124: pm.Kmeans k-means++ x3, MAD or DBSCAN
@@ -172,7 +182,7 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
  * in pooled fit order, for parity tests.
  */
 int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p,
-                      const int32_t *fit_list, int32_t n_fit,
+                      const int32_t *fit_list, int32_t n_fit, const int32_t *fit_count,
                       yc_fit_out_t *out, uint8_t *status,
                       int8_t *labels, int32_t max_fit_rows, void *stream);
 
@@ -186,7 +196,7 @@ int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p,
  * for yc_gtest_smpred_batch, which replaces it with the rounded counts.
  */
 int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p,
-                    const int32_t *fit_list, int32_t n_fit,
+                    const int32_t *fit_list, int32_t n_fit, const int32_t *fit_count,
                     yc_fit_out_t *out, uint8_t *status, void *stream);
 
 /*
@@ -201,25 +211,42 @@ int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p,
  * int64, zeroed by the call) counts reads written; post_capacity is in reads.
  */
 int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p,
-                          const int32_t *fit_list, int32_t n_fit,
+                          const int32_t *fit_list, int32_t n_fit, const int32_t *fit_count,
                           yc_fit_out_t *out, const uint8_t *status,
                           double *post, int64_t post_capacity,
                           int64_t *post_cursor, void *stream);
 
 /*
- * Result rows in slot order (one launch): for every gated position its final
- * status, KS D (GMMTestResults.ks_stat, stats.py:442), the device KS p-value
- * and the control / total complete-window read counts (what the host needs
- * to re-decide a p-value that sits within YC_KS_P_GUARD of the threshold,
- * stats.py:465) and dist1_stds / dist2_stds = sqrt(diag(cov))
- * (stats.py:277-280), so that a caller fetches contiguous per-fit rows
- * instead of gathering on the host.  stds [n_fit*2*w], the others [n_fit].
+ * Fixed-width result rows in slot order (one launch): everything the host
+ * tail (GMMTestResults, stats.py:423-442; the records of gmmtest.py:164-172)
+ * reads per gated position as one row of YC_ROW_WIDTH(w) doubles, so that a
+ * shard's results are ONE contiguous device->host copy and one fixed-width
+ * block in the multi-GPU gather.  Row layout:
+ *   [YC_ROW_STATUS]   final status (YC_ST_TESTED / YC_ST_FIT_FAILED)
+ *   [YC_ROW_KS_STAT]  KS D (GMMTestResults.ks_stat)
+ *   [YC_ROW_KS_PVAL]  device KS p-value: serves the gate only; the host
+ *                     re-decides values within YC_KS_P_GUARD of the threshold
+ *                     with SciPy (stats.py:465) from the two counts below
+ *   [YC_ROW_N_CNTRL]  complete-window control rows, [YC_ROW_N_ALL] all rows
+ *   [YC_ROW_COLUMN]   global column index (= fit_list[slot])
+ *   [YC_ROW_STATS..+8] g, hom_g, p, cntrl_frac, treat_frac, log_odds, lower, upper
+ *   [YC_ROW_MU..+2w]   dist1_means, dist2_means          (stats.py:277-280)
+ *   [YC_ROW_MU+2w..+2w] dist1_stds, dist2_stds = sqrt(diag(cov))
+ * rows [n_fit * YC_ROW_WIDTH(w)]; slots [0, min(n_fit, *fit_count)) are written.
  */
-int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, int32_t window_size,
+#define YC_ROW_STATUS   0
+#define YC_ROW_KS_STAT  1
+#define YC_ROW_KS_PVAL  2
+#define YC_ROW_N_CNTRL  3
+#define YC_ROW_N_ALL    4
+#define YC_ROW_COLUMN   5
+#define YC_ROW_STATS    6
+#define YC_ROW_MU       14
+#define YC_ROW_WIDTH(w) (14 + 4 * (w))
+int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, const int32_t *fit_count, int32_t window_size,
                        const uint8_t *status, const double *ks_stat, const double *ks_pval,
-                       const int32_t *n_c, const int32_t *n_t, const double *cov,
-                       uint8_t *status_fit, double *ks_stat_fit, double *ks_pval_fit,
-                       double *stds, int32_t *nc_fit, int32_t *nall_fit, void *stream);
+                       const int32_t *n_c, const int32_t *n_t, const yc_fit_out_t *out,
+                       double *rows, void *stream);
 
 /*
  * Stages 2a + 2b + 3 back to back on one stream (convenience; same outputs
@@ -232,7 +259,7 @@ int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, int32_t window_si
  * the environment force the general kernels.
  */
 int yc_gmm_fit_batch(const yc_batch_t *b, const yc_params_t *p,
-                     const int32_t *fit_list, int32_t n_fit,
+                     const int32_t *fit_list, int32_t n_fit, const int32_t *fit_count,
                      yc_fit_out_t *out, uint8_t *status,
                      int8_t *labels, int32_t max_fit_rows,
                      double *post, int64_t post_capacity,

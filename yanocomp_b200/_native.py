@@ -18,6 +18,13 @@ ST_NOT_A_WINDOW, ST_KS_FILTERED, ST_TESTED, ST_FIT_FAILED, ST_DEGENERATE, ST_KS_
 
 YC_EINVAL, YC_ECAPACITY, YC_ENOGPU = -1, -2, -3
 YC_COV_FULL, YC_COV_DIAG = 0, 1
+# fixed-width result rows of yc_gather_fit_rows (include/yanocomp_b200.h)
+ROW_STATUS, ROW_KS_STAT, ROW_KS_PVAL, ROW_N_CNTRL, ROW_N_ALL, ROW_COLUMN, ROW_STATS, ROW_MU = 0, 1, 2, 3, 4, 5, 6, 14
+
+
+def row_width(w):
+    return 14 + 4 * w
+
 YC_OUTLIER_MAD, YC_OUTLIER_DBSCAN = 0, 1
 
 
@@ -68,14 +75,15 @@ _PROTOTYPES = {
     'yc_smem_bytes': (C.c_int, [_P(Batch), _P(Params), _P(C.c_int64)]),
     'yc_fill_col_feature': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'yc_ks_batch': (C.c_int, [_P(Batch), _P(Params)] + [C.c_void_p] * 8),
-    'yc_gmm_init_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut),
+    # (fit_list, n_fit, fit_count): fit_count = device int32 written by yc_ks_batch, or None for exactly n_fit slots
+    'yc_gmm_init_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, C.c_void_p, _P(FitOut),
                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
-    'yc_gmm_em_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut),
+    'yc_gmm_em_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, C.c_void_p, _P(FitOut),
                                   C.c_void_p, C.c_void_p]),
-    'yc_gtest_smpred_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut),
+    'yc_gtest_smpred_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, C.c_void_p, _P(FitOut),
                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    'yc_gather_fit_rows': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 13),
-    'yc_gmm_fit_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, _P(FitOut), C.c_void_p,
+    'yc_gather_fit_rows': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + [_P(FitOut), C.c_void_p, C.c_void_p]),
+    'yc_gmm_fit_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, C.c_void_p, _P(FitOut), C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'yc_kolmogorov_sf_host': (C.c_double, [C.c_double]),
     'yc_chi2_sf_1dof_host': (C.c_double, [C.c_double]),

@@ -181,27 +181,33 @@ int compact_gated(const uint8_t *status, long long n, int32_t *fit_list, int32_t
     return (int)(e != cudaSuccess ? e : e2);
 }
 
-// result rows of the gated positions in slot order: what the host tail reads per fit
-// (status, KS D, sqrt of the covariance diagonals = dist*_stds of stats.py:277-280, complete-window rows)
-__global__ void gather_fit_rows_kernel(const int32_t *__restrict__ fit_list, int n_fit, int w,
+// Fixed-width result rows of the gated positions in slot order: everything the host tail reads per fit as ONE
+// row of YC_ROW_WIDTH(w) doubles (layout in include/yanocomp_b200.h), so that a shard's results are a single
+// contiguous device->host copy and a single fixed-width block in the multi-GPU gather.
+__global__ void gather_fit_rows_kernel(const int32_t *__restrict__ fit_list, int n_fit,
+                                       const int32_t *__restrict__ fit_count, int w,
                                        const uint8_t *__restrict__ status, const double *__restrict__ ks_stat,
                                        const double *__restrict__ ks_pval,
                                        const int32_t *__restrict__ n_c, const int32_t *__restrict__ n_t,
-                                       const double *__restrict__ cov,
-                                       uint8_t *__restrict__ status_fit, double *__restrict__ ks_stat_fit,
-                                       double *__restrict__ ks_pval_fit, double *__restrict__ stds,
-                                       int32_t *__restrict__ nc_fit, int32_t *__restrict__ nall_fit) {
+                                       const double *__restrict__ mu, const double *__restrict__ cov,
+                                       const double *__restrict__ stats, double *__restrict__ rows) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_fit) return;
+    if (slot >= n_fit || (fit_count != nullptr && slot >= *fit_count)) return;
     const int g = fit_list[slot];
-    status_fit[slot] = status[g];
-    ks_stat_fit[slot] = ks_stat[g];
-    ks_pval_fit[slot] = ks_pval[g];
-    nc_fit[slot] = n_c[g];
-    nall_fit[slot] = n_c[g] + n_t[g];
+    const int rw = YC_ROW_WIDTH(w);
+    double *r = rows + (size_t)slot * rw;
+    r[YC_ROW_STATUS] = (double)status[g];
+    r[YC_ROW_KS_STAT] = ks_stat[g];
+    r[YC_ROW_KS_PVAL] = ks_pval[g];
+    r[YC_ROW_N_CNTRL] = (double)n_c[g];
+    r[YC_ROW_N_ALL] = (double)(n_c[g] + n_t[g]);
+    r[YC_ROW_COLUMN] = (double)g;
+    for (int k = 0; k < 8; ++k) r[YC_ROW_STATS + k] = stats[(size_t)slot * 8 + k];
     for (int k = 0; k < 2; ++k)
-        for (int a = 0; a < w; ++a)
-            stds[((size_t)slot * 2 + k) * w + a] = sqrt(cov[(((size_t)slot * 2 + k) * w + a) * w + a]);
+        for (int a = 0; a < w; ++a) {
+            r[YC_ROW_MU + k * w + a] = mu[((size_t)slot * 2 + k) * w + a];
+            r[YC_ROW_MU + 2 * w + k * w + a] = sqrt(cov[(((size_t)slot * 2 + k) * w + a) * w + a]);
+        }
 }
 
 template <int D>
@@ -288,33 +294,33 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
 }
 
 int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
-                      yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows, void *stream) {
+                      const int32_t *fit_count, yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows, void *stream) {
     if (int e = check_common(b, p)) return e;
     if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_init_batch: null pointer");
     if (n_fit <= 0) return 0;
     if (use_warp_fit(*b, *p))
-        return cuda_fail(yc::init_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows,
+        return cuda_fail(yc::init_warp_dispatch(*b, *p, fit_list, n_fit, fit_count, *out, status, labels, max_fit_rows,
                                                 (cudaStream_t)stream), "yc_gmm_init_batch (warp path)");
     if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 0), "yc_gmm_init_batch")) return e;
-    return cuda_fail(yc::init_dispatch(*b, *p, fit_list, n_fit, *out, status, labels, max_fit_rows,
+    return cuda_fail(yc::init_dispatch(*b, *p, fit_list, n_fit, fit_count, *out, status, labels, max_fit_rows,
                                        (cudaStream_t)stream), "yc_gmm_init_batch");
 }
 
 int yc_gmm_em_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
-                    yc_fit_out_t *out, uint8_t *status, void *stream) {
+                    const int32_t *fit_count, yc_fit_out_t *out, uint8_t *status, void *stream) {
     if (int e = check_common(b, p)) return e;
     if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gmm_em_batch: null pointer");
     if (n_fit <= 0) return 0;
     if (use_warp_fit(*b, *p))
-        return cuda_fail(yc::em_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
+        return cuda_fail(yc::em_warp_dispatch(*b, *p, fit_list, n_fit, fit_count, *out, status, (cudaStream_t)stream),
                          "yc_gmm_em_batch (warp path)");
     if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 1), "yc_gmm_em_batch")) return e;
-    return cuda_fail(yc::em_dispatch(*b, *p, fit_list, n_fit, *out, status, (cudaStream_t)stream),
+    return cuda_fail(yc::em_dispatch(*b, *p, fit_list, n_fit, fit_count, *out, status, (cudaStream_t)stream),
                      "yc_gmm_em_batch");
 }
 
 int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
-                          yc_fit_out_t *out, const uint8_t *status, double *post, int64_t post_capacity,
+                          const int32_t *fit_count, yc_fit_out_t *out, const uint8_t *status, double *post, int64_t post_capacity,
                           int64_t *post_cursor, void *stream) {
     if (int e = check_common(b, p)) return e;
     if (!out || !fit_list || !status) return fail(YC_EINVAL, "yc_gtest_smpred_batch: null pointer");
@@ -326,34 +332,31 @@ int yc_gtest_smpred_batch(const yc_batch_t *b, const yc_params_t *p, const int32
     }
     if (n_fit <= 0) return 0;
     if (use_warp_fit(*b, *p))
-        return cuda_fail(yc::gtest_warp_dispatch(*b, *p, fit_list, n_fit, *out, status, post, post_capacity,
+        return cuda_fail(yc::gtest_warp_dispatch(*b, *p, fit_list, n_fit, fit_count, *out, status, post, post_capacity,
                                                  post_cursor, st), "yc_gtest_smpred_batch (warp path)");
     if (int e = check_smem(yc::fit_smem_bytes(*b, *p, 2), "yc_gtest_smpred_batch")) return e;
-    return cuda_fail(yc::gtest_dispatch(*b, *p, fit_list, n_fit, *out, status, post, post_capacity,
+    return cuda_fail(yc::gtest_dispatch(*b, *p, fit_list, n_fit, fit_count, *out, status, post, post_capacity,
                                         post_cursor, st), "yc_gtest_smpred_batch");
 }
 
-int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, int32_t window_size, const uint8_t *status,
-                       const double *ks_stat, const double *ks_pval, const int32_t *n_c, const int32_t *n_t,
-                       const double *cov, uint8_t *status_fit, double *ks_stat_fit, double *ks_pval_fit,
-                       double *stds, int32_t *nc_fit, int32_t *nall_fit, void *stream) {
+int yc_gather_fit_rows(const int32_t *fit_list, int32_t n_fit, const int32_t *fit_count, int32_t window_size,
+                       const uint8_t *status, const double *ks_stat, const double *ks_pval,
+                       const int32_t *n_c, const int32_t *n_t, const yc_fit_out_t *out, double *rows, void *stream) {
     if (n_fit <= 0) return 0;
-    if (!fit_list || !status || !ks_stat || !ks_pval || !n_c || !n_t || !cov || !status_fit || !ks_stat_fit ||
-        !ks_pval_fit || !stds || !nc_fit || !nall_fit)
+    if (!fit_list || !status || !ks_stat || !ks_pval || !n_c || !n_t || !out || !out->mu || !out->cov || !out->stats || !rows)
         return fail(YC_EINVAL, "yc_gather_fit_rows: null pointer");
     gather_fit_rows_kernel<<<(n_fit + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        fit_list, n_fit, window_size, status, ks_stat, ks_pval, n_c, n_t, cov, status_fit, ks_stat_fit, ks_pval_fit,
-        stds, nc_fit, nall_fit);
+        fit_list, n_fit, fit_count, window_size, status, ks_stat, ks_pval, n_c, n_t, out->mu, out->cov, out->stats, rows);
     yc::count_launches(1);
     return cuda_fail((int)cudaGetLastError(), "yc_gather_fit_rows");
 }
 
 int yc_gmm_fit_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
-                     yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows,
+                     const int32_t *fit_count, yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows,
                      double *post, int64_t post_capacity, int64_t *post_cursor, void *stream) {
-    if (int e = yc_gmm_init_batch(b, p, fit_list, n_fit, out, status, labels, max_fit_rows, stream)) return e;
-    if (int e = yc_gmm_em_batch(b, p, fit_list, n_fit, out, status, stream)) return e;
-    return yc_gtest_smpred_batch(b, p, fit_list, n_fit, out, status, post, post_capacity, post_cursor, stream);
+    if (int e = yc_gmm_init_batch(b, p, fit_list, n_fit, fit_count, out, status, labels, max_fit_rows, stream)) return e;
+    if (int e = yc_gmm_em_batch(b, p, fit_list, n_fit, fit_count, out, status, stream)) return e;
+    return yc_gtest_smpred_batch(b, p, fit_list, n_fit, fit_count, out, status, post, post_capacity, post_cursor, stream);
 }
 
 // ---- host-side scalar entry points: the same __host__ __device__ code the

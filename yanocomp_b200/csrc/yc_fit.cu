@@ -203,7 +203,7 @@ __device__ __forceinline__ int nth_inlier(const int8_t *lab, int i0c, int i1c, i
 template <int W>
 __global__ void __launch_bounds__(YC_BLOCK, YC_INITC_MINBLOCKS)
 gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
-                const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+                const int32_t *__restrict__ fit_list, const int32_t *__restrict__ fit_count, const yc_fit_out_t out,
                 uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = b.n_samples, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -214,6 +214,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     int8_t *lab = reinterpret_cast<int8_t *>(smem_raw + L.lab_off);
     int *ired = reinterpret_cast<int *>(red);
     const int slot = blockIdx.x;
+    if (fit_count != nullptr && slot >= *fit_count) return;            // the grid is an upper bound: the count lives on the device
     const int64_t g = fit_list[slot];
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
 
@@ -551,7 +552,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 template <int W>
 __global__ void __launch_bounds__(YC_BLOCK, YC_EMC_MINBLOCKS)
 gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
-              const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+              const int32_t *__restrict__ fit_list, const int32_t *__restrict__ fit_count, const yc_fit_out_t out,
               uint8_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = b.n_samples, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -562,6 +563,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     double *carry = part + YC_NWARPS * NP;
     double *wsum = reinterpret_cast<double *>(smem_raw + L.wsum_off);    // [NWARPS][R][3]
     const int slot = blockIdx.x;
+    if (fit_count != nullptr && slot >= *fit_count) return;            // the grid is an upper bound: the count lives on the device
     const int64_t g = fit_list[slot];
     if (status[g] != YC_ST_GATED) return;                                // init failed
 
@@ -790,7 +792,7 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 template <int W>
 __global__ void __launch_bounds__(YC_BLOCK)
 gtest_smpred_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
-                    const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
+                    const int32_t *__restrict__ fit_list, const int32_t *__restrict__ fit_count, const yc_fit_out_t out,
                     const uint8_t *__restrict__ status, double *__restrict__ post,
                     const long long post_capacity, unsigned long long *__restrict__ post_cursor) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -799,6 +801,7 @@ gtest_smpred_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     EmPar<W> *par = reinterpret_cast<EmPar<W> *>(smem_raw + L.par_off);
     long long *soff = reinterpret_cast<long long *>(smem_raw + L.sel_off);
     const int slot = blockIdx.x;
+    if (fit_count != nullptr && slot >= *fit_count) return;            // the grid is an upper bound: the count lives on the device
     const int64_t g = fit_list[slot];
     if (status[g] != YC_ST_TESTED) {                                     // failed fit: no row
         if (tid == 0) out.post_off[slot] = -1;
@@ -921,7 +924,7 @@ int fit_smem_bytes(const yc_batch_t &b, const yc_params_t &p, int which) {
 }
 
 int init_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                  const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st) {
+                  const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st) {
     if (n_fit <= 0) return 0;
     const int cap = fit_cap(b, p);
     const int smem = fit_smem_bytes(b, p, 0);
@@ -929,14 +932,14 @@ int init_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(gmm_init_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        gmm_init_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
+        gmm_init_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, fit_count, out, status, labels, max_fit_rows);
         count_launches(1);
         return (int)cudaGetLastError();
     });
 }
 
 int em_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
+                const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
     if (n_fit <= 0) return 0;
     const int cap = fit_cap(b, p);
     const int smem = fit_smem_bytes(b, p, 1);
@@ -944,14 +947,14 @@ int em_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_li
         constexpr int W_ = decltype(tag)::value;
         cudaError_t e = cudaFuncSetAttribute(gmm_em_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        gmm_em_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, out, status);
+        gmm_em_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(b, p, cap, fit_list, fit_count, out, status);
         count_launches(1);
         return (int)cudaGetLastError();
     });
 }
 
 int gtest_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                   const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
+                   const int32_t *fit_count, const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
                    int64_t *post_cursor, cudaStream_t st) {
     if (n_fit <= 0) return 0;
     const int cap = fit_cap(b, p);
@@ -961,7 +964,7 @@ int gtest_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit
         cudaError_t e = cudaFuncSetAttribute(gtest_smpred_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         gtest_smpred_kernel<W_><<<n_fit, YC_BLOCK, smem, st>>>(
-            b, p, cap, fit_list, out, status, post, (long long)post_capacity,
+            b, p, cap, fit_list, fit_count, out, status, post, (long long)post_capacity,
             reinterpret_cast<unsigned long long *>(post_cursor));
         count_launches(1);
         return (int)cudaGetLastError();

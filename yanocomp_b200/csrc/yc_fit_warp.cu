@@ -26,6 +26,37 @@
 
 namespace yc {
 
+// Scheduling (round 2): PERSISTENT warps.  A kernel is launched with as many one-warp CTAs as the device holds at
+// once, and every warp fetches the next unprocessed slot of fit_list from a device counter until the list is
+// exhausted.  Compared with one CTA per position this pays no CTA launch per position, still balances the very
+// uneven EM lengths dynamically, and lets the number of gated positions stay ON THE DEVICE (*fit_count, written by
+// yc_ks_batch): the host never waits for it.
+// The CTA stays ONE warp, and the fetched slot travels through shared memory, on purpose: the compiler's divergence
+// analysis treats an atomic's result (and anything shuffled from it, and threadIdx.x >> 5) as thread-varying, and
+// then guards every __shfl_sync / __ballot_sync of the per-position program with a BRA.DIV slow path (a four-warp
+// variant of the init kernel grew from 3 352 to 4 560 instructions and ran 11 % slower).  A value loaded from a
+// uniform shared-memory address is provably warp-uniform, so the per-position code compiles as it did when the
+// slot was blockIdx.x.
+#define YC_FW_WARPS 1
+
+__device__ __forceinline__ int fw_next_slot(int *work, int lane) {
+    __shared__ int s_slot;
+    if (lane == 0) s_slot = atomicAdd(work, 1);
+    __syncwarp();
+    const int s = s_slot;
+    __syncwarp();
+    return s;
+}
+// A kernel parameter re-read through an empty asm: the optimiser cannot prove it invariant over the persistent
+// loop, so it does not clone the whole per-position program once per value of the flag (loop unswitching made the
+// init kernel 36 % larger, and these kernels live or die by their instruction-cache footprint).
+__device__ __forceinline__ int fw_opaque(int v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ int fw_slot_count(int n_fit, const int32_t *fit_count) {
+    if (fit_count == nullptr) return n_fit;
+    const int c = *fit_count;
+    return c < n_fit ? c : n_fit;
+}
+
 struct FwSmem {
     int xs_off, srow_off, lab_off, buf_off, par_off, mask_off, cnt_off, fstart_off, wtmp_off, carry_off, red_off, total;
 };
@@ -221,16 +252,15 @@ __device__ __forceinline__ bool fw_front(const yc_batch_t &b, const yc_params_t 
 // than 512 rows (warp_sort_long).  A template parameter because merely carrying the other sort variants' code
 // made the kernel slower (3.49 -> 3.63 ms on cfg2 with the long sort's 2 100 unexecuted instructions).
 template <int W, int SE>
-__global__ void __launch_bounds__(32, YC_FW_INIT_MINBLOCKS)
-init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
-                 const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
-                 uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R = b.n_samples, lane = threadIdx.x;
-    const FwSmem L = fw_layout(W, R, cap, 0);
+__device__ __forceinline__ void
+init_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, const int slot,
+                   const int32_t *__restrict__ fit_list, const yc_fit_out_t &out,
+                   uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows,
+                   unsigned char *smem_raw, const FwSmem &L, const int lane) {
+    const int R = b.n_samples;
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
-    const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
+    const bool add_uniform = fw_opaque(p.add_uniform) != 0, want_labels = fw_opaque(labels_out != nullptr) != 0;
     FwCtx<W> c;
     if (!fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c)) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
     const int n = c.n;
@@ -353,7 +383,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 
     // ---- nearest-centroid labels; MAD outliers unless --no-uniform (stats.py:114-122, A1)
     int n_out = 0;
-    if (!p.add_uniform) {
+    if (!add_uniform) {
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) {
             double x[W];
@@ -415,7 +445,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     n_out = warp_sum_i(n_out);
     __syncwarp();
     }
-    if (labels_out)
+    if (want_labels)
         for (int i = lane; i < n && i < max_fit_rows; i += 32) labels_out[(size_t)slot * max_fit_rows + i] = lab[i];
 
     // ---- ML Gaussians per label from exact sufficient statistics (stats.py:148-152)
@@ -487,7 +517,7 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 #pragma unroll
         for (int j = 0; j < W; ++j) {
             lo[j] = warp_min(lo[j]); hi[j] = warp_max(hi[j]);
-            if (p.add_uniform) ok_all &= hi[j] > lo[j];
+            if (add_uniform) ok_all &= hi[j] > lo[j];
             if (lane == 0) { out.box[((size_t)slot * W + j) * 2] = lo[j]; out.box[((size_t)slot * W + j) * 2 + 1] = hi[j]; }
         }
     }
@@ -503,13 +533,31 @@ init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             double v = 0.0;
             if (e > a) {
                 const int kk = lane == 0 ? k0 : (lane == 1 ? k1 : (e - a) - k0 - k1);
-                v = log(((double)kk + 0.5) / ((double)(e - a) + (p.add_uniform ? 1.5 : 1.0)));
-                if (lane == 2 && !p.add_uniform) v = -INFINITY;       // two-component model
+                v = log(((double)kk + 0.5) / ((double)(e - a) + (add_uniform ? 1.5 : 1.0)));
+                if (lane == 2 && !add_uniform) v = -INFINITY;       // two-component model
             }
             out.logw[((size_t)slot * R + s) * 3 + lane] = v;
         }
     }
     if (lane == 0 && !ok_all) status[g] = YC_ST_FIT_FAILED;
+}
+
+template <int W, int SE>
+__global__ void __launch_bounds__(32 * YC_FW_WARPS, YC_FW_INIT_MINBLOCKS / YC_FW_WARPS)
+init_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+                 const int32_t *__restrict__ fit_list, const int n_fit, const int32_t *__restrict__ fit_count,
+                 int *__restrict__ work, const yc_fit_out_t out,
+                 uint8_t *__restrict__ status, int8_t *__restrict__ labels_out, const int max_fit_rows) {
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int lane = threadIdx.x;
+    const FwSmem L = fw_layout(W, b.n_samples, cap, 0);
+    unsigned char *smem_raw = smem_all;
+    const int n = fw_slot_count(n_fit, fit_count);
+#pragma unroll 1
+    for (int slot = fw_next_slot(work, lane); slot < n; slot = fw_next_slot(work, lane)) {
+        init_warp_position<W, SE>(b, p, cap, slot, fit_list, out, status, labels_out, max_fit_rows, smem_raw, L, lane);
+        __syncwarp();
+    }
 }
 
 // ===========================================================================
@@ -652,14 +700,12 @@ constexpr int kEmUnroll1 = YC_EM_UNROLL1, kEmUnroll2 = YC_EM_UNROLL2;
 #endif
 
 template <int W>
-__global__ void __launch_bounds__(32, YC_FW_MINBLOCKS)
-em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
-               const int32_t *__restrict__ fit_list, const yc_fit_out_t out, uint8_t *__restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R = b.n_samples, lane = threadIdx.x;
-    const FwSmem L = fw_layout(W, R, cap, 1);
+__device__ __forceinline__ void
+em_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, const int slot,
+                 const int32_t *__restrict__ fit_list, const yc_fit_out_t &out, uint8_t *__restrict__ status,
+                 unsigned char *smem_raw, const FwSmem &L, const int lane) {
+    const int R = b.n_samples;
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT, NP = 2 * NS + 1;
-    const int slot = blockIdx.x;
     const int64_t g = fit_list[slot];
     if (status[g] != YC_ST_GATED) return;                               // the initialisation failed
     FwCtx<W> c;
@@ -673,7 +719,7 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     const int *fstart = c.fstart;
     load_model<W>(par, out, slot, lane, out.logw + (size_t)slot * R * 3, R * 3);
     bool failed = par->ok == 0;
-    const bool uni = p.add_uniform != 0;
+    const bool uni = fw_opaque(p.add_uniform) != 0;
 
     double *carry = reinterpret_cast<double *>(smem_raw + L.carry_off);   // [2][NS]: summaries kept when S0 < 1e-7 (A3)
     for (int q = lane; q < 2 * NS; q += 32) carry[q] = 0.0;
@@ -745,7 +791,15 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         llsum += log(seprod);
         // ---- bookkeeping of em() BEFORE the statistics pass: the summaries of the last E-step are discarded
         //      (stats.py:224), so when this E-step ends the loop the second pass is not run at all
-        const double ll = warp_sum(llsum);
+        // the total goes through shared memory: a value loaded from a uniform address is provably warp-uniform, so
+        // the loop conditions below are uniform branches and the shuffles / ballots of the loop body need no
+        // divergence guards (a shuffled value counts as thread-varying in the compiler's analysis)
+        {
+            const double t = warp_sum(llsum);
+            if (lane == 0) par->ll = t;
+        }
+        __syncwarp();
+        const double ll = par->ll;
         if (iteration > 0) improvement = ll - last;
         ++iteration;
         last = ll;
@@ -852,20 +906,36 @@ em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     for (int i = lane; i < R * 3; i += 32) out.logw[(size_t)slot * R * 3 + i] = par->logw[i / 3][i % 3];
 }
 
+template <int W>
+__global__ void __launch_bounds__(32 * YC_FW_WARPS, YC_FW_MINBLOCKS / YC_FW_WARPS)
+em_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+               const int32_t *__restrict__ fit_list, const int n_fit, const int32_t *__restrict__ fit_count,
+               int *__restrict__ work, const yc_fit_out_t out, uint8_t *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int lane = threadIdx.x;
+    const FwSmem L = fw_layout(W, b.n_samples, cap, 1);
+    unsigned char *smem_raw = smem_all;
+    const int n = fw_slot_count(n_fit, fit_count);
+#pragma unroll 1
+    for (int slot = fw_next_slot(work, lane); slot < n; slot = fw_next_slot(work, lane)) {
+        em_warp_position<W>(b, p, cap, slot, fit_list, out, status, smem_raw, L, lane);
+        __syncwarp();
+    }
+}
+
 // ===========================================================================
 // Kernel 3 (warp): rounded counts, G-tests, fractions, posteriors
 // ===========================================================================
 template <int W>
-__global__ void __launch_bounds__(32)
-gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
-                  const int32_t *__restrict__ fit_list, const yc_fit_out_t out,
-                  const uint8_t *__restrict__ status, double *__restrict__ post,
-                  const long long post_capacity, unsigned long long *__restrict__ post_cursor) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R = b.n_samples, Rc = b.n_cntrl, lane = threadIdx.x;
-    const FwSmem L = fw_layout(W, R, cap, 2);
-    const int slot = blockIdx.x;
+__device__ __forceinline__ void
+gtest_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, const int slot,
+                    const int32_t *__restrict__ fit_list, const yc_fit_out_t &out,
+                    const uint8_t *__restrict__ status, double *__restrict__ post,
+                    const long long post_capacity, unsigned long long *__restrict__ post_cursor,
+                    unsigned char *smem_raw, const FwSmem &L, const int lane) {
+    const int R = b.n_samples, Rc = b.n_cntrl;
     const int64_t g = fit_list[slot];
+    const bool want_post = fw_opaque(post != nullptr) != 0, add_uniform = fw_opaque(p.add_uniform) != 0;
     if (status[g] != YC_ST_TESTED) {                                     // failed fit: no row
         if (lane == 0) out.post_off[slot] = -1;
         if (lane < 8) out.stats[(size_t)slot * 8 + lane] = nan("");
@@ -875,7 +945,7 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
     // kernel (preds[.][s][0]) and the event data is not touched at all.
     FwCtx<W> c;
     int n = 0;
-    if (post != nullptr) { fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c); n = c.n; }
+    if (want_post) { fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c); n = c.n; }
     double *spr = reinterpret_cast<double *>(smem_raw + L.red_off);     // [3R] rounded counts, then [3R] compacted
     double *cpr = spr + 3 * YC_MAX_SAMPLES;
     // preds = np.round(weights * ORIGINAL sizes)  (stats.py:296): one lane per (sample, component)
@@ -887,7 +957,7 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             szq[h] = 0;
             if (q < 3 * R) {
                 const int s2 = q / 3;
-                szq[h] = post != nullptr ? c.fstart[s2 + 1] - c.fstart[s2]
+                szq[h] = want_post ? c.fstart[s2 + 1] - c.fstart[s2]
                                          : (int)out.preds[((size_t)slot * R + s2) * 3];
             }
         }
@@ -916,10 +986,10 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             }
         }
         double st8[8];
-        gtest_fractions(cpr, rows_c, rows_t, p.fdr_threshold, st8, p.add_uniform ? 3 : 2);
+        gtest_fractions(cpr, rows_c, rows_t, p.fdr_threshold, st8, add_uniform ? 3 : 2);
 #pragma unroll 1
         for (int k = 0; k < 8; ++k) out.stats[(size_t)slot * 8 + k] = st8[k];
-        if (post != nullptr && st8[2] < p.fdr_threshold) {
+        if (want_post && st8[2] < p.fdr_threshold) {
             off = (long long)atomicAdd(post_cursor, (unsigned long long)n);
             if (off + n > post_capacity) off = -2;
         }
@@ -956,12 +1026,31 @@ gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         const double l0 = par->cst[0] - 0.5 * q0 + par->logw[0][0];
         const double l1 = par->cst[1] - 0.5 * q1 + par->logw[0][1];
-        const double l2 = (inside && p.add_uniform) ? par->ulogp + par->logw[0][2] : -INFINITY;
+        const double l2 = (inside && add_uniform) ? par->ulogp + par->logw[0][2] : -INFINITY;
         const double mx = fmax(fmax(l0, l1), l2);
         const double e0 = exp_nonpos(l0 - mx), e1 = exp_nonpos(l1 - mx), e2 = exp_nonpos(l2 - mx);
         const double inv = 1.0 / (e0 + e1 + e2);
         post[2 * (off + i)] = e1 * inv;
         post[2 * (off + i) + 1] = e2 * inv;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * YC_FW_WARPS)
+gtest_warp_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
+                  const int32_t *__restrict__ fit_list, const int n_fit, const int32_t *__restrict__ fit_count,
+                  int *__restrict__ work, const yc_fit_out_t out,
+                  const uint8_t *__restrict__ status, double *__restrict__ post,
+                  const long long post_capacity, unsigned long long *__restrict__ post_cursor) {
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int lane = threadIdx.x;
+    const FwSmem L = fw_layout(W, b.n_samples, cap, 2);
+    unsigned char *smem_raw = smem_all;
+    const int n = fw_slot_count(n_fit, fit_count);
+#pragma unroll 1
+    for (int slot = fw_next_slot(work, lane); slot < n; slot = fw_next_slot(work, lane)) {
+        gtest_warp_position<W>(b, p, cap, slot, fit_list, out, status, post, post_capacity, post_cursor, smem_raw, L, lane);
+        __syncwarp();
     }
 }
 
@@ -981,8 +1070,8 @@ static int fw_smem(const yc_batch_t &b, const yc_params_t &p, int which) {
     return fw_layout(p.window_size, b.n_samples, fw_cap(b), which).total;
 }
 
-int fit_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p) {       // the largest of the three kernels
-    return std::max(fw_smem(b, p, 0), std::max(fw_smem(b, p, 1), fw_smem(b, p, 2)));
+int fit_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p) {       // per CTA, the largest of the three kernels
+    return YC_FW_WARPS * std::max(fw_smem(b, p, 0), std::max(fw_smem(b, p, 1), fw_smem(b, p, 2)));
 }
 
 template <typename F>
@@ -995,56 +1084,84 @@ static int dispatch_w135(int W, F &&f) {
     return YC_EINVAL;
 }
 
+// Persistent launch: the device counter the warps fetch slots from comes stream-ordered from the memory pool
+// (one int per launch, zeroed, returned after the kernel), the grid is what the device holds at once.
+struct FwLaunch {
+    int *work = nullptr;
+    int grid = 0;
+    int prepare(const void *kernel, int smem, int n_fit, cudaStream_t st) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0, sms = 0, per_sm = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * YC_FW_WARPS, smem)) != cudaSuccess)
+            return (int)e;
+        if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+        const int want = (n_fit + YC_FW_WARPS - 1) / YC_FW_WARPS;
+        grid = std::min(want, sms * per_sm);
+        keep_pool_memory();
+        if ((e = cudaMallocAsync(reinterpret_cast<void **>(&work), sizeof(int), st)) != cudaSuccess) return (int)e;
+        return (int)cudaMemsetAsync(work, 0, sizeof(int), st);
+    }
+    int finish(cudaStream_t st) {
+        const cudaError_t e = cudaGetLastError();
+        const cudaError_t e2 = cudaFreeAsync(work, st);
+        count_launches(1);
+        return (int)(e != cudaSuccess ? e : e2);
+    }
+};
+
 int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                       const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st) {
+                       const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, int8_t *labels,
+                       int max_fit_rows, cudaStream_t st) {
     if (n_fit <= 0) return 0;
-    const int cap = fw_cap(b), smem = fw_smem(b, p, 0);
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 0) * YC_FW_WARPS;
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
-        void (*kern)(const yc_batch_t, const yc_params_t, const int, const int32_t *, const yc_fit_out_t, uint8_t *,
-                     int8_t *, const int);
+        void (*kern)(const yc_batch_t, const yc_params_t, const int, const int32_t *, const int, const int32_t *, int *,
+                     const yc_fit_out_t, uint8_t *, int8_t *, const int);
         if (cap <= 32) kern = init_warp_kernel<W_, 1>;
         else if (cap <= 64) kern = init_warp_kernel<W_, 2>;
         else if (cap <= 128) kern = init_warp_kernel<W_, 4>;
         else if (cap <= 256) kern = init_warp_kernel<W_, 8>;
         else if (cap <= 512) kern = init_warp_kernel<W_, 16>;
         else kern = init_warp_kernel<W_, 0>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, labels, max_fit_rows);
-        count_launches(1);
-        return (int)cudaGetLastError();
+        FwLaunch l;
+        if (int e = l.prepare(reinterpret_cast<const void *>(kern), smem, n_fit, st)) return e;
+        kern<<<l.grid, 32 * YC_FW_WARPS, smem, st>>>(b, p, cap, fit_list, n_fit, fit_count, l.work, out, status, labels,
+                                                     max_fit_rows);
+        return l.finish(st);
     });
 }
 
 int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                     const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
+                     const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, cudaStream_t st) {
     if (n_fit <= 0) return 0;
     if (int e = upload_em_steps()) return e;
-    const int cap = fw_cap(b), smem = fw_smem(b, p, 1);
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 1) * YC_FW_WARPS;
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
-        cudaError_t e = cudaFuncSetAttribute(em_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        em_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status);
-        count_launches(1);
-        return (int)cudaGetLastError();
+        FwLaunch l;
+        if (int e = l.prepare(reinterpret_cast<const void *>(em_warp_kernel<W_>), smem, n_fit, st)) return e;
+        em_warp_kernel<W_><<<l.grid, 32 * YC_FW_WARPS, smem, st>>>(b, p, cap, fit_list, n_fit, fit_count, l.work, out, status);
+        return l.finish(st);
     });
 }
 
 int gtest_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                        const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
-                        int64_t *post_cursor, cudaStream_t st) {
+                        const int32_t *fit_count, const yc_fit_out_t &out, const uint8_t *status, double *post,
+                        int64_t post_capacity, int64_t *post_cursor, cudaStream_t st) {
     if (n_fit <= 0) return 0;
-    const int cap = fw_cap(b), smem = fw_smem(b, p, 2);
+    const int cap = fw_cap(b), smem = fw_smem(b, p, 2) * YC_FW_WARPS;
     return dispatch_w135(p.window_size, [&](auto tag) -> int {
         constexpr int W_ = decltype(tag)::value;
-        cudaError_t e = cudaFuncSetAttribute(gtest_warp_kernel<W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        gtest_warp_kernel<W_><<<n_fit, 32, smem, st>>>(b, p, cap, fit_list, out, status, post, (long long)post_capacity,
-                                                       reinterpret_cast<unsigned long long *>(post_cursor));
-        count_launches(1);
-        return (int)cudaGetLastError();
+        FwLaunch l;
+        if (int e = l.prepare(reinterpret_cast<const void *>(gtest_warp_kernel<W_>), smem, n_fit, st)) return e;
+        gtest_warp_kernel<W_><<<l.grid, 32 * YC_FW_WARPS, smem, st>>>(
+            b, p, cap, fit_list, n_fit, fit_count, l.work, out, status, post, (long long)post_capacity,
+            reinterpret_cast<unsigned long long *>(post_cursor));
+        return l.finish(st);
     });
 }
 

@@ -25,19 +25,19 @@ int ks_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, double *ks_stat,
 bool fit_warp_eligible(const yc_batch_t &b, const yc_params_t &p);
 int fit_warp_smem_bytes(const yc_batch_t &b, const yc_params_t &p);
 int init_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                       const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st);
+                       const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st);
 int em_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                     const yc_fit_out_t &out, uint8_t *status, cudaStream_t st);
+                     const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, cudaStream_t st);
 int gtest_warp_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                        const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
+                        const int32_t *fit_count, const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
                         int64_t *post_cursor, cudaStream_t st);
 int fit_cap(const yc_batch_t &b, const yc_params_t &p);
 int fit_smem_bytes(const yc_batch_t &b, const yc_params_t &p, int which);
 int init_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                  const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st);
+                  const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, int8_t *labels, int max_fit_rows, cudaStream_t st);
 int em_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                const yc_fit_out_t &out, uint8_t *status, cudaStream_t st);
+                const int32_t *fit_count, const yc_fit_out_t &out, uint8_t *status, cudaStream_t st);
 int gtest_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
-                   const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
+                   const int32_t *fit_count, const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
                    int64_t *post_cursor, cudaStream_t st);
 }  // namespace yc

@@ -64,6 +64,7 @@ class BatchResult:
     mu: np.ndarray                    # (n_fit, 2, w)
     stds: np.ndarray                  # (n_fit, 2, w) sqrt of the covariance diagonals
     stats: np.ndarray                 # (n_fit, 8) g, hom_g, p, cntrl_frac, treat_frac, log_odds, lo, hi
+    rows: np.ndarray = None           # (n_fit, row_width(w)) the fixed-width result rows (yc_gather_fit_rows)
     ks_pval_fit: np.ndarray = None    # (n_fit,) device KS p-value of each gated position (gate only; see _host_ks_pvalues)
     nc_fit: np.ndarray = None         # (n_fit,) complete-window control rows of each gated position
     nall_fit: np.ndarray = None       # (n_fit,) complete-window rows of each gated position
@@ -146,6 +147,7 @@ class Engine:
         self._copy_stream = None
         self._fetch_stream = None
         self._fit_stream = None
+        self._gate_frac = 1.0            # running estimate of gated / candidate positions (capacity of the fit outputs)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
     def upload(self, host: HostBatch) -> DeviceBatch:
@@ -157,8 +159,9 @@ class Engine:
         software pipeline, so that neither the PCIe copies nor the host's two synchronisation
         points leave the GPU idle:
           A(k)  host->device copy on the copy stream, KS kernels, gated-position count -> pinned int
-          B(k)  wait for that count only (KS of batch k+1 is already queued behind it), size the
-                outputs, launch init / EM / G-test, gather the result rows
+          B(k)  init / EM / G-test on the fit stream, gather of the fixed-width result rows; the kernels read
+                the count on the device, so the host waits for nothing here (posterior / full fetches
+                still read the 4-byte count first to size their buffers exactly)
           C(k)  device->host copy of the result rows on the fetch stream, wait for it
         issued in the order A0 A1 B0 | A2 B1 C0 | A3 B2 C1 | ...  `hosts` is consumed lazily with two
         batches of look-ahead.  A result stays valid until three more batches have been fetched
@@ -200,7 +203,9 @@ class Engine:
             if a_q:
                 h, ctx = a_q.pop(0)
                 if fit_stream is not None:
-                    fit_stream.wait_event(ctx['counted'])    # KS of this batch has finished
+                    fit_stream.wait_event(ctx['ks_done'])    # KS of this batch has finished
+                    ctx['col_arena'].record_stream(fit_stream)   # allocated on the compute stream, used on this one
+                    ctx['dev'].record_stream(fit_stream)
                     with torch.cuda.stream(fit_stream):
                         ctx = self._launch_fit(ctx, fetch)
                 else:
@@ -255,31 +260,47 @@ class Engine:
             dev.struct, ps, t['ks_stat'].data_ptr(), t['ks_pval'].data_ptr(), t['n_c'].data_ptr(),
             t['n_t'].data_ptr(), t['status'].data_ptr(), t['fit_list'].data_ptr(), t['fit_count'].data_ptr(),
             stream)))
+        ks_done = torch.cuda.current_stream(d).record_event()
         counts = torch.empty(2, dtype=torch.int64, pin_memory=True)     # [n_fit, posterior reads written]
         counts.zero_()
         cnt32 = counts.view(torch.int32)
         cnt32[:1].copy_(t['fit_count'], non_blocking=True)
         return dict(dev=dev, t=t, col_arena=col_arena, col_ext=col_ext, ps=ps, timed=timed, want_labels=want_labels,
-                    launches=int(lib.yc_kernel_launches() - launches0),   # counted by the library at every <<< >>>
-                    counts=counts, counted=torch.cuda.current_stream(d).record_event())
+                    launches_ks=int(lib.yc_kernel_launches() - launches0),   # counted by the library at every <<< >>>
+                    counts=counts, ks_done=ks_done, counted=torch.cuda.current_stream(d).record_event())
 
-    # ---- stage B: size the outputs from the count, fit kernels, gather of the result rows
-    def _launch_fit(self, ctx, fetch):
+    # ---- stage B: fit kernels + gather of the fixed-width result rows
+    def _launch_fit(self, ctx, fetch, force_exact=False):
+        '''
+        Two modes.  FAST (the production path: records without posteriors): nothing waits for the number of gated
+        positions -- the fit kernels read it on the device (`fit_count` of the C ABI), the slot-indexed outputs are
+        sized by a capacity (a running estimate of the gated fraction; an overflow is detected at fetch time and
+        the range re-fitted exactly), so a range is ONE stream-ordered submission.  EXACT (posteriors, labels,
+        full fetches of the tests): the host reads the 4-byte count first and sizes everything by it.
+        '''
         lib, p, d = self.lib, self.params, self.device
         dev, t, ps, timed = ctx['dev'], ctx['t'], ctx['ps'], ctx['timed']
         w, R = p.window_size, dev.host.n_samples
         stream = torch.cuda.current_stream(d).cuda_stream
         f64, i32 = torch.float64, torch.int32
         status, fit_list, n_c, n_t = t['status'], t['fit_list'], t['n_c'], t['n_t']
-        ctx['counted'].synchronize()                                     # the 4-byte count only
+        total = dev.host.total_cols
+        gmm = bool(p.gmm and total)
+        want_labels = ctx['want_labels']
+        exact = bool(force_exact or p.generate_sm_preds or want_labels or fetch in (True, 'full') or not gmm)
         fit_launches0 = lib.yc_kernel_launches()
-        n_fit = int(ctx['counts'].view(torch.int32)[0]) if (p.gmm and dev.host.total_cols) else 0
-        m = max(n_fit, 1)
-        # per-fit outputs in one zero-filled arena (one memset instead of a fill per array), ordered so that
-        # each fetch level is a prefix: records | + sm-preds | + full
-        specs = [('status_fit', (m,), torch.uint8), ('ks_stat_fit', (m,), f64), ('ks_pval_fit', (m,), f64),
-                 ('nc_fit', (m,), i32), ('nall_fit', (m,), i32), ('mu', (m, 2, w), f64),
-                 ('stds', (m, 2, w), f64), ('stats', (m, 8), f64),
+        if exact:
+            ctx['counted'].synchronize()                                 # the 4-byte count only
+            n_fit = int(ctx['counts'].view(torch.int32)[0]) if gmm else 0
+            m, count_ptr = max(n_fit, 1), None
+        else:
+            n_fit = None                                                 # known at fetch time
+            m = int(min(total, max(1024, total * self._gate_frac)))
+            count_ptr = t['fit_count'].data_ptr()
+        # per-fit outputs in one zero-filled arena (one memset instead of a fill per array); `rows` is what a
+        # records fetch copies (fixed-width rows, yc_gather_fit_rows), the rest only full / posterior fetches
+        RW = N.row_width(w)
+        specs = [('rows', (m, RW), f64), ('mu', (m, 2, w), f64), ('stats', (m, 8), f64),
                  ('cov', (m, 2, w, w), f64), ('box', (m, w, 2), f64),
                  ('cw', (m, 3), f64), ('post_off', (m,), torch.int64),
                  ('logw', (m, R, 3), f64), ('iters', (m,), i32), ('loglik', (m,), f64), ('preds', (m, R, 3), f64)]
@@ -292,12 +313,12 @@ class Engine:
         post_cursor = torch.empty(1, dtype=torch.int64, device=d)       # zeroed by yc_gtest_smpred_batch
         b = dev.struct
         ks_stat, ks_pval = t['ks_stat'], t['ks_pval']
-        want_labels = ctx['want_labels']
-        if n_fit:
+        if gmm and (n_fit is None or n_fit > 0):
+            n_slots = m if n_fit is None else n_fit
             # fit_list arrives in ascending column order (ordered compaction inside yc_ks_batch)
             if want_labels:
                 max_fit_rows = int(min(dev.host.max_reads, R * p.max_fit_depth))
-                labels = torch.full((n_fit, max_fit_rows), -1, dtype=torch.int8, device=d)
+                labels = torch.full((n_slots, max_fit_rows), -1, dtype=torch.int8, device=d)
             cap = 0
             if p.generate_sm_preds:
                 # upper bound: every gated position writes all of its complete-window reads
@@ -305,28 +326,26 @@ class Engine:
                 cap = int((n_c[idx].long() + n_t[idx].long()).sum().item())
                 post = torch.empty(max(cap, 1) * 2, dtype=f64, device=d)
             N.check(timed('gmm_init', lambda: lib.yc_gmm_init_batch(
-                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                b, ps, fit_list.data_ptr(), n_slots, count_ptr, out, status.data_ptr(),
                 labels.data_ptr() if labels is not None else None, max_fit_rows, stream)))
             N.check(timed('gmm_em', lambda: lib.yc_gmm_em_batch(
-                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(), stream)))
+                b, ps, fit_list.data_ptr(), n_slots, count_ptr, out, status.data_ptr(), stream)))
             N.check(timed('gtest_smpred', lambda: lib.yc_gtest_smpred_batch(
-                b, ps, fit_list.data_ptr(), n_fit, out, status.data_ptr(),
+                b, ps, fit_list.data_ptr(), n_slots, count_ptr, out, status.data_ptr(),
                 post.data_ptr() if post is not None else None, cap, post_cursor.data_ptr(), stream)))
-            # the per-fit rows the host tail reads, gathered on the device in slot order
+            # the fixed-width rows the host tail reads, gathered on the device in slot order
             N.check(lib.yc_gather_fit_rows(
-                fit_list.data_ptr(), n_fit, w, status.data_ptr(), ks_stat.data_ptr(), ks_pval.data_ptr(),
-                n_c.data_ptr(), n_t.data_ptr(), out_t['cov'].data_ptr(), out_t['status_fit'].data_ptr(),
-                out_t['ks_stat_fit'].data_ptr(), out_t['ks_pval_fit'].data_ptr(), out_t['stds'].data_ptr(),
-                out_t['nc_fit'].data_ptr(), out_t['nall_fit'].data_ptr(), stream))
-        launches = ctx['launches'] + int(lib.yc_kernel_launches() - fit_launches0)
-        ctx.update(n_fit=n_fit, launches=launches)
+                fit_list.data_ptr(), n_slots, count_ptr, w, status.data_ptr(), ks_stat.data_ptr(), ks_pval.data_ptr(),
+                n_c.data_ptr(), n_t.data_ptr(), out, out_t['rows'].data_ptr(), stream))
+        launches = ctx['launches_ks'] + int(lib.yc_kernel_launches() - fit_launches0)
+        ctx.update(n_fit=n_fit, capacity=m, exact=exact, launches=launches,
+                   fit_stream=torch.cuda.current_stream(d))
         if not fetch:
-            dev_out = {k: v for k, v in out_t.items()
-                       if k not in ('status_fit', 'ks_stat_fit', 'ks_pval_fit', 'stds', 'nc_fit', 'nall_fit')}
+            dev_out = {k: v for k, v in out_t.items() if k != 'rows'}
             flat = {k: dev_out[k].reshape(-1) for k in dev_out}
             ctx['device'] = dict(status=status, ks_stat=ks_stat, ks_pval=ks_pval, n_c=n_c, n_t=n_t,
-                                 fit_list=fit_list[:n_fit], post=post, post_cursor=post_cursor,
-                                 labels=labels, launches=launches, **flat)
+                                 fit_list=fit_list, fit_count=t['fit_count'], rows=out_t['rows'], post=post,
+                                 post_cursor=post_cursor, labels=labels, launches=launches, capacity=m, **flat)
             return ctx
         level = 'full' if fetch is True else fetch
         if post is not None:
@@ -339,29 +358,44 @@ class Engine:
     def _fetch_result(self, ctx, stage_key=0):
         '''
         Device -> host with a handful of copies: the per-column arena prefix (status, fit_list[:n_fit]; the whole
-        arena for fetch='full' / --no-gmm), the per-fit arena prefix of the fetch level, and the posteriors /
-        labels when present.  The numpy results are views of one pinned staging buffer.
+        arena for fetch='full' / --no-gmm), the fixed-width result rows [:n_fit], and for posterior / full fetches
+        the per-fit arena, posteriors and labels.  The numpy results are views of one pinned staging buffer.
         '''
         d, p = self.device, self.params
-        dev, t, n_fit, level = ctx['dev'], ctx['t'], ctx['n_fit'], ctx['level']
+        dev, t, level = ctx['dev'], ctx['t'], ctx['level']
         nc = dev.host.total_cols
-        n = max(nc, 1)
         w, R = p.window_size, dev.host.n_samples
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(d)
             self._fetch_stream = torch.cuda.Stream(d)
         fs = self._fetch_stream
+        n_fit = ctx['n_fit']
+        if n_fit is None:                                                # fast mode: the count arrived long ago
+            ctx['counted'].synchronize()
+            n_fit = int(ctx['counts'].view(torch.int32)[0])
+            if n_fit > ctx['capacity']:
+                # more gated positions than the capacity estimate: fit this range again, sized exactly
+                with torch.cuda.stream(ctx['fit_stream']):
+                    ctx = self._launch_fit(ctx, level, force_exact=True)
+                n_fit = ctx['n_fit']
+            if nc:
+                self._gate_frac = min(1.0, max(1.5 * n_fit / nc + 0.02, 0.75 * self._gate_frac))
         post, labels = ctx['post'], ctx['labels']
         used = 0
         if post is not None:
             ctx['done'].synchronize()                                    # needs the number of posterior rows
-            used = int(ctx['counts'][1])
+            used = min(int(ctx['counts'][1]), post.numel() // 2)
         col_ext, fit_ext = ctx['col_ext'], ctx['fit_ext']
         want_cols = level == 'full' or not p.gmm
+        want_fits = level == 'full' or p.generate_sm_preds              # exact mode: the arena holds n_fit rows
         col_bytes = (col_ext['n_t'][0] + col_ext['n_t'][1]) if want_cols else (col_ext['fit_list'][0] + 4 * n_fit)
-        last = 'preds' if level == 'full' else ('post_off' if p.generate_sm_preds else 'stats')
-        fit_bytes = fit_ext[last][0] + fit_ext[last][1]
-        chunks = [('cols', ctx['col_arena'], col_bytes), ('fits', ctx['fit_arena'], fit_bytes)]
+        RW = N.row_width(w)
+        last = 'preds' if level == 'full' else 'post_off'
+        chunks = [('cols', ctx['col_arena'], col_bytes)]
+        if want_fits:
+            chunks.append(('fits', ctx['fit_arena'], fit_ext[last][0] + fit_ext[last][1]))
+        else:
+            chunks.append(('fits', ctx['fit_arena'], n_fit * RW * 8))    # `rows` leads the arena
         if post is not None:
             chunks.append(('post', post.view(torch.uint8), used * 16))
         if labels is not None and level == 'full':
@@ -374,6 +408,8 @@ class Engine:
         if stage is None or stage.numel() < total + _ALIGN:
             stage = self._stages[stage_key] = torch.empty(int((total + _ALIGN) * 1.25), dtype=torch.uint8, pin_memory=True)
         fs.wait_event(ctx['done'])
+        for _, src, _ in chunks:
+            src.record_stream(fs)                                        # allocated on the compute / fit stream
         with torch.cuda.stream(fs):
             for name, src, nb in chunks:
                 if nb:
@@ -387,7 +423,6 @@ class Engine:
             a = a.reshape(shape) if count is None else a[:count]
             return a
 
-        m = max(n_fit, 1)
         c0, f0 = offs['cols'], offs['fits']
         host = dict(status=view(c0, col_ext, 'status', None, np.uint8, nc),
                     fit_list=view(c0, col_ext, 'fit_list', None, np.int32, n_fit))
@@ -398,11 +433,20 @@ class Engine:
             host.update(n_c=view(c0, col_ext, 'n_c', None, np.int32, nc), n_t=view(c0, col_ext, 'n_t', None, np.int32, nc))
         elif want_cols:
             host.update(_n_c=view(c0, col_ext, 'n_c', None, np.int32, nc), _n_t=view(c0, col_ext, 'n_t', None, np.int32, nc))
-        np_dtype = {torch.uint8: np.uint8, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}
-        for name, shape, dtype in ctx['fit_specs']:
-            host[name] = view(f0, fit_ext, name, shape, np_dtype[dtype])[:n_fit]
-            if name == last:
-                break
+        # the fixed-width rows -> the per-fit columns of the host tail
+        rows = hs[f0:f0 + n_fit * RW * 8].view(np.float64).reshape(n_fit, RW)
+        host.update(rows=rows, status_fit=rows[:, N.ROW_STATUS].astype(np.uint8), ks_stat_fit=rows[:, N.ROW_KS_STAT],
+                    ks_pval_fit=rows[:, N.ROW_KS_PVAL], nc_fit=rows[:, N.ROW_N_CNTRL].astype(np.int32),
+                    nall_fit=rows[:, N.ROW_N_ALL].astype(np.int32), stats=rows[:, N.ROW_STATS:N.ROW_STATS + 8],
+                    mu=rows[:, N.ROW_MU:N.ROW_MU + 2 * w].reshape(n_fit, 2, w),
+                    stds=rows[:, N.ROW_MU + 2 * w:N.ROW_MU + 4 * w].reshape(n_fit, 2, w))
+        if want_fits:
+            np_dtype = {torch.uint8: np.uint8, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}
+            for name, shape, dtype in ctx['fit_specs']:
+                if name not in ('rows', 'mu', 'stats'):
+                    host[name] = view(f0, fit_ext, name, shape, np_dtype[dtype])[:n_fit]
+                if name == last:
+                    break
         if post is not None:
             host['post'] = hs[offs['post']:offs['post'] + used * 16].view(np.float64).reshape(used, 2)
         if labels is not None and level == 'full':
@@ -428,6 +472,7 @@ class Engine:
                 exact = _host_ks_pvalues(host['ks_stat_fit'][near], nc, host['nall_fit'][near] - nc, p.max_fit_depth)
                 drop = near[~(exact < thr)]
                 host['status_fit'][drop] = N.ST_KS_FILTERED
+                host['rows'][drop, N.ROW_STATUS] = N.ST_KS_FILTERED
                 host['status'][host['fit_list'][drop]] = N.ST_KS_FILTERED
         if want_cols:
             st = host['status']
