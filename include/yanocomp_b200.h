@@ -141,6 +141,23 @@ int yc_fill_col_feature(int32_t n_features, const int64_t *col_off,
                         int32_t *col_feature, void *stream);
 
 /*
+ * Ingest -- the cross-sample half of the reference's pivot (load_gene_events, yanocomp/io.py:296-343:
+ * `unstack` per file, `concat` over the files of a condition) on the device.  The per-FILE half
+ * (keep-first de-duplication, dwell filter, reads in read-id order) is done once, when a sample file is
+ * converted to the dense container (yanocomp_b200/dense.py); its [n_pos][ld] binary16 blocks are uploaded
+ * as they are (`raw`) and copied here to rows [row0, row0 + n_reads) of their feature, column by column.
+ *   tasks [n_tasks * 8] int64, one row per (feature, sample) block:
+ *       {feature, offset of the block in raw (elements), 0, block ld, n_pos, n_reads, row0,
+ *        offset into colmap of the block's column map or -1 (block positions == feature positions)}
+ *   colmap  int32: feature column of every block position (for the blocks that need one)
+ *   x_off, ld  per feature, as in yc_batch_t;  events [n_event_elems] receives the batch's event buffer
+ *       (NaN = no event; 16-byte aligned);  max_n_pos = the largest n_pos over the tasks.
+ */
+int yc_assemble_batch(const uint16_t *raw, const int64_t *tasks, int32_t n_tasks, int32_t max_n_pos,
+                      const int32_t *colmap, const int64_t *x_off, const int32_t *ld,
+                      uint16_t *events, int64_t n_event_elems, void *stream);
+
+/*
  * Stage 1 -- window filters + PCA + two-sample KS over every candidate position
  * (three kernels: moments, LAPACK axis replay one thread per position, sort + D;
  * one warp or one CTA per position; then an ordered

@@ -74,6 +74,8 @@ _PROTOTYPES = {
     'yc_kernel_launches': (C.c_uint64, []),
     'yc_smem_bytes': (C.c_int, [_P(Batch), _P(Params), _P(C.c_int64)]),
     'yc_fill_col_feature': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'yc_assemble_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.c_void_p]),
     'yc_ks_batch': (C.c_int, [_P(Batch), _P(Params)] + [C.c_void_p] * 8),
     # (fit_list, n_fit, fit_count): fit_count = device int32 written by yc_ks_batch, or None for exactly n_fit slots
     'yc_gmm_init_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, C.c_void_p, _P(FitOut),

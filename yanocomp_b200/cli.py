@@ -53,7 +53,25 @@ def _profile_until_exit():
     prof.enable()
 
 
-@click.group(commands={'prep': nanopolish_collapse, 'gmmtest': gmm_test})
+@click.command(short_help='Convert a prep output (HDF5 / packed) to the dense sample container gmmtest ingests fastest')
+@click.argument('in_fn', type=click.Path(exists=True, dir_okay=False))
+@click.argument('out_fn', type=click.Path(dir_okay=False))
+def pack(in_fn, out_fn):
+    '''
+    IN_FN: one sample's collapsed events (the reference's HDF5 or this package's packed prep output).
+    OUT_FN: the dense container (yanocomp_b200/dense.py): the per-file half of gmmtest's pivot done once.
+    Not in the reference; `gmmtest -c / -t` take either kind of file.
+    '''
+    from . import dense
+    n = [0]
+
+    def tick(_):
+        n[0] += 1
+    dense.convert(in_fn, out_fn, progress=tick)
+    logger.info(f'{n[0]:,} genes written to {out_fn}')
+
+
+@click.group(commands={'prep': nanopolish_collapse, 'gmmtest': gmm_test, 'pack': pack})
 @click.option('-v', '--verbosity', default='INFO', metavar='LVL', expose_value=False,
               callback=_set_verbosity, is_eager=True,
               help='Either CRITICAL, ERROR, WARNING, INFO or DEBUG')

@@ -267,6 +267,18 @@ int yc_fill_col_feature(int32_t n_features, const int64_t *col_off, int32_t *col
     return cuda_fail((int)cudaGetLastError(), "yc_fill_col_feature");
 }
 
+int yc_assemble_batch(const uint16_t *raw, const int64_t *tasks, int32_t n_tasks, int32_t max_n_pos,
+                      const int32_t *colmap, const int64_t *x_off, const int32_t *ld,
+                      uint16_t *events, int64_t n_event_elems, void *stream) {
+    if (n_tasks < 0 || max_n_pos < 0 || n_event_elems < 0) return fail(YC_EINVAL, "yc_assemble_batch: negative size");
+    if (n_event_elems == 0) return 0;
+    if (!events || !x_off || !ld || (n_tasks > 0 && (!raw || !tasks || !colmap)))
+        return fail(YC_EINVAL, "yc_assemble_batch: null pointer");
+    if ((reinterpret_cast<uintptr_t>(events) & 15u) != 0) return fail(YC_EINVAL, "yc_assemble_batch: events must be 16-byte aligned");
+    return cuda_fail(yc::assemble_dispatch(raw, tasks, n_tasks, max_n_pos, colmap, x_off, ld, events, n_event_elems,
+                                           (cudaStream_t)stream), "yc_assemble_batch");
+}
+
 int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
                 double *ks_stat, double *ks_pval, int32_t *n_c, int32_t *n_t,
                 uint8_t *status, int32_t *fit_list, int32_t *fit_count, void *stream) {

@@ -582,45 +582,69 @@ static int upload_em_steps() {
     return 0;
 }
 
-// M-step of one shared Gaussian (reference stats.py:202-205 via pomegranate from_summaries,
-// assumptions A3/A4).  One lane per component runs it, so it is written for latency: everything
-// in registers, fully unrolled for the small W of this path, reciprocals instead of divisions,
-// one log for the determinant (log of the product of the Cholesky pivots).  Unlike the
-// initialisation (cholesky_inverse, bit-exact with the oracle) EM is compared with a tolerance.
+// M-step of the two shared Gaussians (reference stats.py:202-205 via pomegranate from_summaries, assumptions
+// A3/A4), spread over the warp (round-2 profile: the M-step ran on 2 of 32 lanes and was a fifth of the kernel's
+// issue slots):
+//   em_blend   one lane per (component, statistic): totals + carried summaries; one lane per (component, mean
+//              coordinate) and per (component, covariance entry) for the ML estimate and the inertia blend;
+//   em_factor  one lane per component for what is serial: Cholesky, triangular inverse, product of the pivots.
+// The logarithm of the determinant is NOT taken here: the caller takes one log for the two determinants and the
+// 3 R sample weights together (a single log sequence per iteration instead of two divergent ones).
+// Unlike the initialisation (cholesky_inverse, bit-exact with the oracle) EM is compared with a tolerance.
 template <int W>
-__device__ __forceinline__ void em_mstep(EmPar<W> *par, int k, const double *red, double *carry, double step) {
+__device__ __forceinline__ void em_blend(EmPar<W> *par, const double *red, double *carry, double *ubuf, double step,
+                                      int lane, bool &skip0, bool &skip1) {
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
-    double S[NS];
-#pragma unroll
-    for (int q = 0; q < NS; ++q) S[q] = red[(k * NS + q) * 33 + 32] + carry[q];
-    if (S[0] < 1e-7) {                                                   // skipped, summaries kept
-#pragma unroll
-        for (int q = 0; q < NS; ++q) carry[q] = S[q];
-        return;
+#pragma unroll 1
+    for (int idx = lane; idx < 2 * NS; idx += 32) carry[idx] += red[idx * 33 + 32];
+    __syncwarp();
+    skip0 = carry[0] < 1e-7;                                             // skipped, summaries kept (A3)
+    skip1 = carry[NS] < 1e-7;
+    const double keep = 1.0 - step;
+    if (lane < 2 * W) {
+        const int k = lane >= W, a = lane - k * W;
+        if (!(k ? skip1 : skip0)) {
+            const double u = carry[k * NS + 1 + a] * (1.0 / carry[k * NS]);
+            ubuf[lane] = u;
+            par->mu[k][a] = par->mu[k][a] * step + u * keep;
+        }
     }
+    __syncwarp();
+#pragma unroll 1
+    for (int idx = lane; idx < 2 * NT; idx += 32) {
+        const int k = idx >= NT, q = idx - k * NT;
+        if (!(k ? skip1 : skip0)) {
+            int a = 0, rem = q;                                          // (a, c) of upper-triangle entry q
 #pragma unroll
-    for (int q = 0; q < NS; ++q) carry[q] = 0.0;
-    const double inv0 = 1.0 / S[0], keep = 1.0 - step;
-    double u[W], A[NT];                                                  // A: blended covariance, upper triangle
-#pragma unroll
-    for (int a = 0; a < W; ++a) {
-        u[a] = S[1 + a] * inv0;
-        par->mu[k][a] = par->mu[k][a] * step + u[a] * keep;
+            for (int t = 0; t < W - 1; ++t) if (rem >= W - a) { rem -= W - a; ++a; }
+            const int c2 = a + rem;
+            const double *S = carry + k * NS, *u = ubuf + k * W;
+            const double inv0 = 1.0 / S[0];
+            const double cv = (S[1 + W + q] - S[1 + a] * u[c2] - u[a] * S[1 + c2] + S[0] * (u[a] * u[c2])) * inv0;
+            const double nv = par->cov[k][a * W + c2] * step + cv * keep;
+            par->cov[k][a * W + c2] = nv; par->cov[k][c2 * W + a] = nv;
+        }
     }
+    __syncwarp();
+}
+
+// Cholesky A = L L^T of par->cov[k] (L lower, packed by rows), L^-1 -> par->linv[k]; returns the product of the
+// pivots (= |A|) and in `sumlog` the sum of their logs when the product leaves the double range; par->ok = 0 on a
+// non-positive / non-finite pivot (A4).  One lane per component: everything in registers, reciprocal square roots
+// instead of square roots and divisions.
+template <int W>
+__device__ __forceinline__ double em_factor(EmPar<W> *par, int k, double &sumlog) {
+    constexpr int NT = W * (W + 1) / 2;
+    double A[NT];
     {
         int q = 0;
 #pragma unroll
         for (int a = 0; a < W; ++a)
 #pragma unroll
-            for (int c2 = a; c2 < W; ++c2) {
-                const double cv = (S[1 + W + q] - S[1 + a] * u[c2] - u[a] * S[1 + c2] + S[0] * (u[a] * u[c2])) * inv0;
-                const double nv = par->cov[k][a * W + c2] * step + cv * keep;
-                par->cov[k][a * W + c2] = nv; par->cov[k][c2 * W + a] = nv;
-                A[q++] = nv;
-            }
+            for (int c2 = a; c2 < W; ++c2) A[q++] = par->cov[k][a * W + c2];
     }
-    // Cholesky A = L L^T (L lower, packed by rows), L^-1, log|A| = log prod(pivots)
-    double Lp[NT], Li[NT], rinv[W], prod = 1.0, sumlog = 0.0;
+    double Lp[NT], Li[NT], rinv[W], prod = 1.0;
+    sumlog = 0.0;
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
@@ -640,7 +664,7 @@ __device__ __forceinline__ void em_mstep(EmPar<W> *par, int k, const double *red
             }
         }
     }
-    if (!ok) { par->ok = 0; return; }                                    // A4
+    if (!ok) { par->ok = 0; return 1.0; }                                // A4
     if (!(prod > 1e-290 && prod < 1e290)) {                              // product out of range: sum of logs
         prod = 1.0;
 #pragma unroll
@@ -661,7 +685,19 @@ __device__ __forceinline__ void em_mstep(EmPar<W> *par, int k, const double *red
     for (int r = 0; r < W; ++r)
 #pragma unroll
         for (int c2 = 0; c2 <= r; ++c2) par->linv[k][r * W + c2] = Li[r * (r + 1) / 2 + c2];
-    par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + log(prod) + sumlog);
+    return prod;
+}
+
+// 1 / x for 1 <= x <= 3 (the soft-max denominator of the E-step): hardware seed (MUFU.RCP64H, ~2^-22) and two
+// Newton steps, without the range / special-case handling of the division (x is never 0, inf or denormal here;
+// a NaN propagates).  Within 1 ulp; the E-step is compared with a tolerance.
+__device__ __forceinline__ double rcp_1to3(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
 }
 
 // model of slot -> shared memory parameter block (+ Cholesky factors, uniform log density)
@@ -783,7 +819,7 @@ em_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, const
                 double ea, eb;
                 exp_nonpos2((m0 ? l1 : l0) - m, ((m0 || m1) ? l2 : l1) - m, ea, eb);
                 const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
-                const double se = e0 + e1 + e2, inv = 1.0 / se;
+                const double se = e0 + e1 + e2, inv = rcp_1to3(se);
                 rb0[i] = e0 * inv; rb1[i] = e1 * inv;
                 llsum += m; seprod *= se;
             }
@@ -851,15 +887,47 @@ em_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, const
             rq[32] = (ta + tb) + (tc + td);
         }
         __syncwarp();
-        // ---- M-step of the shared Gaussians on lanes 0 / 1 (stats.py:202-205, A3/A4) and, in the same
-        //      divergent region so that the two serial chains can interleave, the weights from the per-sample
-        //      sums on the lanes above (stats.py:206-211; one lane per (sample, component); the uniform
-        //      component's sum is n_s - sum r0 - sum r1: responsibilities sum to one)
-        if (lane < 2) {
-            em_mstep<W>(par, lane, red, carry + lane * NS, c_em_step[iteration]);
-        } else {
+        // ---- M-step (stats.py:202-211): blend of the shared Gaussians spread over the lanes, then lanes 0 / 1 factor
+        //      their covariance while lanes 2.. prepare the weight ratios of (sample, component) from the per-sample
+        //      sums (the uniform component's sum is n_s - sum r0 - sum r1: responsibilities sum to one); ONE
+        //      logarithm then serves the two determinants and the weights
+        {
+            bool skip0, skip1;
+            em_blend<W>(par, red, carry, c.wtmp, c_em_step[iteration], lane, skip0, skip1);
+            double arg = 1.0, sumlog = 0.0;
+            bool have = false;
+            int ws = 0, wk = 0;
+            if (lane < 2) {
+                if (!(lane ? skip1 : skip0)) {
+                    arg = em_factor<W>(par, lane, sumlog);
+                    have = par->ok != 0;
 #pragma unroll 1
-            for (int q = lane - 2; q < 3 * R; q += 30) {
+                    for (int q = 0; q < NS; ++q) carry[lane * NS + q] = 0.0;
+                }
+            } else if (lane - 2 < 3 * R) {
+                const int q = lane - 2;
+                ws = q / 3; wk = q - 3 * ws;
+                const int ns = fstart[ws + 1] - fstart[ws];
+                if (ns > 0) {
+                    const double t0s = ssum[(2 * ws) * 33 + 32], t1s = ssum[(2 * ws + 1) * 33 + 32];
+                    const double t2s = uni ? fmax((double)ns - t0s - t1s, 0.0) : 0.0;
+                    if (t0s + t1s + t2s != 0.0) {
+                        const double vk = (wk == 0 ? t0s : (wk == 1 ? t1s : t2s)) + 0.5;
+                        const double den = (t0s + 0.5) + (t1s + 0.5) + (uni ? t2s + 0.5 : 0.0);
+                        arg = vk / den;
+                        have = true;
+                    }
+                }
+            }
+            __syncwarp();
+            const double lg = log(arg);                                  // one log sequence for all of them
+            if (have) {
+                if (lane < 2) par->cst[lane] = -0.5 * ((double)W * YC_LOG_2PI + lg + sumlog);
+                else par->logw[ws][wk] = (wk == 2 && !uni) ? -INFINITY : lg;
+            }
+            // more than 10 samples: the remaining (sample, component) pairs
+#pragma unroll 1
+            for (int q = lane + 30; q < 3 * R; q += 32) {
                 const int s = q / 3, k = q - 3 * s;
                 const int ns = fstart[s + 1] - fstart[s];
                 if (ns > 0) {

@@ -40,4 +40,6 @@ int em_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_li
 int gtest_dispatch(const yc_batch_t &b, const yc_params_t &p, const int32_t *fit_list, int n_fit,
                    const int32_t *fit_count, const yc_fit_out_t &out, const uint8_t *status, double *post, int64_t post_capacity,
                    int64_t *post_cursor, cudaStream_t st);
+int assemble_dispatch(const uint16_t *raw, const int64_t *tasks, int n_tasks, int max_n_pos, const int32_t *colmap,
+                      const int64_t *x_off, const int32_t *ld, uint16_t *events, int64_t n_event_elems, cudaStream_t st);
 }  // namespace yc

@@ -22,7 +22,8 @@ import pandas as pd
 
 from . import _native as N
 from . import dist as ycdist
-from .batch import HostBatch
+from . import dense as ycdense
+from .batch import HostBatch, DenseHostBatch
 from .io import (hdf5_list, get_shared_keys, load_model_priors, load_gene_features, load_gene_features_cached,
                  FeatureCache,
                  save_gmmtest_results, save_sm_preds)
@@ -335,9 +336,46 @@ def test_chunk(opts, gene_ids):
                     if pending[k]:
                         yield HostBatch(pending[k], R, n_cntrl)
 
-    # every batch is cut into PIPELINE_RANGES feature ranges (views, no copy): the upload of range k+1 overlaps
-    # the kernels of range k and the fetch of range k-1 (engine.run_pipelined), also when a whole chunk is one batch
-    for host, res in engine.run_pipelined(r for hb in batches() for r in hb.split(PIPELINE_RANGES)):
+    def dense_batches():
+        '''
+        All inputs are dense sample files (dense.py): no per-gene decode and no host pivot.  The genes are cut into
+        ranges of ~BATCH_EVENT_BYTES / PIPELINE_RANGES (shallow and deep genes apart, as above); a range is a handful
+        of large copies out of the memory maps into one pinned buffer plus a small task table, and the feature
+        matrices are assembled on the device (yc_assemble_batch).  Building range k+1 overlaps the kernels of range k.
+        '''
+        n_cntrl = len(opts.cntrl_hdf5_fns)
+        with hdf5_list(opts.cntrl_hdf5_fns + opts.treat_hdf5_fns) as files:
+            ids = list(gene_ids)
+            rows = [f.index[[f.gene_index(g) for g in ids]] for f in files] if ids else []
+            if not ids:
+                return
+            n_reads = np.stack([r['n_reads'].astype(np.int64) for r in rows])            # (R, genes)
+            nbytes = sum(r['n_pos'].astype(np.int64) * r['ld'].astype(np.int64) * 2 for r in rows)
+            cond = np.maximum(n_reads[:n_cntrl].sum(0), n_reads[n_cntrl:].sum(0))
+            shallow = (n_reads.sum(0) <= 1024) & (cond <= opts.max_fit_depth)
+            limit = max(BATCH_EVENT_BYTES // PIPELINE_RANGES, 1)
+            for k in (True, False):
+                pending, acc = [], 0
+                for j in np.flatnonzero(shallow == k).tolist():
+                    pending.append(ids[j])
+                    acc += int(nbytes[j])
+                    if acc >= limit:
+                        yield DenseHostBatch(files, pending, n_cntrl, by_t, copy_threads=max(1, opts.processes))
+                        pending, acc = [], 0
+                if pending:
+                    yield DenseHostBatch(files, pending, n_cntrl, by_t, copy_threads=max(1, opts.processes))
+
+    fns = list(opts.cntrl_hdf5_fns) + list(opts.treat_hdf5_fns)
+    is_dense = [ycdense.is_dense(fn) for fn in fns]
+    if any(is_dense) and not all(is_dense):
+        raise click.UsageError('dense sample files (python -m yanocomp_b200 pack) cannot be mixed with HDF5 / packed inputs')
+    if all(is_dense) and fns:
+        source = dense_batches()
+    else:
+        # every batch is cut into PIPELINE_RANGES feature ranges (views, no copy): the upload of range k+1 overlaps
+        # the kernels of range k and the fetch of range k-1 (engine.run_pipelined), also when a chunk is one batch
+        source = (r for hb in batches() for r in hb.split(PIPELINE_RANGES))
+    for host, res in engine.run_pipelined(source):
         recs, sm = _batch_records(host, res, opts)
         chunk_res.extend(recs)
         for k, v in sm.items():

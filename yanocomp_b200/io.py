@@ -21,7 +21,7 @@ from contextlib import contextmanager
 
 import numpy as np
 
-from . import h5lite, packed
+from . import dense, h5lite, packed
 from .batch import Feature
 
 logger = logging.getLogger('yanocomp')
@@ -35,12 +35,16 @@ DEFAULT_PRIORS_MODEL_FN = os.path.join(
 def hdf5_list(hdf5_fns):
     '''
     context manager for a list of event files (reference io.py:246-256): HDF5 written by the
-    reference's prep, or the packed container written by this package's prep, told apart by magic
+    reference's prep, the packed container written by this package's prep, or the dense per-sample
+    container (`python -m yanocomp_b200 pack`, dense.py), told apart by magic
     '''
     handles = []
     try:
         for fn in hdf5_fns:
-            handles.append(packed.File(fn, 'r') if packed.is_packed(fn) else h5lite.File(fn, 'r'))
+            if dense.is_dense(fn):
+                handles.append(dense.File(fn, 'r'))
+            else:
+                handles.append(packed.File(fn, 'r') if packed.is_packed(fn) else h5lite.File(fn, 'r'))
     except Exception:
         for f in handles:
             f.close()

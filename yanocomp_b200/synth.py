@@ -81,3 +81,36 @@ CONFIGS = {
     5: dict(name='cfg5: 20k transcripts x 500 positions, 3x3 replicates, 100 reads/replicate, all positions fitted',
             seed=4, n_features=20000, n_pos=500, reads_per_sample=100, n_cntrl=3, n_treat=3, window=3),
 }
+
+
+def write_dense_dataset(features, n_cntrl, n_treat, out_dir, prefix='synth'):
+    '''
+    Write synthetic features as one dense sample file per replicate (dense.py), as `pack` would from a prep output:
+    returns (control file names, treatment file names).  Read ids are per-sample sorted strings (make_feature with_ids).
+    '''
+    import os
+    from . import dense
+    R = n_cntrl + n_treat
+    fns = [os.path.join(out_dir, f'{prefix}_{"cntrl" if s < n_cntrl else "treat"}{(s if s < n_cntrl else s - n_cntrl) + 1}.ycd')
+           for s in range(R)]
+    writers = [dense.Writer(fn) for fn in fns]
+    try:
+        for f in features:
+            pos = np.asarray(f.positions, dtype=np.int64)
+            kmers = np.empty(len(pos), dtype=dense.KMER_DTYPE)
+            kmers['pos'] = pos
+            kmers['kmer'] = np.asarray([f.kmers[int(p)] for p in pos.tolist()], dtype='S5')
+            for s, w in enumerate(writers):
+                a, e = int(f.samp_start[s]), int(f.samp_start[s + 1])
+                Xs = f.X[:, a:e]
+                keep = ~np.isnan(Xs).all(axis=1) if e > a else np.zeros(len(pos), dtype=bool)
+                ids = f.read_ids[a:e] if f.read_ids is not None else [f's{s}-{i:07d}' for i in range(e - a)]
+                w.add_gene(f.feature_id, f.chrom, f.strand, [f.feature_id + '.t1'], kmers, ids, pos[keep],
+                           np.ascontiguousarray(Xs[keep]))
+    except BaseException:
+        for w in writers:
+            w.close(ok=False)
+        raise
+    for w in writers:
+        w.close()
+    return fns[:n_cntrl], fns[n_cntrl:]
