@@ -16,10 +16,16 @@ Printed JSON (one line, rank 0):
   value      positions entering position_stats / s, inputs resident in HBM,
              timed with CUDA events on the launching stream
   e2e        the same through the public host-buffer call
-             (yanocomp_b200.api.test_host_batch: pinned host -> device copy of
-             the packed batch, kernels, device -> host copy of all results, BH)
+             (yanocomp_b200.api.test_host_batch_pipelined: pinned host -> device
+             copy of the packed batch, kernels, device -> host copy of the result
+             rows; the once-per-job BH correction is NOT inside, see `job`)
+  job        the reference's real boundary, wall-clocked: synthetic sample files written once
+             (outside the timer) -> yanocomp_b200.gmmtest.parallel_test(opts) -> the DataFrame
+             with BH-FDR (gmmtest.py:182-224), per host-side stage.  N = 1: cfg2; N > 1: cfg3,
+             STRONG-scaled (20 000 transcripts sharded over the ranks), gather + BH inside
+  other_configs   (N = 1) full-size resident lines of cfg3, cfg4 and cfg5, events generated on the device
   roofline   dominant kernel (by measured time) against the measured HBM peak,
-             algorithmic bytes as in DESIGN.md; fp64 figures beside it
+             algorithmic bytes as in DESIGN.md; fp64 figures beside it (flat keys)
   cpu_baseline  the CPU oracle (NumPy/SciPy restatement of the reference; the
              reference itself cannot be installed offline) on a bounded sample
              of the same workload on the host cores
@@ -193,6 +199,142 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------
+def run_job(args, torch, dist, world, rank):
+    '''
+    The reference's real boundary (the timed region is parallel_test(opts),
+    gmmtest.py:182-224): sample files on disk (page-cache warm, written outside the timer) -> ingest ->
+    kernels -> records -> gather over the ranks -> DataFrame + BH-FDR on rank 0.  Wall clock, max over ranks.
+    N = 1: cfg2.  N > 1: cfg3 STRONG-scaled (the 20 000 transcripts are sharded over the ranks by parallel_test).
+    '''
+    import shutil
+    import tempfile
+    from yanocomp_b200 import gmmtest as ycg
+    from yanocomp_b200 import synth
+    cfg_id = int(os.environ.get('YC_BENCH_JOB_CONFIG', '2' if world == 1 else '3'))
+    cfg = dict(synth.CONFIGS[cfg_id])
+    n_features = int(os.environ.get('YC_BENCH_JOB_FEATURES', cfg['n_features']))
+    box = [None]
+    t_write = 0.0
+    if rank == 0:
+        root = os.environ.get('YC_BENCH_TMP') or tempfile.gettempdir()
+        d = tempfile.mkdtemp(prefix='yc_job_', dir=root)
+        t0 = time.perf_counter()
+        c_fns, t_fns, _ = synth.write_dense_config(cfg, d, torch.device('cuda', torch.cuda.current_device()),
+                                                   n_features=n_features)
+        t_write = time.perf_counter() - t0
+        box = [(d, c_fns, t_fns)]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    d, c_fns, t_fns = box[0]
+    torch.cuda.empty_cache()
+    kw = dict(window_size=cfg['window'])
+    if cfg_id == 5:
+        kw.update(min_ks=0.0, fdr_threshold=1.0, test_level='transcript')
+    opts = ycg.GMMTestOpts(cntrl_hdf5_fns=tuple(c_fns), treat_hdf5_fns=tuple(t_fns), output_bed_fn=os.path.join(d, 'job.bed'),
+                           processes=int(os.environ.get('YC_BENCH_JOB_THREADS', '4')), random_seed=0, **kw)
+    reps = []
+    try:
+        for rep in range(int(os.environ.get('YC_BENCH_JOB_REPS', '3'))):
+            ycg.STAGES.clear()
+            ycg.COUNTS.clear()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res, _ = ycg.parallel_test(opts)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            stages = dict(ycg.STAGES)
+            names = ('open', 'ingest', 'device', 'records', 'gather', 'frame_bh')
+            vec = torch.tensor([wall, float(ycg.COUNTS['positions_tested']), float(ycg.COUNTS['positions_fitted'])]
+                               + [stages.get(k, 0.0) for k in names], dtype=torch.float64, device='cuda')
+            vmax, vsum = vec.clone(), vec.clone()
+            if world > 1:
+                dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(vsum, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                st_max = dict(zip(names, [float(x) for x in vmax[3:].tolist()]))
+                reps.append({'seconds': float(vmax[0]), 'positions_tested': int(vsum[1]), 'positions_fitted': int(vsum[2]),
+                             'rows': int(len(res)), 'significant_at_fdr': int((res.fdr < opts.fdr_threshold).sum()) if len(res) else 0,
+                             'stage_seconds_max_over_ranks': st_max, 'stage_seconds_rank0': {k: stages.get(k, 0.0) for k in names}})
+    finally:
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
+    if rank != 0:
+        return None
+    best = min(reps, key=lambda r: r['seconds'])
+    slowest = max(best['stage_seconds_max_over_ranks'], key=best['stage_seconds_max_over_ranks'].get)
+    in_bytes = sum(2 * cfg['n_pos'] * ((cfg['reads_per_sample'] + 7) // 8 * 8) for _ in range(cfg['n_cntrl'] + cfg['n_treat'])) * n_features
+    return {'workload': cfg['name'] + ('' if n_features == cfg['n_features'] else f' [REDUCED to {n_features} transcripts]'),
+            'boundary': 'yanocomp_b200.gmmtest.parallel_test(opts) -> DataFrame with BH-FDR (reference gmmtest.py:182-224)',
+            'inputs': f'{cfg["n_cntrl"] + cfg["n_treat"]} dense sample files, {in_bytes / 1e6:.0f} MB of events, page-cache warm '
+                      f'(written in {t_write:.1f} s outside the timer)',
+            'scaling': 'single GPU' if world == 1 else 'strong (genes sharded over the ranks by parallel_test, gather + BH on rank 0)',
+            'seconds': best['seconds'], 'positions_per_s': best['positions_tested'] / best['seconds'],
+            'positions_tested': best['positions_tested'], 'positions_fitted': best['positions_fitted'], 'rows': best['rows'],
+            'significant_at_fdr': best['significant_at_fdr'], 'slowest_stage': slowest,
+            'stage_seconds_max_over_ranks': best['stage_seconds_max_over_ranks'],
+            'stage_seconds_rank0': best['stage_seconds_rank0'], 'seconds_all_reps': [r['seconds'] for r in reps]}
+
+
+def run_other_configs(args, torch):
+    '''full-size resident lines of the other BASELINE.json configurations on one GPU (events generated on the device)'''
+    from yanocomp_b200 import synth
+    from yanocomp_b200.batch import DeviceBatch
+    from yanocomp_b200.engine import Engine, EngineParams
+    out = {}
+    which = [int(x) for x in os.environ.get('YC_BENCH_OTHER', '3,4,5').split(',') if x.strip()]
+    for cid in which:
+        cfg = dict(synth.CONFIGS[cid])
+        n_features = int(os.environ.get(f'YC_BENCH_CFG{cid}_FEATURES', cfg['n_features']))
+        kw = dict(window_size=cfg['window'])
+        if cid == 4:
+            kw['generate_sm_preds'] = True
+        if cid == 5:
+            kw.update(min_ks=0.0, fdr_threshold=1.0)
+        try:
+            torch.cuda.empty_cache()
+            t0 = time.perf_counter()
+            host = synth.make_device_batch(cfg, torch.device('cuda', torch.cuda.current_device()), n_features=n_features)
+            eng = Engine(EngineParams(**kw))
+            dev = DeviceBatch(host)
+            torch.cuda.synchronize()
+            t_gen = time.perf_counter() - t0
+            fetch = False                                     # resident: results (and cfg4's posteriors) stay in HBM
+            steps = 2
+            eng.run(dev, fetch=fetch)
+            torch.cuda.synchronize()
+            events = []
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            for _ in range(steps):
+                o = eng.run(dev, fetch=fetch, events=events)
+            e.record()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) / steps
+            ms = a.elapsed_time(e) / steps
+            n_tested = int((o['status'][:host.total_cols] != 0).sum().item())
+            n_fit = int(o['fit_count'].item())
+            extra = {'wall_ms_per_step': wall * 1e3}
+            if o['post'] is not None:
+                extra['posterior_reads_written'] = int(o['post_cursor'].item())
+            kms = {}
+            for name, x, y in events:
+                kms.setdefault(name, []).append(x.elapsed_time(y))
+            out[f'cfg{cid}'] = dict({'workload': cfg['name'] + ('' if n_features == cfg['n_features'] else f' [REDUCED to {n_features}]'),
+                                     'positions_per_s': n_tested / (ms * 1e-3), 'ms_per_step': ms, 'positions_tested': n_tested,
+                                     'positions_fitted': n_fit, 'input_bytes': host.nbytes, 'generate_seconds': t_gen,
+                                     'kernel_ms': {k: float(np.mean(v)) for k, v in kms.items()}}, **extra)
+            del dev, host, eng, o
+        except Exception as exc:                              # a line that cannot be measured says why
+            out[f'cfg{cid}'] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args, cfg, opts_kw):
     import torch
     import torch.distributed as dist
@@ -287,10 +429,14 @@ def run_gpu(args, cfg, opts_kw):
     ms_resident_max, ms_e2e_max = [float(x) for x in t_res.tolist()]
     tot_tested, tot_fit = [float(x) for x in cnt.tolist()]
 
+    del dev, out
+    torch.cuda.empty_cache()
+    job = None if args.no_job else run_job(args, torch, dist, world, rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    other = run_other_configs(args, torch) if (world == 1 and not args.no_other_configs) else None
     hbm_peak, sm_max, peak_kind = load_peaks()
     value = tot_tested * args.steps / (ms_resident_max * 1e-3)
     e2e_value = tot_tested * args.steps / (ms_e2e_max * 1e-3)
@@ -307,27 +453,36 @@ def run_gpu(args, cfg, opts_kw):
     }
     dom = max(kavg, key=kavg.get) if kavg else 'ks'
     achieved = alg[dom] / (kavg[dom] * 1e-3) / 1e9 if kavg else 0.0
-    # FP64 work of the EM kernel: flop/read/E-step from DESIGN.md section 5
+    # FP64 work of the EM kernel per read and E-step.  `executed`: the arithmetic the kernel
+    # issues (pass 1: 2d subtractions, d(d+1) triangular-solve FMAs, 2d squares, 2 exponentials of 15 FMAs + 1, one
+    # Newton reciprocal, soft-max / likelihood bookkeeping; pass 2: d(d+1) + 2d FMAs / multiplies / adds of the
+    # sufficient statistics), an FMA counted as 2; `survey`: SURVEY.md section 8d's model 2(2d^2 + 7d + 1) + 30
     d = w
-    flop_read_iter = 2 * (d * (d + 1) + 2 * d) + 2 * (1 + d + d * (d + 1)) + 120
+    flop_read_iter = 4 * d * (d + 1) + 10 * d + 89
+    flop_read_iter_survey = 2 * (2 * d * d + 7 * d + 1) + 30
     em_flops = sum_iters * Nreads * flop_read_iter
     fp64_peak = 148 * 64 * 2 * sm_max * 1e6      # 64 FP64 FMA lanes / SM / clk
     em_name = 'gmm_em'
     em_ms = kavg.get(em_name, float('inf'))
-    traffic = None
-    tfn = os.path.join(ROOT, 'profiles', 'r01g_traffic.json')
+    traffic, traffic_source = None, None
+    tfn = os.path.join(ROOT, 'profiles', 'r02h_traffic.json')
     if os.path.exists(tfn) and args.config == 2 and not args.features:
         with open(tfn) as fh:
-            traffic = json.load(fh).get(dom)        # ncu --set full capture of the same workload
+            tdoc = json.load(fh)
+        traffic = tdoc['kernels'].get(dom)          # NOT measured by this run: a committed ncu --set full capture
+        traffic_source = tdoc['source']
+    em_tflops = em_flops / (em_ms * 1e-3) / 1e12
     roofline = {
         'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-        'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_kind': peak_kind,
-        'kernel_ms': kavg, 'algorithmic_bytes': alg,
-        'note': 'the path is FP64-latency bound, not HBM bound (DESIGN.md section 5); fp64 block below',
-        'fp64': {'kernel': em_name, 'achieved_tflops': em_flops / (em_ms * 1e-3) / 1e12,
-                 'peak_tflops': fp64_peak / 1e12, 'frac': em_flops / (em_ms * 1e-3) / fp64_peak,
-                 'flop_per_read_iter': flop_read_iter, 'mean_em_iters': mean_iters},
+        'frac': achieved / hbm_peak, 'traffic': traffic, 'traffic_source': traffic_source, 'peak_kind': peak_kind,
+        'algorithmic_bytes_' + dom: alg[dom],
+        'note': 'the path is FP64 issue / latency bound, not HBM bound (DESIGN.md section 5): fp64_* keys',
+        'fp64_kernel': em_name, 'fp64_achieved_tflops': em_tflops, 'fp64_peak_tflops': fp64_peak / 1e12,
+        'fp64_frac': em_tflops * 1e12 / fp64_peak, 'fp64_flop_per_read_iter_executed': flop_read_iter,
+        'fp64_frac_survey_model': em_tflops * 1e12 / fp64_peak * flop_read_iter_survey / flop_read_iter,
+        'fp64_flop_per_read_iter_survey_model': flop_read_iter_survey, 'mean_em_iters': mean_iters,
     }
+    roofline.update({'kernel_ms_' + k: v for k, v in kavg.items()})
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -356,6 +511,8 @@ def run_gpu(args, cfg, opts_kw):
         'clocks': sampler.summary(),
         'roofline': roofline,
         'cpu_baseline': cpu,
+        'job': job,
+        'other_configs': other,
     }
     print(json.dumps(line))
     if world > 1:
@@ -371,6 +528,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--features', type=int, default=None, help='override the number of transcripts (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-job', action='store_true', help='skip the parallel_test job block')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the full-size cfg3 / cfg4 / cfg5 resident lines')
     args = ap.parse_args()
     from yanocomp_b200 import synth
     cfg = dict(synth.CONFIGS[args.config])

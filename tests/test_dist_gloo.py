@@ -61,3 +61,62 @@ def test_two_rank_gather_equals_single_rank(tmp_path):
     a = open(tmp_path / 'w2.csv').read()
     b = open(tmp_path / 'w1.csv').read()
     assert a == b and a.count('\n') == 24     # results do not depend on the number of ranks
+
+
+def _rowblock_worker(rank, world, port, out_dir, gmm):
+    '''the route test_chunk's records take: fixed-width row blocks gathered as tensors (dist._gather_rowblocks)'''
+    sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from yanocomp_b200 import _native as N, dist as ycdist
+    from yanocomp_b200.gmmtest import Records, RowBlock, _to_frame, materialise_array_columns
+    assert ycdist.init_from_env(backend='gloo') == (world, rank)
+    genes = [f'gene{i:03d}' for i in range(17)]
+    # rank `world - 1` of a 3-rank job gets nothing: an empty rank must not stall or break the exchange
+    mine = [g for i, g in enumerate(genes) if i % max(world - (world == 3), 1) == rank] if world > 1 else genes
+    w, RW = 3, N.row_width(3)
+    blocks, sm = [], {}
+    for g in mine:
+        i = int(g[4:])
+        rng = np.random.default_rng(i)                      # rows depend on the gene only, not on the rank
+        n = 1 + i % 4
+        pos = 100 + 10 * np.arange(n) + i
+        kmers = np.array([[b'AAAAA', b'GGACT', b'ACGTN' if i == 5 else b'TTTTT']] * n, dtype='S5')
+        if gmm:
+            rows = rng.random((n, RW))
+            rows[:, N.ROW_STATUS] = N.ST_TESTED
+            if i == 3:
+                rows[0, N.ROW_STATS + 2] = np.nan           # dropped by dropna(p_val)
+            blocks.append(RowBlock([g], ['chr%d' % (i % 3)], ['+-'[i % 2]], np.zeros(n, np.int32), pos, kmers, rows=rows))
+        else:
+            blocks.append(RowBlock([g], ['chr%d' % (i % 3)], ['+-'[i % 2]], np.zeros(n, np.int32), pos, kmers,
+                                   p_val=rng.random(n), ks=rng.random(n)))
+        sm[g] = dict.fromkeys(pos.tolist())
+    recs = Records()
+    for b in blocks:
+        recs.add_block(b)
+    n_mine = len(recs)
+    recs, sm = ycdist.gather_results(recs, sm)
+    if rank == 0:
+        assert isinstance(recs, Records) and len(recs) == sum(1 + int(g[4:]) % 4 for g in genes)
+        assert recs.row_blocks() is not None or world == 1
+        res = materialise_array_columns(_to_frame(recs))
+        assert materialise_array_columns(_to_frame(list(recs))).to_csv() == res.to_csv()      # same frame from the tuples
+        assert sorted(sm) == genes and all(v is None for d in sm.values() for v in d.values())
+        assert sum(len(d) for d in sm.values()) == len(recs)
+        res.to_csv(os.path.join(out_dir, 'rb%d_%d.csv' % (world, gmm)))
+    else:
+        assert recs == [] and sm == {} and (n_mine > 0 or rank == world - 1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_row_blocks_gathered_as_tensors_equal_single_rank(tmp_path):
+    for gmm in (1, 0):
+        for world in (2, 3, 1):
+            mp.spawn(_rowblock_worker, args=(world, _free_port(), str(tmp_path), gmm), nprocs=world, join=True)
+        one = open(tmp_path / ('rb1_%d.csv' % gmm)).read()
+        assert open(tmp_path / ('rb2_%d.csv' % gmm)).read() == one == open(tmp_path / ('rb3_%d.csv' % gmm)).read()
+        assert one.count('\n') > 30

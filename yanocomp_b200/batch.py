@@ -10,6 +10,8 @@ shard is a single host->device copy and every window is `w` adjacent,
 contiguous rows of that buffer.  See include/yanocomp_b200.h for the layout.
 '''
 import dataclasses
+import os
+import weakref
 
 import numpy as np
 
@@ -60,6 +62,50 @@ class Feature:
         return self.X.shape[1]
 
 
+class _PinnedPool:
+    '''
+    Page-locked host buffers, reused.  acquire() hands out a uint8 array of at least the requested size (best fit among
+    the free buffers, else a new cudaHostAlloc rounded up to 32 MB); the buffer returns to the pool when `owner` is
+    garbage collected, or never (owner=None: the caller keeps the array alive for as long as it needs it and the pool
+    simply forgets the buffer).  Returns None without CUDA.
+    '''
+    GRAIN = 32 << 20
+
+    def __init__(self):
+        self._free = []                                  # torch uint8 tensors
+        self._lock = None
+
+    def acquire(self, nbytes, owner=None):
+        import threading
+        import weakref
+        try:
+            import torch
+        except ImportError:
+            return None
+        if not torch.cuda.is_available():
+            return None
+        if self._lock is None:
+            self._lock = threading.Lock()
+        t = None
+        with self._lock:
+            fits = [(x.numel(), i) for i, x in enumerate(self._free) if x.numel() >= nbytes]
+            if fits:
+                t = self._free.pop(min(fits)[1])
+        if t is None:
+            t = torch.empty((nbytes + self.GRAIN - 1) // self.GRAIN * self.GRAIN, dtype=torch.uint8, pin_memory=True)
+        if owner is not None:
+            weakref.finalize(owner, self._release, t)     # views of the array must not outlive `owner` (HostBatch.view
+        return t.numpy()                                  # keeps its parent alive); without an owner the array owns it
+
+    def _release(self, t):
+        with self._lock:
+            if sum(x.numel() for x in self._free) + t.numel() <= (4 << 30):     # keep at most 4 GB parked
+                self._free.append(t)
+
+
+PINNED = _PinnedPool()
+
+
 class HostBatch:
     '''features packed into flat numpy buffers (pinned when torch has CUDA)'''
 
@@ -86,7 +132,7 @@ class HostBatch:
         self.col_pos = (np.concatenate([f.positions for f in self.features]).astype(np.int64)
                         if F else np.zeros(0, dtype=np.int64))
         self.reverse = np.zeros(F, dtype=np.uint8)
-        self.events = self._alloc_events(total, pin)
+        self.events = self._alloc_events(total, pin, owner=self)
         ev16 = self.events.view(np.float16)
         for i, f in enumerate(self.features):
             if f.X.dtype != np.float16:
@@ -105,7 +151,7 @@ class HostBatch:
             # of a pipelined upload are all asynchronous
             for name in ('n_cols', 'n_reads', 'ld', 'x_off', 'col_off', 'samp_start', 'feature_key',
                          'col_pos', 'reverse'):
-                setattr(self, name, self._pinned_copy(getattr(self, name)))
+                setattr(self, name, self._pinned_copy(getattr(self, name), owner=self))
         self.max_reads = int(self.n_reads.max()) if F else 0
         split = self.samp_start[:, n_cntrl] if F else np.zeros(0, dtype=np.int32)
         self.max_cond_reads = int(max(split.max(), (self.n_reads - split).max())) if F else 0
@@ -113,6 +159,7 @@ class HostBatch:
     def view(self, f0, f1):
         '''features [f0, f1) as a HostBatch sharing this batch's (pinned) buffers: no copy'''
         v = object.__new__(HostBatch)
+        v._parent = self                                 # the pinned event buffer returns to the pool when `self` dies
         v.features = self.features[f0:f1]
         v.n_samples, v.n_cntrl = self.n_samples, self.n_cntrl
         v.n_cols, v.n_reads, v.ld = self.n_cols[f0:f1], self.n_reads[f0:f1], self.ld[f0:f1]
@@ -155,23 +202,26 @@ class HostBatch:
         return [self.view(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
 
     @staticmethod
-    def _pinned_copy(a):
-        import torch
-        if not torch.cuda.is_available() or a.size == 0:
+    def _pinned_copy(a, owner=None):
+        '''small tables travel from pageable memory (a pinned allocation costs far more than their copy); large ones
+        (the column positions of a big batch) from a pooled pinned buffer that returns to the pool with `owner`'''
+        if a.size == 0 or a.nbytes < (4 << 20):
             return a
-        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].view(np.int64) if a.dtype == np.uint64 else a[:0]).dtype,
-                        pin_memory=True)
-        out = t.numpy().view(a.dtype)
+        buf = PINNED.acquire(a.nbytes, owner=owner)
+        if buf is None:
+            return a
+        out = buf[:a.nbytes].view(a.dtype).reshape(a.shape)
         out[...] = a
         return out
 
     @staticmethod
-    def _alloc_events(total, pin):
+    def _alloc_events(total, pin, owner=None):
+        '''uint16 event buffer of `total` elements; pinned buffers come from (and, when `owner` dies, return to) a pool:
+        cudaHostAlloc of a 56 MB buffer takes ~40 ms, more than uploading and testing its contents'''
         if pin:
-            import torch
-            if torch.cuda.is_available():
-                t = torch.empty(max(total, 1), dtype=torch.int16, pin_memory=True)
-                return t.numpy().view(np.uint16)[:total]
+            buf = PINNED.acquire(max(total, 1) * 2, owner=owner)
+            if buf is not None:
+                return buf[:total * 2].view(np.uint16)
         return np.empty(total, dtype=np.uint16)
 
     @property
@@ -230,6 +280,8 @@ class DeviceBatch:
             N.check(N.lib().yc_assemble_batch(
                 raw.data_ptr(), tasks.data_ptr(), len(host.tasks32), max_n_pos, colmap.data_ptr(), self.x_off.data_ptr(),
                 self.ld.data_ptr(), self.events.data_ptr(), host.n_events_elems, torch.cuda.current_stream(dev).cuda_stream))
+        elif hasattr(host, 'events_device'):
+            self.events = host.events_device                 # generated on the device (synth.make_device_batch)
         else:
             self.events = torch.from_numpy(host.events.view(np.int16)).to(dev, non_blocking=True)
         self.col_off = up(host.col_off, np.int64)
@@ -259,17 +311,20 @@ class DeviceBatch:
 # ---------------------------------------------------------------------------------------------
 class DenseFeature:
     '''
-    Host-side description of one feature of a DenseHostBatch: what the record assembly needs (ids, positions,
-    kmers per column) is precomputed as arrays; what only single-molecule predictions need (the event matrix
-    and the read ids) is assembled from the memory-mapped files on first use.
+    Host-side view of one feature of a DenseHostBatch, built on demand (the record assembly works on the batch's
+    column arrays; only single-molecule predictions and tests look at features one by one): the event matrix and
+    the read ids are assembled from the memory-mapped files on first use.
     '''
 
-    def __init__(self, feature_id, chrom, strand, positions, samp_start, genes, colmaps, kmers_by_column):
-        self.feature_id, self.chrom, self.strand = feature_id, chrom, strand
-        self.positions = positions
-        self.samp_start = samp_start
-        self._genes, self._colmaps = genes, colmaps
-        self._kmers_by_column = kmers_by_column
+    def __init__(self, host, fi):
+        # a weak reference: features are cached on the batch, and a batch <-> feature cycle would leave the batch (and its
+        # pooled pinned buffer) to the cyclic garbage collector instead of freeing it when the last user lets go
+        self._host, self._fi = (host if isinstance(host, weakref.ProxyType) else weakref.proxy(host)), fi
+        self.feature_id, self.chrom, self.strand = host.feature_ids[fi], host.chroms[fi], host.strands[fi]
+        c0, c1 = int(host.col_off[fi]), int(host.col_off[fi + 1])
+        self.positions = np.asarray(host.col_pos[c0:c1])
+        self.samp_start = np.asarray(host.samp_start[fi])
+        self._kmers_by_column = host.kmer_strings(c0, c1)
         self._X = self._read_ids = self._kmers = None
 
     @property
@@ -284,14 +339,21 @@ class DenseFeature:
     def pos0(self):
         return int(self.positions[0]) if len(self.positions) else 0
 
+    def _blocks(self):
+        '''(sample, dense.Gene, feature column of every block position or None) of the samples with events'''
+        h = self._host
+        for s, f in enumerate(h.files):
+            g = f.gene(h.gene_of_feature[self._fi])
+            if g.n_pos and g.n_reads:
+                same = g.n_pos == self.n_cols and np.array_equal(g.positions, self.positions)
+                yield s, g, (None if same else np.searchsorted(self.positions, g.positions))
+
     @property
     def X(self):
         if self._X is None:
             X = np.full((self.n_cols, self.n_reads), np.nan, dtype=np.float16)
-            for s, (g, cm) in enumerate(zip(self._genes, self._colmaps)):
-                if g is not None and g.n_pos:
-                    rows = slice(None) if cm is None else cm
-                    X[rows, self.samp_start[s]:self.samp_start[s + 1]] = g.events[:, :g.n_reads]
+            for s, g, cm in self._blocks():
+                X[slice(None) if cm is None else cm, self.samp_start[s]:self.samp_start[s + 1]] = g.events[:, :g.n_reads]
             self._X = X
         return self._X
 
@@ -299,9 +361,8 @@ class DenseFeature:
     def read_ids(self):
         if self._read_ids is None:
             ids = []
-            for g in self._genes:
-                if g is not None:
-                    ids.extend(np.char.decode(g.read_ids, 'ascii').tolist())
+            for _, g, _ in self._blocks():
+                ids.extend(g.read_ids.astype('U').tolist())
             self._read_ids = ids
         return self._read_ids
 
@@ -312,23 +373,25 @@ class DenseFeature:
         return self._kmers
 
 
-def _kmers_for_positions(genes, positions):
-    '''pos -> kmer over the files in order, later files win (reference io.py:270-281), for the given positions'''
-    tables = [g.kmers for g in genes if g is not None and len(g.kmers)]
-    out = np.full(len(positions), None, dtype=object)
-    if not tables or not len(positions):
-        return out
-    pos = np.concatenate([t['pos'] for t in tables]).astype(np.int64)
-    kmer = np.concatenate([t['kmer'] for t in tables])
-    order = np.argsort(pos, kind='stable')                       # stable: later files stay behind earlier ones
-    pos, kmer = pos[order], kmer[order]
-    last = np.flatnonzero(np.r_[pos[1:] != pos[:-1], True])      # the last record of every position wins
-    upos, ukmer = pos[last], kmer[last]
-    at = np.searchsorted(upos, positions)
-    at[at == len(upos)] = 0
-    hit = upos[at] == positions
-    out[hit] = np.char.decode(ukmer[at[hit]], 'ascii')
-    return out
+class _LazyFeatures:
+    def __init__(self, host):
+        self._host, self._cache = weakref.proxy(host), {}
+
+    def __len__(self):
+        return len(self._host.feature_ids)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        f = self._cache.get(i)
+        if f is None:
+            f = self._cache[i] = DenseFeature(self._host, i)
+        return f
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
 
 
 class DenseHostBatch:
@@ -339,8 +402,13 @@ class DenseHostBatch:
       tasks     one row per (feature, sample): where its [n_pos][ld] matrix sits in `raw`, and where its rows go
       colmap    for samples whose positions are not the feature's: feature column of every sample position
     plus the per-feature tables of include/yanocomp_b200.h.  The device batch is built by yc_assemble_batch.
+
+    Everything is computed from the files' index arrays for all genes at once; only genes whose samples cover
+    different position sets (told by the position hashes of the index) take a per-gene step (union of the
+    positions, column maps).  A position's kmer comes from the last file that has events there (every sample
+    is aligned to the same reference, so this is the reference's "later files win", io.py:270-281).
     '''
-    TASK_FIELDS = 8        # feature, src offset (elements, int64 split in two), src ld, n_pos, n_reads, first row, colmap offset
+    TASK_FIELDS = 8        # feature, src offset (elements of raw), 0, src ld, n_pos, n_reads, first row, colmap offset | -1
 
     def __init__(self, files, gene_ids, n_cntrl, by_transcript=False, pin=True, copy_threads=4):
         R = len(files)
@@ -348,58 +416,68 @@ class DenseHostBatch:
             raise ValueError(f'need 1 <= n_cntrl < n_samples <= {N.YC_MAX_SAMPLES}')
         self.n_samples, self.n_cntrl = R, n_cntrl
         self.files = files
-        feats, tasks, colmaps = [], [], []
-        colmap_len = 0
-        spans = [[] for _ in range(R)]                           # per sample: (file offset, bytes, task index)
-        for gene_id in gene_ids:
-            genes = [f.gene(gene_id) for f in files]
-            if by_transcript and any(g.n_tx > 1 for g in genes):
+        gene_ids = list(gene_ids)
+        G = len(gene_ids)
+        idx = [np.fromiter((f.gene_index(g) for g in gene_ids), dtype=np.int64, count=G) for f in files]
+        rows = [f.index[i] for f, i in zip(files, idx)]
+        n_pos = np.stack([r['n_pos'].astype(np.int64) for r in rows]) if G else np.zeros((R, 0), np.int64)
+        n_rd = np.stack([r['n_reads'].astype(np.int64) for r in rows]) if G else np.zeros((R, 0), np.int64)
+        live = (n_pos > 0) & (n_rd > 0)                                    # (R, G)
+        n_rd = np.where(live, n_rd, 0)
+        keep = live.any(axis=0)
+        if by_transcript and G:
+            n_tx = np.stack([r['n_tx'] for r in rows])
+            if (n_tx[live] > 1).any():
                 raise NotImplementedError('dense batches hold one feature per gene; genes with several transcripts '
                                           'take the host route (io.load_gene_features) at --test-level transcript')
-            present = [g for g in genes if g.n_pos and g.n_reads]
-            if not present:
-                continue
-            if by_transcript:
-                # valid_transcripts = in both conditions (reference gmmtest.py:99); one transcript per gene here
-                names = {g.transcript_ids[0] for g in present if g.n_tx}
-                has_c = any(g.n_pos and g.n_reads for g in genes[:n_cntrl])
-                has_t = any(g.n_pos and g.n_reads for g in genes[n_cntrl:])
-                if len(names) != 1 or not (has_c and has_t):
-                    if len(names) > 1:
-                        raise NotImplementedError('the samples name different transcripts for one gene: host route')
-                    continue
-                feature_id = names.pop()
-            else:
-                feature_id = gene_id
-            first = present[0].positions
-            same = all(g.n_pos == len(first) and (g is present[0] or np.array_equal(g.positions, first)) for g in present)
-            positions = first.astype(np.int64) if same else np.unique(np.concatenate([g.positions for g in present])).astype(np.int64)
-            samp_start = np.zeros(R + 1, dtype=np.int32)
-            f_index = len(feats)
-            f_colmaps = []
-            for s, g in enumerate(genes):
-                live = g.n_pos and g.n_reads
-                samp_start[s + 1] = samp_start[s] + (g.n_reads if live else 0)
-                cm_off = -1
-                cm = None
-                if live and not (same or (g.n_pos == len(positions) and np.array_equal(g.positions, positions))):
-                    cm = np.searchsorted(positions, g.positions).astype(np.int32)
-                    colmaps.append(cm)
-                    cm_off = colmap_len
-                    colmap_len += len(cm)
-                f_colmaps.append(cm)
-                if live:
-                    spans[s].append((g.events_off, g.n_pos * g.ld * 2, len(tasks)))
-                    tasks.append([f_index, 0, 0, g.ld, g.n_pos, g.n_reads, int(samp_start[s]), cm_off])
-            a = genes[0].attrs
-            feats.append(DenseFeature(feature_id, a['chrom'], a['strand'], positions, samp_start,
-                                      [g if (g.n_pos and g.n_reads) else None for g in genes], f_colmaps,
-                                      _kmers_for_positions(genes, positions)))
-        self.features = feats
-        F = len(feats)
-        self.n_cols = np.array([f.n_cols for f in feats], dtype=np.int32)
-        self.n_reads = np.array([f.n_reads for f in feats], dtype=np.int32)
+            # valid_transcripts = in both conditions (reference gmmtest.py:99); one transcript per gene here
+            keep &= live[:n_cntrl].any(axis=0) & live[n_cntrl:].any(axis=0)
+        gsel = np.flatnonzero(keep)
+        F = len(gsel)
+        live, n_pos, n_rd = live[:, gsel], n_pos[:, gsel], n_rd[:, gsel]
+        rows = [r[gsel] for r in rows]
+        self.gene_of_feature = [gene_ids[g] for g in gsel.tolist()]
+        first = np.argmax(live, axis=0) if F else np.zeros(0, np.int64)    # first sample with events, per feature
+        last = (R - 1 - np.argmax(live[::-1], axis=0)) if F else np.zeros(0, np.int64)
+        ar = np.arange(F)
+        hashes = np.stack([r['pos_hash'] for r in rows]) if F else np.zeros((R, 0), np.uint64)
+        h0 = hashes[first, ar] if F else hashes[0]
+        uniform = ((hashes == h0) | ~live).all(axis=0) if F else np.zeros(0, bool)
+        # ---- per-feature tables
+        self.samp_start = np.zeros((F, R + 1), dtype=np.int32)
+        if F:
+            self.samp_start[:, 1:] = np.cumsum(n_rd.T, axis=1)
+        self.n_reads = self.samp_start[:, R].copy()
         self.ld = ((self.n_reads + 7) // 8 * 8).astype(np.int32)
+        n_cols = n_pos[first, ar].astype(np.int32) if F else np.zeros(0, np.int32)
+        pos_parts = [None] * F
+        kmer_parts = [None] * F
+        colmaps, cm_off_of = [], {}
+        colmap_len = 0
+        pos_off = np.stack([r['pos_off'].astype(np.int64) for r in rows]) if F else None
+        kat_off = np.stack([r['kmer_at_pos_off'].astype(np.int64) for r in rows]) if F else None
+        mms = [f._mm for f in files]
+        for fi in np.flatnonzero(~uniform).tolist():                      # ragged genes: union + column maps
+            ss = np.flatnonzero(live[:, fi]).tolist()
+            ps = [np.frombuffer(mms[s], dtype='<u4', count=int(n_pos[s, fi]), offset=int(pos_off[s, fi])) for s in ss]
+            union = np.unique(np.concatenate(ps)).astype(np.int64)
+            km = np.full(len(union), b'', dtype='S5')
+            for s, p in zip(ss, ps):
+                cm = np.searchsorted(union, p).astype(np.int32)
+                km[cm] = np.frombuffer(mms[s], dtype='S5', count=len(p), offset=int(kat_off[s, fi]))    # later files win
+                if len(p) != len(union):
+                    cm_off_of[(fi, s)] = colmap_len
+                    colmaps.append(cm)
+                    colmap_len += len(cm)
+            pos_parts[fi], kmer_parts[fi] = union, km
+            n_cols[fi] = len(union)
+        # uniform genes: positions of the first live sample, kmers of the last one; consecutive genes of a file are
+        # contiguous in its positions / kmers sections, so runs are taken with one frombuffer each
+        uni = np.flatnonzero(uniform)
+        if len(uni):
+            self._take_runs(mms, uni, first, pos_off, n_cols, '<u4', 4, pos_parts, to_int64=True)
+            self._take_runs(mms, uni, last, kat_off, n_cols, 'S5', 5, kmer_parts, to_int64=False)
+        self.n_cols = n_cols
         sizes = self.n_cols.astype(np.int64) * self.ld
         self.x_off = np.zeros(F, dtype=np.int64)
         if F:
@@ -408,54 +486,117 @@ class DenseHostBatch:
         self.col_off = np.zeros(F + 1, dtype=np.int64)
         self.col_off[1:] = np.cumsum(self.n_cols)
         self.total_cols = int(self.col_off[-1])
-        self.samp_start = (np.stack([f.samp_start for f in feats]) if F else np.zeros((0, R + 1), np.int32)).astype(np.int32)
-        self.feature_key = np.array([feature_key(f.feature_id) for f in feats], dtype=np.uint64)
-        self.col_pos = np.concatenate([f.positions for f in feats]).astype(np.int64) if F else np.zeros(0, np.int64)
-        self.reverse = np.array([f.strand == '-' for f in feats], dtype=np.uint8)
+        self.col_pos = np.concatenate(pos_parts).astype(np.int64, copy=False) if F else np.zeros(0, np.int64)
+        self.kmer_of_col = np.concatenate(kmer_parts) if F else np.zeros(0, 'S5')     # S5 per column, b'' = none
+        # ---- names
+        strands = rows[0]['strand'] if F else np.zeros(0, 'S1')
+        self.reverse = (strands == b'-').astype(np.uint8)
+        self.strands = strands.astype('U1').tolist()
+        f0 = files[0]
+        self.chroms = [f0._str(o, ln) for o, ln in zip(rows[0]['chrom_off'].tolist(), rows[0]['chrom_len'].tolist())] if F else []
+        if by_transcript:
+            names = []
+            for fi in range(F):
+                s = int(first[fi])
+                r = rows[s][fi]
+                names.append(files[s]._str(r['tx_names_off'], r['tx_names_len']).split('\n')[0])
+            self.feature_ids = names
+        else:
+            self.feature_ids = list(self.gene_of_feature)
+        self.feature_key = np.array([feature_key(x) for x in self.feature_ids], dtype=np.uint64)
+        self.features = _LazyFeatures(self)
         self.max_reads = int(self.n_reads.max()) if F else 0
         split = self.samp_start[:, n_cntrl] if F else np.zeros(0, dtype=np.int32)
         self.max_cond_reads = int(max(split.max(), (self.n_reads - split).max())) if F else 0
-        # ---- raw buffer: per sample, the byte ranges of its genes coalesced into as few copies as possible
-        self.tasks = np.array(tasks, dtype=np.int64).reshape(-1, self.TASK_FIELDS)
-        copies, total = [], 0                                    # (sample, file offset, bytes, destination byte offset)
+        # ---- tasks: one row per live (sample, feature), sample-major so that a sample's blocks follow the file order
+        ev_off = np.stack([r['events_off'].astype(np.int64) for r in rows]) if F else np.zeros((R, 0), np.int64)
+        s_ld = np.stack([r['ld'].astype(np.int64) for r in rows]) if F else np.zeros((R, 0), np.int64)
+        task_blocks, copies, total = [], [], 0
         for s in range(R):
-            run = None
-            for off, nb, ti in spans[s]:
-                if run is not None and 0 <= off - (run[0] + run[1]) <= 4 * _RAW_GAP:
-                    run[1] = off + nb - run[0]                   # extend over the alignment gap
-                else:
-                    if run is not None:
-                        copies.append((s, run[0], run[1], run[2]))
-                        total = run[2] + _round_up64(run[1])
-                    run = [off, nb, total]
-                self.tasks[ti, 1] = (run[2] + off - run[0]) // 2          # element offset inside `raw`
-            if run is not None:
-                copies.append((s, run[0], run[1], run[2]))
-                total = run[2] + _round_up64(run[1])
-        self.raw = HostBatch._alloc_events(total // 2, pin)
+            fsel = np.flatnonzero(live[s])
+            if not len(fsel):
+                continue
+            off = ev_off[s, fsel]
+            nb = n_pos[s, fsel] * s_ld[s, fsel] * 2
+            # runs of blocks that are adjacent in the file (up to the 64-byte alignment gaps) are copied at once
+            gap = off[1:] - (off[:-1] + nb[:-1])
+            brk = np.flatnonzero((gap < 0) | (gap > 4 * _RAW_GAP)) + 1
+            starts = np.r_[0, brk]
+            ends = np.r_[brk, len(fsel)]
+            run_off = off[starts]
+            run_nb = off[ends - 1] + nb[ends - 1] - run_off
+            run_dst = total + np.r_[0, np.cumsum((run_nb + 63) // 64 * 64)[:-1]]
+            total = int(run_dst[-1] + (run_nb[-1] + 63) // 64 * 64)
+            copies.extend((s, int(o), int(b), int(dd)) for o, b, dd in zip(run_off.tolist(), run_nb.tolist(), run_dst.tolist()))
+            run_of = np.repeat(np.arange(len(starts)), ends - starts)
+            src = (run_dst[run_of] + off - run_off[run_of]) // 2
+            cm = np.full(len(fsel), -1, dtype=np.int64)
+            if cm_off_of:
+                for j, fi in enumerate(fsel.tolist()):
+                    cm[j] = cm_off_of.get((fi, s), -1)
+            t = np.zeros((len(fsel), self.TASK_FIELDS), dtype=np.int64)
+            t[:, 0], t[:, 1], t[:, 3], t[:, 4] = fsel, src, s_ld[s, fsel], n_pos[s, fsel]
+            t[:, 5], t[:, 6], t[:, 7] = n_rd[s, fsel], self.samp_start[fsel, s], cm
+            task_blocks.append(t)
+        self.tasks32 = np.concatenate(task_blocks) if task_blocks else np.zeros((0, self.TASK_FIELDS), np.int64)
+        self.raw = HostBatch._alloc_events(total // 2, pin, owner=self)
         raw8 = self.raw.view(np.uint8)
-        bufs = [f.buffer() for f in files]
+        fds = [f.fileno() for f in files]
 
         def copy(c):
+            # positional reads straight into the pinned buffer: the page cache is copied once and the file mapping is
+            # not touched (faulting a fresh mapping in cost 5x the copy itself)
             s, off, nb, dst = c
-            raw8[dst:dst + nb] = bufs[s][off:off + nb]
-        if copy_threads > 1 and len(copies) > 1:
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(copy_threads) as pool:      # memcpy releases the GIL
-                list(pool.map(copy, _split_copies(copies)))
+            view = memoryview(raw8[dst:dst + nb])
+            done = 0
+            while done < nb:
+                k = os.preadv(fds[s], [view[done:]], off + done)
+                if k <= 0:
+                    raise IOError(f'{files[s].filename}: short read at offset {off + done}')
+                done += k
+        pieces = _split_copies(copies)
+        if copy_threads > 1 and len(pieces) > 1:
+            with _copy_pool(copy_threads) as pool:                       # memcpy releases the GIL
+                list(pool.map(copy, pieces))
         else:
-            for c in copies:
+            for c in pieces:
                 copy(c)
         self.colmap = np.concatenate(colmaps).astype(np.int32) if colmaps else np.zeros(1, dtype=np.int32)
-        self.tasks32 = np.ascontiguousarray(self.tasks).astype(np.int64)
         if pin:
             for name in ('n_cols', 'n_reads', 'ld', 'x_off', 'col_off', 'samp_start', 'feature_key', 'col_pos', 'reverse',
                          'colmap', 'tasks32'):
-                setattr(self, name, HostBatch._pinned_copy(getattr(self, name)))
+                setattr(self, name, HostBatch._pinned_copy(getattr(self, name), owner=self))
+
+    @staticmethod
+    def _take_runs(mms, feats, sample_of, offs, n_cols, dtype, itemsize, out, to_int64):
+        '''out[fi] = the feature's array of the chosen sample's section; features that sit back to back in one file share a read'''
+        s_of = sample_of[feats]
+        o = offs[s_of, feats]
+        n = n_cols[feats].astype(np.int64)
+        brk = np.flatnonzero((s_of[1:] != s_of[:-1]) | (o[1:] != o[:-1] + n[:-1] * itemsize)) + 1
+        starts, ends = np.r_[0, brk], np.r_[brk, len(feats)]
+        for a, e in zip(starts.tolist(), ends.tolist()):
+            cnt = int(n[a:e].sum())
+            arr = np.frombuffer(mms[int(s_of[a])], dtype=dtype, count=cnt, offset=int(o[a]))
+            if to_int64:
+                arr = arr.astype(np.int64)
+            if e - a == 1:
+                out[int(feats[a])] = arr
+            else:
+                cuts = np.cumsum(n[a:e])[:-1]
+                for fi, part in zip(feats[a:e].tolist(), np.split(arr, cuts)):
+                    out[fi] = part
+
+    def kmer_strings(self, c0, c1):
+        '''kmers of columns [c0, c1) as an object array of str (None = no kmer recorded)'''
+        k = self.kmer_of_col[c0:c1]
+        out = k.astype('U5').astype(object)
+        out[k == b''] = None
+        return out
 
     @property
     def n_features(self):
-        return len(self.features)
+        return len(self.feature_ids)
 
     @property
     def nbytes(self):
@@ -474,13 +615,27 @@ class DenseHostBatch:
 
 
 _RAW_GAP = 64
+_POOLS = {}
 
 
-def _round_up64(n):
-    return (n + 63) // 64 * 64
+class _copy_pool:
+    '''a process-wide thread pool for the page-cache -> pinned copies (creating one per batch costs more than a copy)'''
+
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        pool = _POOLS.get(self.n)
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = _POOLS[self.n] = ThreadPoolExecutor(self.n)
+        return pool
+
+    def __exit__(self, *exc):
+        return False
 
 
-def _split_copies(copies, piece=32 << 20):
+def _split_copies(copies, piece=8 << 20):
     '''large copies cut into pieces so that a few threads share them evenly'''
     out = []
     for s, off, nb, dst in copies:

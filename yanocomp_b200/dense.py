@@ -16,7 +16,8 @@ once: for every gene of one sample
                 15 per event
     transcripts [n_pos][ld] uint8 transcript index per event, only for genes with more than one
                 transcript (needed for --test-level transcript)
-    kmers       the file's (position, kmer) table, as in the reference
+    kmers       the kmer of every one of those positions, and the file's whole (position, kmer)
+                table as the reference keeps it
 
 so that `gmmtest` ingests a sample with one large read per file and batch, uploads the bytes
 as they are and assembles the per-gene matrices ON THE DEVICE (yc_assemble_batch).
@@ -26,7 +27,9 @@ Physical layout (little endian, every blob 64-byte aligned):
     bytes 0..7   magic b'YCDENS01'
     events       the event matrices of all genes, back to back in gene order: a run of
                  consecutive genes is ONE contiguous byte range
-    metadata     positions / read ids / kmers / transcript matrices of all genes
+    metadata     section by section, each in gene order: positions (<u4, packed), kmers at those
+                 positions (S5, packed), read ids, kmer tables, transcript matrices -- the positions
+                 and kmers of a run of consecutive genes are one contiguous range each
     strings      gene, chromosome and transcript names
     index        GENE_DTYPE record per gene
     last 40 B    <u8 strings offset, length, index offset, number of genes, magic check
@@ -35,6 +38,7 @@ Written by `python -m yanocomp_b200 pack IN OUT` from the reference's HDF5 or th
 prep output (`convert`), which applies the reference's row rules through the same functions the
 HDF5 route uses (io._clean_events, io._sample_block).
 '''
+import hashlib
 import mmap
 import struct
 
@@ -47,8 +51,12 @@ GENE_DTYPE = np.dtype([
     ('name_off', '<u4'), ('name_len', '<u4'), ('chrom_off', '<u4'), ('chrom_len', '<u4'),
     ('tx_names_off', '<u4'), ('tx_names_len', '<u4'), ('strand', 'S1'), ('n_tx', '<u2'),
     ('n_pos', '<u4'), ('n_reads', '<u4'), ('ld', '<u4'), ('n_kmers', '<u4'), ('n_events', '<u8'),
-    ('events_off', '<u8'), ('pos_off', '<u8'), ('read_ids_off', '<u8'), ('kmers_off', '<u8'), ('tx_off', '<u8'),
+    ('pos_hash', '<u8'),          # blake2b-64 of the packed <u4 positions: equal hashes = equal position sets
+    ('events_off', '<u8'), ('pos_off', '<u8'), ('kmer_at_pos_off', '<u8'), ('read_ids_off', '<u8'),
+    ('kmers_off', '<u8'), ('tx_off', '<u8'),
 ])
+_SECTIONS = ('pos_off', 'kmer_at_pos_off', 'read_ids_off', 'kmers_off', 'tx_off')
+_PACKED = ('pos_off', 'kmer_at_pos_off')          # no padding between the genes of these sections
 _ALIGN = 64
 _FOOTER = struct.Struct('<QQQQ8s')
 
@@ -58,8 +66,11 @@ class DenseFormatError(IOError):
 
 
 def is_dense(fn):
-    with open(fn, 'rb') as f:
-        return f.read(len(MAGIC)) == MAGIC
+    try:
+        with open(fn, 'rb') as f:
+            return f.read(len(MAGIC)) == MAGIC
+    except OSError:
+        return False
 
 
 def _round_up(n, k):
@@ -77,7 +88,7 @@ class Writer:
         self._f.write(MAGIC)
         self._pad()
         self._rows = []
-        self._meta = []               # (row index, field, bytes)
+        self._meta = {k: [] for k in _SECTIONS}      # field -> [(row index, bytes)]
         self._strings = bytearray()
         self._seen = set()
 
@@ -127,25 +138,41 @@ class Writer:
         self._f.write(block.tobytes())
         kmers = np.ascontiguousarray(kmers, dtype=KMER_DTYPE)
         row['n_kmers'] = len(kmers)
+        pos_bytes = positions.astype('<u4').tobytes()
+        row['pos_hash'] = int.from_bytes(hashlib.blake2b(pos_bytes, digest_size=8).digest(), 'little')
+        # kmer of every present position from the file's own table (the last record of a position wins, io.py:186)
+        at = np.full(n_pos, b'', dtype='S5')
+        if n_pos and len(kmers):
+            order = np.argsort(kmers['pos'], kind='stable')
+            kp, kk = kmers['pos'][order].astype(np.int64), kmers['kmer'][order]
+            last = np.flatnonzero(np.r_[kp[1:] != kp[:-1], True])
+            kp, kk = kp[last], kk[last]
+            j = np.minimum(np.searchsorted(kp, positions), len(kp) - 1)
+            hit = kp[j] == positions
+            at[hit] = kk[j[hit]]
         i = len(self._rows)
         self._rows.append(row)
-        self._meta.append((i, 'pos_off', positions.astype('<u4').tobytes()))
-        self._meta.append((i, 'read_ids_off', np.asarray(
+        self._meta['pos_off'].append((i, pos_bytes))
+        self._meta['kmer_at_pos_off'].append((i, at.tobytes()))
+        self._meta['read_ids_off'].append((i, np.asarray(
             [str(r).encode('ascii')[:READ_ID_LEN] for r in read_ids], dtype=f'S{READ_ID_LEN}').tobytes()))
-        self._meta.append((i, 'kmers_off', kmers.tobytes()))
+        self._meta['kmers_off'].append((i, kmers.tobytes()))
         if tx is not None and len(transcript_ids) > 1:
             tb = np.zeros((n_pos, ld), dtype=np.uint8)
             tb[:, :n_reads] = tx
-            self._meta.append((i, 'tx_off', tb.tobytes()))
+            self._meta['tx_off'].append((i, tb.tobytes()))
 
     def close(self, ok=True):
         if self._f is None:
             return
         if ok:
-            for i, field, blob in self._meta:
+            for field in _SECTIONS:
                 self._pad()
-                self._rows[i][field] = self._f.tell()
-                self._f.write(blob)
+                for i, blob in self._meta[field]:
+                    if field not in _PACKED:
+                        self._pad()
+                    self._rows[i][field] = self._f.tell()
+                    self._f.write(blob)
             self._pad()
             s_off = self._f.tell()
             self._f.write(bytes(self._strings))
@@ -194,6 +221,11 @@ class Gene:
             return None
         return np.frombuffer(self._f._mm, dtype=np.uint8, count=self.n_pos * self.ld,
                              offset=int(self.row['tx_off'])).reshape(self.n_pos, self.ld)
+
+    @property
+    def kmer_at_pos(self):
+        '''(n_pos,) S5: kmer of every present position (b'' = none recorded)'''
+        return np.frombuffer(self._f._mm, dtype='S5', count=self.n_pos, offset=int(self.row['kmer_at_pos_off']))
 
     @property
     def read_ids(self):
@@ -262,6 +294,9 @@ class File:
         if gene in self._by_name and leaf == 'events':
             return _Sized(int(self.index[self._by_name[gene]]['n_events']))
         raise KeyError(path)
+
+    def fileno(self):
+        return self._fh.fileno()
 
     def buffer(self):
         '''the whole file as a uint8 array (memory map): batches copy byte ranges of the event section out of it'''

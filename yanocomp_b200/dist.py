@@ -64,16 +64,93 @@ def shard_by_size(items, sizes, n_shards):
     return [[items[i] for i in sorted(a)] for a in assign]
 
 
+def _gather_rowblocks(blocks, sm_preds, world, rank):
+    '''
+    The exchange step of the path on fixed-width rows: every rank contributes ONE float64 matrix
+    (result rows | feature index | position) and one byte matrix (window kmers), padded to the longest rank and
+    collected with `dist.gather` (NCCL over NVLink between GPUs, gloo in the CPU tests); only the small per-feature name
+    tables travel as Python objects.  Returns rank 0's merged (RowBlock or None, sm_preds).
+    '''
+    import torch
+    import torch.distributed as dist
+    from .gmmtest import RowBlock
+    blk = RowBlock.concat(blocks) if blocks else None
+    n = len(blk) if blk is not None else 0
+    has_rows = blk is not None and blk.rows is not None
+    width = (blk.rows.shape[1] if has_rows else 2) if blk is not None else 0
+    w = blk.window if blk is not None else 0
+    any_preds = any(v is not None for d in sm_preds.values() for v in d.values())
+    tables = (blk.feature_ids, blk.chroms, blk.strands) if blk is not None else ([], [], [])
+    metas = [None] * world
+    dist.all_gather_object(metas, (n, width, w, has_rows, tables, sm_preds if any_preds else None))
+    n_max = max(m[0] for m in metas)
+    width = max(m[1] for m in metas)
+    w = max(m[2] for m in metas)
+    gmm = any(m[3] for m in metas)
+    if n_max == 0:
+        return None, {}
+    use_cuda = dist.get_backend() == 'nccl'
+    dev = torch.device('cuda', torch.cuda.current_device()) if use_cuda else torch.device('cpu')
+    num = torch.zeros((n_max, width + 2), dtype=torch.float64)
+    kmb = torch.zeros((n_max, 5 * w), dtype=torch.uint8)
+    if n:
+        body = blk.rows if has_rows else np.stack([blk.p_val, blk.ks], axis=1)
+        num[:n, :width] = torch.from_numpy(np.ascontiguousarray(body))
+        num[:n, width] = torch.from_numpy(blk.fidx.astype(np.float64))
+        num[:n, width + 1] = torch.from_numpy(blk.pos.astype(np.float64))
+        kmb[:n] = torch.from_numpy(np.ascontiguousarray(blk.kmers).view(np.uint8).reshape(n, 5 * w))
+    num, kmb = num.to(dev), kmb.to(dev)
+    got_num = [torch.empty_like(num) for _ in range(world)] if rank == 0 else None
+    got_kmb = [torch.empty_like(kmb) for _ in range(world)] if rank == 0 else None
+    dist.gather(num, got_num, dst=0)
+    dist.gather(kmb, got_kmb, dst=0)
+    if rank != 0:
+        return None, {}
+    parts, all_sm = [], {}
+    for (m_n, _, _, _, (ids, chroms, strands), sm), tn, tk in zip(metas, got_num, got_kmb):
+        if m_n:
+            a = tn[:m_n].cpu().numpy()
+            k = tk[:m_n].cpu().numpy().reshape(m_n, w, 5).copy().view('S5').reshape(m_n, w)
+            fidx, pos = a[:, width].astype(np.int32), a[:, width + 1].astype(np.int64)
+            if gmm:
+                parts.append(RowBlock(ids, chroms, strands, fidx, pos, k, rows=np.ascontiguousarray(a[:, :width])))
+            else:
+                parts.append(RowBlock(ids, chroms, strands, fidx, pos, k, p_val=a[:, 0].copy(), ks=a[:, 1].copy()))
+            if sm is None:                                  # no predictions were made: {feature: {pos: None}} rebuilt here
+                cuts = np.flatnonzero(np.diff(fidx)) + 1
+                pl = pos.tolist()
+                for lo, hi in zip(np.r_[0, cuts].tolist(), np.r_[cuts, m_n].tolist()):
+                    all_sm.setdefault(ids[int(fidx[lo])], {}).update(dict.fromkeys(pl[lo:hi]))
+        if sm is not None:
+            for k2, v in sm.items():
+                all_sm.setdefault(k2, {}).update(v)
+    return RowBlock.concat(parts), all_sm
+
+
 def gather_results(records, sm_preds):
     '''
     Gather per-rank (records, sm_preds) on rank 0 (the pickled return of the
     reference's pool workers, gmmtest.py:204-208).  Rank 0 gets the
-    concatenation in rank order; other ranks get ([], {}).
+    concatenation in rank order; other ranks get ([], {}).  Records that are
+    fixed-width row blocks on every rank (what test_chunk returns) travel as
+    tensors (_gather_rowblocks); anything else as pickled objects.
     '''
     world, rank = world_info()
     if world == 1:
         return records, sm_preds
     import torch.distributed as dist
+    blocks = records.row_blocks() if hasattr(records, 'row_blocks') else None
+    mine_ok = blocks is not None or (hasattr(records, 'blocks') and not records.blocks)
+    oks = [None] * world
+    dist.all_gather_object(oks, bool(mine_ok))
+    if all(oks):
+        blk, all_sm = _gather_rowblocks(blocks or [], sm_preds, world, rank)
+        if rank != 0:
+            return [], {}
+        out = type(records)()
+        if blk is not None:
+            out.add_block(blk)
+        return out, all_sm
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((records, sm_preds), gathered, dst=0)
     if rank != 0:

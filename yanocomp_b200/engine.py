@@ -261,7 +261,13 @@ class Engine:
             t['n_t'].data_ptr(), t['status'].data_ptr(), t['fit_list'].data_ptr(), t['fit_count'].data_ptr(),
             stream)))
         ks_done = torch.cuda.current_stream(d).record_event()
-        counts = torch.empty(2, dtype=torch.int64, pin_memory=True)     # [n_fit, posterior reads written]
+        # [n_fit, posterior reads written]: pinned, from a ring (a pinned allocation per range costs more than its kernels'
+        # launches; at most a handful of ranges are in flight, so 32 slots never collide)
+        if not hasattr(self, '_count_ring'):
+            self._count_ring = [torch.empty(2, dtype=torch.int64, pin_memory=True) for _ in range(32)]
+            self._count_next = 0
+        counts = self._count_ring[self._count_next % 32]
+        self._count_next += 1
         counts.zero_()
         cnt32 = counts.view(torch.int32)
         cnt32[:1].copy_(t['fit_count'], non_blocking=True)

@@ -10,10 +10,13 @@ are packed into ragged device batches (`io.load_gene_features`,
 `batch.HostBatch`) and the whole KS -> GMM -> G-test -> posterior path runs in
 the CUDA kernels of libyanocomp_b200 (`engine.Engine`).
 '''
+import collections
 import collections.abc
 import dataclasses
+import itertools
 import logging
 import os
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 import click
@@ -32,6 +35,27 @@ from .stats import (benjamini_hochberg, assign_modified_distribution, format_mod
 
 logger = logging.getLogger('yanocomp')
 
+# wall-clock seconds per host-side stage of the last parallel_test / test_chunk calls of this process (bench.py's
+# `job` block reads and resets it): 'open' listing the genes of the input files and sharding them, 'ingest' building
+# the packed batches, 'device' launching the kernels and waiting for their results (uploads, kernels and fetches
+# overlap inside it), 'records' the column-block record assembly, 'gather' the exchange with rank 0, 'frame_bh' the
+# DataFrame and the BH correction
+STAGES = collections.defaultdict(float)
+COUNTS = collections.Counter()      # positions_tested (entered position_stats) / positions_fitted of the same calls
+
+
+def _timed_iter(gen, name):
+    it = iter(gen)
+    while True:
+        t0 = time.perf_counter()
+        try:
+            x = next(it)
+        except StopIteration:
+            STAGES[name] += time.perf_counter() - t0
+            return
+        STAGES[name] += time.perf_counter() - t0
+        yield x
+
 # DataFrame columns of parallel_test (reference gmmtest.py:216-220, stats.py:423-442)
 POS_COLUMNS = ['chrom', 'pos', 'gene_id', 'strand']
 RESULT_COLUMNS = ['kmer', 'kmers', 'centre', 'log_odds', 'log_odds_lower_ci', 'log_odds_upper_ci',
@@ -44,6 +68,93 @@ PIPELINE_RANGES = 4              # feature ranges per batch in the upload | kern
 
 # columns whose cells are arrays of length window_size
 _ARRAY_COLUMNS = {'kmers', 'dist1_means', 'dist1_stds', 'dist2_means', 'dist2_stds'}
+
+
+_B4 = np.full(256, -1, dtype=np.int16)
+for _i, _c in enumerate(b'ACGT'):
+    _B4[_c] = _i
+KMER_TABLE = np.array([''.join(k) for k in itertools.product('ACGT', repeat=5)], dtype=object)
+
+
+def kmer_strings(k):
+    '''S5 array (any shape) -> object array of str.  A, C, G, T kmers go through a 1 024-entry table (a numeric code and
+    one gather; `astype(str)` costs 120 ns per kmer); anything else takes the general conversion.'''
+    k = np.ascontiguousarray(k)
+    if k.dtype != np.dtype('S5'):
+        return k.astype(str).astype(object)
+    d = _B4[k.view(np.uint8).reshape(k.shape + (5,))]
+    if d.size and d.min() < 0:
+        return k.astype('U5').astype(object)
+    return KMER_TABLE[(((d[..., 0] * 4 + d[..., 1]) * 4 + d[..., 2]) * 4 + d[..., 3]) * 4 + d[..., 4]]
+
+
+@dataclasses.dataclass
+class RowBlock:
+    '''
+    The records of one batch as the device produced them: the fixed-width result rows (yc_gather_fit_rows) plus, per
+    row, the feature index, the position and the window's kmers as bytes, and the batch's small per-feature tables.
+    No per-row Python object exists until somebody asks for one (`columns`, iteration over `Records`); the DataFrame
+    of parallel_test and the gather over the ranks work on these arrays directly.
+    '''
+    feature_ids: list
+    chroms: list
+    strands: list
+    fidx: np.ndarray                   # (n,) index into the three tables
+    pos: np.ndarray                    # (n,) int64
+    kmers: np.ndarray                  # (n, w) S5, window order (reversed on the - strand, gmmtest.py:37-38)
+    rows: np.ndarray = None            # (n, row_width(w)) float64; None for --no-gmm
+    p_val: np.ndarray = None           # --no-gmm: KS p-value and D
+    ks: np.ndarray = None
+    _cols: list = None
+
+    def __len__(self):
+        return len(self.pos)
+
+    @property
+    def window(self):
+        return self.kmers.shape[1]
+
+    def columns(self):
+        '''the 21 GMMTestRecord columns (reference gmmtest.py:120-136), cached'''
+        if self._cols is None:
+            n, w = len(self), self.window
+            centre = w // 2
+            obj = lambda values: np.array(list(values) + [None], dtype=object)[:-1]
+            win = kmer_strings(self.kmers).astype(str)
+            if self.rows is not None:
+                r = self.rows
+                st = [np.ascontiguousarray(r[:, N.ROW_STATS + j]) for j in range(8)]
+                g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = st
+                mu = r[:, N.ROW_MU:N.ROW_MU + 2 * w].reshape(n, 2, w)
+                sd = r[:, N.ROW_MU + 2 * w:N.ROW_MU + 4 * w].reshape(n, 2, w)
+                dists = [np.ascontiguousarray(mu[:, 0]), np.ascontiguousarray(sd[:, 0]),
+                         np.ascontiguousarray(mu[:, 1]), np.ascontiguousarray(sd[:, 1])]
+                ks = np.ascontiguousarray(r[:, N.ROW_KS_STAT])
+            else:
+                nan_col = np.full(n, np.nan)
+                p_val, ks = self.p_val, self.ks
+                g_stat = hom_g = c_frac = t_frac = lor = lo = hi = nan_col
+                dists = [np.full(n, None, dtype=object)] * 4
+            f = self.fidx
+            self._cols = [obj(self.chroms)[f], self.pos, obj(self.feature_ids)[f], obj(self.strands)[f],
+                          win[:, centre].astype(object), win, np.full(n, centre, dtype=np.int64), lor, lo, hi, p_val,
+                          np.ones(n), c_frac, t_frac, g_stat, hom_g] + dists + [ks]
+        return self._cols
+
+    @staticmethod
+    def concat(blocks):
+        '''one block out of several (feature tables appended, indices shifted)'''
+        blocks = [b for b in blocks if len(b)]
+        if not blocks:
+            return None
+        if len(blocks) == 1:
+            return blocks[0]
+        off = np.cumsum([0] + [len(b.feature_ids) for b in blocks])
+        cat = lambda name: (np.concatenate([getattr(b, name) for b in blocks]) if getattr(blocks[0], name) is not None else None)
+        return RowBlock(feature_ids=sum((list(b.feature_ids) for b in blocks), []), chroms=sum((list(b.chroms) for b in blocks), []),
+                        strands=sum((list(b.strands) for b in blocks), []),
+                        fidx=np.concatenate([b.fidx.astype(np.int64) + o for b, o in zip(blocks, off)]),
+                        pos=cat('pos'), kmers=cat('kmers'), rows=cat('rows'), p_val=cat('p_val'), ks=cat('ks'))
 
 
 class Records(collections.abc.Sequence):
@@ -61,10 +172,24 @@ class Records(collections.abc.Sequence):
         self.extend(rows)
 
     def add_block(self, columns):
+        if isinstance(columns, RowBlock):
+            if len(columns):
+                self.blocks.append(columns)
+            return
         n = len(columns[1])
         if n:
             assert len(columns) == len(COLUMNS) and all(len(c) == n for c in columns)
             self.blocks.append(list(columns))
+
+    def _column_blocks(self):
+        return [b.columns() if isinstance(b, RowBlock) else b for b in self.blocks]
+
+    def row_blocks(self):
+        '''the blocks if every one of them is a RowBlock of the same kind, else None'''
+        if self.blocks and all(isinstance(b, RowBlock) for b in self.blocks):
+            if len({(b.rows is None, b.window) for b in self.blocks}) == 1:
+                return self.blocks
+        return None
 
     def extend(self, rows):
         if isinstance(rows, Records):
@@ -83,10 +208,10 @@ class Records(collections.abc.Sequence):
             self.add_block(cols)
 
     def __len__(self):
-        return sum(len(b[1]) for b in self.blocks)
+        return sum(len(b) if isinstance(b, RowBlock) else len(b[1]) for b in self.blocks)
 
     def __iter__(self):
-        for b in self.blocks:
+        for b in self._column_blocks():
             yield from zip(*(c.tolist() if c.ndim == 1 and c.dtype != object else c for c in b))
 
     def __getitem__(self, i):
@@ -94,7 +219,7 @@ class Records(collections.abc.Sequence):
             return list(self)[i]
         if i < 0:
             i += len(self)
-        for b in self.blocks:
+        for b in self._column_blocks():
             n = len(b[1])
             if i < n:
                 return tuple(c[i].item() if (c.ndim == 1 and c.dtype != object) else c[i] for c in b)
@@ -104,7 +229,7 @@ class Records(collections.abc.Sequence):
     def column(self, j):
         '''column j over all blocks: 1-D array, or object array of row arrays for the array-valued fields'''
         parts = []
-        for b in self.blocks:
+        for b in self._column_blocks():
             c = b[j]
             if c.ndim == 2:
                 o = np.empty(len(c), dtype=object)
@@ -213,19 +338,33 @@ def _kmers_by_column(feat):
     return kb
 
 
+def _record_attrs(host):
+    '''per-feature tables + the kmer of every column of a batch, computed once per batch (shared by its ranges)'''
+    attrs = getattr(host, '_record_attrs', None)
+    if attrs is None:
+        if hasattr(host, 'kmer_of_col'):                                      # dense batches carry them as arrays
+            attrs = (list(host.chroms), list(host.feature_ids), list(host.strands), host.kmer_of_col)
+        else:
+            feats = host.features
+            kb = np.concatenate([_kmers_by_column(f) for f in feats]) if len(feats) else np.zeros(0, dtype=object)
+            missing = kb == None                                              # noqa: E711 (elementwise)
+            k5 = np.where(missing, '', kb).astype('S5')
+            attrs = ([f.chrom for f in feats], [f.feature_id for f in feats], [f.strand for f in feats], k5)
+        host._record_attrs = attrs
+    return attrs
+
+
 def _batch_records(host, res, opts):
     '''
-    Device results of one batch -> (records, sm_preds) in the reference's shapes
-    (GMMTestRecord fields, reference gmmtest.py:120-136, 164-178).  The records are built as whole
-    columns (`Records`): feature attributes, positions and window kmers are gathers over the
-    batch's column index, the statistics are slices of the result rows.  Only the positions that
-    carry single-molecule predictions are visited one by one.
+    Device results of one batch -> (records, sm_preds) in the reference's shapes (GMMTestRecord fields, reference
+    gmmtest.py:120-136, 164-178).  The records are ONE RowBlock: the fixed-width result rows as fetched, plus
+    feature index, position and window kmers gathered over the batch's column index -- no per-row Python object.
+    Only the positions that carry single-molecule predictions are visited one by one.
     '''
     w = opts.window_size
     centre = w // 2
     n_cntrl = host.n_cntrl
     records, sm = Records(), {}
-    feats = host.features
     if not opts.gmm:
         cols = np.flatnonzero(res.status == N.ST_KS_ONLY)
         slots = None
@@ -236,54 +375,59 @@ def _batch_records(host, res, opts):
     if n == 0:
         return records, sm
     fidx = np.searchsorted(host.col_off, cols, side='right') - 1
-    attrs = getattr(host, '_record_attrs', None)
-    if attrs is None:                                                         # per batch, shared by its ranges
-        obj = lambda values: np.array(list(values) + [None], dtype=object)[:-1]
-        attrs = host._record_attrs = (obj(f.chrom for f in feats), obj(f.feature_id for f in feats),
-                                      obj(f.strand for f in feats),
-                                      np.concatenate([_kmers_by_column(f) for f in feats]))
-    chrom, gene_id, strand, kmer_of_col = attrs
+    chroms, feature_ids, strands, kmer_of_col = _record_attrs(host)
     pos = np.asarray(host.col_pos)[cols].astype(np.int64)
     step = np.where(np.asarray(host.reverse)[fidx] != 0, -1, 1)               # '-' strand: window read right to left
     win = kmer_of_col[cols[:, None] + step[:, None] * np.arange(-centre, centre + 1)[None, :]]
-    if (win == None).any():                                                   # noqa: E711 (elementwise)
+    if (win == b'').any():
         raise KeyError('no kmer recorded for a tested window')
-    win = win.astype(str)
-    nan_col = np.full(n, np.nan)
+    post_off = None
     if slots is not None:
-        stats = np.asarray(res.stats)[slots]                                  # fancy indexing = copies: the
-        mu, sd = np.asarray(res.mu)[slots], np.asarray(res.stds)[slots]       # staging buffer is reused later
-        g_stat, hom_g, p_val, c_frac, t_frac, lor, lo, hi = (np.ascontiguousarray(stats[:, j]) for j in range(8))
-        dists = [np.ascontiguousarray(mu[:, 0]), np.ascontiguousarray(sd[:, 0]),
-                 np.ascontiguousarray(mu[:, 1]), np.ascontiguousarray(sd[:, 1])]
-        ks = np.asarray(res.ks_stat_fit)[slots]
+        rows = (np.asarray(res.rows)[slots] if res.rows is not None else
+                _rows_from_arrays(res, slots, w))                             # fancy indexing = a copy: the staging buffer is reused
         post_off = np.asarray(res.post_off)[slots] if res.post_off is not None else None
         if post_off is not None and (post_off == -2).any():
             raise RuntimeError('single-molecule posterior buffer overflow (internal sizing error)')
+        block = RowBlock(feature_ids, chroms, strands, fidx.astype(np.int32), pos, win, rows=rows)
     else:
-        p_val, ks = np.asarray(res.ks_pval)[cols], np.asarray(res.ks_stat)[cols]
-        g_stat = hom_g = c_frac = t_frac = lor = lo = hi = nan_col
-        dists = [np.full(n, None, dtype=object)] * 4
-        post_off = None
-    records.add_block([chrom[fidx], pos, gene_id[fidx], strand[fidx], win[:, centre].astype(object), win,
-                       np.full(n, centre, dtype=np.int64), lor, lo, hi, p_val, np.ones(n), c_frac, t_frac,
-                       g_stat, hom_g] + dists + [ks])
+        block = RowBlock(feature_ids, chroms, strands, fidx.astype(np.int32), pos, win,
+                         p_val=np.asarray(res.ks_pval)[cols], ks=np.asarray(res.ks_stat)[cols])
+    records.add_block(block)
     # sm_preds[feature][pos]: None unless the position is significant and -s was asked for
     run_starts = np.concatenate(([0], np.flatnonzero(np.diff(fidx)) + 1, [n])).tolist()
     pos_list = pos.tolist()
+    win_str = None
     for a, b in zip(run_starts[:-1], run_starts[1:]):
         fi = int(fidx[a])
-        f = feats[fi]
-        fsm = sm.setdefault(f.feature_id, {})
+        fsm = sm.setdefault(feature_ids[fi], {})
         fsm.update(dict.fromkeys(pos_list[a:b]))
         if post_off is not None and res.post is not None:
-            for i in (np.flatnonzero(post_off[a:b] >= 0) + a).tolist():
-                s = int(slots[i])
-                off = int(post_off[i])
-                model = format_model(mu[i], res.cov[s], res.box[s] if opts.add_uniform else None, res.cw[s])
-                fsm[pos_list[i]] = _position_sm_preds(f, int(cols[i] - host.col_off[fi]), win[i], opts, n_cntrl, model,
-                                                      res.post[off:off + int(res.nall_fit[s])].copy())
+            hits = (np.flatnonzero(post_off[a:b] >= 0) + a).tolist()
+            if hits:
+                f = host.features[fi]
+                if win_str is None:
+                    win_str = kmer_strings(win).astype(str)
+                mu = rows[:, N.ROW_MU:N.ROW_MU + 2 * w].reshape(n, 2, w)
+                for i in hits:
+                    s = int(slots[i])
+                    off = int(post_off[i])
+                    model = format_model(mu[i], res.cov[s], res.box[s] if opts.add_uniform else None, res.cw[s])
+                    fsm[pos_list[i]] = _position_sm_preds(f, int(cols[i] - host.col_off[fi]), win_str[i], opts, n_cntrl, model,
+                                                          res.post[off:off + int(res.nall_fit[s])].copy())
     return records, sm
+
+
+def _rows_from_arrays(res, slots, w):
+    '''the fixed-width rows of the given slots from a BatchResult that carries separate arrays only (tests)'''
+    n = len(slots)
+    rows = np.full((n, N.row_width(w)), np.nan)
+    rows[:, N.ROW_STATUS] = np.asarray(res.status_fit)[slots]
+    rows[:, N.ROW_KS_STAT] = np.asarray(res.ks_stat_fit)[slots]
+    rows[:, N.ROW_COLUMN] = np.asarray(res.fit_list)[slots]
+    rows[:, N.ROW_STATS:N.ROW_STATS + 8] = np.asarray(res.stats)[slots]
+    rows[:, N.ROW_MU:N.ROW_MU + 2 * w] = np.asarray(res.mu)[slots].reshape(n, 2 * w)
+    rows[:, N.ROW_MU + 2 * w:N.ROW_MU + 4 * w] = np.asarray(res.stds)[slots].reshape(n, 2 * w)
+    return rows
 
 
 def test_chunk(opts, gene_ids):
@@ -375,18 +519,150 @@ def test_chunk(opts, gene_ids):
         # every batch is cut into PIPELINE_RANGES feature ranges (views, no copy): the upload of range k+1 overlaps
         # the kernels of range k and the fetch of range k-1 (engine.run_pipelined), also when a chunk is one batch
         source = (r for hb in batches() for r in hb.split(PIPELINE_RANGES))
-    for host, res in engine.run_pipelined(source):
+    ingest0 = STAGES['ingest']
+    t_pipe = 0.0
+    pipe = iter(engine.run_pipelined(_timed_iter(source, 'ingest')))
+    while True:
+        t0 = time.perf_counter()
+        item = next(pipe, None)
+        t_pipe += time.perf_counter() - t0
+        if item is None:
+            break
+        host, res = item
+        t0 = time.perf_counter()
+        COUNTS['positions_tested'] += res.n_tested
+        COUNTS['positions_fitted'] += res.n_fitted
         recs, sm = _batch_records(host, res, opts)
         chunk_res.extend(recs)
         for k, v in sm.items():
             chunk_sm.setdefault(k, {}).update(v)
+        STAGES['records'] += time.perf_counter() - t0
+    STAGES['device'] += t_pipe - (STAGES['ingest'] - ingest0)
     return chunk_res, chunk_sm
+
+
+def _arrow_lists(matrix):
+    '''(n, w) float matrix -> a pandas column whose cells are length-w lists, backed by ONE Arrow buffer (no per-row object)'''
+    import pyarrow as pa
+    values = pa.array(np.ascontiguousarray(matrix.reshape(-1), dtype=np.float64))
+    return pd.arrays.ArrowExtensionArray(pa.FixedSizeListArray.from_arrays(values, matrix.shape[1]))
+
+
+def _string_column(table, codes):
+    '''
+    table[codes] as a pandas string column.  With pandas' Arrow-backed default string dtype the gather runs in Arrow
+    (pyarrow.compute.take) and no Python string is created per row; the column equals the one pandas would infer
+    from the object array.  `codes` may be 2-d: the cells are then fixed-size lists of strings (the `kmers` column).
+    '''
+    codes = np.asarray(codes)
+    dt = pd.Series(['x']).dtype
+    if isinstance(dt, pd.StringDtype) and getattr(dt, 'storage', None) == 'pyarrow':
+        import pyarrow as pa
+        import pyarrow.compute as pc
+        taken = pc.take(pa.array(list(table), type=pa.large_string()), pa.array(np.ascontiguousarray(codes.reshape(-1))))
+        if codes.ndim == 2:
+            return pd.arrays.ArrowExtensionArray(pa.FixedSizeListArray.from_arrays(taken, codes.shape[1]))
+        return dt.construct_array_type()(pa.chunked_array([taken]), dtype=dt)
+    obj = np.array(list(table) + [None], dtype=object)[:-1][codes]
+    if codes.ndim == 2:
+        cells = np.empty(len(codes), dtype=object)
+        cells[:] = list(obj)
+        return cells
+    return obj
+
+
+def kmer_codes(k):
+    '''(…,) S5 array -> base-4 codes into KMER_TABLE, or None when a kmer has letters other than A, C, G, T'''
+    k = np.ascontiguousarray(k)
+    if k.dtype != np.dtype('S5'):
+        return None
+    d = _B4[k.view(np.uint8).reshape(k.shape + (5,))]
+    if d.size and d.min() < 0:
+        return None
+    return (((d[..., 0] * 4 + d[..., 1]) * 4 + d[..., 2]) * 4 + d[..., 3]) * 4 + d[..., 4]
+
+
+def materialise_array_columns(res):
+    '''
+    Array-valued columns (kmers, dist*_means, dist*_stds) of a frame as object columns of NumPy arrays -- the cell type of
+    the reference's frame.  parallel_test backs them by Arrow fixed-size lists (cells read as lists) because one object per
+    cell costs more than the whole GPU pass; the filtered frame (significant rows only) gets the arrays back.
+    '''
+    for name in _ARRAY_COLUMNS:
+        col = res[name]
+        if isinstance(col.dtype, pd.ArrowDtype):
+            cells = np.empty(len(col), dtype=object)
+            if len(col):
+                m = np.asarray(col.array._pa_array.combine_chunks().flatten().to_numpy(zero_copy_only=False)).reshape(len(col), -1)
+                cells[:] = list(m)
+            res[name] = cells
+    return res
+
+
+def _order_of_keys(key):
+    '''ascending order of unique int64 keys: equal-key rows do not exist, so any sort will do (GPU for large inputs)'''
+    from .stats import _argsort
+    return _argsort(key)
+
+
+def _frame_from_rowblocks(blocks):
+    '''the DataFrame of parallel_test straight from the fixed-width rows (same rows, order and values as the tuple route)'''
+    blk = RowBlock.concat(blocks)
+    w = blk.window
+    centre = w // 2
+    n = len(blk)
+    # canonical row order (feature id, position); ids compare as Python strings (code point order)
+    uniq = sorted(set(blk.feature_ids))
+    rank_of = {g: i for i, g in enumerate(uniq)}
+    rank = np.fromiter((rank_of[g] for g in blk.feature_ids), dtype=np.int64, count=len(blk.feature_ids))
+    p_all = blk.rows[:, N.ROW_STATS + 2] if blk.rows is not None else blk.p_val
+    if n and blk.pos.min() >= 0 and blk.pos.max() < (1 << 40):
+        key = (rank[blk.fidx] << 40) | blk.pos                                 # one key per row; rows of a rank arrive sorted
+        order_all = np.arange(n) if (key[1:] >= key[:-1]).all() else _order_of_keys(key)
+    else:
+        order_all = np.lexsort((blk.pos, rank[blk.fidx]))                      # stable, like sorted()
+    kept = ~np.isnan(p_all[order_all])                                         # reference gmmtest.py:221 (dropna on p_val)
+    order, index = order_all[kept], np.flatnonzero(kept)                       # the index keeps the gaps, as dropna does
+    f = blk.fidx[order]
+    codes = kmer_codes(blk.kmers[order])
+    if codes is not None:
+        kmer_col, kmers_col = _string_column(KMER_TABLE, codes[:, centre]), _string_column(KMER_TABLE, codes)
+    else:                                                                      # kmers with other letters: the general conversion
+        win = blk.kmers[order].astype('U5')
+        uk, inv = np.unique(win.ravel(), return_inverse=True)
+        kmer_col = _string_column(uk.tolist(), inv.reshape(win.shape)[:, centre])
+        kmers_col = _string_column(uk.tolist(), inv.reshape(win.shape))
+    data = {'chrom': _string_column(blk.chroms, f), 'pos': blk.pos[order], 'gene_id': _string_column(blk.feature_ids, f),
+            'strand': _string_column(blk.strands, f), 'kmer': kmer_col, 'kmers': kmers_col,
+            'centre': np.full(len(order), centre, dtype=np.int64)}
+    if blk.rows is not None:
+        r = blk.rows[order]
+        st = r[:, N.ROW_STATS:N.ROW_STATS + 8]
+        p_val = np.ascontiguousarray(st[:, 2])
+        data.update(log_odds=st[:, 5].copy(), log_odds_lower_ci=st[:, 6].copy(), log_odds_upper_ci=st[:, 7].copy(), p_val=p_val,
+                    fdr=benjamini_hochberg(p_val) if len(order) else np.ones(0), cntrl_frac_mod=st[:, 3].copy(),
+                    treat_frac_mod=st[:, 4].copy(), g_stat=st[:, 0].copy(), hom_g_stat=st[:, 1].copy())
+        mu, sd = r[:, N.ROW_MU:N.ROW_MU + 2 * w], r[:, N.ROW_MU + 2 * w:N.ROW_MU + 4 * w]
+        data.update(dist1_means=_arrow_lists(mu[:, :w]), dist1_stds=_arrow_lists(sd[:, :w]),
+                    dist2_means=_arrow_lists(mu[:, w:]), dist2_stds=_arrow_lists(sd[:, w:]), ks_stat=r[:, N.ROW_KS_STAT].copy())
+    else:
+        nan_col = np.full(len(order), np.nan)
+        p_val = blk.p_val[order]
+        none_col = np.full(len(order), None, dtype=object)
+        data.update(log_odds=nan_col, log_odds_lower_ci=nan_col, log_odds_upper_ci=nan_col, p_val=p_val,
+                    fdr=benjamini_hochberg(p_val) if len(order) else np.ones(0), cntrl_frac_mod=nan_col, treat_frac_mod=nan_col,
+                    g_stat=nan_col, hom_g_stat=nan_col, dist1_means=none_col, dist1_stds=none_col, dist2_means=none_col,
+                    dist2_stds=none_col, ks_stat=blk.ks[order])
+    return pd.DataFrame(data, columns=COLUMNS, index=pd.Index(index), copy=False)
 
 
 def _to_frame(records):
     # canonical row order (feature, position): the output must not depend on how genes were
     # sharded over ranks / batches (the reference's order depends on its pool scheduling)
     if isinstance(records, Records):
+        blocks = records.row_blocks()
+        if blocks is not None:
+            return _frame_from_rowblocks(blocks)
         cols = [records.column(j) for j in range(len(COLUMNS))]
         if len(cols[1]):
             codes = np.unique(cols[2].astype(str), return_inverse=True)[1]      # codepoint order, as Python's str
@@ -402,6 +678,16 @@ def _to_frame(records):
     return res
 
 
+def _gene_sizes(handles, gene_ids):
+    '''events per gene over all files (what the shards are balanced by); dense files answer from their index'''
+    if all(isinstance(d, ycdense.File) for d in handles):
+        total = np.zeros(len(gene_ids), dtype=np.int64)
+        for d in handles:
+            total += d.index['n_events'][[d.gene_index(g) for g in gene_ids]].astype(np.int64)
+        return total.tolist()
+    return [sum(len(d[f'{g}/events']) for d in handles) for g in gene_ids]
+
+
 def parallel_test(opts):
     '''
     Runs the tests on every gene found in all HDF5 files (reference
@@ -409,22 +695,29 @@ def parallel_test(opts):
     (one GPU each) and gathered on rank 0; other ranks return empty results.
     Returns (DataFrame with COLUMNS, sm_preds dict).
     '''
+    t0 = time.perf_counter()
     with hdf5_list(opts.cntrl_hdf5_fns) as cntrl_h5, hdf5_list(opts.treat_hdf5_fns) as treat_h5:
         gene_ids = sorted(get_shared_keys(cntrl_h5 + treat_h5))
-        sizes = [sum(len(d[f'{g}/events']) for d in cntrl_h5 + treat_h5) for g in gene_ids]
+        sizes = _gene_sizes(cntrl_h5 + treat_h5, gene_ids)
     world, rank = ycdist.world_info()
     logger.info(f'{len(gene_ids):,} genes to be processed on {max(world, 1)} GPU worker(s)')
     mine = ycdist.shard_by_size(gene_ids, sizes, world)[rank]
+    STAGES['open'] += time.perf_counter() - t0
     res, sm_preds = test_chunk(opts, (mine, opts.random_seed))
+    t0 = time.perf_counter()
     res, sm_preds = ycdist.gather_results(res, sm_preds)
+    STAGES['gather'] += time.perf_counter() - t0
     if rank == 0:
         logger.info(f'Complete. Tested {len(res):,} positions')
-    return _to_frame(res), sm_preds
+    t0 = time.perf_counter()
+    frame = _to_frame(res)
+    STAGES['frame_bh'] += time.perf_counter() - t0
+    return frame, sm_preds
 
 
 def filter_results(res, sm_preds, fdr_threshold):
     '''reference gmmtest.py:227-242'''
-    sig_res = res[res.fdr < fdr_threshold]
+    sig_res = materialise_array_columns(res[res.fdr < fdr_threshold].copy())
     logger.info(f'{len(sig_res):,} positions significant at {fdr_threshold * 100:.0f}% level')
     sig_sm_preds = {}
     for gene_id, pos in sig_res[['gene_id', 'pos']].itertuples(index=False):
