@@ -70,7 +70,8 @@ def _rowblock_worker(rank, world, port, out_dir, gmm):
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
     from yanocomp_b200 import _native as N, dist as ycdist
-    from yanocomp_b200.gmmtest import Records, RowBlock, _to_frame, materialise_array_columns
+    from yanocomp_b200.gmmtest import (Records, RowBlock, RowTable, TestedPositions, _frame_from_table, _to_frame,
+                                       materialise_array_columns)
     assert ycdist.init_from_env(backend='gloo') == (world, rank)
     genes = [f'gene{i:03d}' for i in range(17)]
     # rank `world - 1` of a 3-rank job gets nothing: an empty rank must not stall or break the exchange
@@ -99,12 +100,21 @@ def _rowblock_worker(rank, world, port, out_dir, gmm):
     n_mine = len(recs)
     recs, sm = ycdist.gather_results(recs, sm)
     if rank == 0:
-        assert isinstance(recs, Records) and len(recs) == sum(1 + int(g[4:]) % 4 for g in genes)
-        assert recs.row_blocks() is not None or world == 1
-        res = materialise_array_columns(_to_frame(recs))
-        assert materialise_array_columns(_to_frame(list(recs))).to_csv() == res.to_csv()      # same frame from the tuples
+        n_all = sum(1 + int(g[4:]) % 4 for g in genes)
+        if world == 1:
+            assert isinstance(recs, Records) and len(recs) == n_all
+            res = materialise_array_columns(_to_frame(recs))
+            assert materialise_array_columns(_to_frame(list(recs))).to_csv() == res.to_csv()  # same frame from the tuples
+        else:
+            # one padded matrix on rank 0, finished with torch (here on the CPU; on the GPU box on the device);
+            # no rank made predictions, so the {feature: {pos: None}} entries come lazily from the table
+            assert isinstance(recs, RowTable) and sm is None and len(recs) >= n_all
+            res, tested = _frame_from_table(recs, want_tested=True)
+            res = materialise_array_columns(res)
+            sm = TestedPositions(recs.feature_ids, tested[0], tested[1])
+            assert sm.get('nothing', {}).get(5) is None and 'gene003' in sm
         assert sorted(sm) == genes and all(v is None for d in sm.values() for v in d.values())
-        assert sum(len(d) for d in sm.values()) == len(recs)
+        assert sum(len(d) for d in sm.values()) == n_all
         res.to_csv(os.path.join(out_dir, 'rb%d_%d.csv' % (world, gmm)))
     else:
         assert recs == [] and sm == {} and (n_mine > 0 or rank == world - 1)

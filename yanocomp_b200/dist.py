@@ -68,12 +68,14 @@ def _gather_rowblocks(blocks, sm_preds, world, rank):
     '''
     The exchange step of the path on fixed-width rows: every rank contributes ONE float64 matrix
     (result rows | feature index | position) and one byte matrix (window kmers), padded to the longest rank and
-    collected with `dist.gather` (NCCL over NVLink between GPUs, gloo in the CPU tests); only the small per-feature name
-    tables travel as Python objects.  Returns rank 0's merged (RowBlock or None, sm_preds).
+    collected with `dist.gather` straight into one matrix on rank 0's device (NCCL over NVLink between GPUs, gloo in the
+    CPU tests); only the small per-feature name tables travel as Python objects.  Rank 0 returns
+    (gmmtest.RowTable or None, sm_preds); sm_preds is None when no rank made single-molecule predictions (the
+    {feature: {pos: None}} entries are then served from the table, gmmtest.TestedPositions).
     '''
     import torch
     import torch.distributed as dist
-    from .gmmtest import RowBlock
+    from .gmmtest import RowBlock, RowTable
     blk = RowBlock.concat(blocks) if blocks else None
     n = len(blk) if blk is not None else 0
     has_rows = blk is not None and blk.rows is not None
@@ -89,42 +91,47 @@ def _gather_rowblocks(blocks, sm_preds, world, rank):
     gmm = any(m[3] for m in metas)
     if n_max == 0:
         return None, {}
+    f_off = int(sum(len(m[4][0]) for m in metas[:rank]))                       # this rank's offset in the merged tables
     use_cuda = dist.get_backend() == 'nccl'
     dev = torch.device('cuda', torch.cuda.current_device()) if use_cuda else torch.device('cpu')
     num = torch.zeros((n_max, width + 2), dtype=torch.float64)
+    num[:, width] = -1.0                                                      # padding rows
     kmb = torch.zeros((n_max, 5 * w), dtype=torch.uint8)
     if n:
         body = blk.rows if has_rows else np.stack([blk.p_val, blk.ks], axis=1)
         num[:n, :width] = torch.from_numpy(np.ascontiguousarray(body))
-        num[:n, width] = torch.from_numpy(blk.fidx.astype(np.float64))
+        num[:n, width] = torch.from_numpy(blk.fidx.astype(np.float64) + f_off)
         num[:n, width + 1] = torch.from_numpy(blk.pos.astype(np.float64))
         kmb[:n] = torch.from_numpy(np.ascontiguousarray(blk.kmers).view(np.uint8).reshape(n, 5 * w))
     num, kmb = num.to(dev), kmb.to(dev)
-    got_num = [torch.empty_like(num) for _ in range(world)] if rank == 0 else None
-    got_kmb = [torch.empty_like(kmb) for _ in range(world)] if rank == 0 else None
-    dist.gather(num, got_num, dst=0)
-    dist.gather(kmb, got_kmb, dst=0)
+    all_num = torch.empty((world, n_max, width + 2), dtype=torch.float64, device=dev) if rank == 0 else None
+    all_kmb = torch.empty((world, n_max, 5 * w), dtype=torch.uint8, device=dev) if rank == 0 else None
+    dist.gather(num, list(all_num.unbind(0)) if rank == 0 else None, dst=0)
+    dist.gather(kmb, list(all_kmb.unbind(0)) if rank == 0 else None, dst=0)
     if rank != 0:
         return None, {}
-    parts, all_sm = [], {}
-    for (m_n, _, _, _, (ids, chroms, strands), sm), tn, tk in zip(metas, got_num, got_kmb):
-        if m_n:
-            a = tn[:m_n].cpu().numpy()
-            k = tk[:m_n].cpu().numpy().reshape(m_n, w, 5).copy().view('S5').reshape(m_n, w)
-            fidx, pos = a[:, width].astype(np.int32), a[:, width + 1].astype(np.int64)
-            if gmm:
-                parts.append(RowBlock(ids, chroms, strands, fidx, pos, k, rows=np.ascontiguousarray(a[:, :width])))
-            else:
-                parts.append(RowBlock(ids, chroms, strands, fidx, pos, k, p_val=a[:, 0].copy(), ks=a[:, 1].copy()))
-            if sm is None:                                  # no predictions were made: {feature: {pos: None}} rebuilt here
+    ids, chroms, strands = [], [], []
+    all_sm = {} if any(m[5] is not None for m in metas) else None
+    for m in metas:
+        ids += list(m[4][0])
+        chroms += list(m[4][1])
+        strands += list(m[4][2])
+    table = RowTable(ids, chroms, strands, all_num.reshape(world * n_max, width + 2), all_kmb.reshape(world * n_max, 5 * w), gmm, w)
+    if all_sm is not None:
+        # some rank made predictions: the dictionaries are merged as they are, and the None entries of the ranks that
+        # sent none are filled in from their rows
+        for r, m in enumerate(metas):
+            if m[5] is not None:
+                for k2, v in m[5].items():
+                    all_sm.setdefault(k2, {}).update(v)
+            elif m[0]:
+                a = all_num[r, :m[0]].cpu().numpy()
+                fidx, pos = a[:, width].astype(np.int64), a[:, width + 1].astype(np.int64)
                 cuts = np.flatnonzero(np.diff(fidx)) + 1
                 pl = pos.tolist()
-                for lo, hi in zip(np.r_[0, cuts].tolist(), np.r_[cuts, m_n].tolist()):
+                for lo, hi in zip(np.r_[0, cuts].tolist(), np.r_[cuts, m[0]].tolist()):
                     all_sm.setdefault(ids[int(fidx[lo])], {}).update(dict.fromkeys(pl[lo:hi]))
-        if sm is not None:
-            for k2, v in sm.items():
-                all_sm.setdefault(k2, {}).update(v)
-    return RowBlock.concat(parts), all_sm
+    return table, all_sm
 
 
 def gather_results(records, sm_preds):
@@ -144,13 +151,12 @@ def gather_results(records, sm_preds):
     oks = [None] * world
     dist.all_gather_object(oks, bool(mine_ok))
     if all(oks):
-        blk, all_sm = _gather_rowblocks(blocks or [], sm_preds, world, rank)
+        table, all_sm = _gather_rowblocks(blocks or [], sm_preds, world, rank)
         if rank != 0:
             return [], {}
-        out = type(records)()
-        if blk is not None:
-            out.add_block(blk)
-        return out, all_sm
+        if table is None:
+            return type(records)(), {}
+        return table, all_sm
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((records, sm_preds), gathered, dst=0)
     if rank != 0:

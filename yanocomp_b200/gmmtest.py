@@ -44,6 +44,57 @@ STAGES = collections.defaultdict(float)
 COUNTS = collections.Counter()      # positions_tested (entered position_stats) / positions_fitted of the same calls
 
 
+def _prefetch(gen, depth=2):
+    '''
+    Run the batch source on a helper thread, `depth` batches ahead: building the next packed batch (file reads into
+    pinned memory, index arithmetic -- all of it releases the GIL or is short) overlaps the kernel launches and the
+    record assembly of the current one.  Exceptions of the source are re-raised in the consumer.
+    '''
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    done = object()
+    stop = threading.Event()
+    device = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            device = torch.cuda.current_device()          # the current device is per thread: hand it to the helper
+    except ImportError:
+        pass
+
+    def produce():
+        try:
+            if device is not None:
+                import torch
+                torch.cuda.set_device(device)
+            for item in gen:
+                while not stop.is_set():
+                    try:
+                        q.put((item, None), timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if stop.is_set():
+                    return
+            q.put((done, None))
+        except BaseException as exc:                      # noqa: B902 -- handed to the consumer
+            q.put((done, exc))
+
+    t = threading.Thread(target=produce, daemon=True)
+    t.start()
+    try:
+        while True:
+            item, exc = q.get()
+            if exc is not None:
+                raise exc
+            if item is done:
+                return
+            yield item
+    finally:
+        stop.set()
+
+
 def _timed_iter(gen, name):
     it = iter(gen)
     while True:
@@ -514,7 +565,7 @@ def test_chunk(opts, gene_ids):
     if any(is_dense) and not all(is_dense):
         raise click.UsageError('dense sample files (python -m yanocomp_b200 pack) cannot be mixed with HDF5 / packed inputs')
     if all(is_dense) and fns:
-        source = dense_batches()
+        source = _prefetch(dense_batches())
     else:
         # every batch is cut into PIPELINE_RANGES feature ranges (views, no copy): the upload of range k+1 overlaps
         # the kernels of range k and the fetch of range k-1 (engine.run_pipelined), also when a chunk is one batch
@@ -599,66 +650,174 @@ def materialise_array_columns(res):
     return res
 
 
-def _order_of_keys(key):
-    '''ascending order of unique int64 keys: equal-key rows do not exist, so any sort will do (GPU for large inputs)'''
-    from .stats import _argsort
-    return _argsort(key)
+@dataclasses.dataclass
+class RowTable:
+    '''
+    All result rows of a job as ONE matrix, on the device that will finish them: what the gather over the ranks
+    delivers on rank 0 (dist._gather_rowblocks) or, in a single process, the concatenation of the batches' RowBlocks.
+      num   (M, width + 2) float64 torch tensor: result rows (or [p_val, ks] for --no-gmm) | feature index | position;
+            padding rows (the gather pads every rank to the longest) carry feature index -1
+      kmb   (M, 5 w) uint8 torch tensor: the window kmers as bytes
+    plus the merged per-feature tables.  `_frame_from_table` sorts, drops, corrects and transposes it with torch
+    operations on that device, so that the host receives finished, contiguous columns in one copy.
+    '''
+    feature_ids: list
+    chroms: list
+    strands: list
+    num: object
+    kmb: object
+    gmm: bool
+    window: int
+
+    def __len__(self):
+        return int(self.num.shape[0])
+
+    @staticmethod
+    def from_blocks(blocks):
+        import torch
+        blk = RowBlock.concat(blocks)
+        n, w = len(blk), blk.window
+        body = blk.rows if blk.rows is not None else np.stack([blk.p_val, blk.ks], axis=1)
+        num = np.empty((n, body.shape[1] + 2))
+        num[:, :-2], num[:, -2], num[:, -1] = body, blk.fidx, blk.pos
+        kmb = np.ascontiguousarray(blk.kmers).view(np.uint8).reshape(n, 5 * w)
+        num, kmb = torch.from_numpy(num), torch.from_numpy(kmb)
+        if n >= 16384 and torch.cuda.is_available():
+            num, kmb = num.cuda(non_blocking=True), kmb.cuda(non_blocking=True)
+        return RowTable(blk.feature_ids, blk.chroms, blk.strands, num, kmb, blk.rows is not None, w)
+
+
+class TestedPositions(collections.abc.Mapping):
+    '''
+    sm_preds of a run that made no single-molecule predictions: {feature id: {position: None}} for every tested position
+    (reference gmmtest.py:173-178), materialised per feature on access instead of as millions of dictionary entries.
+    '''
+
+    def __init__(self, feature_ids, fidx, pos):
+        # fidx / pos: all tested rows in canonical (feature id, position) order
+        self._ids = list(feature_ids)
+        self._fidx, self._pos = np.asarray(fidx, dtype=np.int64), np.asarray(pos, dtype=np.int64)
+        cuts = np.flatnonzero(np.diff(self._fidx)) + 1 if len(self._fidx) else np.zeros(0, np.int64)
+        lo, hi = np.r_[0, cuts], np.r_[cuts, len(self._fidx)]
+        self._span = {self._ids[int(self._fidx[a])]: (int(a), int(e)) for a, e in zip(lo.tolist(), hi.tolist())} if len(self._fidx) else {}
+
+    def __getitem__(self, feature_id):
+        a, e = self._span[feature_id]
+        return dict.fromkeys(self._pos[a:e].tolist())
+
+    def __iter__(self):
+        return iter(self._span)
+
+    def __len__(self):
+        return len(self._span)
+
+
+def _frame_from_table(tab, want_tested=False):
+    '''
+    The DataFrame of parallel_test (reference gmmtest.py:216-224) from a RowTable: canonical (feature id, position)
+    order, rows without a p-value dropped, BH-FDR over the rest -- computed with torch on the table's device; the host
+    gets the finished columns, contiguous, in one copy.  Same rows, index and values as the tuple route.
+    With want_tested also returns (feature index, position) of ALL tested rows in canonical order.
+    '''
+    import torch
+    num, kmb, w = tab.num, tab.kmb, tab.window
+    centre = w // 2
+    dev = num.device
+    width = num.shape[1] - 2
+    pcol = N.ROW_STATS + 2 if tab.gmm else 0
+    fidx = num[:, width].long()
+    pos = num[:, width + 1].long()
+    real = fidx >= 0
+    # canonical row order (feature id, position); ids compare as Python strings (code point order)
+    uniq = sorted(set(tab.feature_ids))
+    rank_of = {g: i for i, g in enumerate(uniq)}
+    rank = torch.from_numpy(np.fromiter((rank_of[g] for g in tab.feature_ids), dtype=np.int64,
+                                        count=len(tab.feature_ids))).to(dev)
+    n_real = int(real.sum())
+    if n_real and (int(pos[real].min()) < 0 or int(pos[real].max()) >= (1 << 40)):
+        raise OverflowError('positions outside [0, 2^40) are not supported')
+    big = torch.iinfo(torch.int64).max
+    key = torch.where(real, (rank[fidx.clamp(min=0)] << 40) | pos, torch.full_like(pos, big)) if len(rank) else torch.full_like(pos, big)
+    if key.numel() > 1 and bool((key[1:] >= key[:-1]).all()):
+        order_all = torch.arange(key.numel(), device=dev)                      # rows of one process arrive sorted
+    else:
+        order_all = torch.argsort(key)                                         # keys of real rows are unique
+    order_all = order_all[:n_real]                                             # padding sorts last
+    p_sorted = num[order_all, pcol]
+    kept = ~torch.isnan(p_sorted)                                              # reference gmmtest.py:221 (dropna on p_val)
+    order = order_all[kept]
+    index = torch.nonzero(kept).reshape(-1)                                    # the index keeps the gaps, as dropna does
+    R = num[order]
+    n = int(R.shape[0])
+    p = R[:, pcol].contiguous()
+    if n:                                                                      # multipletests(p, 'fdr_bh')[1], stats.benjamini_hochberg
+        o2 = torch.argsort(p)
+        raw = p[o2] / (torch.arange(1, n + 1, dtype=torch.float64, device=dev) / float(n))
+        adj = torch.flip(torch.cummin(torch.flip(raw, [0]), 0).values, [0]).clamp(max=1.0)
+        fdr = torch.empty_like(p)
+        fdr[o2] = adj
+    else:
+        fdr = p
+    cols = torch.cat([R.t(), fdr[None], index.double()[None]]).contiguous()    # (width + 4, n): one column per row
+    lut = torch.from_numpy(_B4).to(dev)
+    d = lut[kmb[order].long()].reshape(n, w, 5).long()
+    acgt = not bool((d < 0).any())
+    codes = ((((d[..., 0] * 4 + d[..., 1]) * 4 + d[..., 2]) * 4 + d[..., 3]) * 4 + d[..., 4]).to(torch.int32).contiguous()
+    tested = (torch.stack([fidx[order_all], pos[order_all]]).contiguous() if want_tested else None)
+    if dev.type == 'cuda':
+        from .batch import PINNED
+        stage = PINNED.acquire(cols.numel() * 8 + codes.numel() * 4 + 64)
+        h_cols = torch.from_numpy(stage[:cols.numel() * 8].view(np.float64).reshape(cols.shape))
+        h_cols.copy_(cols, non_blocking=True)
+        h_codes = codes.cpu()
+        torch.cuda.synchronize(dev)
+        c, codes_h = h_cols.numpy(), h_codes.numpy()
+        kmb_h = None if acgt else kmb[order].cpu().numpy()
+        tested_h = tested.cpu().numpy() if tested is not None else None
+    else:
+        c, codes_h = cols.numpy(), codes.numpy()
+        kmb_h = None if acgt else kmb[order].numpy()
+        tested_h = tested.numpy() if tested is not None else None
+    f = c[width].astype(np.int64)
+    if acgt:
+        kmer_col, kmers_col = _string_column(KMER_TABLE, codes_h[:, centre]), _string_column(KMER_TABLE, codes_h)
+    else:                                                                      # kmers with other letters: the general conversion
+        win = np.ascontiguousarray(kmb_h).view('S5').reshape(n, w).astype('U5')
+        uk, inv = np.unique(win.ravel(), return_inverse=True)
+        kmer_col = _string_column(uk.tolist(), inv.reshape(win.shape)[:, centre])
+        kmers_col = _string_column(uk.tolist(), inv.reshape(win.shape))
+    data = {'chrom': _string_column(tab.chroms, f), 'pos': c[width + 1].astype(np.int64), 'gene_id': _string_column(tab.feature_ids, f),
+            'strand': _string_column(tab.strands, f), 'kmer': kmer_col, 'kmers': kmers_col,
+            'centre': np.full(n, centre, dtype=np.int64)}
+    if tab.gmm:
+        st = c[N.ROW_STATS:N.ROW_STATS + 8]
+        data.update(log_odds=st[5], log_odds_lower_ci=st[6], log_odds_upper_ci=st[7], p_val=st[2], fdr=c[width + 2],
+                    cntrl_frac_mod=st[3], treat_frac_mod=st[4], g_stat=st[0], hom_g_stat=st[1])
+        mu, sd = c[N.ROW_MU:N.ROW_MU + 2 * w], c[N.ROW_MU + 2 * w:N.ROW_MU + 4 * w]
+        data.update(dist1_means=_arrow_lists(mu[:w].T), dist1_stds=_arrow_lists(sd[:w].T),
+                    dist2_means=_arrow_lists(mu[w:].T), dist2_stds=_arrow_lists(sd[w:].T), ks_stat=c[N.ROW_KS_STAT])
+    else:
+        nan_col = np.full(n, np.nan)
+        none_col = np.full(n, None, dtype=object)
+        data.update(log_odds=nan_col, log_odds_lower_ci=nan_col, log_odds_upper_ci=nan_col, p_val=c[0], fdr=c[width + 2],
+                    cntrl_frac_mod=nan_col, treat_frac_mod=nan_col, g_stat=nan_col, hom_g_stat=nan_col, dist1_means=none_col,
+                    dist1_stds=none_col, dist2_means=none_col, dist2_stds=none_col, ks_stat=c[1])
+    frame = pd.DataFrame(data, columns=COLUMNS, index=pd.Index(c[width + 3].astype(np.int64)), copy=False)
+    if want_tested:
+        return frame, tested_h
+    return frame
 
 
 def _frame_from_rowblocks(blocks):
     '''the DataFrame of parallel_test straight from the fixed-width rows (same rows, order and values as the tuple route)'''
-    blk = RowBlock.concat(blocks)
-    w = blk.window
-    centre = w // 2
-    n = len(blk)
-    # canonical row order (feature id, position); ids compare as Python strings (code point order)
-    uniq = sorted(set(blk.feature_ids))
-    rank_of = {g: i for i, g in enumerate(uniq)}
-    rank = np.fromiter((rank_of[g] for g in blk.feature_ids), dtype=np.int64, count=len(blk.feature_ids))
-    p_all = blk.rows[:, N.ROW_STATS + 2] if blk.rows is not None else blk.p_val
-    if n and blk.pos.min() >= 0 and blk.pos.max() < (1 << 40):
-        key = (rank[blk.fidx] << 40) | blk.pos                                 # one key per row; rows of a rank arrive sorted
-        order_all = np.arange(n) if (key[1:] >= key[:-1]).all() else _order_of_keys(key)
-    else:
-        order_all = np.lexsort((blk.pos, rank[blk.fidx]))                      # stable, like sorted()
-    kept = ~np.isnan(p_all[order_all])                                         # reference gmmtest.py:221 (dropna on p_val)
-    order, index = order_all[kept], np.flatnonzero(kept)                       # the index keeps the gaps, as dropna does
-    f = blk.fidx[order]
-    codes = kmer_codes(blk.kmers[order])
-    if codes is not None:
-        kmer_col, kmers_col = _string_column(KMER_TABLE, codes[:, centre]), _string_column(KMER_TABLE, codes)
-    else:                                                                      # kmers with other letters: the general conversion
-        win = blk.kmers[order].astype('U5')
-        uk, inv = np.unique(win.ravel(), return_inverse=True)
-        kmer_col = _string_column(uk.tolist(), inv.reshape(win.shape)[:, centre])
-        kmers_col = _string_column(uk.tolist(), inv.reshape(win.shape))
-    data = {'chrom': _string_column(blk.chroms, f), 'pos': blk.pos[order], 'gene_id': _string_column(blk.feature_ids, f),
-            'strand': _string_column(blk.strands, f), 'kmer': kmer_col, 'kmers': kmers_col,
-            'centre': np.full(len(order), centre, dtype=np.int64)}
-    if blk.rows is not None:
-        r = blk.rows[order]
-        st = r[:, N.ROW_STATS:N.ROW_STATS + 8]
-        p_val = np.ascontiguousarray(st[:, 2])
-        data.update(log_odds=st[:, 5].copy(), log_odds_lower_ci=st[:, 6].copy(), log_odds_upper_ci=st[:, 7].copy(), p_val=p_val,
-                    fdr=benjamini_hochberg(p_val) if len(order) else np.ones(0), cntrl_frac_mod=st[:, 3].copy(),
-                    treat_frac_mod=st[:, 4].copy(), g_stat=st[:, 0].copy(), hom_g_stat=st[:, 1].copy())
-        mu, sd = r[:, N.ROW_MU:N.ROW_MU + 2 * w], r[:, N.ROW_MU + 2 * w:N.ROW_MU + 4 * w]
-        data.update(dist1_means=_arrow_lists(mu[:, :w]), dist1_stds=_arrow_lists(sd[:, :w]),
-                    dist2_means=_arrow_lists(mu[:, w:]), dist2_stds=_arrow_lists(sd[:, w:]), ks_stat=r[:, N.ROW_KS_STAT].copy())
-    else:
-        nan_col = np.full(len(order), np.nan)
-        p_val = blk.p_val[order]
-        none_col = np.full(len(order), None, dtype=object)
-        data.update(log_odds=nan_col, log_odds_lower_ci=nan_col, log_odds_upper_ci=nan_col, p_val=p_val,
-                    fdr=benjamini_hochberg(p_val) if len(order) else np.ones(0), cntrl_frac_mod=nan_col, treat_frac_mod=nan_col,
-                    g_stat=nan_col, hom_g_stat=nan_col, dist1_means=none_col, dist1_stds=none_col, dist2_means=none_col,
-                    dist2_stds=none_col, ks_stat=blk.ks[order])
-    return pd.DataFrame(data, columns=COLUMNS, index=pd.Index(index), copy=False)
+    return _frame_from_table(RowTable.from_blocks(blocks))
 
 
 def _to_frame(records):
     # canonical row order (feature, position): the output must not depend on how genes were
     # sharded over ranks / batches (the reference's order depends on its pool scheduling)
+    if isinstance(records, RowTable):
+        return _frame_from_table(records)
     if isinstance(records, Records):
         blocks = records.row_blocks()
         if blocks is not None:
@@ -707,11 +866,16 @@ def parallel_test(opts):
     t0 = time.perf_counter()
     res, sm_preds = ycdist.gather_results(res, sm_preds)
     STAGES['gather'] += time.perf_counter() - t0
-    if rank == 0:
-        logger.info(f'Complete. Tested {len(res):,} positions')
     t0 = time.perf_counter()
-    frame = _to_frame(res)
+    if isinstance(res, RowTable) and sm_preds is None:
+        # the ranks made no single-molecule predictions: {feature: {pos: None}} is served lazily from the row table
+        frame, tested = _frame_from_table(res, want_tested=True)
+        sm_preds = TestedPositions(res.feature_ids, tested[0], tested[1])
+    else:
+        frame = _to_frame(res)
     STAGES['frame_bh'] += time.perf_counter() - t0
+    if rank == 0:
+        logger.info(f'Complete. Tested {len(frame):,} positions')
     return frame, sm_preds
 
 
@@ -720,7 +884,7 @@ def filter_results(res, sm_preds, fdr_threshold):
     sig_res = materialise_array_columns(res[res.fdr < fdr_threshold].copy())
     logger.info(f'{len(sig_res):,} positions significant at {fdr_threshold * 100:.0f}% level')
     sig_sm_preds = {}
-    for gene_id, pos in sig_res[['gene_id', 'pos']].itertuples(index=False):
+    for gene_id, pos in ([] if isinstance(sm_preds, TestedPositions) else sig_res[['gene_id', 'pos']].itertuples(index=False)):
         p = sm_preds.get(gene_id, {}).get(pos)
         if p is not None:
             sig_sm_preds.setdefault(gene_id, {})[pos] = p
