@@ -86,21 +86,22 @@ class Writer:
                                               dtype=f'S{READ_ID_LEN}'))
         g['transcript_ids'] = [str(t) for t in transcript_ids]
 
-    def close(self):
+    def close(self, ok=True):
         if self._f is None:
             return
-        index = json.dumps({'genes': self._genes}, separators=(',', ':')).encode('utf-8')
-        off = self._f.tell()
-        self._f.write(index)
-        self._f.write(struct.pack('<QQ', off, len(index)))
-        self._f.close()
-        self._f = None
+        if ok:
+            index = json.dumps({'genes': self._genes}, separators=(',', ':')).encode('utf-8')
+            off = self._f.tell()
+            self._f.write(index)
+            self._f.write(struct.pack('<QQ', off, len(index)))
+        self._f.close()                 # without the footer the reader rejects the file: a failed collapse leaves no
+        self._f = None                  # truncated output that looks complete
 
     def __enter__(self):
         return self
 
-    def __exit__(self, *exc):
-        self.close()
+    def __exit__(self, exc_type, *exc):
+        self.close(ok=exc_type is None)
 
 
 class _Dataset:

@@ -6,8 +6,10 @@ Same command, options and per-gene logical output as the reference, with two
 deliberate differences:
 
 * records are handled as columns, not as one dict per line: the TSV is parsed
-  by pandas' C reader (`float_precision='round_trip'`, so every value is the
-  same double Python's float() gives), runs of events of one
+  by Arrow's CSV reader (`pyarrow.csv`; its number conversion is correctly
+  rounded, so every value is the same double Python's float() gives; pyarrow
+  is required by this command and its absence is reported when it starts), runs
+  of events of one
   (transcript, position, kmer, read) are found with array comparisons, and
   the pooled statistics are evaluated for all runs of the same length at once
   IN THE REFERENCE'S ORDER OF OPERATIONS (left-to-right sums, the i<j pair
@@ -245,6 +247,10 @@ def nanopolish_collapse(**kw):
     gmmtest reads (reference prep.py:168-190).
     '''
     opts = CollapseOpts(**kw)
+    try:
+        import pyarrow.csv  # noqa: F401 -- the table parser of this command
+    except ImportError as exc:
+        raise click.ClickException('`prep` parses the eventalign table with pyarrow.csv: install pyarrow') from exc
     save_events_to_packed(
         parallel_collapse(opts.eventalign_fn, opts.summary_fn, opts.gtf_fn, opts.processes, opts.chunksize),
         opts.hdf5_fn)
