@@ -234,7 +234,7 @@ def run_job(args, torch, dist, world, rank):
                            processes=int(os.environ.get('YC_BENCH_JOB_THREADS', '4')), random_seed=0, **kw)
     reps = []
     try:
-        for rep in range(int(os.environ.get('YC_BENCH_JOB_REPS', '3'))):
+        for rep in range(int(os.environ.get('YC_BENCH_JOB_REPS', '4'))):
             ycg.STAGES.clear()
             ycg.COUNTS.clear()
             if world > 1:
@@ -431,7 +431,14 @@ def run_gpu(args, cfg, opts_kw):
 
     del dev, out
     torch.cuda.empty_cache()
-    job = None if args.no_job else run_job(args, torch, dist, world, rank)
+    job = None
+    if not args.no_job:
+        try:
+            job = run_job(args, torch, dist, world, rank)
+        except Exception as exc:                              # the headline line must survive a failing job block
+            if world > 1:
+                raise                                         # ... but ranks must not part ways inside collectives
+            job = {'error': f'{type(exc).__name__}: {exc}'[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
