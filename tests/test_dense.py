@@ -126,3 +126,42 @@ def test_truncated_or_foreign_files_are_rejected(tmp_path):
     with pytest.raises(dense.DenseFormatError):
         dense.File(str(tmp_path / 'aborted.ycd'))
     assert not dense.is_dense(CNTRL)
+
+
+def test_transcript_level_on_multi_transcript_genes_takes_the_host_split(tmp_path):
+    '''--test-level transcript: genes whose dense blocks hold several transcripts are split on the host from the per-event
+    transcript index the container keeps; the features equal what load_gene_features builds from the event records'''
+    import mock_h5
+    from yanocomp_b200.io import dense_transcript_features, load_gene_features
+    rng = np.random.default_rng(31)
+    genes = {'geneA': (100, 30, ['tA1', 'tA2', 'tA3']), 'geneB': (500, 25, ['tB1']), 'geneC': (40, 20, ['tC1', 'tC2'])}
+    handles = [mock_h5.random_file(rng, genes, n, read_prefix=f's{i}_') for i, n in enumerate((30, 26, 33, 28))]
+    fns = []
+    for i, h in enumerate(handles):
+        fn = str(tmp_path / f's{i}.ycd')
+        dense.convert_handle(h, fn)
+        fns.append(fn)
+    with ycio.hdf5_list(fns) as files:
+        assert files[0].gene('geneA').n_tx == 3 and files[0].gene('geneA').transcript_matrix is not None
+        assert files[0].gene('geneB').transcript_matrix is None
+        n_feat = 0
+        for gene in genes:
+            want = load_gene_features(gene, handles[:2], handles[2:], by_transcript_ids=True)
+            got = dense_transcript_features(gene, files, 2)
+            assert [f.feature_id for f in got] == [f.feature_id for f in want] and len(want) >= 1
+            for a, b in zip(got, want):
+                assert (a.chrom, a.strand) == (b.chrom, b.strand)
+                assert np.array_equal(a.positions, b.positions) and np.array_equal(a.samp_start, b.samp_start)
+                assert list(a.read_ids) == list(b.read_ids)
+                assert np.array_equal(a.X.view(np.uint16), b.X.view(np.uint16))
+                assert all(a.kmers[int(p)] == b.kmers[int(p)] for p in a.positions)
+                n_feat += 1
+        assert n_feat >= 5
+        # a batch of the single-transcript gene is still a dense batch; the multi-transcript ones are refused there
+        one = DenseHostBatch(files, ['geneB'], 2, by_transcript=True, pin=False)
+        assert one.feature_ids == ['tB1']
+        with pytest.raises(NotImplementedError):
+            DenseHostBatch(files, ['geneA'], 2, by_transcript=True, pin=False)
+        # gene level: the same genes as dense batches equal the HDF5-route batch
+        feats = [f for g in sorted(genes) for f in load_gene_features(g, handles[:2], handles[2:])]
+        assert_same_batch(DenseHostBatch(files, sorted(genes), 2, pin=False), HostBatch(feats, 4, 2, pin=False))

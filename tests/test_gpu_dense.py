@@ -80,3 +80,32 @@ def test_gmmtest_on_packed_fixtures_is_byte_identical_to_the_hdf5_route(tmp_path
         assert len(outs['h5', level][0]) > 1000
         assert outs['h5', level][0] == outs['dense', level][0]
         assert outs['h5', level][1] == outs['dense', level][1]
+
+
+def test_transcript_level_with_multi_transcript_genes_equals_the_host_route(tmp_path):
+    '''dense inputs at --test-level transcript: single-transcript genes go through dense batches, multi-transcript genes
+    through the host split; together they give the frame the host route gives on the same events'''
+    import mock_h5
+    from yanocomp_b200.batch import HostBatch
+    from yanocomp_b200.engine import Engine
+    from yanocomp_b200.gmmtest import GMMTestOpts, Records, _batch_records, _to_frame, materialise_array_columns, parallel_test
+    from yanocomp_b200.io import load_gene_features
+    rng = np.random.default_rng(77)
+    genes = {f'gene{i:02d}': (100 * i, 40, [f't{i:02d}a'] if i % 2 else [f't{i:02d}a', f't{i:02d}b']) for i in range(6)}
+    mod = {g: {v[0] + 20: 6.0, v[0] + 21: -5.0} for g, v in genes.items()}
+    handles = [mock_h5.random_file(rng, genes, 60, read_prefix=f's{i}_', mod=mod if i >= 2 else None) for i in range(4)]
+    fns = []
+    for i, h in enumerate(handles):
+        fns.append(str(tmp_path / f's{i}.ycd'))
+        dense.convert_handle(h, fns[-1])
+    opts = GMMTestOpts(cntrl_hdf5_fns=tuple(fns[:2]), treat_hdf5_fns=tuple(fns[2:]), output_bed_fn=str(tmp_path / 'o.bed'),
+                       test_level='transcript', random_seed=3, min_ks=0.0, fdr_threshold=0.5)
+    got, _ = parallel_test(opts)
+    feats = [f for g in sorted(genes) for f in load_gene_features(g, handles[:2], handles[2:], by_transcript_ids=True)]
+    host = HostBatch(feats, 4, 2)
+    eng = Engine(opts.engine_params())
+    recs, _ = _batch_records(host, eng.run(eng.upload(host), fetch='records'), opts)
+    want = _to_frame(recs)
+    assert len(want) > 50 and set(want.gene_id) >= {'t00a', 't00b', 't01a'}
+    a, b = materialise_array_columns(got), materialise_array_columns(want)
+    assert a.to_csv() == b.to_csv()

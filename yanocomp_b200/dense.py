@@ -330,7 +330,14 @@ def convert(in_fn, out_fn, progress=None):
     features bit for bit (tests/test_dense.py).
     '''
     from . import io as ycio
-    with ycio.hdf5_list([in_fn]) as (src,), Writer(out_fn) as out:
+    with ycio.hdf5_list([in_fn]) as (src,):
+        convert_handle(src, out_fn, progress)
+
+
+def convert_handle(src, out_fn, progress=None):
+    '''`convert` for an open event file (anything with the small h5py-like interface the gmmtest loaders use)'''
+    from . import io as ycio
+    with Writer(out_fn) as out:
         for gene_id in src.keys():
             e, r_ids = ycio._clean_events(src, gene_id)
             chrom, strand = ycio.load_gene_attrs(gene_id, [src])

@@ -28,6 +28,7 @@ from . import dist as ycdist
 from . import dense as ycdense
 from .batch import HostBatch, DenseHostBatch
 from .io import (hdf5_list, get_shared_keys, load_model_priors, load_gene_features, load_gene_features_cached,
+                 dense_transcript_features,
                  FeatureCache,
                  save_gmmtest_results, save_sm_preds)
 from .stats import (benjamini_hochberg, assign_modified_distribution, format_model,
@@ -549,9 +550,28 @@ def test_chunk(opts, gene_ids):
             cond = np.maximum(n_reads[:n_cntrl].sum(0), n_reads[n_cntrl:].sum(0))
             shallow = (n_reads.sum(0) <= 1024) & (cond <= opts.max_fit_depth)
             limit = max(BATCH_EVENT_BYTES // PIPELINE_RANGES, 1)
+            # --test-level transcript: genes whose blocks hold several transcripts are split on the host
+            # (io.dense_transcript_features) and go through ordinary packed batches
+            multi = (np.stack([r['n_tx'] for r in rows]).max(axis=0) > 1) if by_t else np.zeros(len(ids), dtype=bool)
+            if multi.any():
+                R = len(files)
+                pend = {True: [], False: []}
+                size = {True: 0, False: 0}
+                for j in np.flatnonzero(multi).tolist():
+                    for f in dense_transcript_features(ids[j], files, n_cntrl):
+                        split = int(f.samp_start[n_cntrl])
+                        k = f.n_reads <= 1024 and max(split, f.n_reads - split) <= opts.max_fit_depth
+                        pend[k].append(f)
+                        size[k] += f.X.nbytes
+                        if size[k] >= limit:
+                            yield HostBatch(pend[k], R, n_cntrl)
+                            pend[k], size[k] = [], 0
+                for k in (True, False):
+                    if pend[k]:
+                        yield HostBatch(pend[k], R, n_cntrl)
             for k in (True, False):
                 pending, acc = [], 0
-                for j in np.flatnonzero(shallow == k).tolist():
+                for j in np.flatnonzero((shallow == k) & ~multi).tolist():
                     pending.append(ids[j])
                     acc += int(nbytes[j])
                     if acc >= limit:

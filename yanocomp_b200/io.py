@@ -406,6 +406,57 @@ def load_gene_features(gene_id, cntrl_datasets, treat_datasets, by_transcript_id
     return feats
 
 
+def dense_transcript_features(gene_id, files, n_cntrl):
+    '''
+    --test-level transcript for a gene whose dense sample blocks hold several transcripts: the host route.  One Feature
+    per transcript that has events in both conditions (reference gmmtest.py:99), from the per-event transcript index the
+    dense container keeps for such genes -- the same rows, columns and order load_gene_features(by_transcript_ids=True)
+    builds from the event records (the keep-first de-duplication across transcripts happened when the file was packed,
+    as it happens before the split in the reference, io.py:308-312).
+    '''
+    R = len(files)
+    genes = [f.gene(gene_id) for f in files]
+    a = genes[0].attrs
+    per_t = {}
+    for s, g in enumerate(genes):
+        if not (g.n_pos and g.n_reads):
+            continue
+        X = g.events[:, :g.n_reads]
+        tx = g.transcript_matrix
+        ids = g.read_ids.astype('U')
+        for t_idx, t_id in enumerate(g.transcript_ids):
+            has = ~np.isnan(X) if tx is None else (~np.isnan(X) & (tx[:, :g.n_reads] == t_idx))
+            if tx is None and t_idx > 0:
+                continue
+            rows, cols = has.any(axis=0), has.any(axis=1)
+            if not rows.any():
+                continue
+            block = np.where(has, X, np.float16(np.nan))[cols][:, rows]
+            per_t.setdefault(t_id, [None] * R)[s] = (ids[rows], g.positions[cols].astype(np.int64), block)
+    kmers = {}
+    for g in genes:                                       # later files win (reference io.py:270-281)
+        k = g.kmers
+        kmers.update(zip(k['pos'].tolist(), np.char.decode(k['kmer'], 'ascii').tolist()))
+    feats = []
+    for t_id in sorted(per_t):
+        blocks = per_t[t_id]
+        if all(b is None for b in blocks[:n_cntrl]) or all(b is None for b in blocks[n_cntrl:]):
+            continue
+        positions = np.unique(np.concatenate([b[1] for b in blocks if b is not None]))
+        samp_start = np.zeros(R + 1, dtype=np.int32)
+        for s, b in enumerate(blocks):
+            samp_start[s + 1] = samp_start[s] + (len(b[0]) if b is not None else 0)
+        X = np.full((len(positions), int(samp_start[-1])), np.nan, dtype=np.float16)
+        read_ids = []
+        for s, b in enumerate(blocks):
+            if b is not None:
+                X[np.searchsorted(positions, b[1]), samp_start[s]:samp_start[s + 1]] = b[2]
+                read_ids.extend(b[0].tolist())
+        feats.append(Feature(feature_id=t_id, chrom=a['chrom'], strand=a['strand'], pos0=0, X=X, samp_start=samp_start,
+                             read_ids=read_ids, kmers=kmers, positions=positions))
+    return feats
+
+
 class FeatureCache:
     '''
     On-disk cache of packed features: the second run over the same prep files skips the HDF5 decode
