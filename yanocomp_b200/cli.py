@@ -56,7 +56,9 @@ def _profile_until_exit():
 @click.command(short_help='Convert a prep output (HDF5 / packed) to the dense sample container gmmtest ingests fastest')
 @click.argument('in_fn', type=click.Path(exists=True, dir_okay=False))
 @click.argument('out_fn', type=click.Path(dir_okay=False))
-def pack(in_fn, out_fn):
+@click.option('-p', '--processes', default=1, show_default=True, type=click.IntRange(1, None),
+              help='Host threads decoding genes side by side')
+def pack(in_fn, out_fn, processes):
     '''
     IN_FN: one sample's collapsed events (the reference's HDF5 or this package's packed prep output).
     OUT_FN: the dense container (yanocomp_b200/dense.py): the per-file half of gmmtest's pivot done once.
@@ -67,7 +69,7 @@ def pack(in_fn, out_fn):
 
     def tick(_):
         n[0] += 1
-    dense.convert(in_fn, out_fn, progress=tick)
+    dense.convert(in_fn, out_fn, progress=tick, threads=processes)
     logger.info(f'{n[0]:,} genes written to {out_fn}')
 
 

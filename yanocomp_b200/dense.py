@@ -322,39 +322,55 @@ class _Sized:
         return self._n
 
 
-def convert(in_fn, out_fn, progress=None):
+def convert(in_fn, out_fn, progress=None, threads=1):
     '''
     HDF5 (reference prep) or packed (this package's prep) sample file -> dense sample file.  The row rules are
     applied by the functions the HDF5 route uses at every run (io._clean_events: keep-first de-duplication and the
     dwell filter; io._sample_block: reads in read-id order, present positions), so both routes build the same
-    features bit for bit (tests/test_dense.py).
+    features bit for bit (tests/test_dense.py).  `threads` genes are decoded side by side (inflating HDF5 chunks
+    releases the GIL); the file is written in the input's gene order whatever the thread count.
     '''
     from . import io as ycio
     with ycio.hdf5_list([in_fn]) as (src,):
-        convert_handle(src, out_fn, progress)
+        convert_handle(src, out_fn, progress, threads)
 
 
-def convert_handle(src, out_fn, progress=None):
-    '''`convert` for an open event file (anything with the small h5py-like interface the gmmtest loaders use)'''
+def _dense_gene(src, gene_id):
+    '''the add_gene arguments of one gene of an open event file'''
     from . import io as ycio
+    e, r_ids = ycio._clean_events(src, gene_id)
+    chrom, strand = ycio.load_gene_attrs(gene_id, [src])
+    t_ids = [str(t) for t in src[f'{gene_id}/transcript_ids'][:]]
+    k = src[f'{gene_id}/kmers'][:]
+    kmers = np.empty(len(k), dtype=KMER_DTYPE)
+    kmers['pos'], kmers['kmer'] = k['pos'], np.asarray(k['kmer']).astype('S5')
+    if len(e):
+        ids, upos, row, col, mean = ycio._sample_block(e, r_ids)
+        X = np.full((len(upos), len(ids)), np.nan, dtype=np.float16)
+        X[col, row] = mean
+        tx = None
+        if len(t_ids) > 1:
+            tx = np.zeros(X.shape, dtype=np.uint8)
+            tx[col, row] = e['transcript_idx']
+    else:
+        ids, upos, X, tx = np.zeros(0, dtype='U32'), np.zeros(0, dtype=np.int64), np.zeros((0, 0), np.float16), None
+    return gene_id, chrom, strand, t_ids, kmers, ids.tolist(), upos, X, tx
+
+
+def convert_handle(src, out_fn, progress=None, threads=1):
+    '''`convert` for an open event file (anything with the small h5py-like interface the gmmtest loaders use)'''
+    genes = list(src.keys())
     with Writer(out_fn) as out:
-        for gene_id in src.keys():
-            e, r_ids = ycio._clean_events(src, gene_id)
-            chrom, strand = ycio.load_gene_attrs(gene_id, [src])
-            t_ids = [str(t) for t in src[f'{gene_id}/transcript_ids'][:]]
-            k = src[f'{gene_id}/kmers'][:]
-            kmers = np.empty(len(k), dtype=KMER_DTYPE)
-            kmers['pos'], kmers['kmer'] = k['pos'], np.asarray(k['kmer']).astype('S5')
-            if len(e):
-                ids, upos, row, col, mean = ycio._sample_block(e, r_ids)
-                X = np.full((len(upos), len(ids)), np.nan, dtype=np.float16)
-                X[col, row] = mean
-                tx = None
-                if len(t_ids) > 1:
-                    tx = np.zeros(X.shape, dtype=np.uint8)
-                    tx[col, row] = e['transcript_idx']
-            else:
-                ids, upos, X, tx = np.zeros(0, dtype='U32'), np.zeros(0, dtype=np.int64), np.zeros((0, 0), np.float16), None
-            out.add_gene(gene_id, chrom, strand, t_ids, kmers, ids.tolist(), upos, X, tx)
-            if progress is not None:
-                progress(gene_id)
+        if threads > 1 and len(genes) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as pool:
+                done = pool.map(lambda g: _dense_gene(src, g), genes)       # results come back in gene order
+                for args in done:
+                    out.add_gene(*args)
+                    if progress is not None:
+                        progress(args[0])
+        else:
+            for g in genes:
+                out.add_gene(*_dense_gene(src, g))
+                if progress is not None:
+                    progress(g)
