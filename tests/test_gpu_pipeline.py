@@ -71,3 +71,28 @@ def test_streaming_pipeline_with_rotating_staging_buffers(growth):
         np.testing.assert_array_equal(stats, one.stats)
         np.testing.assert_array_equal(mu, one.mu)
         assert launches == one.launches > 0
+
+
+def test_capacity_overflow_is_refitted_exactly():
+    '''
+    The records path sizes the slot-indexed outputs by an ESTIMATE of the gated fraction and never waits for the count
+    (the fit kernels read it on the device).  When more positions pass the gate than the estimate allows, the range is
+    fitted again with the exact size when its results are fetched: same rows as the exact (full-fetch) route.
+    '''
+    from yanocomp_b200.engine import Engine, EngineParams
+    feats = synth.make_dataset(29, 6, 400, [44, 38, 41, 36], 2, 2, planted_frac=0.2)
+    host = HostBatch(feats, 4, 2)
+    params = EngineParams(window_size=3, min_ks=0.0, fdr_threshold=1.0)        # every window passes the gate: 6 x 398 slots
+    exact = Engine(params)
+    want = exact.run(exact.upload(host), fetch='full')
+    assert want.n_fitted == 6 * 398
+    eng = Engine(params)
+    eng._gate_frac = 0.01                                                     # capacity = max(1 024, 1 % of the columns)
+    got = eng.run(eng.upload(host), fetch='records')
+    assert got.n_fitted == want.n_fitted > 1024 and (want.status_fit == 2).sum() > 1500      # most of them really fitted
+    np.testing.assert_array_equal(got.fit_list, want.fit_list)
+    np.testing.assert_array_equal(got.rows, want.rows)
+    assert eng._gate_frac > 0.9                                               # ... and the estimate has learnt
+    again = eng.run(eng.upload(host), fetch='records')                        # now sized generously: no second fit
+    np.testing.assert_array_equal(again.rows, want.rows)
+    assert again.launches < got.launches

@@ -299,6 +299,10 @@ class Engine:
             ctx['counted'].synchronize()                                 # the 4-byte count only
             n_fit = int(ctx['counts'].view(torch.int32)[0]) if gmm else 0
             m, count_ptr = max(n_fit, 1), None
+            if force_exact and n_fit:
+                # a second fit of this range (the capacity estimate was too small): the first pass has already moved
+                # the positions it reached from GATED to their final status
+                status[fit_list[:n_fit].long()] = N.ST_GATED
         else:
             n_fit = None                                                 # known at fetch time
             m = int(min(total, max(1024, total * self._gate_frac)))
@@ -343,7 +347,7 @@ class Engine:
             N.check(lib.yc_gather_fit_rows(
                 fit_list.data_ptr(), n_slots, count_ptr, w, status.data_ptr(), ks_stat.data_ptr(), ks_pval.data_ptr(),
                 n_c.data_ptr(), n_t.data_ptr(), out, out_t['rows'].data_ptr(), stream))
-        launches = ctx['launches_ks'] + int(lib.yc_kernel_launches() - fit_launches0)
+        launches = (ctx['launches'] if force_exact else ctx['launches_ks']) + int(lib.yc_kernel_launches() - fit_launches0)
         ctx.update(n_fit=n_fit, capacity=m, exact=exact, launches=launches,
                    fit_stream=torch.cuda.current_stream(d))
         if not fetch:
