@@ -173,3 +173,25 @@ def test_prep_then_gmmtest_matches_the_hdf5_route(tmp_path):
     assert len(outs['h5'][0]) > 1000
     assert outs['h5'][0] == outs['packed'][0]
     assert outs['h5'][1] == outs['packed'][1]
+
+
+def test_cli_no_gmm_matches_the_oracle_byte_for_byte(tmp_path):
+    '''--no-gmm: P values / FDRs are for the KS test only (stats.py:460-462).  KS D and p are bit-exact (p from SciPy's own
+    routine on the device D), so the whole BED must equal the oracle's, from HDF5 and from packed-dense inputs'''
+    from click.testing import CliRunner
+    import yanocomp_oracle as yo
+    from yanocomp_b200 import dense
+    from yanocomp_b200.cli import cli
+    from yanocomp_b200.io import DEFAULT_PRIORS_MODEL_FN
+    want = yo.gmmtest([CNTRL], [TREAT], yo.Options(window_size=3, gmm=False, random_seed=0), DEFAULT_PRIORS_MODEL_FN)
+    assert want.count('\n') == 13
+    packed = []
+    for name, src in (('wt', CNTRL), ('mettl3', TREAT)):
+        packed.append(str(tmp_path / f'{name}.ycd'))
+        dense.convert(src, packed[-1])
+    for name, (c, t) in {'h5': (CNTRL, TREAT), 'dense': tuple(packed)}.items():
+        bed_fn = str(tmp_path / f'{name}.bed')
+        r = CliRunner().invoke(cli, ['gmmtest', '-c', c, '-t', t, '-o', bed_fn, '--no-gmm', '--random-seed', '0'],
+                               catch_exceptions=False)
+        assert r.exit_code == 0, r.output
+        assert open(bed_fn).read() == want, name
