@@ -283,3 +283,24 @@ def test_mixed_hdf5_and_packed_inputs(tmp_path):
     with pytest.raises(FileNotFoundError):
         with hdf5_list([c_h5, str(tmp_path / 'missing.ycp')]):
             pass
+
+
+def test_prep_dense_fn_equals_pack_of_its_packed_output(tmp_path):
+    '''prep --dense-fn: one command from the eventalign table to the dense sample container; the file equals what `pack`
+    writes from prep's packed output, and what `pack` writes from the reference's HDF5 the table was regenerated from'''
+    from yanocomp_b200 import dense
+    h5_fn = os.path.join(GOLD, 'hek293t_wt.collapsed.hdf5')
+    tsv = tmp_path / 'wt.tsv'
+    _fixture_to_eventalign(h5_fn, tsv)
+    _prep(['-e', tsv, '-h', tmp_path / 'wt.ycp', '--dense-fn', tmp_path / 'wt.ycd', '-p', 3])
+    dense.convert(str(tmp_path / 'wt.ycp'), str(tmp_path / 'again.ycd'))
+    assert dense.is_dense(str(tmp_path / 'wt.ycd'))
+    assert open(tmp_path / 'wt.ycd', 'rb').read() == open(tmp_path / 'again.ycd', 'rb').read()
+    dense.convert(h5_fn, str(tmp_path / 'from_h5.ycd'))
+    with dense.File(str(tmp_path / 'wt.ycd')) as a, dense.File(str(tmp_path / 'from_h5.ycd')) as b:
+        assert sorted(a.keys()) == sorted(b.keys())
+        for g in a.keys():
+            ga, gb = a.gene(g), b.gene(g)
+            assert np.array_equal(ga.positions, gb.positions) and np.array_equal(ga.read_ids, gb.read_ids)
+            assert np.array_equal(ga.events.view(np.uint16), gb.events.view(np.uint16))
+            assert np.array_equal(ga.kmer_at_pos, gb.kmer_at_pos)

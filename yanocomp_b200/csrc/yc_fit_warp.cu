@@ -47,10 +47,6 @@ __device__ __forceinline__ int fw_next_slot(int *work, int lane) {
     __syncwarp();
     return s;
 }
-// A kernel parameter re-read through an empty asm: the optimiser cannot prove it invariant over the persistent
-// loop, so it does not clone the whole per-position program once per value of the flag (loop unswitching made the
-// init kernel 36 % larger, and these kernels live or die by their instruction-cache footprint).
-__device__ __forceinline__ int fw_opaque(int v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ int fw_slot_count(int n_fit, const int32_t *fit_count) {
     if (fit_count == nullptr) return n_fit;
     const int c = *fit_count;
@@ -265,7 +261,7 @@ init_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, con
     const int R = b.n_samples;
     constexpr int NT = W * (W + 1) / 2, NS = 1 + W + NT;
     const int64_t g = fit_list[slot];
-    const bool add_uniform = fw_opaque(p.add_uniform) != 0, want_labels = fw_opaque(labels_out != nullptr) != 0;
+    const bool add_uniform = p.add_uniform != 0, want_labels = labels_out != nullptr;
     FwCtx<W> c;
     if (!fw_front<W>(b, p, g, smem_raw, L, cap, lane, true, c)) { if (lane == 0) status[g] = YC_ST_FIT_FAILED; return; }
     const int n = c.n;
@@ -760,7 +756,7 @@ em_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, const
     const int *fstart = c.fstart;
     load_model<W>(par, out, slot, lane, out.logw + (size_t)slot * R * 3, R * 3);
     bool failed = par->ok == 0;
-    const bool uni = fw_opaque(p.add_uniform) != 0;
+    const bool uni = p.add_uniform != 0;
 
     double *carry = reinterpret_cast<double *>(smem_raw + L.carry_off);   // [2][NS]: summaries kept when S0 < 1e-7 (A3)
     for (int q = lane; q < 2 * NS; q += 32) carry[q] = 0.0;
@@ -1013,7 +1009,7 @@ gtest_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, co
                     unsigned char *smem_raw, const FwSmem &L, const int lane) {
     const int R = b.n_samples, Rc = b.n_cntrl;
     const int64_t g = fit_list[slot];
-    const bool want_post = fw_opaque(post != nullptr) != 0, add_uniform = fw_opaque(p.add_uniform) != 0;
+    const bool want_post = post != nullptr, add_uniform = p.add_uniform != 0;
     if (status[g] != YC_ST_TESTED) {                                     // failed fit: no row
         if (lane == 0) out.post_off[slot] = -1;
         if (lane < 8) out.stats[(size_t)slot * 8 + lane] = nan("");

@@ -241,6 +241,9 @@ class CollapseOpts:
                     'transcriptomic coordinates to genomic'))
 @click.option('-p', '--processes', required=False, default=1, show_default=True)
 @click.option('-n', '--chunksize', required=False, default=1_000_000, hidden=True)
+@click.option('--dense-fn', required=False, default=None,
+              help=('Also write the dense sample container gmmtest ingests fastest (the `pack` step done here; '
+                    'not in the reference)'))
 def nanopolish_collapse(**kw):
     '''
     Parse nanopolish eventalign tabular data into the per-gene event tables
@@ -254,6 +257,9 @@ def nanopolish_collapse(**kw):
     save_events_to_packed(
         parallel_collapse(opts.eventalign_fn, opts.summary_fn, opts.gtf_fn, opts.processes, opts.chunksize),
         opts.hdf5_fn)
+    if getattr(opts, 'dense_fn', None):
+        from . import dense
+        dense.convert(opts.hdf5_fn, opts.dense_fn, threads=max(1, int(opts.processes)))
 
 
 if __name__ == '__main__':
