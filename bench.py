@@ -221,6 +221,7 @@ def run_job(args, torch, dist, world, rank):
         t0 = time.perf_counter()
         c_fns, t_fns, _ = synth.write_dense_config(cfg, d, torch.device('cuda', torch.cuda.current_device()),
                                                    n_features=n_features)
+        os.sync()                 # the inputs are "page-cache warm", not "still being written back": flush the dirty pages
         t_write = time.perf_counter() - t0
         box = [(d, c_fns, t_fns)]
     if world > 1:
@@ -276,7 +277,8 @@ def run_job(args, torch, dist, world, rank):
             'positions_tested': best['positions_tested'], 'positions_fitted': best['positions_fitted'], 'rows': best['rows'],
             'significant_at_fdr': best['significant_at_fdr'], 'slowest_stage': slowest,
             'stage_seconds_max_over_ranks': best['stage_seconds_max_over_ranks'],
-            'stage_seconds_rank0': best['stage_seconds_rank0'], 'seconds_all_reps': [r['seconds'] for r in reps]}
+            'stage_seconds_rank0': best['stage_seconds_rank0'], 'seconds_all_reps': [r['seconds'] for r in reps],
+            'stage_seconds_rank0_all_reps': [r['stage_seconds_rank0'] for r in reps]}
 
 
 def run_other_configs(args, torch):

@@ -42,15 +42,12 @@ def test_parallel_test_matches_oracle(level, strand, extra, monkeypatch):
     recs, everything = yo.test_features([files['file0'], files['file1']], [files['file2'], files['file3']], o_opts)
     ref = {(r['gene_id'], r['pos']): r for r in recs}
     got = {(r.gene_id, r.pos): r for r in res.itertuples(index=False)}
-    # rank-deficient initial clusters may flip between "failed" and "fitted": compare the common rows
-    common = set(ref) & set(got)
-    assert len(common) >= 0.85 * max(len(ref), len(got)) and len(common) >= 8, (len(ref), len(got), len(common))
+    # the same positions come out tested on both sides (rank-deficient starts fail by the same exact rule, A4)
+    assert set(ref) == set(got) and len(ref) >= 8, (len(ref), len(got), sorted(set(ref) ^ set(got))[:5])
+    common = set(ref)
     n = 0
     for key in common:
         g, o = got[key], ref[key]['result']
-        counts = np.bincount(o.fit.init_pred, minlength=3)
-        if ((counts[:2] > 0) & (counts[:2] <= 3)).any():
-            continue
         assert g.chrom == ref[key]['chrom'] and g.strand == strand and g.kmer == o.kmer
         assert list(g.kmers) == list(o.kmers) and g.centre == 1
         assert g.ks_stat == o.ks_stat
@@ -67,10 +64,18 @@ def test_parallel_test_matches_oracle(level, strand, extra, monkeypatch):
                 for rep in s[cond]:
                     assert s[cond][rep]['read_ids'] == o.sm_preds[cond][rep]['read_ids']
                     assert s[cond][rep]['events'] == o.sm_preds[cond][rep]['events']
-                    np.testing.assert_allclose(s[cond][rep]['preds'], o.sm_preds[cond][rep]['preds'], rtol=1e-3, atol=1e-9)
+                    np.testing.assert_allclose(s[cond][rep]['preds'], o.sm_preds[cond][rep]['preds'], rtol=1e-6, atol=1e-9)
         n += 1
     assert n >= 6
     # BH over the same set of rows gives the same FDR
-    if set(ref) == set(got):
-        for key in common:
-            assert abs(got[key].fdr - ref[key]['result'].fdr) <= 1e-4 * ref[key]['result'].fdr
+    for key in common:
+        assert abs(got[key].fdr - ref[key]['result'].fdr) <= 1e-4 * ref[key]['result'].fdr
+    # without -s the same call returns {feature: {pos: None}} for the same tested positions, served lazily
+    opts2 = G.GMMTestOpts(cntrl_hdf5_fns=('file0', 'file1'), treat_hdf5_fns=('file2', 'file3'), output_bed_fn='x.bed',
+                          test_level=level, random_seed=3, processes=2, **extra)
+    res2, sm2 = G.parallel_test(opts2)
+    assert isinstance(sm2, G.TestedPositions)
+    assert sm2 == {f: dict.fromkeys(d) for f, d in sm.items()}
+    assert G.materialise_array_columns(res2).to_csv() == G.materialise_array_columns(res).to_csv()
+    sig, sig_sm = G.filter_results(res2, sm2, 0.05)
+    assert sig_sm == {} and len(sig) == int((res.fdr < 0.05).sum())

@@ -81,7 +81,7 @@ def _gather_rowblocks(blocks, sm_preds, world, rank):
     has_rows = blk is not None and blk.rows is not None
     width = (blk.rows.shape[1] if has_rows else 2) if blk is not None else 0
     w = blk.window if blk is not None else 0
-    any_preds = any(v is not None for d in sm_preds.values() for v in d.values())
+    any_preds = any(v is not None for d in (sm_preds or {}).values() for v in d.values())
     tables = (blk.feature_ids, blk.chroms, blk.strands) if blk is not None else ([], [], [])
     metas = [None] * world
     dist.all_gather_object(metas, (n, width, w, has_rows, tables, sm_preds if any_preds else None))

@@ -135,6 +135,22 @@ def _carve(specs, device=None, zero=False):
     return arena, views, ext, total
 
 
+_ENGINES = {}
+
+
+def shared_engine(params):
+    '''
+    One Engine per (device, parameters) and process: its pinned staging buffers, count ring and streams are kept
+    between calls (test_chunk is called once per job or per --test-gene list; creating them anew costs more page-locked
+    allocations than a small job has kernels).
+    '''
+    key = (torch.cuda.current_device(), tuple(sorted(dataclasses.asdict(params).items())))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = _ENGINES[key] = Engine(params)
+    return eng
+
+
 class Engine:
     '''owns the per-device scratch and launches the kernels of one batch'''
 
@@ -264,7 +280,8 @@ class Engine:
         # [n_fit, posterior reads written]: pinned, from a ring (a pinned allocation per range costs more than its kernels'
         # launches; at most a handful of ranges are in flight, so 32 slots never collide)
         if not hasattr(self, '_count_ring'):
-            self._count_ring = [torch.empty(2, dtype=torch.int64, pin_memory=True) for _ in range(32)]
+            ring = torch.empty(64, dtype=torch.int64, pin_memory=True)     # ONE pinned allocation, 32 slots of two
+            self._count_ring = [ring[2 * i:2 * i + 2] for i in range(32)]
             self._count_next = 0
         counts = self._count_ring[self._count_next % 32]
         self._count_next += 1

@@ -45,57 +45,6 @@ STAGES = collections.defaultdict(float)
 COUNTS = collections.Counter()      # positions_tested (entered position_stats) / positions_fitted of the same calls
 
 
-def _prefetch(gen, depth=2):
-    '''
-    Run the batch source on a helper thread, `depth` batches ahead: building the next packed batch (file reads into
-    pinned memory, index arithmetic -- all of it releases the GIL or is short) overlaps the kernel launches and the
-    record assembly of the current one.  Exceptions of the source are re-raised in the consumer.
-    '''
-    import queue
-    import threading
-    q = queue.Queue(maxsize=depth)
-    done = object()
-    stop = threading.Event()
-    device = None
-    try:
-        import torch
-        if torch.cuda.is_available():
-            device = torch.cuda.current_device()          # the current device is per thread: hand it to the helper
-    except ImportError:
-        pass
-
-    def produce():
-        try:
-            if device is not None:
-                import torch
-                torch.cuda.set_device(device)
-            for item in gen:
-                while not stop.is_set():
-                    try:
-                        q.put((item, None), timeout=0.1)
-                        break
-                    except queue.Full:
-                        continue
-                if stop.is_set():
-                    return
-            q.put((done, None))
-        except BaseException as exc:                      # noqa: B902 -- handed to the consumer
-            q.put((done, exc))
-
-    t = threading.Thread(target=produce, daemon=True)
-    t.start()
-    try:
-        while True:
-            item, exc = q.get()
-            if exc is not None:
-                raise exc
-            if item is done:
-                return
-            yield item
-    finally:
-        stop.set()
-
-
 def _timed_iter(gen, name):
     it = iter(gen)
     while True:
@@ -406,7 +355,7 @@ def _record_attrs(host):
     return attrs
 
 
-def _batch_records(host, res, opts):
+def _batch_records(host, res, opts, none_entries=True):
     '''
     Device results of one batch -> (records, sm_preds) in the reference's shapes (GMMTestRecord fields, reference
     gmmtest.py:120-136, 164-178).  The records are ONE RowBlock: the fixed-width result rows as fetched, plus
@@ -446,6 +395,8 @@ def _batch_records(host, res, opts):
                          p_val=np.asarray(res.ks_pval)[cols], ks=np.asarray(res.ks_stat)[cols])
     records.add_block(block)
     # sm_preds[feature][pos]: None unless the position is significant and -s was asked for
+    if not none_entries and (post_off is None or res.post is None):
+        return records, sm
     run_starts = np.concatenate(([0], np.flatnonzero(np.diff(fidx)) + 1, [n])).tolist()
     pos_list = pos.tolist()
     win_str = None
@@ -482,19 +433,20 @@ def _rows_from_arrays(res, slots, w):
     return rows
 
 
-def test_chunk(opts, gene_ids):
+def test_chunk(opts, gene_ids, tested_positions_later=False):
     '''
     Run the tests on a subset of gene ids (reference gmmtest.py:139-179).
     `gene_ids` = (ids, seed) as in the reference; the seed is taken from
     opts.random_seed (results do not depend on the chunking, see dist.py).
-    Returns (records, sm_preds).
+    Returns (records, sm_preds).  With tested_positions_later (parallel_test without -s) the {feature: {pos: None}}
+    entries of sm_preds are left out: the caller serves them from the records (TestedPositions).
     '''
-    from .engine import Engine
+    from .engine import shared_engine
     if isinstance(opts, dict):
         opts = GMMTestOpts(**{k: v for k, v in opts.items()
                               if k in {f.name for f in dataclasses.fields(GMMTestOpts) if f.init}})
     gene_ids, _ = gene_ids
-    engine = Engine(opts.engine_params())
+    engine = shared_engine(opts.engine_params())
     by_t = opts.test_level == 'transcript'
     R = len(opts.cntrl_hdf5_fns) + len(opts.treat_hdf5_fns)
     chunk_res, chunk_sm = Records(), {}
@@ -537,7 +489,8 @@ def test_chunk(opts, gene_ids):
         All inputs are dense sample files (dense.py): no per-gene decode and no host pivot.  The genes are cut into
         ranges of ~BATCH_EVENT_BYTES / PIPELINE_RANGES (shallow and deep genes apart, as above); a range is a handful
         of large copies out of the memory maps into one pinned buffer plus a small task table, and the feature
-        matrices are assembled on the device (yc_assemble_batch).  Building range k+1 overlaps the kernels of range k.
+        matrices are assembled on the device (yc_assemble_batch).  Building range k+1 overlaps the kernels of range k (the
+        launches are asynchronous).
         '''
         n_cntrl = len(opts.cntrl_hdf5_fns)
         with hdf5_list(opts.cntrl_hdf5_fns + opts.treat_hdf5_fns) as files:
@@ -549,7 +502,9 @@ def test_chunk(opts, gene_ids):
             nbytes = sum(r['n_pos'].astype(np.int64) * r['ld'].astype(np.int64) * 2 for r in rows)
             cond = np.maximum(n_reads[:n_cntrl].sum(0), n_reads[n_cntrl:].sum(0))
             shallow = (n_reads.sum(0) <= 1024) & (cond <= opts.max_fit_depth)
-            limit = max(BATCH_EVENT_BYTES // PIPELINE_RANGES, 1)
+            # ranges of 1/PIPELINE_RANGES of the shard, at most BATCH_EVENT_BYTES / PIPELINE_RANGES and at least 8 MB: a small
+            # job is pipelined (read | upload | kernels | records) like a large one instead of being one serial batch
+            limit = int(min(BATCH_EVENT_BYTES // PIPELINE_RANGES, max(int(nbytes.sum()) // PIPELINE_RANGES, 8 << 20)))
             # --test-level transcript: genes whose blocks hold several transcripts are split on the host
             # (io.dense_transcript_features) and go through ordinary packed batches
             multi = (np.stack([r['n_tx'] for r in rows]).max(axis=0) > 1) if by_t else np.zeros(len(ids), dtype=bool)
@@ -585,7 +540,10 @@ def test_chunk(opts, gene_ids):
     if any(is_dense) and not all(is_dense):
         raise click.UsageError('dense sample files (python -m yanocomp_b200 pack) cannot be mixed with HDF5 / packed inputs')
     if all(is_dense) and fns:
-        source = _prefetch(dense_batches())
+        # built on this thread, between the (asynchronous) launches of the previous ranges: a helper thread was tried and
+        # made things worse -- every kernel launch re-acquires the GIL, and a thread busy building the next batch keeps it for
+        # a whole switch interval (job times of 0.06 - 0.8 s instead of a steady 0.06 s)
+        source = dense_batches()
     else:
         # every batch is cut into PIPELINE_RANGES feature ranges (views, no copy): the upload of range k+1 overlaps
         # the kernels of range k and the fetch of range k-1 (engine.run_pipelined), also when a chunk is one batch
@@ -603,7 +561,7 @@ def test_chunk(opts, gene_ids):
         t0 = time.perf_counter()
         COUNTS['positions_tested'] += res.n_tested
         COUNTS['positions_fitted'] += res.n_fitted
-        recs, sm = _batch_records(host, res, opts)
+        recs, sm = _batch_records(host, res, opts, none_entries=not tested_positions_later)
         chunk_res.extend(recs)
         for k, v in sm.items():
             chunk_sm.setdefault(k, {}).update(v)
@@ -694,17 +652,46 @@ class RowTable:
 
     @staticmethod
     def from_blocks(blocks):
+        '''one table out of the batches' RowBlocks (single process): filled block by block into one (pinned, when a GPU
+        will finish it) buffer, feature tables appended and indices shifted'''
         import torch
-        blk = RowBlock.concat(blocks)
-        n, w = len(blk), blk.window
-        body = blk.rows if blk.rows is not None else np.stack([blk.p_val, blk.ks], axis=1)
-        num = np.empty((n, body.shape[1] + 2))
-        num[:, :-2], num[:, -2], num[:, -1] = body, blk.fidx, blk.pos
-        kmb = np.ascontiguousarray(blk.kmers).view(np.uint8).reshape(n, 5 * w)
-        num, kmb = torch.from_numpy(num), torch.from_numpy(kmb)
-        if n >= 16384 and torch.cuda.is_available():
-            num, kmb = num.cuda(non_blocking=True), kmb.cuda(non_blocking=True)
-        return RowTable(blk.feature_ids, blk.chroms, blk.strands, num, kmb, blk.rows is not None, w)
+        blocks = [b for b in blocks if len(b)]
+        n = sum(len(b) for b in blocks)
+        w = blocks[0].window
+        gmm = blocks[0].rows is not None
+        width = blocks[0].rows.shape[1] if gmm else 2
+        on_gpu = n >= 16384 and torch.cuda.is_available()
+        num = kmb = None
+        if on_gpu:
+            from .batch import PINNED
+            buf = PINNED.acquire(n * (width + 2) * 8 + n * 5 * w + 64)
+            if buf is not None:
+                num = buf[:n * (width + 2) * 8].view(np.float64).reshape(n, width + 2)
+                kmb = buf[n * (width + 2) * 8:n * (width + 2) * 8 + n * 5 * w].reshape(n, 5 * w)
+        if num is None:
+            num, kmb = np.empty((n, width + 2)), np.empty((n, 5 * w), dtype=np.uint8)
+        ids, chroms, strands = [], [], []
+        at = 0
+        for b in blocks:
+            m = len(b)
+            sl = slice(at, at + m)
+            if gmm:
+                num[sl, :width] = b.rows
+            else:
+                num[sl, 0], num[sl, 1] = b.p_val, b.ks
+            num[sl, width] = b.fidx
+            num[sl, width] += len(ids)
+            num[sl, width + 1] = b.pos
+            kmb[sl] = np.ascontiguousarray(b.kmers).view(np.uint8).reshape(m, 5 * w)
+            ids += list(b.feature_ids)
+            chroms += list(b.chroms)
+            strands += list(b.strands)
+            at += m
+        tnum, tkmb = torch.from_numpy(num), torch.from_numpy(kmb)
+        if on_gpu:
+            tnum, tkmb = tnum.cuda(non_blocking=True), tkmb.cuda(non_blocking=True)
+            torch.cuda.current_stream().synchronize()         # the pinned staging buffer may be released after this
+        return RowTable(ids, chroms, strands, tnum, tkmb, gmm, w)
 
 
 class TestedPositions(collections.abc.Mapping):
@@ -730,6 +717,13 @@ class TestedPositions(collections.abc.Mapping):
 
     def __len__(self):
         return len(self._span)
+
+    def __eq__(self, other):
+        if isinstance(other, collections.abc.Mapping):
+            return len(self) == len(other) and all(k in other and self[k] == other[k] for k in self)
+        return NotImplemented
+
+    __hash__ = None
 
 
 def _frame_from_table(tab, want_tested=False):
@@ -882,11 +876,16 @@ def parallel_test(opts):
     logger.info(f'{len(gene_ids):,} genes to be processed on {max(world, 1)} GPU worker(s)')
     mine = ycdist.shard_by_size(gene_ids, sizes, world)[rank]
     STAGES['open'] += time.perf_counter() - t0
-    res, sm_preds = test_chunk(opts, (mine, opts.random_seed))
+    lazy = not (opts.generate_sm_preds and opts.gmm)       # no predictions will exist: None entries served from the rows
+    res, sm_preds = test_chunk(opts, (mine, opts.random_seed), tested_positions_later=lazy)
     t0 = time.perf_counter()
-    res, sm_preds = ycdist.gather_results(res, sm_preds)
+    res, sm_preds = ycdist.gather_results(res, None if (lazy and world == 1) else sm_preds)
     STAGES['gather'] += time.perf_counter() - t0
     t0 = time.perf_counter()
+    if lazy and world == 1 and isinstance(res, Records) and res.row_blocks() is not None:
+        res = RowTable.from_blocks(res.row_blocks())
+    if lazy and rank == 0 and not isinstance(res, RowTable):
+        sm_preds = {}                                       # nothing was tested
     if isinstance(res, RowTable) and sm_preds is None:
         # the ranks made no single-molecule predictions: {feature: {pos: None}} is served lazily from the row table
         frame, tested = _frame_from_table(res, want_tested=True)
