@@ -272,6 +272,7 @@ class DeviceBatch:
         self.ld = up(host.ld, np.int32)
         if isinstance(host, DenseHostBatch):
             # the sample files' bytes as they are + the task table; the feature matrices are assembled on the device
+            host.wait()
             raw = torch.from_numpy(host.raw.view(np.int16)).to(dev, non_blocking=True)
             tasks = up(host.tasks32.reshape(-1), np.int64) if len(host.tasks32) else torch.zeros(8, dtype=torch.int64, device=dev)
             colmap = up(host.colmap, np.int32)
@@ -410,8 +411,11 @@ class DenseHostBatch:
     '''
     TASK_FIELDS = 8        # feature, src offset (elements of raw), 0, src ld, n_pos, n_reads, first row, colmap offset | -1
 
-    def __init__(self, files, gene_ids, n_cntrl, by_transcript=False, pin=True, copy_threads=4):
+    def __init__(self, files, gene_ids, n_cntrl, by_transcript=False, pin=True, copy_threads=4, wait=True):
+        '''wait=False: return as soon as the tables are built and the file reads are queued on the copy threads; whoever needs
+        `raw` calls wait() first (DeviceBatch does).  The reads release the GIL, so they overlap the caller's Python.'''
         R = len(files)
+        self._pending = []
         if not 1 <= n_cntrl < R <= N.YC_MAX_SAMPLES:
             raise ValueError(f'need 1 <= n_cntrl < n_samples <= {N.YC_MAX_SAMPLES}')
         self.n_samples, self.n_cntrl = R, n_cntrl
@@ -556,8 +560,10 @@ class DenseHostBatch:
                 done += k
         pieces = _split_copies(copies)
         if copy_threads > 1 and len(pieces) > 1:
-            with _copy_pool(copy_threads) as pool:                       # memcpy releases the GIL
-                list(pool.map(copy, pieces))
+            with _copy_pool(copy_threads) as pool:                       # the reads release the GIL
+                self._pending = [pool.submit(copy, c) for c in pieces]
+            if wait:
+                self.wait()
         else:
             for c in pieces:
                 copy(c)
@@ -566,6 +572,20 @@ class DenseHostBatch:
             for name in ('n_cols', 'n_reads', 'ld', 'x_off', 'col_off', 'samp_start', 'feature_key', 'col_pos', 'reverse',
                          'colmap', 'tasks32'):
                 setattr(self, name, HostBatch._pinned_copy(getattr(self, name), owner=self))
+
+    def wait(self):
+        '''block until every file read into `raw` has finished (re-raises a failed read)'''
+        pending, self._pending = self._pending, []
+        for f in pending:
+            f.result()
+
+    def __del__(self):
+        # reads still in flight write into the pooled pinned buffer: it must not return to the pool before they end
+        for f in getattr(self, '_pending', []):
+            try:
+                f.result()
+            except Exception:
+                pass
 
     @staticmethod
     def _take_runs(mms, feats, sample_of, offs, n_cols, dtype, itemsize, out, to_int64):

@@ -524,25 +524,31 @@ def test_chunk(opts, gene_ids, tested_positions_later=False):
                 for k in (True, False):
                     if pend[k]:
                         yield HostBatch(pend[k], R, n_cntrl)
+            # one range ahead: the file reads of range k+1 are queued on the copy threads (they hold no GIL) before range k
+            # is handed out, so they run while this thread launches and harvests range k
+            ahead = None
             for k in (True, False):
                 pending, acc = [], 0
-                for j in np.flatnonzero((shallow == k) & ~multi).tolist():
+                sel = np.flatnonzero((shallow == k) & ~multi).tolist()
+                for n_done, j in enumerate(sel, 1):
                     pending.append(ids[j])
                     acc += int(nbytes[j])
-                    if acc >= limit:
-                        yield DenseHostBatch(files, pending, n_cntrl, by_t, copy_threads=max(1, opts.processes))
+                    if acc >= limit or n_done == len(sel):
+                        nxt = DenseHostBatch(files, pending, n_cntrl, by_t, copy_threads=max(2, opts.processes), wait=False)
                         pending, acc = [], 0
-                if pending:
-                    yield DenseHostBatch(files, pending, n_cntrl, by_t, copy_threads=max(1, opts.processes))
+                        if ahead is not None:
+                            yield ahead
+                        ahead = nxt
+            if ahead is not None:
+                yield ahead
 
     fns = list(opts.cntrl_hdf5_fns) + list(opts.treat_hdf5_fns)
     is_dense = [ycdense.is_dense(fn) for fn in fns]
     if any(is_dense) and not all(is_dense):
         raise click.UsageError('dense sample files (python -m yanocomp_b200 pack) cannot be mixed with HDF5 / packed inputs')
     if all(is_dense) and fns:
-        # built on this thread, between the (asynchronous) launches of the previous ranges: a helper thread was tried and
-        # made things worse -- every kernel launch re-acquires the GIL, and a thread busy building the next batch keeps it for
-        # a whole switch interval (job times of 0.06 - 0.8 s instead of a steady 0.06 s)
+        # tables are built on this thread, between the (asynchronous) launches of the previous ranges; only the file reads
+        # run on helper threads.  (A helper thread building whole batches was tried: it holds the GIL while it runs Python.)
         source = dense_batches()
     else:
         # every batch is cut into PIPELINE_RANGES feature ranges (views, no copy): the upload of range k+1 overlaps
