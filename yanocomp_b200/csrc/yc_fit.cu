@@ -61,37 +61,6 @@ __host__ __device__ inline FitSmem fit_smem_layout(int W, int R, int max_reads, 
 // ---------------------------------------------------------------------------
 // shared front end: complete rows -> per-sample sub-sampling -> compaction
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int block_excl_scan_i(int v, int *scratch, int &total) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(YC_FULL, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) scratch[wid] = inc;
-    __syncthreads();
-    int base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < YC_NWARPS; ++w) { if (w < wid) base += scratch[w]; tot += scratch[w]; }
-    __syncthreads();
-    total = tot;
-    return base + inc - v;
-}
-
-// ordered exclusive prefix of popc(mask[wd]) into wordoff[wd]; returns total
-__device__ __forceinline__ int mask_word_prefix(const uint32_t *mask, int nwords, int *wordoff, int *scratch) {
-    const int C = (nwords + YC_BLOCK - 1) / YC_BLOCK;
-    const int w0 = threadIdx.x * C, w1 = min(w0 + C, nwords);
-    int loc = 0;
-    for (int wd = w0; wd < w1; ++wd) loc += __popc(mask[wd]);
-    int total;
-    int run = block_excl_scan_i(loc, scratch, total);
-    for (int wd = w0; wd < w1; ++wd) { wordoff[wd] = run; run += __popc(mask[wd]); }
-    __syncthreads();
-    return total;
-}
-
 template <int W>
 struct FitCtx {
     Window<W> w;
@@ -197,6 +166,66 @@ __device__ __forceinline__ int nth_inlier(const int8_t *lab, int i0c, int i1c, i
 // ---------------------------------------------------------------------------
 // Kernel 2a
 // ---------------------------------------------------------------------------
+// One Lloyd pass over the fit rows: nearest of the two centroids per row, column sums and size of cluster 1, total
+// distance (acc[0..W) | acc[W] | acc[W + 1], per thread).
+//  * The nearer centroid is decided from d_k = |x|^2 - 2 x.c_k + |c_k|^2 (|x|^2 precomputed, FMA chains: W + 2
+//    operations per centroid instead of 3 W - 1 separately rounded ones); only when the two lie within the error bound
+//    of that form (2^-44 of the magnitudes involved is > 64 times the bound) are the NumPy-order distances compared,
+//    which is the comparison the oracle makes (A2).  The cluster sums are sums of binary16 values: exact either way.
+//  * U rows per step, branch-free (predicates as 0/1 weights, one rare branch for the exact comparison): at 2 CTAs
+//    per SM the pass is bound by dependency latency, and rows are the only independent work there is.
+#define YC_LLOYD_GUARD 5.6843418860808015e-14     /* 2^-44 */
+#ifndef YC_LLOYD_U
+#define YC_LLOYD_U 4
+#endif
+template <int W, int U>
+__device__ __forceinline__ void lloyd_pass(const FitCtx<W> &c, const double *__restrict__ xx, const int8_t *__restrict__ lab,
+                                           const bool db, const int n, const double (&cen)[2 * W], double (&acc)[W + 2]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < W + 2; ++k) acc[k] = 0.0;
+    double m0[W], m1[W], cc0 = 0.0, cc1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        m0[j] = -2.0 * cen[j]; m1[j] = -2.0 * cen[W + j];
+        cc0 = fma(cen[j], cen[j], cc0); cc1 = fma(cen[W + j], cen[W + j], cc1);
+    }
+    const double ccmax = fmax(cc0, cc1);
+#pragma unroll 1
+    for (int i0 = tid; i0 < n; i0 += U * YC_BLOCK) {
+        double x[U][W], d0[U], d1[U];
+        bool k[U], use[U], need = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * YC_BLOCK;
+            use[u] = i < n;
+            const int ii = use[u] ? i : i0;
+            if (db && lab[ii] == 2) use[u] = false;
+            load_row<W>(c, ii, x[u]);
+            const double xi = xx[ii];
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) { t0 = fma(x[u][j], m0[j], t0); t1 = fma(x[u][j], m1[j], t1); }
+            d0[u] = (xi + cc0) + t0; d1[u] = (xi + cc1) + t1;
+            const double diff = d1[u] - d0[u];
+            k[u] = diff < 0.0;
+            need |= fabs(diff) <= YC_LLOYD_GUARD * ((xi + ccmax) + (fabs(t0) + fabs(t1)));
+        }
+        if (need) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) k[u] = sqdist<W>(x[u], cen + W) < sqdist<W>(x[u], cen);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double w1 = (use[u] && k[u]) ? 1.0 : 0.0;
+            const double dsel = k[u] ? d1[u] : d0[u];
+            acc[W] += use[u] ? dsel : 0.0;
+            acc[W + 1] += w1;
+#pragma unroll
+            for (int j = 0; j < W; ++j) acc[j] = fma(w1, x[u][j], acc[j]);
+        }
+    }
+}
 #ifndef YC_INITC_MINBLOCKS
 #define YC_INITC_MINBLOCKS 1
 #endif
@@ -282,10 +311,29 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         block_sum<W>(sumx, red);
     }
 
+    // |x|^2 of every fit row, parked in the (still unused) MAD sort buffer: Lloyd decides the nearer centroid from
+    // d_k = |x|^2 - 2 x.c_k + |c_k|^2 (FMA chains, W + 2 operations per centroid instead of 3 W - 1 separately rounded
+    // ones) and falls back to the NumPy-order distances only when the two are closer than the error bound of that form
+    double *xx = sortbuf;
+    for (int i = tid; i < n; i += YC_BLOCK) {
+        double x[W];
+        load_row<W>(c, i, x);
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) t = fma(x[j], x[j], t);
+        xx[i] = t;
+    }
+    __syncthreads();
+
     // ---------------- k-means++ x3 + Lloyd on the inliers  (assumption A2)
     double best[2 * W], best_total = INFINITY;
     bool have_best = false;
-    const int C = (n + YC_BLOCK - 1) / YC_BLOCK;
+    // every thread owns a contiguous chunk of rows (the cumulative sum of the D^2 sampling runs in row order).  The chunk
+    // length is rounded up to 2 (mod 4): with binary16 rows in shared memory the lanes of a warp then start 17, 19, ...
+    // 32-bit words apart -- distinct banks -- where the natural length for 4 000 rows, 32, put them on two banks
+    // (16-way conflicts on every load of the six seeding passes)
+    int C = (n + YC_BLOCK - 1) / YC_BLOCK;
+    while ((C & 3) != 2) ++C;
     const int i0c = min(tid * C, n), i1c = min(i0c + C, n);
     for (int restart = 0; restart < 3 && n_in > 0; ++restart) {
         double cen[2 * W];
@@ -300,6 +348,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         }
         {   // second centre: D^2 sampling through the cumulative sum
             double loc = 0.0;
+#pragma unroll 2
             for (int i = i0c; i < i1c; ++i) {
                 if (db && lab[i] == 2) continue;
                 double x[W]; load_row<W>(c, i, x); loc = add_rn(loc, sqdist<W>(x, cen));
@@ -318,6 +367,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             const double u1 = rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 1);
             const double target = mul_rn(u1, total);
             int below = 0;
+#pragma unroll 2
             for (int i = i0c; i < i1c; ++i) {
                 if (db && lab[i] == 2) continue;
                 double x[W]; load_row<W>(c, i, x); run = add_rn(run, sqdist<W>(x, cen)); below += (run <= target);
@@ -344,19 +394,7 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                     if (n1 > 0.0) cen[W + j] = div_rn(acc[j], n1);       // an empty cluster keeps its centroid (A2)
                 }
             }
-#pragma unroll
-            for (int k = 0; k < W + 2; ++k) acc[k] = 0.0;
-            for (int i = tid; i < n; i += YC_BLOCK) {
-                if (db && lab[i] == 2) continue;
-                double x[W];
-                load_row<W>(c, i, x);
-                const double d0 = sqdist<W>(x, cen), d1 = sqdist<W>(x, cen + W);
-                const bool k = d1 < d0;
-                acc[W] += k ? d1 : d0;
-                acc[W + 1] += k ? 1.0 : 0.0;
-#pragma unroll
-                for (int j = 0; j < W; ++j) acc[j] += k ? x[j] : 0.0;
-            }
+            lloyd_pass<W, YC_LLOYD_U>(c, xx, lab, db, n, cen, acc);
             block_sum<W + 2>(acc, red);
             have_sums = true;
             total = acc[W];
@@ -621,6 +659,8 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 #pragma unroll
         for (int j = 0; j < W; ++j) { mu0[j] = par->mu[0][j]; mu1[j] = par->mu[1][j]; }
         double seprod = 1.0;
+        int cur_s = -1;
+        double ps0 = 0.0, ps1 = 0.0, ps2 = 0.0;
         for (int base = wid * 32; base < n; base += YC_NWARPS * 32) {
             const int i = base + lane;
             const bool valid = i < n;
@@ -668,17 +708,35 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                     for (int bb = a; bb < W; ++bb) { acc[q] = fma(xa0, x[bb], acc[q]); acc[NS + q] = fma(xa1, x[bb], acc[NS + q]); ++q; }
                 }
             }
-            // per-sample responsibility sums (gmm.summaries): a 32-row chunk spans few samples
+            // per-sample responsibility sums (gmm.summaries).  Rows are ordered by sample, so nearly every 32-row chunk
+            // lies inside one sample: those only add to per-lane partials of the current sample `cur_s` (warp-uniform),
+            // reduced over the warp when the sample changes; a chunk that straddles samples is reduced directly.
             const int s_lo = __shfl_sync(YC_FULL, s, 0);
             const int s_hi = c.srow[min(base + 31, n - 1)] & 0x7f;
-            for (int ss = s_lo; ss <= s_hi; ++ss) {
-                const bool mine = valid && s == ss;
-                const double t0 = warp_sum(mine ? r0 : 0.0), t1 = warp_sum(mine ? r1 : 0.0), t2 = warp_sum(mine ? r2 : 0.0);
-                if (lane == 0) {
-                    double *ws = wsum + (wid * YC_MAX_SAMPLES + ss) * 3;
-                    ws[0] += t0; ws[1] += t1; ws[2] += t2;
+            if (s_lo != cur_s || s_hi != cur_s) {
+                if (cur_s >= 0) {
+                    const double t0 = warp_sum(ps0), t1 = warp_sum(ps1), t2 = warp_sum(ps2);
+                    if (lane == 0) { double *ws = wsum + (wid * YC_MAX_SAMPLES + cur_s) * 3; ws[0] += t0; ws[1] += t1; ws[2] += t2; }
+                }
+                ps0 = ps1 = ps2 = 0.0;
+                cur_s = s_lo == s_hi ? s_lo : -1;
+            }
+            if (cur_s >= 0) {
+                ps0 += r0; ps1 += r1; ps2 += r2;                      // rows beyond n carry zeros
+            } else {
+                for (int ss = s_lo; ss <= s_hi; ++ss) {
+                    const bool mine = valid && s == ss;
+                    const double t0 = warp_sum(mine ? r0 : 0.0), t1 = warp_sum(mine ? r1 : 0.0), t2 = warp_sum(mine ? r2 : 0.0);
+                    if (lane == 0) {
+                        double *ws = wsum + (wid * YC_MAX_SAMPLES + ss) * 3;
+                        ws[0] += t0; ws[1] += t1; ws[2] += t2;
+                    }
                 }
             }
+        }
+        if (cur_s >= 0) {
+            const double t0 = warp_sum(ps0), t1 = warp_sum(ps1), t2 = warp_sum(ps2);
+            if (lane == 0) { double *ws = wsum + (wid * YC_MAX_SAMPLES + cur_s) * 3; ws[0] += t0; ws[1] += t1; ws[2] += t2; }
         }
         acc[2 * NS] += log(seprod);
         warp_sum_array<NP>(acc);
@@ -699,26 +757,30 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         if (!again) break;            // the last E-step's summaries are discarded (stats.py:224)
         // ---- M-step of the NEXT iteration (stats.py:202-211)
         const double step = 1.0 - (0.99 * pow(2.0 + (double)iteration, -1e-3));
-        if (tid < 64 && lane == 0) {
+        if (tid < 64) {
+            // warp k updates component k.  The summaries S = carried + this pass are formed IN `carry` (one lane per
+            // statistic); a skipped update simply leaves them there.  The full-covariance update is spread over the
+            // lanes (one per matrix entry / mean coordinate: same expressions, same results as the serial form that
+            // kept 126 threads at the barrier); only the W x W factorisation stays on one lane.
             const int k = wid;
-            double S[NS];
-            for (int q = 0; q < NS; ++q) {
-                double t = carry[k * NS + q];
+            double *S = carry + k * NS;
+#pragma unroll 1
+            for (int q = lane; q < NS; q += 32) {
+                double t = S[q];
                 for (int w2 = 0; w2 < YC_NWARPS; ++w2) t += part[w2 * NP + k * NS + q];
                 S[q] = t;
             }
+            __syncwarp();
+            const double S0 = S[0];
             if (p.covariance_type == YC_COV_DIAG) {
                 // NormalDistribution.from_summaries per column (A10): skipped below 1e-8, mean AND sigma blended
-                if (S[0] < 1e-8) {
-                    for (int q = 0; q < NS; ++q) carry[k * NS + q] = S[q];
-                } else {
-                    for (int q = 0; q < NS; ++q) carry[k * NS + q] = 0.0;
+                if (S0 >= 1e-8 && lane == 0) {
                     double logdet = 0.0;
 #pragma unroll 1
                     for (int a = 0; a < W; ++a) {
                         const double s2 = S[1 + W + a * W - a * (a - 1) / 2];
-                        const double m_new = S[1 + a] / S[0];
-                        const double sg_new = sqrt(s2 / S[0] - (S[1 + a] * S[1 + a]) / (S[0] * S[0]));
+                        const double m_new = S[1 + a] / S0;
+                        const double sg_new = sqrt(s2 / S0 - (S[1 + a] * S[1 + a]) / (S0 * S0));
                         const double sg = sqrt(par->cov[k][a * W + a]) * step + sg_new * (1.0 - step);
                         par->mu[k][a] = par->mu[k][a] * step + m_new * (1.0 - step);
                         for (int c2 = 0; c2 < W; ++c2) { par->cov[k][a * W + c2] = 0.0; par->linv[k][a * W + c2] = 0.0; }
@@ -727,24 +789,27 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                         logdet += 2.0 * log(sg);
                     }
                     par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+                    for (int q = 0; q < NS; ++q) S[q] = 0.0;
                 }
-            } else if (S[0] < 1e-7) {                                    // A3: skipped, summaries kept
-                for (int q = 0; q < NS; ++q) carry[k * NS + q] = S[q];
-            } else {
-                for (int q = 0; q < NS; ++q) carry[k * NS + q] = 0.0;
-                double u[W];
-                for (int a = 0; a < W; ++a) u[a] = S[1 + a] / S[0];
-                for (int a = 0; a < W; ++a)
-                    for (int c2 = 0; c2 < W; ++c2) {
-                        const int lo = a < c2 ? a : c2, hi = a < c2 ? c2 : a;
-                        const double s2 = S[1 + W + lo * W - lo * (lo - 1) / 2 + (hi - lo)];
-                        const double cv = (s2 - S[1 + a] * u[c2] - u[a] * S[1 + c2] + S[0] * (u[a] * u[c2])) / S[0];
-                        par->cov[k][a * W + c2] = par->cov[k][a * W + c2] * step + cv * (1.0 - step);
-                    }
-                for (int a = 0; a < W; ++a) par->mu[k][a] = par->mu[k][a] * step + u[a] * (1.0 - step);
-                double logdet;
-                if (!cholesky_inverse<W>(par->cov[k], par->linv[k], logdet)) par->ok = 0;   // A4
-                par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+            } else if (S0 >= 1e-7) {                                     // A3: below, skipped and the summaries kept
+#pragma unroll 1
+                for (int e = lane; e < W * W; e += 32) {
+                    const int a = e / W, c2 = e - a * W;
+                    const int lo = a < c2 ? a : c2, hi = a < c2 ? c2 : a;
+                    const double s2 = S[1 + W + lo * W - lo * (lo - 1) / 2 + (hi - lo)];
+                    const double ua = S[1 + a] / S0, uc = S[1 + c2] / S0;
+                    const double cv = (s2 - S[1 + a] * uc - ua * S[1 + c2] + S0 * (ua * uc)) / S0;
+                    par->cov[k][e] = par->cov[k][e] * step + cv * (1.0 - step);
+                }
+                if (lane < W) par->mu[k][lane] = par->mu[k][lane] * step + (S[1 + lane] / S0) * (1.0 - step);
+                __syncwarp();
+#pragma unroll 1
+                for (int q = lane; q < NS; q += 32) S[q] = 0.0;
+                if (lane == 0) {
+                    double logdet;
+                    if (!cholesky_inverse<W>(par->cov[k], par->linv[k], logdet)) par->ok = 0;   // A4
+                    par->cst[k] = -0.5 * ((double)W * YC_LOG_2PI + logdet);
+                }
             }
         }
         if (tid >= 64 && tid < 64 + R) {

@@ -287,7 +287,8 @@ init_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, con
     // ---- k-means++ x3 + Lloyd  (assumption A2)
     double best[2 * W], best_total = INFINITY;
     bool have_best = false;
-    const int C = (n + 31) / 32;
+    int C = (n + 31) / 32;
+    if ((C & 7) == 0) ++C;                               // a chunk length that is a multiple of 8 rows = 4+-way bank conflicts on the binary16 rows
     const int i0c = min(lane * C, n), i1c = min(i0c + C, n);
 #pragma unroll 1
     for (int restart = 0; restart < 3; ++restart) {

@@ -24,7 +24,7 @@ namespace yc {
 
 struct KsSmem {
     // carve-up of the dynamic shared memory block (all offsets in bytes)
-    int sort_off, mask_off, cnt_off, red_off, hist_off, sel_off, misc_off, total;
+    int sort_off, mask_off, wordoff_off, cnt_off, red_off, hist_off, sel_off, misc_off, total;
 };
 
 __host__ __device__ inline KsSmem ks_smem_layout(int W, int R, int max_reads, int sort_cap) {
@@ -35,6 +35,7 @@ __host__ __device__ inline KsSmem ks_smem_layout(int W, int R, int max_reads, in
     s.sel_off = o;  o += 4 * (int)sizeof(unsigned long long);
     s.misc_off = o; o += (16 + 2 * YC_MAX_WINDOW * YC_MAX_WINDOW) * (int)sizeof(double);
     s.mask_off = o; o += ((max_reads + 31) / 32 + 1) * (int)sizeof(uint32_t);
+    s.wordoff_off = o; o += (sort_cap ? (max_reads + 31) / 32 + 1 : 0) * (int)sizeof(int);
     s.cnt_off = o;  o += (W + 1) * R * (int)sizeof(int);
     s.hist_off = o; o += 256 * (int)sizeof(int);
     s.total = (o + 15) & ~15;
@@ -107,41 +108,38 @@ ks_cta_moments_kernel(const yc_batch_t b, const yc_params_t p, const int64_t c0,
         return;
     }
 
-    // ---- pass B: column sums (exact for binary16 inputs) -> means
-    double mu[W];
-    {
-        double s[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) s[j] = 0.0;
-        for (int r = tid; r < n; r += YC_BLOCK) {
-            if ((mask[r >> 5] >> (r & 31)) & 1u) {
-#pragma unroll
-                for (int j = 0; j < W; ++j) s[j] += h2d(__ldg(w.col[j] + r));
-            }
-        }
-        block_sum<W>(s, red);
-#pragma unroll
-        for (int j = 0; j < W; ++j) mu[j] = div_rn(s[j], (double)ntot);
-    }
-    // ---- pass C: centred second moments (upper triangle)
+    // ---- pass B: exact raw first and second moments in ONE pass (binary16 inputs: every partial sum is an exactly
+    // representable double, so neither the order nor the FMA matters), centred afterwards with the same separately
+    // rounded operations as ks_moments_kernel (yc_ks_warp.cu): C_ab = S2_ab - (S1_a S1_b) / n, mean_j = S1_j / n.
+    // Rows outside the selection enter as zeros (no branch: the loads of four rows are in flight together).
     constexpr int NT = W * (W + 1) / 2;
-    double cm[NT];
+    double mu[W], cm[NT];
     {
+        double sm[W + NT];
 #pragma unroll
-        for (int k = 0; k < NT; ++k) cm[k] = 0.0;
+        for (int k = 0; k < W + NT; ++k) sm[k] = 0.0;
+#pragma unroll 4
         for (int r = tid; r < n; r += YC_BLOCK) {
-            if ((mask[r >> 5] >> (r & 31)) & 1u) {
-                double dlt[W];
+            const bool sel_r = (mask[r >> 5] >> (r & 31)) & 1u;
+            double x[W];
 #pragma unroll
-                for (int j = 0; j < W; ++j) dlt[j] = h2d(__ldg(w.col[j] + r)) - mu[j];
-                int k = 0;
+            for (int j = 0; j < W; ++j) { const uint16_t v = __ldg(w.col[j] + r); x[j] = sel_r ? h2d(v) : 0.0; }
+            int k = W;
 #pragma unroll
-                for (int a = 0; a < W; ++a)
+            for (int a = 0; a < W; ++a) {
+                sm[a] += x[a];
 #pragma unroll
-                    for (int c2 = a; c2 < W; ++c2) cm[k++] += dlt[a] * dlt[c2];
+                for (int c2 = a; c2 < W; ++c2) { sm[k] = fma(x[a], x[c2], sm[k]); ++k; }
             }
         }
-        block_sum<NT>(cm, red);
+        block_sum<W + NT>(sm, red);
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < W; ++a) {
+            mu[a] = div_rn(sm[a], (double)ntot);
+#pragma unroll
+            for (int c2 = a; c2 < W; ++c2) { cm[k] = sub_rn(sm[W + k], div_rn(mul_rn(sm[a], sm[c2]), (double)ntot)); ++k; }
+        }
     }
     // population std per column; a zero means a constant column (assumption A9)
     double sig[W];
@@ -218,13 +216,12 @@ ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, con
                 const int32_t *__restrict__ n_c_in, const int32_t *__restrict__ n_t_in,
                 uint8_t *__restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int Rc = b.n_cntrl;
     const KsSmem L = ks_smem_layout(W, b.n_samples, b.max_reads, sort_cap);
     double *sortbuf = reinterpret_cast<double *>(smem_raw + L.sort_off);
     double *red = reinterpret_cast<double *>(smem_raw + L.red_off);
-    double *misc = reinterpret_cast<double *>(smem_raw + L.misc_off);
     uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + L.mask_off);
-    int *icnt = reinterpret_cast<int *>(misc + 12);     // two append cursors
+    int *wordoff = reinterpret_cast<int *>(smem_raw + L.wordoff_off);
+    int *iscr = reinterpret_cast<int *>(red);
     const int tid = threadIdx.x;
     const int i = blockIdx.x;
     const int64_t g = c0 + i;
@@ -233,7 +230,6 @@ ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, con
     const int f = b.col_feature[g];
     const int c = (int)(g - b.col_off[f]);
     const int n = b.n_reads[f];
-    const int split = b.samp_start[(size_t)f * (b.n_samples + 1) + Rc];
     const int64_t ld = b.ld[f];
     const uint16_t *fbase = b.events + b.x_off[f];
     const bool rev = b.reverse[f] != 0;
@@ -248,35 +244,53 @@ ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, con
         cj[j] = scr[(size_t)(2 * W * W + j) * ncol + i];
     }
     const int n1 = min(n_c_in[g], p.max_fit_depth), n2 = min(n_t_in[g], p.max_fit_depth);
-    const int ntot = n1 + n2;
     const int nwords = (n + 31) >> 5;
     for (int wd = tid; wd < nwords; wd += YC_BLOCK) mask[wd] = mask_scr[(size_t)i * nwords_max + wd];
-    if (tid == 0) { icnt[0] = 0; icnt[1] = 0; }
     const int P = max(32, next_pow2(max(n1, n2)));
     for (int q = tid; q < 2 * P; q += YC_BLOCK) sortbuf[q] = INFINITY;
     __syncthreads();
-    // ---- pass D: projections, appended per condition (order is irrelevant before the sort)
+    // ---- pass D: projections, appended per condition in row order: the slot of a selected row is its rank among the
+    // selected rows (word prefix + popcount; controls come first) -- no atomics, and the loads of several rows overlap
+    mask_word_prefix(mask, nwords, wordoff, iscr);
+#pragma unroll 4
     for (int r = tid; r < n; r += YC_BLOCK) {
-        if ((mask[r >> 5] >> (r & 31)) & 1u) {
-            double y = 0.0;
+        const uint32_t m = mask[r >> 5];
+        double y = 0.0;
 #pragma unroll
-            for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(col[j] + r)), cj[j], y);
-            const int cond = r >= split;
-            const int slot = atomicAdd(&icnt[cond], 1);
-            sortbuf[cond * P + slot] = y;
+        for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(col[j] + r)), cj[j], y);
+        if ((m >> (r & 31)) & 1u) {
+            const int rank = wordoff[r >> 5] + __popc(m & ((1u << (r & 31)) - 1u));
+            sortbuf[rank < n1 ? rank : P + rank - n1] = y;
         }
     }
     __syncthreads();
     block_sort_segments_regs(sortbuf, P, 2);
-    // ---- D = max |F1 - F2| over the pooled points (stats.py:39-41)
-    const double *A = sortbuf, *B = sortbuf + P;
+    // ---- D = max |F1 - F2| over the pooled points (stats.py:39-41).  Every thread walks a run of consecutive sorted
+    // values of one sample: the count in the own sample is the index after the last equal value, the count in the other
+    // one a binary search for the first value of the run and a linear advance afterwards (both counts are monotone).
+    // c / n with the separately rounded division of the reference, through div_int_rn.
     double dmax = 0.0;
     const double fn1 = (double)n1, fn2 = (double)n2;
-    for (int q = tid; q < ntot; q += YC_BLOCK) {
-        const double v = (q < n1) ? A[q] : B[q - n1];
-        const int c1 = upper_bound(A, n1, v), c2 = upper_bound(B, n2, v);
-        const double df = fabs(sub_rn(div_rn((double)c1, fn1), div_rn((double)c2, fn2)));
-        dmax = fmax(dmax, df);
+    const double r1 = div_rn(1.0, fn1), r2 = div_rn(1.0, fn2);
+    int C = (max(n1, n2) + YC_BLOCK - 1) / YC_BLOCK;
+    C |= 1;                                             // odd run length: the lanes' first values lie in distinct banks
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const double *own = side ? sortbuf + P : sortbuf, *oth = side ? sortbuf : sortbuf + P;
+        const int n_own = side ? n2 : n1, n_oth = side ? n1 : n2;
+        const int i0 = tid * C, i1 = min(i0 + C, n_own);
+        if (i0 < n_own) {
+            int co = upper_bound(oth, n_oth, own[i0]);
+#pragma unroll 1
+            for (int q = i0; q < i1; ++q) {
+                const double x = own[q];
+                int cs = q + 1;
+                while (cs < n_own && own[cs] == x) ++cs;
+                while (co < n_oth && oth[co] <= x) ++co;
+                const int c1 = side ? co : cs, c2 = side ? cs : co;
+                dmax = fmax(dmax, fabs(sub_rn(div_int_rn((double)c1, fn1, r1), div_int_rn((double)c2, fn2, r2))));
+            }
+        }
     }
     dmax = block_max1(dmax, red);
     if (tid == 0) {
