@@ -26,7 +26,7 @@ namespace yc {
 __host__ __device__ inline int cap_pow2_bytes(int cap) {
     int P = 32;
     while (P < cap) P <<= 1;
-    return P * (int)sizeof(double);
+    return (P + P / 16) * (int)sizeof(double);          // padded sort layout (YC_PAD16)
 }
 
 struct FitSmem {
@@ -384,18 +384,43 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         double improvement = INFINITY, last = INFINITY, total = INFINITY;
         double acc[W + 2];                                   // column sums of cluster 1, total distance, size of cluster 1
         bool have_sums = false;
+        // the centroids of the next pass and the total distance are formed by 2 W + 1 threads between the two barriers
+        // of the reduction (every thread used to run the 2 W IEEE divisions: ~15 % of an iteration's instructions)
+        double *cs = par;
         while (improvement > 0.5 && iteration < 101) {
             if (have_sums) {
-                // cluster 0 = column totals - cluster 1 (sums of binary16 values: exact either way)
-                const double n1 = acc[W + 1], n0 = (double)n_in - n1;
 #pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    if (n0 > 0.0) cen[j] = div_rn(sub_rn(sumx[j], acc[j]), n0);
-                    if (n1 > 0.0) cen[W + j] = div_rn(acc[j], n1);       // an empty cluster keeps its centroid (A2)
-                }
+                for (int q = 0; q < 2 * W; ++q) cen[q] = cs[q];
             }
             lloyd_pass<W, YC_LLOYD_U>(c, xx, lab, db, n, cen, acc);
-            block_sum<W + 2>(acc, red);
+            warp_sum_array<W + 2>(acc);
+#pragma unroll
+            for (int k = 0; k < W + 2; ++k) {
+                if (lane == 0) red[k * YC_NWARPS + wid] = acc[k];
+            }
+            __syncthreads();
+            if (tid < 2 * W) {
+                // cluster 0 = column totals - cluster 1 (sums of binary16 values: exact either way); an empty cluster
+                // keeps its centroid (A2)
+                const int j = tid < W ? tid : tid - W;
+                double s1 = 0.0, n1 = 0.0, sj = 0.0, keep = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < YC_NWARPS; ++w2) { s1 += red[j * YC_NWARPS + w2]; n1 += red[(W + 1) * YC_NWARPS + w2]; }
+#pragma unroll
+                for (int q = 0; q < W; ++q) if (q == j) sj = sumx[q];
+#pragma unroll
+                for (int q = 0; q < 2 * W; ++q) if (q == tid) keep = cen[q];
+                const double den = tid < W ? (double)n_in - n1 : n1;
+                const double num = tid < W ? sub_rn(sj, s1) : s1;
+                cs[tid] = den > 0.0 ? div_rn(num, den) : keep;
+            } else if (tid == 2 * W) {
+                double t = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < YC_NWARPS; ++w2) t += red[W * YC_NWARPS + w2];
+                cs[2 * W] = t;
+            }
+            __syncthreads();
+            acc[W] = cs[2 * W];
             have_sums = true;
             total = acc[W];
             if (iteration > 0) improvement = last - total;
@@ -444,28 +469,28 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
             lab[i] = (int8_t)(d1 < d0);
             dmin = d1 < d0 ? d1 : d0;
         }
-        sortbuf[i] = dmin;
+        sortbuf[YC_PAD16(i)] = dmin;
     }
     __syncthreads();
     block_sort_segments_regs(sortbuf, P, 1);
-    const double med = (n & 1) ? sortbuf[n >> 1] : mul_rn(add_rn(sortbuf[(n >> 1) - 1], sortbuf[n >> 1]), 0.5);
+    const double med = (n & 1) ? sortbuf[YC_PAD16(n >> 1)] : mul_rn(add_rn(sortbuf[YC_PAD16((n >> 1) - 1)], sortbuf[YC_PAD16(n >> 1)]), 0.5);
     __syncthreads();
     // MAD = median of |d - med| WITHOUT a second sort: in the sorted distances the deviations are V-shaped,
     // i.e. two ascending runs (left of the median walked outwards, right of it), so the order statistics of
     // their union follow from merge ranks found by binary search (same selection as init_warp_kernel)
     double *wsel = par + 4;
-    const int m_le = upper_bound(sortbuf, n, med);        // elements <= med form the left run
+    const int m_le = upper_bound_pad(sortbuf, 0, n, med);        // elements <= med form the left run
     const int k_hi = n >> 1, k_lo = (n & 1) ? k_hi : k_hi - 1;
     for (int i = tid; i < n; i += YC_BLOCK) {
-        const double dv = fabs(sub_rn(sortbuf[i], med));
+        const double dv = fabs(sub_rn(sortbuf[YC_PAD16(i)], med));
         int rank;
         if (i < m_le) {                                    // left run, index m_le-1-i; count right-run elements < dv
             int lo = 0, hi = n - m_le;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(sortbuf[m_le + mid], med)) < dv) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(sortbuf[YC_PAD16(m_le + mid)], med)) < dv) lo = mid + 1; else hi = mid; }
             rank = (m_le - 1 - i) + lo;
         } else {                                           // right run, index i-m_le; count left-run elements <= dv
             int lo = 0, hi = m_le;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(sortbuf[m_le - 1 - mid], med)) <= dv) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (fabs(sub_rn(sortbuf[YC_PAD16(m_le - 1 - mid)], med)) <= dv) lo = mid + 1; else hi = mid; }
             rank = (i - m_le) + lo;
         }
         if (rank == k_lo) wsel[0] = dv;

@@ -30,7 +30,7 @@ struct KsSmem {
 __host__ __device__ inline KsSmem ks_smem_layout(int W, int R, int max_reads, int sort_cap) {
     KsSmem s;
     int o = 0;
-    s.sort_off = o; o += 2 * sort_cap * (int)sizeof(double);
+    s.sort_off = o; o += 2 * (sort_cap + sort_cap / 16) * (int)sizeof(double);   // padded sort layout (YC_PAD16)
     s.red_off = o;  o += 48 * YC_NWARPS * (int)sizeof(double);
     s.sel_off = o;  o += 4 * (int)sizeof(unsigned long long);
     s.misc_off = o; o += (16 + 2 * YC_MAX_WINDOW * YC_MAX_WINDOW) * (int)sizeof(double);
@@ -247,7 +247,7 @@ ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, con
     const int nwords = (n + 31) >> 5;
     for (int wd = tid; wd < nwords; wd += YC_BLOCK) mask[wd] = mask_scr[(size_t)i * nwords_max + wd];
     const int P = max(32, next_pow2(max(n1, n2)));
-    for (int q = tid; q < 2 * P; q += YC_BLOCK) sortbuf[q] = INFINITY;
+    for (int q = tid; q < 2 * P; q += YC_BLOCK) sortbuf[YC_PAD16(q)] = INFINITY;
     __syncthreads();
     // ---- pass D: projections, appended per condition in row order: the slot of a selected row is its rank among the
     // selected rows (word prefix + popcount; controls come first) -- no atomics, and the loads of several rows overlap
@@ -260,7 +260,7 @@ ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, con
         for (int j = 0; j < W; ++j) y = fma(h2d(__ldg(col[j] + r)), cj[j], y);
         if ((m >> (r & 31)) & 1u) {
             const int rank = wordoff[r >> 5] + __popc(m & ((1u << (r & 31)) - 1u));
-            sortbuf[rank < n1 ? rank : P + rank - n1] = y;
+            sortbuf[YC_PAD16(rank < n1 ? rank : P + rank - n1)] = y;
         }
     }
     __syncthreads();
@@ -276,17 +276,17 @@ ks_cta_d_kernel(const yc_batch_t b, const yc_params_t p, const int sort_cap, con
     C |= 1;                                             // odd run length: the lanes' first values lie in distinct banks
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
-        const double *own = side ? sortbuf + P : sortbuf, *oth = side ? sortbuf : sortbuf + P;
+        const int own = side ? P : 0, oth = side ? 0 : P;            // logical offsets of the two sorted samples
         const int n_own = side ? n2 : n1, n_oth = side ? n1 : n2;
         const int i0 = tid * C, i1 = min(i0 + C, n_own);
         if (i0 < n_own) {
-            int co = upper_bound(oth, n_oth, own[i0]);
+            int co = upper_bound_pad(sortbuf, oth, n_oth, sortbuf[YC_PAD16(own + i0)]);
 #pragma unroll 1
             for (int q = i0; q < i1; ++q) {
-                const double x = own[q];
+                const double x = sortbuf[YC_PAD16(own + q)];
                 int cs = q + 1;
-                while (cs < n_own && own[cs] == x) ++cs;
-                while (co < n_oth && oth[co] <= x) ++co;
+                while (cs < n_own && sortbuf[YC_PAD16(own + cs)] == x) ++cs;
+                while (co < n_oth && sortbuf[YC_PAD16(oth + co)] <= x) ++co;
                 const int c1 = side ? co : cs, c2 = side ? cs : co;
                 dmax = fmax(dmax, fabs(sub_rn(div_int_rn((double)c1, fn1, r1), div_int_rn((double)c2, fn2, r2))));
             }
