@@ -609,6 +609,11 @@ gmm_init_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
 // ---------------------------------------------------------------------------
 // Kernel 2b
 // ---------------------------------------------------------------------------
+// rows per thread whose E-steps run side by side in gmm_em_kernel.  Measured on cfg4 (B200): U = 1 101.0 ms, U = 2 at 168
+// registers / 3 CTAs per SM 103.0 ms, U = 2 at 240 registers / 2 CTAs per SM 111.9 ms -- the kernel is not latency-bound
+#ifndef YC_EM_U
+#define YC_EM_U 1
+#endif
 #ifndef YC_EMC_MINBLOCKS
 #define YC_EMC_MINBLOCKS 3
 #endif
@@ -686,16 +691,19 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
         double seprod = 1.0;
         int cur_s = -1;
         double ps0 = 0.0, ps1 = 0.0, ps2 = 0.0;
-        for (int base = wid * 32; base < n; base += YC_NWARPS * 32) {
-            const int i = base + lane;
-            const bool valid = i < n;
-            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-            int s = -1;
-            if (valid) {
-                double x[W];
-                load_row<W>(c, i, x);
-                const int sv = c.srow[i];
-                s = sv & 0x7f;
+        // YC_EM_U 32-row chunks per warp and step (1 by default, see above): E-steps first, then the statistics row by
+        // row in the order of the one-row loop (same results for every U).
+        for (int base0 = wid * 32; base0 < n; base0 += YC_EM_U * YC_NWARPS * 32) {
+            double x[YC_EM_U][W], r0[YC_EM_U], r1[YC_EM_U], r2[YC_EM_U];
+            int sidx[YC_EM_U];
+#pragma unroll
+            for (int u = 0; u < YC_EM_U; ++u) {
+                const int i = base0 + u * YC_NWARPS * 32 + lane;
+                const bool valid = i < n;
+                const int ii = valid ? i : 0;
+                load_row<W>(c, ii, x[u]);
+                const int sv = c.srow[ii];
+                const int s = sv & 0x7f;
                 const bool inside = (sv & 0x80) != 0;
                 double q0 = 0.0, q1 = 0.0;
 #pragma unroll
@@ -703,8 +711,8 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                     double y0 = 0.0, y1 = 0.0;
 #pragma unroll
                     for (int bb = 0; bb <= a; ++bb) {
-                        y0 = fma(par->linv[0][a * W + bb], x[bb] - mu0[bb], y0);
-                        y1 = fma(par->linv[1][a * W + bb], x[bb] - mu1[bb], y1);
+                        y0 = fma(par->linv[0][a * W + bb], x[u][bb] - mu0[bb], y0);
+                        y1 = fma(par->linv[1][a * W + bb], x[u][bb] - mu1[bb], y1);
                     }
                     q0 = fma(y0, y0, q0);
                     q1 = fma(y1, y1, q1);
@@ -720,41 +728,48 @@ gmm_em_kernel(const yc_batch_t b, const yc_params_t p, const int cap,
                 exp_nonpos2((m0 ? l1 : l0) - m, ((m0 || m1) ? l2 : l1) - m, ea, eb);
                 const double e0 = m0 ? 1.0 : ea, e1 = m0 ? ea : (m1 ? 1.0 : eb), e2 = (m0 || m1) ? eb : 1.0;
                 const double se = e0 + e1 + e2;
-                const double inv = 1.0 / se;
-                r0 = e0 * inv; r1 = e1 * inv; r2 = e2 * inv;
-                acc[2 * NS] += m; seprod *= se;            // one log per thread: log prod se_i, 1 <= se_i <= 3
-                acc[0] += r0; acc[NS] += r1;
+                const double inv = rcp_1to3(se);
+                r0[u] = valid ? e0 * inv : 0.0; r1[u] = valid ? e1 * inv : 0.0; r2[u] = valid ? e2 * inv : 0.0;
+                sidx[u] = valid ? s : -1;
+                acc[2 * NS] += valid ? m : 0.0;
+                seprod *= valid ? se : 1.0;                  // one log per thread: log prod se_i, 1 <= se_i <= 3
+            }
+#pragma unroll
+            for (int u = 0; u < YC_EM_U; ++u) {
+                const int base = base0 + u * YC_NWARPS * 32;
+                if (base >= n) break;                        // warp-uniform
+                acc[0] += r0[u]; acc[NS] += r1[u];
                 int q = 1 + W;
 #pragma unroll
                 for (int a = 0; a < W; ++a) {
-                    const double xa0 = r0 * x[a], xa1 = r1 * x[a];
+                    const double xa0 = r0[u] * x[u][a], xa1 = r1[u] * x[u][a];
                     acc[1 + a] += xa0; acc[NS + 1 + a] += xa1;
 #pragma unroll
-                    for (int bb = a; bb < W; ++bb) { acc[q] = fma(xa0, x[bb], acc[q]); acc[NS + q] = fma(xa1, x[bb], acc[NS + q]); ++q; }
+                    for (int bb = a; bb < W; ++bb) { acc[q] = fma(xa0, x[u][bb], acc[q]); acc[NS + q] = fma(xa1, x[u][bb], acc[NS + q]); ++q; }
                 }
-            }
-            // per-sample responsibility sums (gmm.summaries).  Rows are ordered by sample, so nearly every 32-row chunk
-            // lies inside one sample: those only add to per-lane partials of the current sample `cur_s` (warp-uniform),
-            // reduced over the warp when the sample changes; a chunk that straddles samples is reduced directly.
-            const int s_lo = __shfl_sync(YC_FULL, s, 0);
-            const int s_hi = c.srow[min(base + 31, n - 1)] & 0x7f;
-            if (s_lo != cur_s || s_hi != cur_s) {
+                // per-sample responsibility sums (gmm.summaries).  Rows are ordered by sample, so nearly every 32-row chunk
+                // lies inside one sample: those only add to per-lane partials of the current sample `cur_s` (warp-uniform),
+                // reduced over the warp when the sample changes; a chunk that straddles samples is reduced directly.
+                const int s_lo = __shfl_sync(YC_FULL, sidx[u], 0);
+                const int s_hi = c.srow[min(base + 31, n - 1)] & 0x7f;
+                if (s_lo != cur_s || s_hi != cur_s) {
+                    if (cur_s >= 0) {
+                        const double t0 = warp_sum(ps0), t1 = warp_sum(ps1), t2 = warp_sum(ps2);
+                        if (lane == 0) { double *ws = wsum + (wid * YC_MAX_SAMPLES + cur_s) * 3; ws[0] += t0; ws[1] += t1; ws[2] += t2; }
+                    }
+                    ps0 = ps1 = ps2 = 0.0;
+                    cur_s = s_lo == s_hi ? s_lo : -1;
+                }
                 if (cur_s >= 0) {
-                    const double t0 = warp_sum(ps0), t1 = warp_sum(ps1), t2 = warp_sum(ps2);
-                    if (lane == 0) { double *ws = wsum + (wid * YC_MAX_SAMPLES + cur_s) * 3; ws[0] += t0; ws[1] += t1; ws[2] += t2; }
-                }
-                ps0 = ps1 = ps2 = 0.0;
-                cur_s = s_lo == s_hi ? s_lo : -1;
-            }
-            if (cur_s >= 0) {
-                ps0 += r0; ps1 += r1; ps2 += r2;                      // rows beyond n carry zeros
-            } else {
-                for (int ss = s_lo; ss <= s_hi; ++ss) {
-                    const bool mine = valid && s == ss;
-                    const double t0 = warp_sum(mine ? r0 : 0.0), t1 = warp_sum(mine ? r1 : 0.0), t2 = warp_sum(mine ? r2 : 0.0);
-                    if (lane == 0) {
-                        double *ws = wsum + (wid * YC_MAX_SAMPLES + ss) * 3;
-                        ws[0] += t0; ws[1] += t1; ws[2] += t2;
+                    ps0 += r0[u]; ps1 += r1[u]; ps2 += r2[u];            // rows beyond n carry zeros
+                } else {
+                    for (int ss = s_lo; ss <= s_hi; ++ss) {
+                        const bool mine = sidx[u] == ss;
+                        const double t0 = warp_sum(mine ? r0[u] : 0.0), t1 = warp_sum(mine ? r1[u] : 0.0), t2 = warp_sum(mine ? r2[u] : 0.0);
+                        if (lane == 0) {
+                            double *ws = wsum + (wid * YC_MAX_SAMPLES + ss) * 3;
+                            ws[0] += t0; ws[1] += t1; ws[2] += t2;
+                        }
                     }
                 }
             }

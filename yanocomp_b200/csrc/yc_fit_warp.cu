@@ -690,18 +690,6 @@ __device__ __forceinline__ double em_factor(EmPar<W> *par, int k, double &sumlog
     return prod;
 }
 
-// 1 / x for 1 <= x <= 3 (the soft-max denominator of the E-step): hardware seed (MUFU.RCP64H, ~2^-22) and two
-// Newton steps, without the range / special-case handling of the division (x is never 0, inf or denormal here;
-// a NaN propagates).  Within 1 ulp; the E-step is compared with a tolerance.
-__device__ __forceinline__ double rcp_1to3(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
-
 // model of slot -> shared memory parameter block (+ Cholesky factors, uniform log density)
 template <int W>
 __device__ __forceinline__ void load_model(EmPar<W> *par, const yc_fit_out_t &out, int slot, int lane,
