@@ -246,6 +246,10 @@ __device__ __forceinline__ bool fw_front(const yc_batch_t &b, const yc_params_t 
 // ===========================================================================
 // Kernel 2a (warp): k-means++ x3, MAD outliers, ML Gaussians, weights, box
 // ===========================================================================
+// unroll factor of the k-means row loops (seeding passes, Lloyd pass) of init_warp_kernel
+#ifndef YC_FW_LLOYD_UNROLL
+#define YC_FW_LLOYD_UNROLL 1
+#endif
 #ifndef YC_FW_INIT_MINBLOCKS
 #define YC_FW_INIT_MINBLOCKS 20
 #endif
@@ -302,7 +306,7 @@ init_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, con
         }
         {   // second centre: D^2 sampling through the (exact) cumulative sum
             double loc = 0.0;
-#pragma unroll 1
+YC_UNROLL(YC_FW_LLOYD_UNROLL)
             for (int i = i0c; i < i1c; ++i) { double x[W]; fw_row<W>(xs, cap, i, x); loc = add_rn(loc, sqdist<W>(x, cen)); }
             double inc = loc;
 #pragma unroll
@@ -311,7 +315,7 @@ init_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, con
             double run = sub_rn(inc, loc);
             const double target = mul_rn(rng_uniform(pkey, YC_STREAM_KMEANS0 + restart, 1), total);
             int below = 0;
-#pragma unroll 1
+YC_UNROLL(YC_FW_LLOYD_UNROLL)
             for (int i = i0c; i < i1c; ++i) { double x[W]; fw_row<W>(xs, cap, i, x); run = add_rn(run, sqdist<W>(x, cen)); below += (run <= target); }
             below = warp_sum_i(below);
             double x[W];
@@ -352,7 +356,7 @@ init_warp_position(const yc_batch_t &b, const yc_params_t &p, const int cap, con
             }
 #pragma unroll
             for (int k = 0; k < W + 2; ++k) acc[k] = 0.0;
-#pragma unroll 1
+YC_UNROLL(YC_FW_LLOYD_UNROLL)
             for (int i = lane; i < n; i += 32) {
                 double x[W];
                 fw_row<W>(xs, cap, i, x);

@@ -29,6 +29,13 @@
 namespace yc {
 
 #define YC_KW_WARPS 4
+// unroll factors of the row loops of ks_moments_kernel / ks_d_kernel (projection pass)
+#ifndef YC_KM_UNROLL
+#define YC_KM_UNROLL 1
+#endif
+#ifndef YC_KD_UNROLL
+#define YC_KD_UNROLL 4
+#endif
 
 // ---------------------------------------------------------------------------
 // Register-resident sort + ECDF difference (round-1 profile: the shared-memory bitonic sort was
@@ -46,6 +53,8 @@ namespace yc {
 // for the first value and a linear advance for the rest (counts are monotone).
 // Returns max |c1/n1 - c2/n2| over the pooled points (np.searchsorted side='right' semantics),
 // with the same separately rounded operations as before: tabA[c] = c / n1, tabB[c] = c / n2.
+// Measured alternative (round 2, rejected): merging the two sorted halves with provenance tags (one more bitonic merge
+// step, counts = prefix sums of the tags, no walk, no table) is bit-exact too but SLOWER: KS 3.06 -> 3.31 ms on cfg2.
 #define YC_KPAD(i) ((i) + ((i) >> 4))
 
 template <int E>
@@ -193,17 +202,19 @@ ks_moments_kernel(const yc_batch_t b, const yc_params_t p, const int64_t c0, con
                 for (int j = 0; j < W; ++j) mu[j] = 0.0;
 #pragma unroll
                 for (int k = 0; k < NT; ++k) cm[k] = 0.0;
-                for (int r = lane; r < n; r += 32)
-                    if ((mask[r >> 5] >> (r & 31)) & 1u) {
-                        double x[W];
+                // incomplete rows enter as zeros (no branch: the loads of YC_KM_UNROLL row groups are in flight together)
+                YC_UNROLL(YC_KM_UNROLL)
+                for (int r = lane; r < n; r += 32) {
+                    const bool sel_r = (mask[r >> 5] >> (r & 31)) & 1u;
+                    double x[W];
 #pragma unroll
-                        for (int j = 0; j < W; ++j) { x[j] = h2d(__ldg(w.col[j] + r)); mu[j] += x[j]; }
-                        int k = 0;
+                    for (int j = 0; j < W; ++j) { const uint16_t v = __ldg(w.col[j] + r); x[j] = sel_r ? h2d(v) : 0.0; mu[j] += x[j]; }
+                    int k = 0;
 #pragma unroll
-                        for (int a = 0; a < W; ++a)
+                    for (int a = 0; a < W; ++a)
 #pragma unroll
-                            for (int c2 = a; c2 < W; ++c2) cm[k++] += x[a] * x[c2];
-                    }
+                        for (int c2 = a; c2 < W; ++c2) cm[k++] += x[a] * x[c2];
+                }
                 warp_sum_array<W>(mu);
                 warp_sum_array<NT>(cm);
                 // C_ab = S2_ab - (S1_a S1_b) / n, mean_j = S1_j / n, sig_a = sqrt(C_aa / n): the same IEEE operations
@@ -371,15 +382,17 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
         __syncwarp();
         int ca = 0, cb = 0;
         const uint32_t lt = (1u << lane) - 1u;
+        YC_UNROLL(YC_KD_UNROLL)
         for (int base = 0; base < n; base += 32) {
             const int r = base + lane;
             bool bit = r < n;
             const bool cond = r >= split;
             double y = 0.0;
-            if (bit) {
+            {
+                const int rr = bit ? r : n - 1;             // loads without a branch: those of the next row group overlap
 #pragma unroll
                 for (int j = 0; j < W; ++j) {
-                    const uint16_t h = __ldg(col[j] + r);
+                    const uint16_t h = __ldg(col[j] + rr);
                     bit &= !h_isnan(h);
                     y = fma(h2d(h), cj[j], y);
                 }
