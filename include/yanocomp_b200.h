@@ -304,6 +304,12 @@ int      yc_first_right_singular_vector_host(int32_t d, const double *G, const d
 int      yc_first_right_singular_vector_device(int32_t d, const double *G, const double *T, double *v,
                                                int32_t count, void *stream);
 
+/* test hook: the KS kernels form c / n (stats.py:39-41: counts over sample sizes) as a reciprocal multiplication with two
+ * residual corrections instead of an IEEE division; this checks that routine against the division on the device for every
+ * pair 0 <= c <= n <= n_max and for n_random pseudo-random pairs with n < 2^31, and writes the number of differing
+ * quotients to *mismatches (device pointer) */
+int      yc_div_int_rn_check_device(int32_t n_max, int64_t n_random, uint64_t seed, uint64_t *mismatches, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,3 +74,29 @@ def test_scratch_chunking_of_the_ks_stage(path, monkeypatch):
     for k, v in keep.items():
         np.testing.assert_array_equal(getattr(many, k), v, err_msg=k)
     assert many.launches > one.launches and one.n_fitted > 5
+
+
+def test_div_int_rn_equals_the_ieee_division():
+    '''the KS kernels' c / n (reciprocal + two residual corrections) against __ddiv_rn on the device: every pair
+    0 <= c <= n <= 4096 and 20 M pseudo-random pairs with n < 2^31'''
+    import torch
+    out = torch.zeros(1, dtype=torch.int64, device='cuda')
+    N.check(N.lib().yc_div_int_rn_check_device(4096, 20_000_000, 12345, out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+    assert int(out.item()) == 0
+
+
+@pytest.mark.parametrize('path', ['warp', 'cta'])
+def test_coarse_values_full_of_ties(path, monkeypatch):
+    '''events on a grid of 4 pA: many reads are bit-identical, rows lie exactly between two centroids (the Lloyd pass of
+    the general kernels must then fall back to the NumPy-order distances), pooled KS points tie within and across the
+    conditions, medians of the MAD rule fall on runs of equal distances'''
+    if path == 'cta':
+        monkeypatch.setenv('YC_KS_PATH', 'cta')
+        monkeypatch.setenv('YC_FIT_PATH', 'cta')
+    feats = synth.make_dataset(78, 3, 30, [40, 36, 44, 38], 2, 2, planted_frac=0.3)
+    for f in feats:
+        X = f.X.astype(np.float32)
+        f.X[...] = (np.round(X / 4.0) * 4.0).astype(np.float16)
+    out = compare(feats, 4, 2, window_size=3, max_fit_discordance=0.1)
+    assert out['windows'] == 3 * 28

@@ -95,6 +95,7 @@ _PROTOTYPES = {
     'yc_mix64_host': (C.c_uint64, [C.c_uint64]),
     'yc_first_right_singular_vector_device': (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     'yc_first_right_singular_vector_host': (C.c_int, [C.c_int32, _P(C.c_double), _P(C.c_double), _P(C.c_double)]),
+    'yc_div_int_rn_check_device': (C.c_int, [C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTS = tuple(_PROTOTYPES)

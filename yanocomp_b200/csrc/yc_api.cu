@@ -240,6 +240,31 @@ void keep_pool_memory() {
 }
 }
 
+// exhaustive + random check of div_int_rn against the IEEE division (test hook, yc_div_int_rn_check_device)
+__global__ void div_int_check_kernel(const int32_t n_max, const int64_t n_random, const uint64_t seed,
+                                     unsigned long long *__restrict__ mismatches) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    // every pair 0 <= c <= n <= n_max: pair index q -> (n, c) by rows of the triangle
+    const int64_t total = ((int64_t)n_max + 1) * ((int64_t)n_max + 2) / 2 - 1;          // n = 0 excluded
+    for (int64_t q = tid; q < total; q += nthreads) {
+        int64_t n = (int64_t)((sqrt(8.0 * (double)(q + 1) + 1.0) - 1.0) * 0.5);
+        while (n * (n + 1) / 2 > q + 1) --n;
+        while ((n + 1) * (n + 2) / 2 <= q + 1) ++n;
+        const int64_t c = q + 1 - n * (n + 1) / 2;                                      // 0 <= c <= n, n >= 1
+        const double fn = (double)n, fc = (double)c;
+        bad += yc::div_int_rn(fc, fn, yc::div_rn(1.0, fn)) != yc::div_rn(fc, fn);
+    }
+    for (int64_t q = tid; q < n_random; q += nthreads) {
+        const uint64_t h = yc::mix64(seed ^ (uint64_t)q), h2 = yc::mix64(h);
+        const int64_t n = 1 + (int64_t)(h % 2147483647ull);                             // 1 .. 2^31 - 1
+        const int64_t c = (int64_t)(h2 % (uint64_t)(n + 1));
+        const double fn = (double)n, fc = (double)c;
+        bad += yc::div_int_rn(fc, fn, yc::div_rn(1.0, fn)) != yc::div_rn(fc, fn);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 extern "C" {
 
 const char *yc_version(void) { return "yanocomp_b200 0.1.0 (sm_100a)"; }
@@ -400,6 +425,14 @@ int yc_first_right_singular_vector_device(int32_t d, const double *G, const doub
         default: return fail(YC_EINVAL, "window size %d is not supported", d);
     }
     return cuda_fail((int)cudaGetLastError(), "yc_first_right_singular_vector_device");
+}
+int yc_div_int_rn_check_device(int32_t n_max, int64_t n_random, uint64_t seed, uint64_t *mismatches, void *stream) {
+    if (!mismatches || n_max < 1 || n_random < 0) return fail(YC_EINVAL, "yc_div_int_rn_check_device: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), st);
+    if (e != cudaSuccess) return cuda_fail((int)e, "yc_div_int_rn_check_device memset");
+    div_int_check_kernel<<<148 * 8, 256, 0, st>>>(n_max, n_random, seed, reinterpret_cast<unsigned long long *>(mismatches));
+    return cuda_fail((int)cudaGetLastError(), "yc_div_int_rn_check_device");
 }
 int yc_first_right_singular_vector_host(int32_t d, const double *G, const double *T, double *v) {
     switch (d) {
