@@ -16,9 +16,10 @@ Printed JSON (one line, rank 0):
   value      positions entering position_stats / s, inputs resident in HBM,
              timed with CUDA events on the launching stream
   e2e        the same through the public host-buffer call
-             (yanocomp_b200.api.test_host_batch_pipelined: pinned host -> device
-             copy of the packed batch, kernels, device -> host copy of the result
-             rows; the once-per-job BH correction is NOT inside, see `job`)
+             (yanocomp_b200.api.test_host_batch_pipelined: pinned host -> device copy of the packed
+             batch in feature ranges, kernels per range, device -> host copy of the result rows;
+             YC_BENCH_E2E=ranged selects the KS-per-range / one-fit-submission call; the
+             once-per-job BH correction is NOT inside, see `job`)
   job        the reference's real boundary, wall-clocked: synthetic sample files written once
              (outside the timer) -> yanocomp_b200.gmmtest.parallel_test(opts) -> the DataFrame
              with BH-FDR (gmmtest.py:182-224), per host-side stage.  N = 1: cfg2; N > 1: cfg3,
@@ -341,7 +342,7 @@ def run_gpu(args, cfg, opts_kw):
     import torch
     import torch.distributed as dist
     from yanocomp_b200 import synth
-    from yanocomp_b200.api import test_host_batch_pipelined, tested_table
+    from yanocomp_b200.api import test_host_batch_pipelined, test_host_batch_ranged, tested_table
     from yanocomp_b200.batch import HostBatch
     from yanocomp_b200.engine import Engine, EngineParams
 
@@ -407,12 +408,21 @@ def run_gpu(args, cfg, opts_kw):
     CHUNKS = int(os.environ.get('YC_BENCH_CHUNKS', '4'))          # feature ranges of the pipelined public call
     GROWTH = float(os.environ.get('YC_BENCH_GROWTH', '1.0'))      # each range this many times the previous one
     FIRST = float(os.environ.get('YC_BENCH_FIRST', '1.0'))        # relative size of the first range
+    # 'pipelined' (default): every stage per range (Engine.run_pipelined); 'ranged': one resident batch, KS per arriving
+    # range, ONE fit submission (Engine.run_ranged) -- measured slower: 13.2 vs 12.3 ms per step on cfg2
+    E2E_MODE = os.environ.get('YC_BENCH_E2E', 'pipelined')
+
+    def e2e_call():
+        if E2E_MODE == 'pipelined':
+            return test_host_batch_pipelined(host, params, eng, chunks=CHUNKS, growth=GROWTH, first=FIRST)
+        return [(host, test_host_batch_ranged(host, params, eng, ranges=CHUNKS, growth=GROWTH, first=FIRST))]
+
     for _ in range(max(1, min(args.warmup, 2))):
-        parts = test_host_batch_pipelined(host, params, eng, chunks=CHUNKS, growth=GROWTH, first=FIRST)
+        parts = e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        parts = test_host_batch_pipelined(host, params, eng, chunks=CHUNKS, growth=GROWTH, first=FIRST)
+        parts = e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -514,7 +524,7 @@ def run_gpu(args, cfg, opts_kw):
                    'sharding': 'features (genes) split across ranks, no data-path collective'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e_max / args.steps,
                 'h2d_bytes_per_step': host.nbytes, 'd2h_bytes_per_step': d2h_bytes,
-                'tested_rows': int(n_rows), 'pipeline_chunks': CHUNKS, 'pipeline_growth': GROWTH, 'pipeline_first': FIRST,
+                'tested_rows': int(n_rows), 'mode': E2E_MODE, 'pipeline_chunks': CHUNKS, 'pipeline_growth': GROWTH, 'pipeline_first': FIRST,
                 'bh_fdr_ms_not_included': bh_ms},
         'gpu_launches': launches,
         'clocks': sampler.summary(),

@@ -179,6 +179,15 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
                 void *stream);
 
 /*
+ * Ordered compaction of the gated columns of `status` ([total_cols], as yc_ks_batch leaves it) into fit_list (ascending
+ * column index) and the device counter fit_count -- what yc_ks_batch does at its end for its own batch.  For callers
+ * that run yc_ks_batch over several feature RANGES of one resident batch while its events are still arriving (each call
+ * on a sub-batch whose pointers are offsets into the same arrays, outputs at the range's column offset) and then fit the
+ * whole batch with ONE submission: gmmtest.py:156-178 has no such step, the loop is per position there.
+ */
+int yc_compact_gated(const uint8_t *status, int64_t total_cols, int32_t *fit_list, int32_t *fit_count, void *stream);
+
+/*
  * The fit stages take the gated positions as (fit_list, n_fit, fit_count):
  * slots [0, min(n_fit, *fit_count)) are processed.  `fit_count` is the DEVICE
  * counter yc_ks_batch wrote, so a caller can queue the three stages right behind

@@ -96,3 +96,35 @@ def test_capacity_overflow_is_refitted_exactly():
     again = eng.run(eng.upload(host), fetch='records')                        # now sized generously: no second fit
     np.testing.assert_array_equal(again.rows, want.rows)
     assert again.launches < got.launches
+
+
+@pytest.mark.parametrize('fetch,sm', [('full', True), ('records', False)])
+def test_ranged_call_equals_single_batch(fetch, sm):
+    '''Engine.run_ranged: the events arrive in feature ranges, KS runs per range (sub-batch views of the resident
+    arrays), ONE compaction and ONE fit submission follow -- every output equals the single-submission call's, bit for
+    bit, with an empty feature and a very uneven range in the mix'''
+    from yanocomp_b200.api import test_host_batch as run_single, test_host_batch_ranged as run_ranged
+    from yanocomp_b200.engine import Engine, EngineParams
+    feats = (synth.make_dataset(31, 5, 40, [22, 30, 25, 28], 2, 2, planted_frac=0.25, with_ids=True)
+             + synth.make_dataset(32, 1, 2, [22, 30, 25, 28], 2, 2)               # narrower than the window: no window
+             + synth.make_dataset(33, 6, 25, [40, 36, 44, 38], 2, 2, planted_frac=0.3, with_ids=True))
+    host = HostBatch(feats, 4, 2)
+    params = EngineParams(window_size=3, generate_sm_preds=sm)
+    one = run_single(host, params, Engine(params), fetch=fetch)
+    for ranges, first in ((4, 1.0), (7, 0.2), (2, 1.0), (1, 1.0)):
+        two = run_ranged(host, params, Engine(params), fetch=fetch, ranges=ranges, first=first)
+        names = ['status', 'fit_list', 'status_fit', 'ks_stat_fit', 'ks_pval_fit', 'nc_fit', 'nall_fit', 'rows']
+        if fetch == 'full':
+            names += ['ks_stat', 'ks_pval', 'n_c', 'n_t', 'mu', 'cov', 'stats', 'preds', 'iters']
+        for k in names:
+            a, b = getattr(one, k), getattr(two, k)
+            assert (a is None) == (b is None), k
+            if a is not None:
+                np.testing.assert_array_equal(a, b, err_msg=f'{k} (ranges={ranges})')
+        if sm:                                   # posterior blocks are reserved with an atomic cursor: compare per slot
+            assert ((one.post_off >= 0) == (two.post_off >= 0)).all() and (one.post_off >= 0).sum() > 5
+            for s_ in np.flatnonzero(one.post_off >= 0):
+                n_ = int(one.nall_fit[s_])
+                np.testing.assert_array_equal(one.post[one.post_off[s_]:one.post_off[s_] + n_],
+                                              two.post[two.post_off[s_]:two.post_off[s_] + n_])
+        assert two.n_fitted == one.n_fitted > 20 and two.h2d_bytes == host.nbytes

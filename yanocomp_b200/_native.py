@@ -77,6 +77,7 @@ _PROTOTYPES = {
     'yc_assemble_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_int64, C.c_void_p]),
     'yc_ks_batch': (C.c_int, [_P(Batch), _P(Params)] + [C.c_void_p] * 8),
+    'yc_compact_gated': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     # (fit_list, n_fit, fit_count): fit_count = device int32 written by yc_ks_batch, or None for exactly n_fit slots
     'yc_gmm_init_batch': (C.c_int, [_P(Batch), _P(Params), C.c_void_p, C.c_int32, C.c_void_p, _P(FitOut),
                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -37,6 +37,18 @@ def test_host_batch_pipelined(host: HostBatch, params: EngineParams, engine: Eng
     return list(eng.run_pipelined(host.split(chunks, growth, first), fetch=fetch, keep_results=True))
 
 
+def test_host_batch_ranged(host: HostBatch, params: EngineParams, engine: Engine = None,
+                           fetch='records', ranges=4, growth=1.0, first=1.0) -> BatchResult:
+    '''
+    Same as test_host_batch with the upload hidden behind the KS stage: the batch stays ONE device batch, its event
+    matrix arrives in `ranges` feature ranges, the KS kernels of a range run while the next one is in flight, and the
+    fit stage is a single submission over the whole batch (Engine.run_ranged).  One BatchResult, identical to
+    test_host_batch's.  Measured slower than test_host_batch_pipelined on cfg2 (13.2 vs 12.3 ms): see Engine.run_ranged.
+    '''
+    eng = engine or Engine(params)
+    return eng.run_ranged(host, n_ranges=ranges, fetch=fetch, growth=growth, first=first)
+
+
 def tested_table(host: HostBatch, res: BatchResult, gmm=True):
     '''
     Rows of the reference's result DataFrame (gmmtest.py:216-224) as arrays:

@@ -179,19 +179,16 @@ class HostBatch:
         v.max_cond_reads = int(max(split.max(), (v.n_reads - split).max())) if f1 > f0 else 0
         return v
 
-    def split(self, k, growth=1.0, first=1.0):
-        '''
-        At most k views for host->device / compute pipelining.  growth = 1: balanced event bytes;
-        growth > 1: every view is `growth` times the previous one, so the first upload (which nothing
-        can hide) is short and the later, larger ones hide behind the kernels of their predecessors.
-        '''
+    def range_cuts(self, k, growth=1.0, first=1.0):
+        '''feature indices [0, ..., F] of at most k ranges of balanced (growth = 1) or geometrically growing event bytes;
+        first < 1 shortens the first range (its upload is the one nothing can hide)'''
         F = self.n_features
         if k <= 1 or F < 2:
-            return [self]
+            return [0, F]
         sizes = self.n_cols.astype(np.int64) * self.ld
         cum = np.cumsum(sizes)
         w = np.power(float(growth), np.arange(k))
-        w[0] *= float(first)                 # a shorter first range: its upload is the one nothing can hide
+        w[0] *= float(first)
         targets = np.cumsum(w) / w.sum()
         cuts = [0]
         for j in range(k - 1):
@@ -199,6 +196,17 @@ class HostBatch:
             if cuts[-1] < c < F:
                 cuts.append(c)
         cuts.append(F)
+        return cuts
+
+    def split(self, k, growth=1.0, first=1.0):
+        '''
+        At most k views for host->device / compute pipelining.  growth = 1: balanced event bytes;
+        growth > 1: every view is `growth` times the previous one, so the first upload (which nothing
+        can hide) is short and the later, larger ones hide behind the kernels of their predecessors.
+        '''
+        cuts = self.range_cuts(k, growth, first)
+        if len(cuts) == 2:
+            return [self]
         return [self.view(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
 
     @staticmethod
@@ -251,31 +259,79 @@ class DeviceBatch:
         '''the buffers were allocated on another stream than the one whose kernels read them'''
         for name in self._TENSORS:
             getattr(self, name).record_stream(stream)
+        if getattr(self, '_blob', None) is not None:
+            self._blob.record_stream(stream)
 
-    def __init__(self, host, device=None, stream=None):
+    def __init__(self, host, device=None, stream=None, events=None, stage=None, extra=None):
+        # events: a device int16 tensor the caller has allocated and is filling itself (Engine.run_ranged copies the
+        #         event matrix range by range on its copy stream); plain HostBatch only
+        # stage:  callable(nbytes) -> (pinned uint8 torch tensor, callback to call once the copy out of it is enqueued).
+        #         With it the per-feature / per-column tables (and the arrays of `extra`, which become self.extra[name])
+        #         travel as ONE asynchronous copy from pinned memory, enqueued BEFORE the event matrix, instead of a dozen
+        #         pageable ones -- a pageable copy blocks the host until every transfer queued before it has finished
+        #         (half of them used to be issued behind the event matrix: ~0.9 ms of host stall per 50 MB range)
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError('yanocomp_b200 needs a CUDA device (no CPU fallback)')
         self.host = host
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         dev = self.device
+        self.extra = {}
+        packed = {}
+        if stage is not None:
+            F0 = host.n_features
+            tables = dict(x_off=(host.x_off, np.int64), n_cols=(host.n_cols, np.int32), n_reads=(host.n_reads, np.int32),
+                          ld=(host.ld, np.int32), col_off=(host.col_off, np.int64),
+                          samp_start=(host.samp_start.reshape(-1), np.int32),
+                          feature_key=(host.feature_key.view(np.int64), np.int64), reverse=(host.reverse, np.uint8))
+            if host.total_cols:
+                tables['col_pos'] = (host.col_pos, np.int64)
+            if isinstance(host, DenseHostBatch):
+                if len(host.tasks32):
+                    tables['tasks'] = (host.tasks32.reshape(-1), np.int64)
+                tables['colmap'] = (host.colmap, np.int32)
+            for k, a in (extra or {}).items():
+                tables['extra:' + k] = (a, a.dtype)
+            offs, at = {}, 0
+            for k, (a, dt) in tables.items():
+                a = np.ascontiguousarray(a)
+                assert a.dtype == dt, (k, a.dtype, dt)
+                offs[k] = (at, a)
+                at += (a.nbytes + 63) & ~63
+            pin, enqueued = stage(max(at, 64))
+            pin_np = pin.numpy()
+            for k, (o, a) in offs.items():
+                if a.nbytes:
+                    pin_np[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+            blob = torch.empty(max(at, 64), dtype=torch.uint8, device=dev)
+            blob.copy_(pin[:max(at, 64)], non_blocking=True)
+            enqueued()
+            self._blob = blob
+            for k, (o, a) in offs.items():
+                t = blob[o:o + a.nbytes].view(getattr(torch, str(a.dtype)))
+                if k.startswith('extra:'):
+                    self.extra[k[6:]] = t
+                else:
+                    packed[k] = t
 
-        def up(a, dtype):
+        def up(a, dtype, name=None):
+            if name in packed:
+                return packed[name]
             a = np.ascontiguousarray(a)
             assert a.dtype == dtype, (a.dtype, dtype)
             return torch.from_numpy(a).to(dev, non_blocking=True)
 
         F = host.n_features
-        self.x_off = up(host.x_off, np.int64)
-        self.n_cols = up(host.n_cols, np.int32)
-        self.n_reads = up(host.n_reads, np.int32)
-        self.ld = up(host.ld, np.int32)
+        self.x_off = up(host.x_off, np.int64, 'x_off')
+        self.n_cols = up(host.n_cols, np.int32, 'n_cols')
+        self.n_reads = up(host.n_reads, np.int32, 'n_reads')
+        self.ld = up(host.ld, np.int32, 'ld')
         if isinstance(host, DenseHostBatch):
             # the sample files' bytes as they are + the task table; the feature matrices are assembled on the device
             host.wait()
             raw = torch.from_numpy(host.raw.view(np.int16)).to(dev, non_blocking=True)
-            tasks = up(host.tasks32.reshape(-1), np.int64) if len(host.tasks32) else torch.zeros(8, dtype=torch.int64, device=dev)
-            colmap = up(host.colmap, np.int32)
+            tasks = up(host.tasks32.reshape(-1), np.int64, 'tasks') if len(host.tasks32) else torch.zeros(8, dtype=torch.int64, device=dev)
+            colmap = up(host.colmap, np.int32, 'colmap')
             self.events = torch.empty(max(host.n_events_elems, 8), dtype=torch.int16, device=dev)
             max_n_pos = int(host.tasks32[:, 4].max()) if len(host.tasks32) else 0
             N.check(N.lib().yc_assemble_batch(
@@ -283,13 +339,15 @@ class DeviceBatch:
                 self.ld.data_ptr(), self.events.data_ptr(), host.n_events_elems, torch.cuda.current_stream(dev).cuda_stream))
         elif hasattr(host, 'events_device'):
             self.events = host.events_device                 # generated on the device (synth.make_device_batch)
+        elif events is not None:
+            self.events = events
         else:
             self.events = torch.from_numpy(host.events.view(np.int16)).to(dev, non_blocking=True)
-        self.col_off = up(host.col_off, np.int64)
-        self.samp_start = up(host.samp_start.reshape(-1), np.int32)
-        self.feature_key = up(host.feature_key.view(np.int64), np.int64)
-        self.col_pos = up(host.col_pos, np.int64) if host.total_cols else torch.zeros(1, dtype=torch.int64, device=dev)
-        self.reverse = up(host.reverse, np.uint8)
+        self.col_off = up(host.col_off, np.int64, 'col_off')
+        self.samp_start = up(host.samp_start.reshape(-1), np.int32, 'samp_start')
+        self.feature_key = up(host.feature_key.view(np.int64), np.int64, 'feature_key')
+        self.col_pos = up(host.col_pos, np.int64, 'col_pos') if host.total_cols else torch.zeros(1, dtype=torch.int64, device=dev)
+        self.reverse = up(host.reverse, np.uint8, 'reverse')
         self.col_feature = torch.empty(max(host.total_cols, 1), dtype=torch.int32, device=dev)
         s = torch.cuda.current_stream(dev).cuda_stream
         if F:

@@ -330,6 +330,15 @@ int yc_ks_batch(const yc_batch_t *b, const yc_params_t *p,
     return cuda_fail(compact_gated(status, b->total_cols, fit_list, fit_count, st), "yc_ks_batch (compaction)");
 }
 
+int yc_compact_gated(const uint8_t *status, int64_t total_cols, int32_t *fit_list, int32_t *fit_count, void *stream) {
+    if (!status || !fit_list || !fit_count || total_cols < 0) return fail(YC_EINVAL, "yc_compact_gated: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaMemsetAsync(fit_count, 0, sizeof(int32_t), st);
+    if (ce != cudaSuccess) return cuda_fail((int)ce, "yc_compact_gated memset");
+    if (total_cols == 0) return 0;
+    return cuda_fail(compact_gated(status, total_cols, fit_list, fit_count, st), "yc_compact_gated");
+}
+
 int yc_gmm_init_batch(const yc_batch_t *b, const yc_params_t *p, const int32_t *fit_list, int32_t n_fit,
                       const int32_t *fit_count, yc_fit_out_t *out, uint8_t *status, int8_t *labels, int32_t max_fit_rows, void *stream) {
     if (int e = check_common(b, p)) return e;

@@ -167,7 +167,25 @@ class Engine:
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
     def upload(self, host: HostBatch) -> DeviceBatch:
+        # the small tables travel as pageable copies here; packing them into one pinned copy (stage=self._table_stage, what
+        # run_ranged does) was measured on the pipelined call and changes nothing: 12.46 vs 12.24-12.38 ms on cfg2
         return DeviceBatch(host, self.device)
+
+    def _table_stage(self, nbytes):
+        '''(pinned staging buffer for the packed tables of one upload, callback marking its copy as enqueued).  A ring of
+        four: the pipeline keeps at most three uploads in flight; a slot is reused only after the copy out of it finished'''
+        if not hasattr(self, '_tstage'):
+            self._tstage, self._tstage_i = [[None, None] for _ in range(4)], 0
+        i = self._tstage_i = (self._tstage_i + 1) % 4
+        slot = self._tstage[i]
+        if slot[1] is not None:
+            slot[1].synchronize()
+        if slot[0] is None or slot[0].numel() < nbytes:
+            slot[0] = torch.empty(max(int(nbytes * 1.5), 1 << 20), dtype=torch.uint8, pin_memory=True)
+
+        def enqueued():
+            slot[1] = torch.cuda.current_stream(self.device).record_event()
+        return slot[0], enqueued
 
     def run_pipelined(self, hosts, fetch='records', keep_results=False, **kw):
         '''
@@ -247,8 +265,73 @@ class Engine:
             return ctx['device']
         return self._fetch_result(ctx, stage_key)
 
+    def run_ranged(self, host: HostBatch, n_ranges=4, fetch='records', growth=1.0, first=1.0, stage_key=0, events=None):
+        '''
+        MEASURED ALTERNATIVE to run_pipelined, not the default: on cfg2 it is slower (13.2 ms against 12.3 ms per batch,
+        B200) -- with the fit stage in one piece nothing but the KS kernels can run while the events arrive (3.7 ms of
+        transfers against 3.1 ms of KS work, and KS on quarter batches is less efficient), so the GPU idles where
+        run_pipelined already fits earlier ranges.  Kept because it returns ONE result per batch and is parity-tested.
+
+        One host batch, host buffers in and host results out, with the upload hidden WITHOUT cutting the fit stage:
+        the batch becomes ONE resident device batch whose event matrix arrives in `n_ranges` feature ranges on the copy
+        stream; the KS kernels of a range start when its bytes have landed (yc_ks_batch on a sub-batch whose pointers are
+        offsets into the resident arrays) and so overlap the upload of the next one; then ONE compaction
+        (yc_compact_gated) and ONE init / EM / G-test submission cover the whole batch (no per-range ramp and tail of
+        the persistent fit kernels, no competition with the next range's KS kernels for the SMs).  Returns one
+        BatchResult for the whole batch; results are those of run() bit for bit (per-position work does not depend on
+        the batch it is part of).
+        '''
+        plain = isinstance(getattr(host, 'events', None), np.ndarray) and not hasattr(host, 'events_device') \
+            and type(host) is HostBatch and host.n_features >= 2 and host.total_cols > 0
+        if not plain or n_ranges <= 1:
+            res = self.run(self.upload(host), fetch=fetch, events=events, stage_key=stage_key)
+            if fetch:
+                res.h2d_bytes = host.nbytes
+            return res
+        d = self.device
+        compute = torch.cuda.current_stream(d)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(d)
+            self._fetch_stream = torch.cuda.Stream(d)
+        cs = self._copy_stream
+        cuts = host.range_cuts(n_ranges, growth, first)
+        # Order on the copy stream: range 0 of the event matrix, the tables (ONE asynchronous copy from a pinned staging
+        # buffer, packed by the host while range 0 travels), the other ranges.  Nothing pageable is copied once transfers
+        # are queued: a pageable copy blocks the host until everything queued before it has finished.
+        ev = torch.empty(max(int(host.events.size), 8), dtype=torch.int16, device=d)
+        cs.wait_stream(compute)      # the buffer may be a block that kernels of the previous call are still reading
+        ev.record_stream(cs)
+        src = torch.from_numpy(host.events.view(np.int16))
+        # per range: column offsets relative to the range's first column (the sub-batches' col_off)
+        rel = np.concatenate([host.col_off[a:b + 1] - host.col_off[a] for a, b in zip(cuts[:-1], cuts[1:])]).astype(np.int64)
+        ready = []
+
+        def copy_range(k):
+            a, b = cuts[k], cuts[k + 1]
+            e0 = int(host.x_off[a])
+            e1 = int(host.x_off[b]) if b < host.n_features else int(host.events.size)
+            if e1 > e0:
+                ev[e0:e1].copy_(src[e0:e1], non_blocking=True)
+            ready.append(cs.record_event())
+
+        with torch.cuda.stream(cs):
+            copy_range(0)
+            dev = DeviceBatch(host, d, events=ev, stage=self._table_stage, extra={'rel': rel})
+            tables_ready = cs.record_event()
+            for k in range(1, len(cuts) - 1):
+                copy_range(k)
+        dev.record_stream(compute)
+        compute.wait_event(tables_ready)
+        ctx = self._launch_ks(dev, events=events, ranges=(cuts, ready))
+        ctx = self._launch_fit(ctx, fetch)
+        if not fetch:
+            return ctx['device']
+        res = self._fetch_result(ctx, stage_key)
+        res.h2d_bytes = host.nbytes
+        return res
+
     # ---- stage A: KS kernels + asynchronous count of the gated positions
-    def _launch_ks(self, dev: DeviceBatch, want_labels=False, events=None):
+    def _launch_ks(self, dev: DeviceBatch, want_labels=False, events=None, ranges=None):
         def timed(name, call):
             if events is None:
                 return call()
@@ -272,10 +355,13 @@ class Engine:
         col_arena, t, col_ext, _ = _carve(specs, d)
         launches0 = lib.yc_kernel_launches()
         ps = p.struct()
-        N.check(timed('ks', lambda: lib.yc_ks_batch(
-            dev.struct, ps, t['ks_stat'].data_ptr(), t['ks_pval'].data_ptr(), t['n_c'].data_ptr(),
-            t['n_t'].data_ptr(), t['status'].data_ptr(), t['fit_list'].data_ptr(), t['fit_count'].data_ptr(),
-            stream)))
+        if ranges is None:
+            N.check(timed('ks', lambda: lib.yc_ks_batch(
+                dev.struct, ps, t['ks_stat'].data_ptr(), t['ks_pval'].data_ptr(), t['n_c'].data_ptr(),
+                t['n_t'].data_ptr(), t['status'].data_ptr(), t['fit_list'].data_ptr(), t['fit_count'].data_ptr(),
+                stream)))
+        else:
+            timed('ks', lambda: self._ks_by_ranges(dev, ps, t, ranges, stream))
         ks_done = torch.cuda.current_stream(d).record_event()
         # [n_fit, posterior reads written]: pinned, from a ring (a pinned allocation per range costs more than its kernels'
         # launches; at most a handful of ranges are in flight, so 32 slots never collide)
@@ -291,6 +377,42 @@ class Engine:
         return dict(dev=dev, t=t, col_arena=col_arena, col_ext=col_ext, ps=ps, timed=timed, want_labels=want_labels,
                     launches_ks=int(lib.yc_kernel_launches() - launches0),   # counted by the library at every <<< >>>
                     counts=counts, ks_done=ks_done, counted=torch.cuda.current_stream(d).record_event())
+
+    def _ks_by_ranges(self, dev, ps, t, ranges, stream):
+        '''yc_ks_batch per feature range of ONE resident batch (run_ranged), then the compaction over all columns'''
+        lib, d, host = self.lib, self.device, dev.host
+        cuts, ready = ranges
+        compute = torch.cuda.current_stream(d)
+        R = host.n_samples
+        rel_d = dev.extra['rel']             # per range: column offsets relative to the range's first column
+        n = max(host.total_cols, 1)
+        cf_rel = torch.empty(n, dtype=torch.int32, device=d)
+        fl_tmp = torch.empty(n, dtype=torch.int32, device=d)          # per-range lists yc_ks_batch also writes: unused
+        fc_tmp = torch.empty(len(cuts), dtype=torch.int32, device=d)
+        b0 = dev.struct
+        at = 0
+        for k, (f0, f1) in enumerate(zip(cuts[:-1], cuts[1:])):
+            c0, c1 = int(host.col_off[f0]), int(host.col_off[f1])
+            rel_ptr = rel_d.data_ptr() + 8 * at
+            at += f1 - f0 + 1
+            compute.wait_event(ready[k])
+            if c1 == c0:
+                continue
+            N.check(lib.yc_fill_col_feature(f1 - f0, rel_ptr, cf_rel.data_ptr() + 4 * c0, stream))
+            sub = N.Batch(
+                n_features=f1 - f0, n_samples=b0.n_samples, n_cntrl=b0.n_cntrl, max_reads=b0.max_reads,
+                max_cond_reads=b0.max_cond_reads, total_cols=c1 - c0, flags=b0.flags,
+                events=b0.events, x_off=b0.x_off + 8 * f0, n_cols=b0.n_cols + 4 * f0, n_reads=b0.n_reads + 4 * f0,
+                ld=b0.ld + 4 * f0, col_off=rel_ptr, samp_start=b0.samp_start + 4 * f0 * (R + 1),
+                feature_key=b0.feature_key + 8 * f0, col_pos=b0.col_pos + 8 * c0, reverse=b0.reverse + f0,
+                col_feature=cf_rel.data_ptr() + 4 * c0)
+            N.check(lib.yc_ks_batch(
+                sub, ps, t['ks_stat'].data_ptr() + 8 * c0, t['ks_pval'].data_ptr() + 8 * c0, t['n_c'].data_ptr() + 4 * c0,
+                t['n_t'].data_ptr() + 4 * c0, t['status'].data_ptr() + c0, fl_tmp.data_ptr() + 4 * c0,
+                fc_tmp.data_ptr() + 4 * k, stream))
+        N.check(lib.yc_compact_gated(t['status'].data_ptr(), host.total_cols, t['fit_list'].data_ptr(),
+                                     t['fit_count'].data_ptr(), stream))
+        return 0
 
     # ---- stage B: fit kernels + gather of the fixed-width result rows
     def _launch_fit(self, ctx, fetch, force_exact=False):
