@@ -484,7 +484,7 @@ def run_gpu(args, cfg, opts_kw):
     em_name = 'gmm_em'
     em_ms = kavg.get(em_name, float('inf'))
     traffic, traffic_source = None, None
-    tfn = os.path.join(ROOT, 'profiles', 'r02h_traffic.json')
+    tfn = os.path.join(ROOT, 'profiles', 'r02ae_traffic.json')
     if os.path.exists(tfn) and args.config == 2 and not args.features:
         with open(tfn) as fh:
             tdoc = json.load(fh)

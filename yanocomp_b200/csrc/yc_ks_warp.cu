@@ -33,6 +33,10 @@ namespace yc {
 #ifndef YC_KM_UNROLL
 #define YC_KM_UNROLL 1
 #endif
+// c / n of the ECDF difference from per-position tables in shared memory (1) or computed per value by div_int_rn (0)
+#ifndef YC_KD_TABLES
+#define YC_KD_TABLES 1
+#endif
 #ifndef YC_KD_UNROLL
 #define YC_KD_UNROLL 4
 #endif
@@ -71,6 +75,10 @@ __device__ __forceinline__ double ks_sort_ecdf(double *a, const double *tabA, co
 #pragma unroll
     for (int e = 0; e < E; ++e) a[YC_KPAD(lane * E + e)] = v[e];
     __syncwarp();
+#if !YC_KD_TABLES
+    const double fn1 = (double)n1, fn2 = (double)n2;
+    const double r1 = div_rn(1.0, fn1), r2 = div_rn(1.0, fn2);
+#endif
     const int own_base = half * P, oth_base = P - own_base;
     const int n_own = half ? n2 : n1, n_oth = half ? n1 : n2;
     const int i0 = l16 * E;
@@ -95,7 +103,11 @@ __device__ __forceinline__ double ks_sort_ecdf(double *a, const double *tabA, co
                 while (cs < n_own && a[YC_KPAD(own_base + cs)] == x) ++cs;
                 if (e > 0) while (co < n_oth && a[YC_KPAD(oth_base + co)] <= x) ++co;
                 const int c1 = half ? co : cs, c2 = half ? cs : co;
+#if YC_KD_TABLES
                 dmax = max_nn(dmax, fabs(sub_rn(tabA[c1], tabB[c2])));
+#else
+                dmax = max_nn(dmax, fabs(sub_rn(div_int_rn((double)c1, fn1, r1), div_int_rn((double)c2, fn2, r2))));
+#endif
             }
         }
     }
@@ -375,8 +387,10 @@ ks_d_kernel(const yc_batch_t b, const yc_params_t p, const int P, const int64_t 
             col[j] = fbase + (int64_t)cc * ld;
             cj[j] = scr[(size_t)(2 * W * W + j) * ncol + i0 + q];
         }
-        if (n1 != tab_n1) { for (int i = lane; i <= n1; i += 32) tabA[i] = div_rn((double)i, (double)n1); tab_n1 = n1; }
-        if (n2 != tab_n2) { for (int i = lane; i <= n2; i += 32) tabB[i] = div_rn((double)i, (double)n2); tab_n2 = n2; }
+        if (YC_KD_TABLES || SE == 0) {                       // c / n tables: the deep path always, the register path by choice
+            if (n1 != tab_n1) { for (int i = lane; i <= n1; i += 32) tabA[i] = div_rn((double)i, (double)n1); tab_n1 = n1; }
+            if (n2 != tab_n2) { for (int i = lane; i <= n2; i += 32) tabB[i] = div_rn((double)i, (double)n2); tab_n2 = n2; }
+        }
         const int Pq = P;                                  // fixed by the batch (padding = +inf)
         for (int i = lane; i < 2 * Pq; i += 32) sortbuf[i] = INFINITY;
         __syncwarp();
