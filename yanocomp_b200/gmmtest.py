@@ -65,7 +65,7 @@ RESULT_COLUMNS = ['kmer', 'kmers', 'centre', 'log_odds', 'log_odds_lower_ci', 'l
 COLUMNS = POS_COLUMNS + RESULT_COLUMNS
 
 BATCH_EVENT_BYTES = 1 << 30      # host->device granularity of test_chunk
-PIPELINE_RANGES = 4              # feature ranges per batch in the upload | kernels | fetch pipeline (bench.py sweeps it)
+PIPELINE_RANGES = int(os.environ.get('YC_PIPELINE_RANGES', '4'))   # feature ranges per batch in the upload | kernels | fetch pipeline
 
 # columns whose cells are arrays of length window_size
 _ARRAY_COLUMNS = {'kmers', 'dist1_means', 'dist1_stds', 'dist2_means', 'dist2_stds'}
