@@ -409,3 +409,32 @@ def test_batch_records_wires_single_molecule_predictions_to_the_right_slots():
         assert n_reads == n_all[s] and want['kmers'] == kmers.tolist()
         seen += 1
     assert seen == 5
+
+
+def test_feature_ranges_are_views_of_the_batch():
+    '''HostBatch.range_cuts / split: ranges cover every feature once, in order, balance the event bytes, share the parent's
+    buffers, and describe the same columns with offsets relative to the range (what the pipelined and the ranged
+    engine calls rely on)'''
+    feats = synth.make_dataset(41, 9, 30, [10, 14, 12, 9], 2, 2) + synth.make_dataset(42, 3, 120, [10, 14, 12, 9], 2, 2)
+    host = HostBatch(feats, 4, 2, pin=False)
+    assert host.range_cuts(1) == [0, host.n_features] and host.split(1) == [host]
+    for k, growth, first in ((4, 1.0, 1.0), (3, 2.0, 1.0), (5, 1.0, 0.3), (40, 1.0, 1.0)):
+        cuts = host.range_cuts(k, growth, first)
+        assert cuts[0] == 0 and cuts[-1] == host.n_features and all(a < b for a, b in zip(cuts[:-1], cuts[1:]))
+        assert len(cuts) - 1 <= k
+        views = host.split(k, growth, first)
+        assert [v.n_features for v in views] == [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+        for v, a, b in zip(views, cuts[:-1], cuts[1:]):
+            c0, c1 = int(host.col_off[a]), int(host.col_off[b])
+            assert v.total_cols == c1 - c0 and v.col_off[0] == 0
+            np.testing.assert_array_equal(v.col_off, host.col_off[a:b + 1] - c0)
+            np.testing.assert_array_equal(v.col_pos, host.col_pos[c0:c1])
+            e0 = int(host.x_off[a])
+            np.testing.assert_array_equal(v.x_off, host.x_off[a:b] - e0)
+            assert np.shares_memory(v.events, host.events) and v.events.size == (
+                (int(host.x_off[b]) if b < host.n_features else host.events.size) - e0)
+            assert v.max_reads == int(host.n_reads[a:b].max())
+    sizes = host.n_cols.astype(np.int64) * host.ld
+    cuts = host.range_cuts(4)
+    per = [int(sizes[a:b].sum()) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert max(per) <= 2.5 * (sizes.sum() / 4)          # three features of 120 columns among nine of 30: still balanced
