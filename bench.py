@@ -217,16 +217,32 @@ def run_job(args, torch, dist, world, rank):
     box = [None]
     t_write = 0.0
     if rank == 0:
-        root = os.environ.get('YC_BENCH_TMP') or tempfile.gettempdir()
-        d = tempfile.mkdtemp(prefix='yc_job_', dir=root)
-        t0 = time.perf_counter()
-        c_fns, t_fns, _ = synth.write_dense_config(cfg, d, torch.device('cuda', torch.cuda.current_device()),
-                                                   n_features=n_features)
-        os.sync()                 # the inputs are "page-cache warm", not "still being written back": flush the dirty pages
-        t_write = time.perf_counter() - t0
-        box = [(d, c_fns, t_fns)]
+        # every failure of the preparation is decided HERE, before the ranks enter collectives together: the headline
+        # line must survive a full disk
+        try:
+            root = os.environ.get('YC_BENCH_TMP') or tempfile.gettempdir()
+            need = sum(2 * cfg['n_pos'] * ((cfg['reads_per_sample'] + 7) // 8 * 8)
+                       for _ in range(cfg['n_cntrl'] + cfg['n_treat'])) * n_features
+            free = shutil.disk_usage(root).free
+            if free < 1.25 * need + (1 << 30):
+                raise OSError(f'{root}: {free / 1e9:.1f} GB free, the job inputs need {need / 1e9:.1f} GB (set YC_BENCH_TMP)')
+            d = tempfile.mkdtemp(prefix='yc_job_', dir=root)
+            try:
+                t0 = time.perf_counter()
+                c_fns, t_fns, _ = synth.write_dense_config(cfg, d, torch.device('cuda', torch.cuda.current_device()),
+                                                           n_features=n_features)
+                os.sync()         # the inputs are "page-cache warm", not "still being written back": flush the dirty pages
+                t_write = time.perf_counter() - t0
+                box = [(d, c_fns, t_fns)]
+            except Exception:
+                shutil.rmtree(d, ignore_errors=True)
+                raise
+        except Exception as exc:
+            box = [{'error': f'{type(exc).__name__}: {exc}'[:300]}]
     if world > 1:
         dist.broadcast_object_list(box, src=0)
+    if isinstance(box[0], dict):
+        return box[0] if rank == 0 else None
     d, c_fns, t_fns = box[0]
     torch.cuda.empty_cache()
     kw = dict(window_size=cfg['window'])
